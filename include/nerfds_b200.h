@@ -1,0 +1,245 @@
+/* nerfds_b200 -- C ABI of the B200-native NeRF-DS ray-marching path.
+ *
+ * The reference (JokerYan/NeRF-DS, JAX/Flax) has no FFI: its "operator API"
+ * for this path is two Python call signatures.  Each entry point below names
+ * the reference interface it stands in for (file:line under /root/reference);
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would
+ * add.  Plain pointers and sizes only, no torch types.  Every function
+ * returns 0 on success or a negative ndsr_status; nothing throws across the
+ * boundary.  Calls are stream-ordered and asynchronous unless stated; a
+ * handle is bound to one CUDA device and admits one in-flight call
+ * (multi-GPU = one handle per rank / process).
+ */
+#ifndef NERFDS_B200_H_
+#define NERFDS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDSR_ABI_VERSION 1
+#define NDSR_MAX_DEPTH 8      /* hidden layers per MLP */
+#define NDSR_MAX_BANDS 12     /* posenc frequency bands per encoder */
+
+typedef enum ndsr_status {
+  NDSR_OK = 0,
+  NDSR_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  NDSR_ERR_CUDA = -2,         /* CUDA runtime error, see ndsr_last_error */
+  NDSR_ERR_PARAMS = -3,       /* missing / mis-shaped parameter tensor */
+  NDSR_ERR_NOT_LOADED = -4,   /* render before ndsr_load_params */
+  NDSR_ERR_UNSUPPORTED = -5   /* valid reference config that this engine does not build */
+} ndsr_status;
+
+/* Which engine evaluates the MLPs. */
+typedef enum ndsr_engine {
+  NDSR_ENGINE_AUTO = 0,   /* tensor-core engine when the config fits it, else SIMT */
+  NDSR_ENGINE_SIMT = 1,   /* fp32 CUDA-core engine: every output incl. d(sigma)/dx */
+  NDSR_ENGINE_TC = 2      /* tcgen05 engine (sm_100a), split-fp16 operands, fp32 accumulate */
+} ndsr_engine;
+
+/* Tensor-core operand precision (NDSR_ENGINE_TC only). */
+typedef enum ndsr_precision {
+  NDSR_PREC_MIXED = 0,    /* 3-term split fp16 on the sigma path (mask, warp, hyper-sheet,
+                             trunk, sigma/normal head), 1-term fp16 on bottleneck + rgb */
+  NDSR_PREC_FP16 = 1,     /* 1-term fp16 everywhere (fast; misses 1e-3 RGB) */
+  NDSR_PREC_SPLIT3 = 2    /* 3-term split everywhere */
+} ndsr_precision;
+
+/* Mirrors the attributes of NerfModel (hypernerf/models.py:116-229), SE3Field
+ * (warping.py:139-157), HyperSheetMLP (modules.py:354-365), MaskMLP
+ * (modules.py:396-407) that the path reads.  `size` = sizeof(ndsr_config). */
+typedef struct ndsr_config {
+  uint32_t size;
+  uint32_t abi_version;
+  float near_, far_;
+  int32_t num_warp_embeds;
+  /* template MLP */
+  int32_t use_viewdirs;
+  int32_t trunk_depth, trunk_width, trunk_skip;          /* skip layer index or -1 */
+  int32_t rgb_depth, rgb_width;
+  /* sampling */
+  int32_t num_coarse_samples, num_fine_samples;
+  int32_t use_stratified_sampling, use_white_background;
+  int32_t use_linear_disparity, use_sample_at_infinity;
+  /* positional encodings */
+  int32_t spatial_min_deg, spatial_max_deg;
+  int32_t hyper_point_min_deg, hyper_point_max_deg;
+  int32_t viewdir_min_deg, viewdir_max_deg;
+  int32_t use_posenc_identity;
+  /* hyper sheet */
+  int32_t use_hyper_sheet, hyper_num_dims;
+  int32_t hyper_sheet_min_deg, hyper_sheet_max_deg;
+  int32_t hyper_sheet_depth, hyper_sheet_width, hyper_sheet_skip;
+  /* SE3 warp field */
+  int32_t use_warp, warp_embed_dims;
+  int32_t warp_min_deg, warp_max_deg, warp_use_posenc_identity;
+  int32_t warp_depth, warp_width, warp_skip;
+  /* normal branch */
+  int32_t predict_norm, norm_input_posenc;
+  int32_t norm_input_min_deg, norm_input_max_deg;
+  int32_t use_x_in_rgb_condition;
+  /* predicted mask */
+  int32_t use_mask_in_warp, use_mask_in_hyper, use_predicted_mask;
+  int32_t use_mask_sharp_weights;
+  int32_t mask_embed_dims, mask_min_deg, mask_max_deg;
+  int32_t mask_depth, mask_width, mask_skip, mask_output_relu;
+  /* engine selection */
+  int32_t engine;      /* ndsr_engine */
+  int32_t precision;   /* ndsr_precision */
+} ndsr_config;
+
+/* One named fp32 parameter in Flax layout: Dense kernels
+ * are [rows=in, cols=out] row-major, biases [1, out], embeddings [ids, dims].
+ * `data` is a HOST pointer; ndsr_load_params copies / repacks it. */
+typedef struct ndsr_tensor {
+  const char* name;     /* e.g. "warp_field/trunk/hidden_0/kernel" */
+  const float* data;
+  int64_t rows, cols;
+} ndsr_tensor;
+
+/* TrainState.extra_params (hypernerf/model_utils.py:41-52) + the scalar
+ * keyword arguments of NerfModel.__call__ (models.py:1436-1441). */
+typedef struct ndsr_extra_params {
+  float nerf_alpha, warp_alpha, hyper_alpha, hyper_sheet_alpha;
+  float norm_input_alpha;
+  float mask_ratio;
+  float sharp_weights_std;
+  float near_override, far_override;     /* NaN = use the configured value */
+  int32_t use_predicted_norm;            /* models.py:1438 */
+  int32_t use_sigma_gradient;            /* models.py:1437 */
+  int32_t sample_at_infinity_override;   /* -1 = configured, 0/1 = override (fine level only,
+                                            models.py:1509 vs 1544) */
+} ndsr_extra_params;
+
+/* Output buffers of one level dict.  Every member is a
+ * caller-allocated, contiguous, row-major fp32 buffer or NULL; NULL = "not
+ * requested" (this is the output mask: work that only feeds NULL outputs is
+ * skipped, e.g. d(sigma)/dx when target_norm is NULL and predict_norm is
+ * set).  B = rays, S = samples of the level, H = hyper_num_dims (0 without a
+ * hyper sheet).  Device pointers for ndsr_render_rays / ndsr_render_samples,
+ * host pointers for ndsr_render_rays_host. */
+typedef struct ndsr_outputs {
+  /* per ray */
+  float* rgb;                    /* [B,3]   model_utils.py:140 */
+  float* depth;                  /* [B]     model_utils.py:141 */
+  float* med_depth;              /* [B]     model_utils.py:142 */
+  float* acc;                    /* [B]     model_utils.py:143-148 */
+  float* ray_norm;               /* [B,3]   models.py:1350-1354 */
+  float* ray_rotation_field;     /* [B,3]   models.py:1356 */
+  float* ray_translation_field;  /* [B,3]   models.py:1359 */
+  float* ray_delta_x;            /* [B,3]   models.py:1364 */
+  float* ray_hyper_points;       /* [B,H]   models.py:1370 */
+  float* ray_predicted_mask;     /* [B]     models.py:1399 */
+  float* med_points;             /* [B,3+H] models.py:1411-1415 */
+  /* per sample */
+  float* z_vals;                 /* [B,S]   (not a reference key; the sample depths used) */
+  float* weights;                /* [B,S]   model_utils.py:135 */
+  float* alpha;                  /* [B,S]   model_utils.py:129 */
+  float* accum_prod;             /* [B,S]   model_utils.py:131-134 */
+  float* sigma;                  /* [B,S]   models.py:1271 (after softplus) */
+  float* sharp_weights;          /* [B,S]   models.py:1245-1246 */
+  float* back_facing;            /* [B,S]   models.py:1341-1344 */
+  float* predicted_mask;         /* [B,S]   models.py:968 */
+  float* points;                 /* [B,S,3] models.py:893 */
+  float* warped_points;          /* [B,S,3+H] models.py:1311 */
+  float* delta_x;                /* [B,S,3] models.py:1363-1365 */
+  float* predicted_norm;         /* [B,S,3] models.py:1326 */
+  float* target_norm;            /* [B,S,3] models.py:1327-1338 (needs d(sigma)/dx) */
+} ndsr_outputs;
+
+typedef struct ndsr_handle ndsr_handle;
+
+/* Replaces models.construct_nerf / NerfModel.setup (models.py:2677-2741,
+ * 324-391): validates the configuration and binds a handle to `device`. */
+int ndsr_create(const ndsr_config* cfg, int device, ndsr_handle** out);
+void ndsr_destroy(ndsr_handle* h);
+const char* ndsr_last_error(const ndsr_handle* h);   /* h may be NULL: last create error */
+
+/* Replaces passing `{'params': P}` to model.apply (render.py:140,
+ * training.py:441): n named host tensors in Flax layout.  Synchronous. */
+int ndsr_load_params(ndsr_handle* h, const ndsr_tensor* tensors, int n);
+
+/* Replaces NerfModel.__call__ (models.py:1419-1565): coarse stratified
+ * sampling -> render_samples('coarse') -> sample_pdf -> render_samples('fine').
+ * All pointers are DEVICE pointers on the handle's device.
+ *   origins, directions [n,3]; viewdirs [n,3] or NULL (= directions, 1475-1478)
+ *   warp_id [n] (metadata['warp'], required when use_warp)
+ *   gt_mask [n] or NULL (rays_dict['mask']; required unless mask_ratio == 1)
+ *   t_rand [n,S_c], u [n,S_f]: the uniform draws of model_utils.py:84,217;
+ *     required when use_stratified_sampling, ignored otherwise.
+ *   coarse / fine: output masks+buffers; either may be NULL.
+ * `stream` is a cudaStream_t passed as void*. */
+int ndsr_render_rays(ndsr_handle* h, void* stream, int64_t n_rays,
+                     const float* origins, const float* directions,
+                     const float* viewdirs, const uint32_t* warp_id,
+                     const float* gt_mask, const float* t_rand, const float* u,
+                     const ndsr_extra_params* ep,
+                     const ndsr_outputs* coarse, const ndsr_outputs* fine);
+
+/* Same contract with HOST buffers for every input and output: copies inputs
+ * host->device, renders, copies the requested outputs device->host on
+ * `stream`, and synchronises the stream before returning.  This is the call
+ * evaluation.render_image's per-chunk round trip maps to
+ * (evaluation.py:119-130: model_fn + device_put(..., cpu)). */
+int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_rays,
+                          const float* origins, const float* directions,
+                          const float* viewdirs, const uint32_t* warp_id,
+                          const float* gt_mask, const float* t_rand, const float* u,
+                          const ndsr_extra_params* ep,
+                          const ndsr_outputs* coarse, const ndsr_outputs* fine);
+
+/* Replaces NerfModel.render_samples (models.py:867-1417): one level on
+ * caller-provided samples.  level 0 = 'coarse', 1 = 'fine' (selects the
+ * NerfMLP).  points [n,S,3] may be NULL (= origins + z_vals * directions). */
+int ndsr_render_samples(ndsr_handle* h, void* stream, int level,
+                        int64_t n_rays, int32_t n_samples,
+                        const float* points, const float* z_vals,
+                        const float* origins, const float* directions,
+                        const float* viewdirs, const uint32_t* warp_id,
+                        const float* gt_mask, const ndsr_extra_params* ep,
+                        int32_t use_sample_at_infinity,
+                        const ndsr_outputs* out);
+
+/* Replaces model_utils.sample_along_rays (model_utils.py:55-92).
+ * z_vals [n,S] out; t_rand [n,S] or NULL (non-stratified). */
+int ndsr_sample_along_rays(ndsr_handle* h, void* stream, int64_t n_rays,
+                           int32_t n_samples, float near_, float far_,
+                           int32_t use_linear_disparity,
+                           const float* t_rand, float* z_vals);
+
+/* Replaces model_utils.sample_pdf / piecewise_constant_pdf
+ * (model_utils.py:193-269).  bins [n,nb], weights [n,nb-1], u [n,nf],
+ * z_vals [n,nc] -> z_out [n,nc+nf] sorted.  Optional diagnostics:
+ * z_samples [n,nf] (pre-sort), idx_lo/idx_hi [n,nf] = positions in bins/cdf
+ * selected by the inverse CDF (the bit-exact contract), cdf [n,nb]. */
+int ndsr_sample_pdf(ndsr_handle* h, void* stream, int64_t n_rays,
+                    int32_t n_bins, int32_t n_fine, int32_t n_coarse,
+                    const float* bins, const float* weights, const float* u,
+                    const float* z_vals, float* z_out, float* z_samples,
+                    int32_t* idx_lo, int32_t* idx_hi, float* cdf);
+
+/* Replaces model_utils.volumetric_rendering (model_utils.py:95-159) +
+ * compute_depth_map.  rgb [n,S,3], sigma [n,S], z_vals [n,S], dirs [n,3]. */
+int ndsr_volumetric_rendering(ndsr_handle* h, void* stream, int64_t n_rays,
+                              int32_t n_samples, const float* rgb,
+                              const float* sigma, const float* z_vals,
+                              const float* dirs, int32_t use_white_background,
+                              int32_t sample_at_infinity,
+                              const ndsr_outputs* out);
+
+/* Introspection used by bench.py / tests. */
+int ndsr_engine_in_use(const ndsr_handle* h);             /* ndsr_engine actually selected */
+int64_t ndsr_kernel_launches(const ndsr_handle* h);       /* kernels launched so far */
+int ndsr_abi_version(void);
+/* sizeof(ndsr_config), sizeof(ndsr_extra_params), sizeof(ndsr_outputs): lets a
+ * foreign-language binding assert its struct mirrors before the first call. */
+void ndsr_struct_sizes(int32_t* config, int32_t* extra_params, int32_t* outputs);
+/* Upper bound on rays processed per internal pass (scratch = 100 B x rays x samples). */
+int ndsr_set_max_chunk(ndsr_handle* h, int64_t max_rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* NERFDS_B200_H_ */

@@ -1,0 +1,330 @@
+// Per-ray stages of the path: stratified sampling, alpha compositing and the
+// per-ray accumulations of render_samples, and the inverse-CDF resampler.
+// THIS FILE IS COMPILED WITH -fmad=false: the discrete results (inverse-CDF
+// bin indices, median-depth index) depend on fp32 rounding, so every scan here
+// is sequential left-to-right with separately rounded mul/add -- the order the
+// oracle documents.  File:line citations refer to /root/reference.
+#include "nds_common.cuh"
+#include "nds_composite.h"
+
+namespace nds {
+
+// ---------------------------------------------------------------------------
+// model_utils.sample_along_rays (model_utils.py:55-92)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float lin_z(int i, int S, float near_, float far_, int lindisp) {
+  // jnp.linspace(0, 1, S)[i] = i / (S-1), last element exactly 1
+  const float t = (i == S - 1) ? 1.f : (float)i / (float)(S - 1);
+  if (!lindisp) return near_ * (1.f - t) + far_ * t;
+  return 1.f / (1.f / near_ * (1.f - t) + 1.f / far_ * t);
+}
+
+__global__ void sample_along_rays_kernel(int64_t total, int S, float near_, float far_, int lindisp,
+                                         const float* __restrict__ t_rand, float* __restrict__ z) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= total) return;
+  const int i = (int)(n % S);
+  const float zi = lin_z(i, S, near_, far_, lindisp);
+  if (!t_rand) { z[n] = zi; return; }
+  const float lower = (i == 0) ? zi : .5f * (zi + lin_z(i - 1, S, near_, far_, lindisp));
+  const float upper = (i == S - 1) ? zi : .5f * (lin_z(i + 1, S, near_, far_, lindisp) + zi);
+  z[n] = lower + (upper - lower) * t_rand[n];
+}
+
+// ---------------------------------------------------------------------------
+// volumetric_rendering + per-ray accumulations (model_utils.py:95-159,
+// 272-317; models.py:1235-1246, 1323-1415).  One warp per ray.
+// ---------------------------------------------------------------------------
+
+__device__ __forceinline__ float softplus_f(float x) {
+  // flax nn.softplus = jnp.logaddexp(x, 0)
+  return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int CW = 4;   // warps per CTA
+
+__global__ void __launch_bounds__(CW * 32)
+composite_kernel(const __grid_constant__ CompositeArgs a) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S;
+  float* s_alpha = sm + (size_t)warp * 3 * S;
+  float* s_w = s_alpha + S;
+  float* s_T = s_w + S;
+  const int64_t ps = a.plane_stride;
+  for (int64_t ray = (int64_t)blockIdx.x * CW + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * CW) {
+    const int64_t base = ray * S;
+    const float dx = a.dirs[ray * 3], dy = a.dirs[ray * 3 + 1], dz = a.dirs[ray * 3 + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);   // jnp.linalg.norm(dirs)
+    const float last = a.sample_at_infinity ? 1e10f : 1e-19f;
+    float alpha_inf_last = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      const float raw = a.planes[P_SIGMA_RAW * ps + base + s];
+      const float sigma = a.sigma_is_activated ? raw : softplus_f(raw);
+      const float zs = a.z[base + s];
+      const float dist = ((s == S - 1) ? last : (a.z[base + s + 1] - zs)) * dnorm;
+      s_alpha[s] = 1.f - expf(-sigma * dist);
+      if (s == S - 1) alpha_inf_last = 1.f - expf(-sigma * (1e10f * dnorm));
+      if (a.out.sigma) a.out.sigma[base + s] = sigma;
+    }
+    __syncwarp();
+    // sequential exclusive cumprod / cumsum (lane 0) -- the documented order
+    int med_idx = 0;
+    float med_found = 0.f;
+    if (lane == 0) {
+      float T = 1.f, cum = 0.f;
+      bool found = false;
+      for (int s = 0; s < S; ++s) {
+        const float al = s_alpha[s];
+        const float w = al * T;
+        s_T[s] = T;
+        s_w[s] = w;
+        cum = cum + w;
+        if (!found && cum >= 0.5f) { found = true; med_idx = s; }
+        T = T * (1.f - al + 1e-10f);
+      }
+      med_found = found ? 1.f : 0.f;
+    }
+    med_idx = __shfl_sync(0xffffffffu, med_idx, 0);
+    med_found = __shfl_sync(0xffffffffu, med_found, 0);
+    __syncwarp();
+    // per-ray reductions
+    float r[3] = {0, 0, 0}, depth = 0, acc = 0, acc_m1 = 0, rn[3] = {0, 0, 0}, rr[3] = {0, 0, 0},
+          rt[3] = {0, 0, 0}, rdx[3] = {0, 0, 0}, rh[2] = {0, 0}, rm = 0;
+    float best_w = -1.f; int best_i = 0;
+    const float vx = a.viewdirs[ray * 3], vy = a.viewdirs[ray * 3 + 1], vz = a.viewdirs[ray * 3 + 2];
+    const float ox = a.origins ? a.origins[ray * 3] : 0.f, oy = a.origins ? a.origins[ray * 3 + 1] : 0.f,
+                oz = a.origins ? a.origins[ray * 3 + 2] : 0.f;
+    for (int s = lane; s < S; s += 32) {
+      const int64_t n = base + s;
+      const float w = s_w[s];
+      const float zs = a.z[n];
+      float c[3], nv[3] = {0, 0, 0}, wp[5], px[3];
+      for (int i = 0; i < 3; ++i) c[i] = a.planes[(P_RGB + i) * ps + n];
+      for (int i = 0; i < 3 + a.H; ++i) wp[i] = a.planes[(P_WARPED + i) * ps + n];
+      if (a.points) { px[0] = a.points[n * 3]; px[1] = a.points[n * 3 + 1]; px[2] = a.points[n * 3 + 2]; }
+      else { px[0] = ox + zs * dx; px[1] = oy + zs * dy; px[2] = oz + zs * dz; }
+      for (int i = 0; i < 3; ++i) r[i] += w * c[i];
+      depth += w * zs;
+      acc += w;
+      if (s < S - 1) acc_m1 += w;
+      if (a.has_norm) {
+        for (int i = 0; i < 3; ++i) { nv[i] = a.planes[(P_NORM + i) * ps + n]; rn[i] += w * nv[i]; }
+        if (a.out.back_facing) {
+          const float bf = fmaxf(nv[0] * vx + nv[1] * vy + nv[2] * vz, 0.f);
+          a.out.back_facing[n] = bf * bf;
+        }
+        if (a.out.predicted_norm) for (int i = 0; i < 3; ++i) a.out.predicted_norm[n * 3 + i] = nv[i];
+      } else if (a.has_grad) {
+        for (int i = 0; i < 3; ++i) rn[i] += w * a.planes[(P_GRAD + i) * ps + n];   // models.py:1353
+      }
+      if (a.has_grad && a.has_norm && a.out.target_norm)
+        for (int i = 0; i < 3; ++i) a.out.target_norm[n * 3 + i] = a.planes[(P_TNORM + i) * ps + n];
+      if (a.has_warp) for (int i = 0; i < 3; ++i) {
+        rr[i] += w * a.planes[(P_ROT + i) * ps + n];
+        rt[i] += w * a.planes[(P_TRANS + i) * ps + n];
+      }
+      for (int i = 0; i < 3; ++i) {
+        const float d = wp[i] - px[i];
+        rdx[i] += w * d;
+        if (a.out.delta_x) a.out.delta_x[n * 3 + i] = d;
+        if (a.out.points) a.out.points[n * 3 + i] = px[i];
+      }
+      for (int i = 0; i < a.H; ++i) rh[i] += w * wp[3 + i];
+      if (a.out.warped_points) for (int i = 0; i < 3 + a.H; ++i) a.out.warped_points[n * (3 + a.H) + i] = wp[i];
+      if (a.has_mask) {
+        const float m = a.planes[P_MASK * ps + n];
+        rm += w * m;
+        if (a.out.predicted_mask) a.out.predicted_mask[n] = m;
+      }
+      if (a.out.weights) a.out.weights[n] = w;
+      if (a.out.alpha) a.out.alpha[n] = s_alpha[s];
+      if (a.out.accum_prod) a.out.accum_prod[n] = s_T[s];
+      if (a.out.z_vals) a.out.z_vals[n] = zs;
+      // cal_weights() weights (always sample_at_infinity, model_utils.py:162) for sharpen_weights
+      const float wsg = (s == S - 1) ? alpha_inf_last * s_T[s] : w;
+      if (a.weights_sg) a.weights_sg[n] = wsg;
+      if (wsg > best_w) { best_w = wsg; best_i = s; }
+    }
+    // argmax (first occurrence) across lanes
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ow = __shfl_xor_sync(0xffffffffu, best_w, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ow > best_w || (ow == best_w && oi < best_i)) { best_w = ow; best_i = oi; }
+    }
+    for (int i = 0; i < 3; ++i) { r[i] = warp_sum(r[i]); rn[i] = warp_sum(rn[i]); rr[i] = warp_sum(rr[i]);
+                                  rt[i] = warp_sum(rt[i]); rdx[i] = warp_sum(rdx[i]); }
+    depth = warp_sum(depth); acc = warp_sum(acc); acc_m1 = warp_sum(acc_m1); rm = warp_sum(rm);
+    rh[0] = warp_sum(rh[0]); rh[1] = warp_sum(rh[1]);
+    if (lane == 0) {
+      const ndsr_outputs& o = a.out;
+      if (a.white_bkgd) for (int i = 0; i < 3; ++i) r[i] = r[i] + (1.f - acc);
+      if (o.rgb) for (int i = 0; i < 3; ++i) o.rgb[ray * 3 + i] = r[i];
+      if (o.depth) o.depth[ray] = depth;
+      if (o.med_depth) o.med_depth[ray] = med_found != 0.f ? a.z[base + med_idx] : 0.f;
+      if (o.acc) o.acc[ray] = a.sample_at_infinity ? acc_m1 : acc;
+      if (o.ray_norm && (a.has_norm || a.has_grad)) for (int i = 0; i < 3; ++i) o.ray_norm[ray * 3 + i] = rn[i];
+      if (o.ray_rotation_field && a.has_warp) for (int i = 0; i < 3; ++i) o.ray_rotation_field[ray * 3 + i] = rr[i];
+      if (o.ray_translation_field && a.has_warp) for (int i = 0; i < 3; ++i) o.ray_translation_field[ray * 3 + i] = rt[i];
+      if (o.ray_delta_x) for (int i = 0; i < 3; ++i) o.ray_delta_x[ray * 3 + i] = rdx[i];
+      if (o.ray_hyper_points) for (int i = 0; i < a.H; ++i) o.ray_hyper_points[ray * a.H + i] = rh[i];
+      if (o.ray_predicted_mask && a.has_mask) o.ray_predicted_mask[ray] = rm;
+      if (o.med_points) for (int i = 0; i < 3 + a.H; ++i)
+        o.med_points[ray * (3 + a.H) + i] = a.planes[(P_WARPED + i) * ps + base + med_idx];
+      if (a.argmax_idx) a.argmax_idx[ray] = (float)best_i;
+    }
+    __syncwarp();
+  }
+}
+
+// model_utils.sharpen_weights (model_utils.py:180-190) INCLUDING the row-gather
+// quirk: the gaussian of ray b is centred on z_vals[clamp(argmax_b, B-1)][s]
+// (a *ray* index).  One warp per ray.
+__global__ void __launch_bounds__(CW * 32)
+sharpen_weights_kernel(int64_t n_rays, int S, const float* __restrict__ weights_sg, const float* __restrict__ z,
+                       const float* __restrict__ argmax_idx, float stdv, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t ray = (int64_t)blockIdx.x * CW + warp; ray < n_rays; ray += (int64_t)gridDim.x * CW) {
+    int64_t src = (int64_t)argmax_idx[ray];
+    if (src > n_rays - 1) src = n_rays - 1;
+    float tot = 0.f;
+    for (int s = lane; s < S; s += 32) {
+      const float d = (z[ray * S + s] - z[src * S + s]) / stdv;
+      const float g = expf(-0.5f * (d * d)) / (2.50662827463100050242f * stdv);   // jscipy.stats.norm.pdf
+      const float v = weights_sg[ray * S + s] * g;
+      out[ray * S + s] = v;
+      tot += v;
+    }
+    tot = warp_sum(tot);
+    for (int s = lane; s < S; s += 32) out[ray * S + s] = out[ray * S + s] / tot;
+  }
+}
+
+// rgb [n,S,3] + sigma [n,S] -> planes, for the stand-alone volumetric_rendering entry point
+__global__ void pack_rgb_sigma_kernel(int64_t total, const float* __restrict__ rgb, const float* __restrict__ sigma,
+                                      float* planes, int64_t ps) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= total) return;
+  planes[P_SIGMA_RAW * ps + n] = sigma[n];
+  for (int i = 0; i < 3; ++i) planes[(P_RGB + i) * ps + n] = rgb[n * 3 + i];
+  for (int i = 0; i < 5; ++i) planes[(P_WARPED + i) * ps + n] = 0.f;
+}
+
+// ---------------------------------------------------------------------------
+// model_utils.piecewise_constant_pdf + sample_pdf (model_utils.py:193-269).
+// One warp per ray.  n = n_bins = len(bins) = len(cdf); weights has n-1 entries.
+// ---------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(CW * 32)
+sample_pdf_kernel(const __grid_constant__ SamplePdfArgs a) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = a.n_bins, nf = a.n_fine, nc = a.n_coarse, nt = nc + nf;
+  float* s_cdf = sm + (size_t)warp * (2 * n + nt);
+  float* s_bins = s_cdf + n;
+  float* s_all = s_bins + n;
+  const float eps = 1e-5f;
+  for (int64_t ray = (int64_t)blockIdx.x * CW + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * CW) {
+    for (int j = lane; j < n - 1; j += 32) s_cdf[j + 1] = a.weights[ray * a.w_stride + j] + eps;   // weights += eps
+    for (int j = lane; j < n; j += 32)
+      s_bins[j] = a.bins ? a.bins[ray * n + j]
+                         : .5f * (a.z_coarse[ray * nc + j + 1] + a.z_coarse[ray * nc + j]);   // models.py:1522
+    for (int j = lane; j < nc; j += 32) s_all[j] = a.z_coarse[ray * nc + j];
+    __syncwarp();
+    if (lane == 0) {
+      float tot = 0.f;
+      for (int j = 1; j < n; ++j) tot = tot + s_cdf[j];          // weights.sum(-1), sequential
+      float c = 0.f;
+      s_cdf[0] = 0.f;
+      for (int j = 1; j < n; ++j) { c = c + s_cdf[j] / tot; s_cdf[j] = c; }   // cumsum(pdf)
+    }
+    __syncwarp();
+    if (a.cdf_out) for (int j = lane; j < n; j += 32) a.cdf_out[ray * n + j] = s_cdf[j];
+    for (int j = lane; j < nf; j += 32) {
+      float uj;
+      if (a.u) uj = a.u[ray * nf + j];
+      else uj = (j == nf - 1) ? 1.f : (float)j / (float)(nf - 1);
+      // k = #{i : cdf_i <= u}  (mask = u >= cdf, model_utils.py:223); cdf is non-decreasing
+      int lo_b = 0, hi_b = n;
+      while (lo_b < hi_b) { const int mid = (lo_b + hi_b) >> 1; if (s_cdf[mid] <= uj) lo_b = mid + 1; else hi_b = mid; }
+      const int k = lo_b;
+      int lo = k - 1; lo = lo < 0 ? 0 : (lo > n - 2 ? n - 2 : lo);     // max-select then min with x[-2]
+      int hi = k; hi = hi < 1 ? 1 : (hi > n - 1 ? n - 1 : hi);         // min-select then max with x[1]
+      const float c0 = s_cdf[lo], c1 = s_cdf[hi], b0 = s_bins[lo], b1 = s_bins[hi];
+      float denom = c1 - c0;
+      denom = denom < eps ? 1.f : denom;
+      const float t = (uj - c0) / denom;
+      const float zs = b0 + t * (b1 - b0);
+      s_all[nc + j] = zs;
+      if (a.z_samples) a.z_samples[ray * nf + j] = zs;
+      if (a.idx_lo) a.idx_lo[ray * nf + j] = lo;
+      if (a.idx_hi) a.idx_hi[ray * nf + j] = hi;
+    }
+    __syncwarp();
+    // jnp.sort(concat([z_vals, z_samples])) by stable rank counting
+    for (int i = lane; i < nt; i += 32) {
+      const float v = s_all[i];
+      int rank = 0;
+      for (int j = 0; j < nt; ++j) {
+        const float o = s_all[j];
+        rank += (o < v || (o == v && j < i)) ? 1 : 0;
+      }
+      a.z_out[ray * nt + rank] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+static int grid_for(int64_t rays, int num_sms) {
+  int64_t g = (rays + CW - 1) / CW;
+  const int64_t cap = (int64_t)num_sms * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+cudaError_t launch_sample_along_rays(int64_t n_rays, int S, float near_, float far_, int lindisp,
+                                     const float* t_rand, float* z, cudaStream_t st) {
+  const int64_t total = n_rays * S;
+  if (total == 0) return cudaSuccess;
+  sample_along_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, S, near_, far_, lindisp, t_rand, z);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_composite(const CompositeArgs& a, int num_sms, cudaStream_t st) {
+  if (a.n_rays == 0) return cudaSuccess;
+  const size_t smem = (size_t)CW * 3 * a.S * sizeof(float);
+  composite_kernel<<<grid_for(a.n_rays, num_sms), CW * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sharpen(int64_t n_rays, int S, const float* wsg, const float* z, const float* argmax_idx,
+                           float stdv, float* out, int num_sms, cudaStream_t st) {
+  if (n_rays == 0) return cudaSuccess;
+  sharpen_weights_kernel<<<grid_for(n_rays, num_sms), CW * 32, 0, st>>>(n_rays, S, wsg, z, argmax_idx, stdv, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_rgb_sigma(int64_t total, const float* rgb, const float* sigma, float* planes, int64_t ps,
+                                  cudaStream_t st) {
+  if (total == 0) return cudaSuccess;
+  pack_rgb_sigma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, rgb, sigma, planes, ps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample_pdf(const SamplePdfArgs& a, int num_sms, cudaStream_t st) {
+  if (a.n_rays == 0) return cudaSuccess;
+  const size_t smem = (size_t)CW * (2 * a.n_bins + a.n_coarse + a.n_fine) * sizeof(float);
+  sample_pdf_kernel<<<grid_for(a.n_rays, num_sms), CW * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace nds

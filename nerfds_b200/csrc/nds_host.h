@@ -1,0 +1,76 @@
+// Host-side declarations shared by the translation units of libnerfds_b200.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "nds_common.cuh"
+
+namespace nds {
+
+// fp32 host copies of the Dense layers (Flax layout), kept so the tensor-core
+// engine can repack them into its split-fp16 shared-memory images.
+struct HostDense {
+  std::vector<float> W, b;
+  int K = 0, N = 0;
+};
+struct HostMlp {
+  std::vector<HostDense> hidden;
+  HostDense logit;
+  int depth = 0, width = 0, in_dim = 0, skip = -1;
+};
+struct HostModel {
+  HostMlp mask, warp, hyper, trunk[2], rgb[2];
+  HostDense warp_w, warp_v, bottleneck[2], alpha[2];
+  std::vector<float> warp_embed, mask_embed;
+};
+
+struct TcEngine;   // opaque, nds_field_tc.cu
+
+}  // namespace nds
+
+struct ndsr_handle {
+  ndsr_config cfg;
+  int device = 0, num_sms = 0, cc_major = 0;
+  int engine = NDSR_ENGINE_SIMT;
+  bool loaded = false;
+  std::string err;
+  int64_t launches = 0;
+  // derived dims
+  int H = 0, dim_mask_in = 0, dim_warp_in = 0, dim_hyper_in = 0, dim_trunk_in = 0, dim_view = 0, dim_norm = 0;
+  int max_in = 0, max_w = 0, rgb_in_full = 0;
+  // parameters
+  float* arena = nullptr;
+  nds::ModelW M;
+  nds::HostModel host_model;
+  nds::TcEngine* tc = nullptr;
+  // scratch (grown on demand)
+  std::vector<void*> scratch_allocs;
+  int64_t cap_rays = 0, cap_samples = 0, max_samples_seen = 0;
+  int64_t max_chunk = 65536;
+  float *planes = nullptr, *z_coarse = nullptr, *z_fine = nullptr, *w_coarse = nullptr, *w_sg = nullptr,
+        *argmax = nullptr;
+  void* in_stage = nullptr;
+  size_t in_stage_bytes = 0;
+};
+
+namespace nds {
+
+void make_call_params(const ndsr_config& c, const ndsr_extra_params& ep, CallParams& cp);
+
+// nds_field_simt.cu
+size_t field_simt_smem_bytes(const ndsr_config& c, int max_in, int max_w, int x2, bool grad, int* ld);
+cudaError_t launch_field_simt(const ModelW& M, const CallParams& cp, const FieldArgs& a, const ndsr_config& cfg,
+                              int max_in, int max_w, int x2, int num_sms, cudaStream_t stream);
+
+// nds_field_tc.cu
+std::string tc_engine_supports(const ndsr_config& c, int cc_major, int cc_minor);
+int tc_engine_load(ndsr_handle* h);
+int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, cudaStream_t st);
+void tc_engine_free(ndsr_handle* h);
+
+}  // namespace nds
+
+// nds_composite.cu (declared here with their arg structs)
+#include "nds_composite.h"
