@@ -76,8 +76,9 @@ def all_gather_level(level: Dict[str, torch.Tensor], group=None) -> Dict[str, to
   W = dist.get_world_size(group)
   names = sorted(level)
   flat = torch.cat([level[k].reshape(-1) for k in names]) if names else torch.empty(0)
-  gathered = torch.empty((W, flat.numel()), dtype=flat.dtype, device=flat.device)
+  gathered = torch.empty(W * flat.numel(), dtype=flat.dtype, device=flat.device)
   dist.all_gather_into_tensor(gathered, flat.contiguous(), group=group)
+  gathered = gathered.view(W, flat.numel())
   out, off = {}, 0
   for k in names:
     n = level[k].numel()
