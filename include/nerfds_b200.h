@@ -239,6 +239,17 @@ void ndsr_struct_sizes(int32_t* config, int32_t* extra_params, int32_t* outputs)
 /* Upper bound on rays processed per internal pass (scratch = 100 B x rays x samples). */
 int ndsr_set_max_chunk(ndsr_handle* h, int64_t max_rays);
 
+/* Diagnostics: runs ONE Dense layer y = act(A W + b) for a 128-row tile through
+ * the tensor-core machinery (weight packing, bulk-TMA ring, tcgen05.mma,
+ * TMEM epilogue, swizzled split-fp16 write-back) on `device`.  Host pointers:
+ * A [128, k_hid + k_in], W [k_hid + k_in, n_out] (Flax layout), bias [n_out],
+ * out [128, n_out]; out_readback (nullable) = the activations as re-read from
+ * the shared-memory operand image (hi + lo).  terms = 1 | 3; out_kind 0 =
+ * hidden layer, 1 = head (n_out <= 16), 2 = hi-only write into the lo region. */
+int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out, int terms, int relu, int out_kind,
+                           const float* A, const float* W, const float* bias, float* out,
+                           float* out_readback);
+
 #ifdef __cplusplus
 }
 #endif
