@@ -239,6 +239,22 @@ void ndsr_struct_sizes(int32_t* config, int32_t* extra_params, int32_t* outputs)
 /* Upper bound on rays processed per internal pass (scratch = 100 B x rays x samples). */
 int ndsr_set_max_chunk(ndsr_handle* h, int64_t max_rays);
 
+/* Per-stage device timing for bench.py's roofline: when enabled, every kernel
+ * the handle launches is bracketed by CUDA events recorded on the call's own
+ * stream.  ndsr_profile_read synchronises those events and returns the
+ * accumulated milliseconds and launch counts per stage since the last enable. */
+#define NDSR_STAGE_COUNT 6
+enum ndsr_stage {
+  NDSR_STAGE_SAMPLE = 0,        /* sample_along_rays */
+  NDSR_STAGE_FIELD_COARSE = 1,  /* field kernel, coarse level */
+  NDSR_STAGE_FIELD_FINE = 2,    /* field kernel, fine level (the dominant kernel) */
+  NDSR_STAGE_COMPOSITE = 3,     /* volumetric_rendering + per-ray accumulations */
+  NDSR_STAGE_RESAMPLE = 4,      /* sample_pdf */
+  NDSR_STAGE_OTHER = 5          /* sharpen_weights, packing, copies */
+};
+int ndsr_profile_enable(ndsr_handle* h, int on);
+int ndsr_profile_read(ndsr_handle* h, double* ms, int64_t* launches);   /* arrays of NDSR_STAGE_COUNT */
+
 /* Diagnostics: runs ONE Dense layer y = act(A W + b) for a 128-row tile through
  * the tensor-core machinery (weight packing, bulk-TMA ring, tcgen05.mma,
  * TMEM epilogue, swizzled split-fp16 write-back) on `device`.  Host pointers:

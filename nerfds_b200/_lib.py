@@ -132,7 +132,8 @@ _lib = None
 EXPORTS = ['ndsr_create', 'ndsr_destroy', 'ndsr_last_error', 'ndsr_load_params', 'ndsr_render_rays',
            'ndsr_render_rays_host', 'ndsr_render_samples', 'ndsr_sample_along_rays', 'ndsr_sample_pdf',
            'ndsr_volumetric_rendering', 'ndsr_engine_in_use', 'ndsr_kernel_launches', 'ndsr_abi_version',
-           'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense']
+           'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense', 'ndsr_profile_enable',
+           'ndsr_profile_read']
 
 
 def load_library() -> C.CDLL:
@@ -167,6 +168,8 @@ def load_library() -> C.CDLL:
   lib.ndsr_struct_sizes.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
   lib.ndsr_struct_sizes.restype = None
   lib.ndsr_set_max_chunk.argtypes = [vp, i64]
+  lib.ndsr_profile_enable.argtypes = [vp, C.c_int]
+  lib.ndsr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   lib.ndsr_selftest_tc_dense.argtypes = [C.c_int] * 7 + [vp] * 5
   if lib.ndsr_abi_version() != NDSR_ABI_VERSION:
     raise ImportError('libnerfds_b200.so ABI version mismatch; rebuild')

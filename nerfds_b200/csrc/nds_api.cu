@@ -31,6 +31,58 @@ static int fail(ndsr_handle* h, int code, const std::string& msg) {
   return code;
 }
 
+// --------------------------------------------------------------- profiling
+namespace {
+cudaEvent_t prof_event(ndsr_handle* h) {
+  if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// brackets the kernels launched inside its scope with events on the call's stream
+struct ProfScope {
+  ndsr_handle* h; cudaStream_t st; int idx = -1;
+  ProfScope(ndsr_handle* h_, cudaStream_t st_, int stage) : h(h_), st(st_) {
+    if (!h->prof) return;
+    ndsr_handle::ProfSpan sp{stage, prof_event(h), prof_event(h)};
+    cudaEventRecord(sp.a, st);
+    idx = (int)h->prof_spans.size();
+    h->prof_spans.push_back(sp);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_spans[idx].b, st); }
+};
+void prof_drain(ndsr_handle* h, bool accumulate) {
+  for (auto& sp : h->prof_spans) {
+    if (accumulate) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+        h->prof_ms[sp.stage] += ms;
+        h->prof_launches[sp.stage] += 1;
+      }
+    }
+    h->prof_pool.push_back(sp.a);
+    h->prof_pool.push_back(sp.b);
+  }
+  h->prof_spans.clear();
+}
+}  // namespace
+
+extern "C" int ndsr_profile_enable(ndsr_handle* h, int on) {
+  if (!h) return NDSR_ERR_INVALID;
+  cudaSetDevice(h->device);
+  prof_drain(h, false);
+  for (int i = 0; i < NDSR_STAGE_COUNT; ++i) { h->prof_ms[i] = 0; h->prof_launches[i] = 0; }
+  h->prof = on != 0;
+  return NDSR_OK;
+}
+extern "C" int ndsr_profile_read(ndsr_handle* h, double* ms, int64_t* launches) {
+  if (!h || !ms || !launches) return NDSR_ERR_INVALID;
+  cudaSetDevice(h->device);
+  prof_drain(h, true);
+  for (int i = 0; i < NDSR_STAGE_COUNT; ++i) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_launches[i]; }
+  return NDSR_OK;
+}
+
 // ------------------------------------------------------------------ create
 static bool width_ok(int w) { return w == 32 || w == 64 || w == 128 || w == 256; }
 
@@ -149,6 +201,9 @@ extern "C" void ndsr_destroy(ndsr_handle* h) {
   cudaSetDevice(h->device);
   free_scratch(h);
   if (h->arena) cudaFree(h->arena);
+  if (h->in_stage) cudaFree(h->in_stage);
+  prof_drain(h, false);
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   tc_engine_free(h);
   delete h;
 }
@@ -431,12 +486,15 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   fa.origins = origins; fa.dirs = dirs; fa.viewdirs = viewdirs ? viewdirs : dirs; fa.warp_id = warp_id;
   fa.gt_mask = gt_mask; fa.planes = h->planes; fa.plane_stride = B * S;
   fa.sigma_only = need_rgb ? 0 : 1; fa.need_grad = need_grad ? 1 : 0;
-  if (h->engine == NDSR_ENGINE_TC && !need_grad) {
-    int rc = tc_engine_field(h, cp, fa, st);
-    if (rc) return rc;
-  } else {
-    NDS_CUDA(h, launch_field_simt(h->M, cp, fa, c, h->max_in, h->max_w, h->dim_view + h->dim_norm, h->num_sms, st));
-    h->launches++;
+  {
+    ProfScope ps(h, st, level == 0 ? NDSR_STAGE_FIELD_COARSE : NDSR_STAGE_FIELD_FINE);
+    if (h->engine == NDSR_ENGINE_TC && !need_grad) {
+      int rc = tc_engine_field(h, cp, fa, st);
+      if (rc) return rc;
+    } else {
+      NDS_CUDA(h, launch_field_simt(h->M, cp, fa, c, h->max_in, h->max_w, h->dim_view + h->dim_norm, h->num_sms, st));
+      h->launches++;
+    }
   }
   CompositeArgs ca;
   memset(&ca, 0, sizeof ca);
@@ -449,8 +507,12 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   const bool sharp = c.use_mask_sharp_weights && o.sharp_weights;
   ca.argmax_idx = sharp ? h->argmax : nullptr;
   ca.weights_sg = sharp ? h->w_sg : nullptr;
-  NDS_CUDA(h, launch_composite(ca, h->num_sms, st));
-  h->launches++;
+  {
+    ProfScope ps(h, st, NDSR_STAGE_COMPOSITE);
+    NDS_CUDA(h, launch_composite(ca, h->num_sms, st));
+    h->launches++;
+  }
+  ProfScope ps(h, st, NDSR_STAGE_OTHER);
   if (weights_keep && o.weights)
     NDS_CUDA(h, cudaMemcpyAsync(o.weights, weights_keep, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (sharp) {
@@ -503,9 +565,12 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   const int Sc = c.num_coarse_samples, Sf = c.num_fine_samples;
   const float near_ = std::isnan(ep.near_override) ? c.near_ : ep.near_override;
   const float far_ = std::isnan(ep.far_override) ? c.far_ : ep.far_override;
-  NDS_CUDA(h, launch_sample_along_rays(B, Sc, near_, far_, c.use_linear_disparity,
-                                       c.use_stratified_sampling ? t_rand : nullptr, h->z_coarse, st));
-  h->launches++;
+  {
+    ProfScope ps(h, st, NDSR_STAGE_SAMPLE);
+    NDS_CUDA(h, launch_sample_along_rays(B, Sc, near_, far_, c.use_linear_disparity,
+                                         c.use_stratified_sampling ? t_rand : nullptr, h->z_coarse, st));
+    h->launches++;
+  }
   // coarse level always uses the configured sample_at_infinity (models.py:1509)
   const bool coarse_rgb = coarse && (coarse->rgb || wants_per_sample(coarse) || coarse->ray_norm);
   int rc = run_level(h, st, 0, B, Sc, nullptr, h->z_coarse, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
@@ -519,8 +584,11 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   sa.w_stride = Sc;
   sa.u = c.use_stratified_sampling ? u : nullptr;
   sa.z_coarse = h->z_coarse; sa.z_out = h->z_fine;
-  NDS_CUDA(h, launch_sample_pdf(sa, h->num_sms, st));
-  h->launches++;
+  {
+    ProfScope ps(h, st, NDSR_STAGE_RESAMPLE);
+    NDS_CUDA(h, launch_sample_pdf(sa, h->num_sms, st));
+    h->launches++;
+  }
   const int inf_fine = ep.sample_at_infinity_override < 0 ? c.use_sample_at_infinity : ep.sample_at_infinity_override;
   return run_level(h, st, 1, B, Sc + Sf, nullptr, h->z_fine, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
                    inf_fine, fine, nullptr, true);

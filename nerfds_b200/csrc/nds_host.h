@@ -53,6 +53,13 @@ struct ndsr_handle {
         *argmax = nullptr;
   void* in_stage = nullptr;
   size_t in_stage_bytes = 0;
+  // per-stage device timing (ndsr_profile_enable / ndsr_profile_read)
+  bool prof = false;
+  struct ProfSpan { int stage; cudaEvent_t a, b; };
+  std::vector<ProfSpan> prof_spans;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[NDSR_STAGE_COUNT] = {0, 0, 0, 0, 0, 0};
+  int64_t prof_launches[NDSR_STAGE_COUNT] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace nds {

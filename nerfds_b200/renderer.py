@@ -100,6 +100,18 @@ class Renderer:
   def set_max_chunk(self, rays: int):
     self._check(self.lib.ndsr_set_max_chunk(self._h, int(rays)), 'ndsr_set_max_chunk')
 
+  STAGES = ('sample', 'field_coarse', 'field_fine', 'composite', 'resample', 'other')
+
+  def profile_enable(self, on: bool = True):
+    self._check(self.lib.ndsr_profile_enable(self._h, int(bool(on))), 'ndsr_profile_enable')
+
+  def profile_read(self):
+    """{stage: (milliseconds, launches)} accumulated since profile_enable (synchronises)."""
+    ms = (C.c_double * len(self.STAGES))()
+    n = (C.c_int64 * len(self.STAGES))()
+    self._check(self.lib.ndsr_profile_read(self._h, ms, n), 'ndsr_profile_read')
+    return {s: (float(ms[i]), int(n[i])) for i, s in enumerate(self.STAGES)}
+
   def _stream(self):
     return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

@@ -199,3 +199,44 @@ def test_sharp_weights_row_gather_quirk(cuda_device):
                 coarse_keys=('sharp_weights', 'weights'))
   c = out['coarse']['sharp_weights'].cpu().numpy()
   assert linf(c, ref['coarse']['sharp_weights']) < 5e-4
+
+
+# ------------------------------------------------- tensor-core engine (tcgen05)
+@pytest.mark.parametrize('kind', ['nerf_ds'])
+def test_tc_render_samples_vs_oracle(cuda_device, kind):
+  """The tcgen05 engine (split-fp16 operands, fp32 accumulate) on the ORACLE's
+  fine-level samples: every render key within the north_star 1e-3."""
+  cfg, params, rays, t_rand, u = make_case(kind, image=12, seed=1)
+  ref = run_oracle(cfg, params, rays, t_rand, u, compute_sigma_gradient=False)
+  m = _model(cfg, cuda_device, engine='tc')
+  assert m.renderer.engine == 'tc'
+  m.renderer.ensure_params(params)
+  extra = m.renderer.make_extra(syn.final_extra_params(), use_predicted_norm=True)
+  keys = [k for k in m.renderer.level_keys(return_points=True, return_weights=True, want_target_norm=False)]
+  for lvl, name in ((0, 'coarse'), (1, 'fine')):
+    r = ref[name]
+    out = _np(m.renderer.render_samples(lvl, r['z_vals'], rays['directions'], origins=rays['origins'],
+                                         warp_id=rays['metadata']['warp'], gt_mask=rays['mask'], extra=extra,
+                                         use_sample_at_infinity=cfg.use_sample_at_infinity, keys=keys))
+    for k in PER_RAY_KEYS:
+      if k in out and r[k].size:
+        assert linf(out[k].reshape(r[k].shape), r[k]) <= RGB_TOL, (name, k, linf(out[k].reshape(r[k].shape), r[k]))
+    for k in ('sigma', 'warped_points', 'predicted_mask', 'predicted_norm'):
+      scale = max(1.0, float(np.abs(r[k]).max()))
+      assert linf(out[k].reshape(r[k].shape), r[k]) <= 5e-4 * scale, (name, k)
+
+
+def test_tc_end_to_end_matches_simt(cuda_device):
+  """Whole NerfModel.__call__ on both engines: same sampling code, so the
+  resampled depths agree except where 1e-6 weight differences flip a bin."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=16, seed=4)
+  outs = {}
+  for eng in ('simt', 'tc'):
+    m = _model(cfg, cuda_device, engine=eng)
+    o = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True,
+                keys=('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'med_points'), coarse_keys=('rgb', 'weights'))
+    outs[eng] = {k: _np(v) for k, v in o.items()}
+  assert linf(outs['tc']['coarse']['rgb'], outs['simt']['coarse']['rgb']) <= RGB_TOL
+  assert linf(outs['tc']['coarse']['weights'], outs['simt']['coarse']['weights']) <= 2e-4
+  err = np.abs(outs['tc']['fine']['rgb'] - outs['simt']['fine']['rgb']).max(-1)
+  assert np.mean(err <= RGB_TOL) >= 0.995, np.sort(err)[-5:]
