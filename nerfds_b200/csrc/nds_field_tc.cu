@@ -3,23 +3,31 @@
 // One persistent CTA per SM processes tiles of 128 samples.  Every Dense layer
 // of the path (hypernerf/modules.py:57-83) is a [128 x K] x [K x N] GEMM issued
 // as tcgen05.mma (kind::f16, fp32 accumulators in TMEM) by ONE thread:
-//   * A = the tile's activations, kept in shared memory as split fp16
-//     (hi + lo, canonical K-major SWIZZLE_128B K-blocks) and rewritten in place
-//     by the epilogue of the previous layer;
+//   * A = the tile's activations as split fp16 (hi + lo).  Successive layers
+//     ALTERNATE between two homes -- tensor memory (TS-mode MMA, written with
+//     tcgen05.st) and shared memory (canonical K-major SWIZZLE_128B K-blocks) --
+//     so the epilogue of layer l never overwrites what layer l's MMAs still read;
 //   * B = the layer's weights, pre-packed on the host into the exact
 //     shared-memory image (scaled by a power of two, split hi + lo, swizzled)
-//     and streamed chunk by chunk through a bulk-TMA (cp.async.bulk) ring;
+//     and streamed image by image through a 4-slot bulk-TMA (cp.async.bulk) ring;
 //   * "3-term" layers issue A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (~fp32 accuracy,
 //     needed on the sigma path for the 1e-3 RGB bound -- tools/precision_study.py),
 //     "1-term" layers issue A_hi*B_hi only (bottleneck, rgb branch).
-// Warp roles: warps 0-3 = one thread per sample (TMEM lane): positional
-// encodings, SE(3) exponential, epilogues (tcgen05.ld -> bias/ReLU -> split ->
-// swizzled st.shared); warp 4 lane 0 = MMA issuer; warp 5 lane 0 = TMA producer.
+// Every layer is split into two N-chunks with separate accumulators and
+// barriers: while the tensor core works on chunk 1, the 16 compute warps drain
+// chunk 0 (tcgen05.ld -> bias/ReLU -> split -> next layer's operand), and the
+// next layer's MMAs start on the K-range chunk 0 produced before chunk 1's
+// epilogue has finished.
+// Warp roles: warps 0-15 = compute (TMEM lane quarter = warp % 4 -> 32 samples,
+// column slice / feature slice = warp / 4): positional encodings, SE(3)
+// exponential, epilogues; warp 16 lane 0 = MMA issuer; warp 17 lane 0 = TMA
+// producer.
 #include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,39 +40,68 @@ namespace nds {
 using namespace tc;
 
 constexpr int TM = 128;                 // samples per tile (UMMA M)
-constexpr int TC_THREADS = 192;
+constexpr int NSUB = 4;                 // compute warps per TMEM lane quarter
+constexpr int N_CWARPS = 4 * NSUB;
+constexpr int WARP_MMA = N_CWARPS, WARP_TMA = N_CWARPS + 1;
+constexpr int TC_THREADS = (N_CWARPS + 2) * 32;
 constexpr uint32_t KBLK = 16384;        // one 128-row K-block (64 fp16 columns)
-constexpr uint32_t OFF_HID_HI = 0;
-constexpr uint32_t OFF_HID_LO = 4 * KBLK;
+// shared memory map
+constexpr uint32_t OFF_XS_HI = 0;
+constexpr uint32_t OFF_XS_LO = 4 * KBLK;
 constexpr uint32_t OFF_IN_HI = 8 * KBLK;
 constexpr uint32_t OFF_IN_LO = 9 * KBLK;
 constexpr uint32_t OFF_RING = 10 * KBLK;
-constexpr uint32_t SLOT_BYTES = 32768;
-constexpr int NSLOT = 2;
+constexpr uint32_t SLOT_BYTES = 16384;  // one weight image: <= 128 rows x 64 fp16
+constexpr int NSLOT = 4;
 constexpr uint32_t OFF_CTRL = OFF_RING + NSLOT * SLOT_BYTES;
 constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 256 + 1024;   // + manual 1024-byte alignment slack
+// tensor memory map (512 columns): accumulators | activations hi | activations lo
+constexpr uint32_t TM_D = 0;            // N-chunk c accumulates at column 128 c
+constexpr uint32_t TM_XT_HI = 256;      // K-block j at column 32 j (two fp16 per column)
+constexpr uint32_t TM_XT_LO = 384;
 constexpr int MAX_KC = 10;
 
-enum OutKind : uint8_t { OUT_HIDDEN = 0, OUT_HEAD = 1, OUT_HIDDEN_LO_REGION = 2 };
+enum OutKind : uint8_t { OUT_XS = 0, OUT_XT = 1, OUT_XS_LO_AS_HI = 2, OUT_XT_HI_ONLY = 3, OUT_HEAD = 4 };
 enum Glue : uint8_t { GLUE_NONE = 0, GLUE_MASK = 1, GLUE_WARP = 2, GLUE_HYPER = 3, GLUE_ALPHA = 4, GLUE_BOTTLENECK = 5,
                       GLUE_RGB = 6, GLUE_SELFTEST = 7 };
-// A-operand source of a K-chunk
-constexpr uint8_t SRC_IN = 4;           // 0..3: HID block j ; 4: IN block ; 8+j: HID_LO block j used as a 1-term operand
+// A-operand source of a K-chunk: 0..3 XS block j (shared) | 4 IN block (shared) | 8+j XS_LO block j used as a
+// 1-term operand | 16+j XT block j (tensor memory)
+constexpr uint8_t SRC_IN = 4, SRC_XS_LO = 8, SRC_XT = 16;
 
+// What the compute warps need to know about one Dense layer.
 struct TcOp {
-  uint32_t w_off;        // byte offset of this op's first chunk in the weight stream
   uint32_t bias_off;     // float offset into the bias array
   float inv_scale;       // accumulators hold (scale * W) x; multiply back
-  uint16_t N;            // output columns, multiple of 16
-  uint16_t nc_rows;      // rows (output columns) per N-chunk
-  uint8_t n_kc, n_nc, terms, relu, out_kind, glue;
-  uint8_t kc_src[MAX_KC];
-  uint8_t kc_steps[MAX_KC];
+  uint16_t N;            // output columns (padded)
+  uint16_t nc_rows;      // output columns per N-chunk
+  uint8_t n_nc, relu, out_kind, glue;
+};
+
+// What the MMA issuer / TMA producer need to know about one weight image
+// (= one ring slot = up to 2 terms x 4 K-steps of tcgen05.mma).
+enum ImgFlags : uint16_t {
+  IMG_A_TMEM = 1, IMG_TWO_TERMS = 2, IMG_FIRST = 4, IMG_LAST = 8, IMG_NC1 = 16, IMG_WAIT_P0 = 32, IMG_WAIT_P1 = 64,
+  IMG_WAIT_GLUE = 128, IMG_PART_NEXT = 256
+};
+struct ImgEntry {
+  uint32_t a_hi;         // shared: byte offset from the (1024-aligned) smem base; tensor memory: column
+  uint32_t a_lo;
+  uint16_t rows;         // rows of the image = N of its MMAs (bytes = rows * 128)
+  uint8_t steps;         // K-steps, 1..4
+  uint8_t pad;
+  uint16_t flags;
+  uint16_t pad2;
+};
+
+constexpr int MAX_OPS = 48;
+constexpr int MAX_IMG = 448;
+struct TcProgram {       // passed by value as a __grid_constant__ kernel parameter (constant bank)
+  int n_ops, n_img;
+  TcOp ops[MAX_OPS];
+  ImgEntry img[MAX_IMG];
 };
 
 struct TcLevel {
-  const TcOp* ops;
-  int n_ops;
   const uint8_t* weights;
   const float* bias;
 };
@@ -75,79 +112,101 @@ struct TcLevel {
 struct Ctrl {
   uint64_t full[NSLOT];
   uint64_t empty[NSLOT];
-  uint64_t a_ready;
-  uint64_t d_ready;
+  uint64_t in_ready;        // compute -> MMA: inputs of the next network written, previous head consumed
+  uint64_t part_ready[2];   // compute -> MMA: N-chunk c of the current op drained and re-written as operand
+  uint64_t d_full[2];       // MMA -> compute: accumulators of N-chunk c complete
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t a_region(uint8_t src, bool lo) {
-  if (src < 4) return (lo ? OFF_HID_LO : OFF_HID_HI) + src * KBLK;
-  if (src == SRC_IN) return lo ? OFF_IN_LO : OFF_IN_HI;
-  return OFF_HID_LO + (src - 8) * KBLK;
+__device__ __forceinline__ void ctrl_init(Ctrl* ctl) {
+  for (int i = 0; i < NSLOT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+  mbar_init(&ctl->in_ready, N_CWARPS);
+  mbar_init(&ctl->part_ready[0], N_CWARPS);
+  mbar_init(&ctl->part_ready[1], N_CWARPS);
+  mbar_init(&ctl->d_full[0], 1);
+  mbar_init(&ctl->d_full[1], 1);
+  mbar_fence_init();
 }
 
-// MMA issuer: all chunks of one op
-__device__ __forceinline__ void issue_op(const TcOp& op, uint32_t smem_base, Ctrl* ctl, uint32_t& chunk_ctr) {
-  const uint32_t idesc = make_idesc_f16(op.nc_rows);
-  const uint32_t lo_off = (uint32_t)op.nc_rows * 128u;
-  for (int kc = 0; kc < op.n_kc; ++kc) {
-    const uint32_t a_hi = smem_base + a_region(op.kc_src[kc], false);
-    const uint32_t a_lo = smem_base + a_region(op.kc_src[kc], true);
-    const int steps = op.kc_steps[kc];
-    for (int nc = 0; nc < op.n_nc; ++nc) {
-      const uint32_t slot = chunk_ctr % NSLOT;
-      mbar_wait(&ctl->full[slot], (chunk_ctr / NSLOT) & 1u);
-      tc_fence_after_sync();
-      const uint32_t b_hi = smem_base + OFF_RING + slot * SLOT_BYTES;
-      const uint32_t d = ctl->tmem_base + (uint32_t)nc * op.nc_rows;
-      uint32_t acc = kc > 0 ? 1u : 0u;
-      for (int t = 0; t < op.terms; ++t) {
-        const uint32_t A = (t == 1) ? a_lo : a_hi;
-        const uint32_t B = (t == 2) ? b_hi + lo_off : b_hi;
-        for (int ks = 0; ks < steps; ++ks) {
-          umma_f16(d, make_smem_desc(A + ks * 32), make_smem_desc(B + ks * 32), idesc, acc);
-          acc = 1u;
+// one arrival per compute warp, after every lane made its writes visible
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  fence_proxy_async_smem();     // st.shared operand images -> async proxy (tcgen05.mma)
+  tmem_st_wait();               // tcgen05.st operand images complete
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
+// MMA issuer: the whole warp walks the image program (uniform control flow and
+// address arithmetic); one elected lane issues the tcgen05 instructions.
+__device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
+                                           bool leader, uint32_t& slot_ctr, uint32_t& part_cnt, uint32_t& glue_cnt) {
+  for (int i = 0; i < P.n_img; ++i) {
+    const ImgEntry e = P.img[i];
+    const uint32_t fl = e.flags;
+    if (fl & IMG_WAIT_GLUE) { mbar_wait(&ctl->in_ready, glue_cnt & 1u); ++glue_cnt; }
+    if (fl & IMG_WAIT_P0) mbar_wait(&ctl->part_ready[0], part_cnt & 1u);
+    if (fl & IMG_WAIT_P1) mbar_wait(&ctl->part_ready[1], part_cnt & 1u);
+    const uint32_t slot = slot_ctr % NSLOT;
+    mbar_wait(&ctl->full[slot], (slot_ctr / NSLOT) & 1u);
+    tc_fence_after_sync();
+    const uint32_t d = tmem_base + TM_D + ((fl & IMG_NC1) ? 128u : 0u);
+    const uint32_t idesc = make_idesc_f16(e.rows);
+    const uint64_t bdesc = make_smem_desc(smem_base + OFF_RING + slot * SLOT_BYTES);
+    uint32_t acc = (fl & IMG_FIRST) ? 0u : 1u;
+    const int steps = e.steps;
+    const int nterm = (fl & IMG_TWO_TERMS) ? 2 : 1;
+    if (leader) {
+      if (fl & IMG_A_TMEM) {
+        for (int t = 0; t < nterm; ++t) {
+          const uint32_t A = tmem_base + (t ? e.a_lo : e.a_hi);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < steps) { umma_f16_ts(d, A + ks * 8, bdesc + 2 * ks, idesc, acc); acc = 1u; }
+        }
+      } else {
+        for (int t = 0; t < nterm; ++t) {
+          const uint64_t adesc = make_smem_desc(smem_base + (t ? e.a_lo : e.a_hi));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < steps) { umma_f16(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, acc); acc = 1u; }
         }
       }
       umma_commit(&ctl->empty[slot]);   // frees the ring slot when these MMAs retire
-      ++chunk_ctr;
+      if (fl & IMG_LAST) umma_commit(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0]);
     }
+    __syncwarp();
+    ++slot_ctr;
+    if (fl & IMG_PART_NEXT) ++part_cnt;
   }
-  umma_commit(&ctl->d_ready);
 }
 
-// TMA producer: all chunks of one op
-__device__ __forceinline__ void produce_op(const TcOp& op, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
-                                           uint32_t& chunk_ctr) {
-  const uint32_t bytes = (uint32_t)op.nc_rows * 128u * (op.terms == 3 ? 2u : 1u);
-  const uint8_t* src = wstream + op.w_off;
-  const int n = op.n_kc * op.n_nc;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t slot = chunk_ctr % NSLOT;
-    if (chunk_ctr >= NSLOT) mbar_wait(&ctl->empty[slot], ((chunk_ctr / NSLOT) - 1u) & 1u);
-    mbar_arrive_expect_tx(&ctl->full[slot], bytes);
-    tma_bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &ctl->full[slot]);
+// TMA producer: streams every image of the program into the ring
+__device__ __forceinline__ void produce_tile(const TcProgram& P, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
+                                             bool leader, uint32_t& slot_ctr) {
+  const uint8_t* src = wstream;
+  for (int i = 0; i < P.n_img; ++i) {
+    const uint32_t bytes = (uint32_t)P.img[i].rows * 128u;
+    const uint32_t slot = slot_ctr % NSLOT;
+    if (slot_ctr >= NSLOT) mbar_wait(&ctl->empty[slot], ((slot_ctr / NSLOT) - 1u) & 1u);
+    if (leader) {
+      mbar_arrive_expect_tx(&ctl->full[slot], bytes);
+      tma_bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &ctl->full[slot]);
+    }
+    __syncwarp();
     src += bytes;
-    ++chunk_ctr;
+    ++slot_ctr;
   }
-}
-
-// store 8 consecutive activations (cols c0..c0+7, c0 % 8 == 0) of row r as split fp16
-__device__ __forceinline__ void store8_split(uint8_t* smem, uint32_t off_hi, uint32_t off_lo, bool write_lo,
-                                             uint32_t r, uint32_t c0, const float* v) {
-  __align__(16) __half2 hi[4];
-  __align__(16) __half2 lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half h0, l0, h1, l1;
-    split_h(v[2 * i], h0, l0);
-    split_h(v[2 * i + 1], h1, l1);
-    hi[i] = __halves2half2(h0, h1);
-    lo[i] = __halves2half2(l0, l1);
-  }
-  const uint32_t o = (c0 >> 6) * KBLK + kblock_offset(r, c0 & 63u);
-  *reinterpret_cast<uint4*>(smem + off_hi + o) = *reinterpret_cast<const uint4*>(hi);
-  if (write_lo) *reinterpret_cast<uint4*>(smem + off_lo + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // write one feature (col c of the IN block) of row r, split
@@ -159,38 +218,98 @@ __device__ __forceinline__ void store_in(uint8_t* smem, uint32_t r, uint32_t c, 
   *reinterpret_cast<__half*>(smem + OFF_IN_LO + o) = l;
 }
 
-// Epilogue of one op for the calling thread's row.  Heads return their (<=16)
-// outputs in hv[]; hidden layers are written back to shared memory.
-__device__ __forceinline__ void epilogue_op(const TcOp& op, const float* __restrict__ bias_base, uint8_t* smem,
-                                            uint32_t tmem_base, uint32_t row, float* hv, float* dbg_out, int dbg_ld) {
-  const uint32_t taddr = tmem_base + ((row & ~31u) << 16);
-  const float* bias = bias_base + op.bias_off;
+// Epilogue of one N-chunk for this thread's row and its CW-column slice:
+// D -> scale/bias/ReLU -> split fp16 -> the next layer's operand home.
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const float* __restrict__ bias_base,
+                                               uint8_t* smem, uint32_t tmem_lane, uint32_t row, int sub,
+                                               float* dbg_out, int dbg_ld) {
+  uint32_t v[CW];
+  tmem_ld<CW>(tmem_lane + TM_D + (uint32_t)nc * 128u + (uint32_t)sub * CW, v);
+  const uint32_t oc0 = (uint32_t)nc * op.nc_rows + (uint32_t)sub * CW;   // first output column of this slice
+  const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off + oc0);
+  float b[CW];
+#pragma unroll
+  for (int i = 0; i < CW / 4; ++i) {
+    const float4 t = __ldg(bias4 + i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+  tmem_ld_wait();
   const float inv = op.inv_scale;
-  if (op.out_kind == OUT_HEAD) {
-    uint32_t v[16];
-    tmem_ld16(taddr, v);
-    tmem_ld_wait();
+  const bool relu = op.relu != 0;
+  uint32_t hi[CW / 2], lo[CW / 2];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) hv[i] = fmaf(__uint_as_float(v[i]), inv, __ldg(bias + i));
-    if (dbg_out) for (int i = 0; i < 16 && i < op.N; ++i) dbg_out[row * dbg_ld + i] = hv[i];
-    return;
+  for (int i = 0; i < CW / 2; ++i) {
+    float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
+    float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
+    if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+    if (dbg_out) { dbg_out[row * dbg_ld + oc0 + 2 * i] = x0; dbg_out[row * dbg_ld + oc0 + 2 * i + 1] = x1; }
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
   }
-  const uint32_t off_hi = (op.out_kind == OUT_HIDDEN_LO_REGION) ? OFF_HID_LO : OFF_HID_HI;
-  const bool write_lo = op.out_kind == OUT_HIDDEN;
-  for (uint32_t c0 = 0; c0 < op.N; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr + c0, v);
-    tmem_ld_wait();
-    float f[32];
+  const uint8_t kind = op.out_kind;
+  if (kind == OUT_XT || kind == OUT_XT_HI_ONLY) {
+    uint32_t (&hi_ref)[CW / 2] = hi;
+    tmem_st<CW / 2>(tmem_lane + TM_XT_HI + (oc0 >> 1), hi_ref);
+    if (kind == OUT_XT) tmem_st<CW / 2>(tmem_lane + TM_XT_LO + (oc0 >> 1), lo);
+  } else {
+    const uint32_t off_hi = (kind == OUT_XS_LO_AS_HI) ? OFF_XS_LO : OFF_XS_HI;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = fmaf(__uint_as_float(v[i]), inv, __ldg(bias + c0 + i));
-      f[i] = op.relu ? fmaxf(x, 0.f) : x;
+    for (int g = 0; g < CW / 8; ++g) {
+      const uint32_t c = oc0 + 8 * g;
+      const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
+      *reinterpret_cast<uint4*>(smem + off_hi + o) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+      if (kind == OUT_XS)
+        *reinterpret_cast<uint4*>(smem + OFF_XS_LO + o) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
     }
-    if (dbg_out) for (int i = 0; i < 32; ++i) dbg_out[row * dbg_ld + c0 + i] = f[i];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) store8_split(smem, off_hi, OFF_HID_LO, write_lo, row, c0 + 8 * g, f + 8 * g);
   }
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint8_t* smem,
+                                                  uint32_t tmem_lane, uint32_t row, int sub, float* dbg, int dbg_ld) {
+  switch (op.nc_rows) {
+    case 128: epilogue_chunk<32>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld); break;
+    case 64: epilogue_chunk<16>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld); break;
+    default: epilogue_chunk<8>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld); break;
+  }
+}
+
+// head (<= 16 outputs): every compute warp of the lane quarter reads all of them
+__device__ __forceinline__ void epilogue_head(const TcOp& op, const float* __restrict__ bias_base, uint32_t tmem_lane,
+                                              float* hv) {
+  uint32_t v[16];
+  tmem_ld16(tmem_lane + TM_D, v);
+  tmem_ld_wait();
+  const float* bias = bias_base + op.bias_off;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hv[i] = fmaf(__uint_as_float(v[i]), op.inv_scale, __ldg(bias + i));
+}
+
+// positional encoding (model_utils.py:398-417) with the (sin, cos) pairs dealt round-robin to the NSUB warps
+// that share a sample; `pair` is the running pair counter, `o` the running feature offset.
+template <typename Store>
+__device__ __forceinline__ int posenc_emit_sub(const float* x, int C, const PosencSpec& pe, Store store, int o,
+                                               int sub, int& pair) {
+  if (pe.identity) {
+    if (sub == 0) for (int c = 0; c < C; ++c) store(o + c, x[c]);
+    o += C;
+  }
+  for (int k = 0; k < pe.num_bands; ++k) {
+    const float s = exp2f((float)(pe.min_deg + k));
+    const float w = pe.window[k];
+    for (int c = 0; c < C; ++c) {
+      if ((pair++ & (NSUB - 1)) == sub) {
+        const float xb = x[c] * s;
+        store(o + c, w * sinf(xb));
+        store(o + C + c, w * sinf(xb + NDS_HALF_PI_F));
+      }
+    }
+    o += 2 * C;
+  }
+  return o;
 }
 
 // ---------------------------------------------------------------------------
@@ -203,8 +322,9 @@ struct TcKernelArgs {
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ CallParams cp,
-                const __grid_constant__ FieldArgs a, const __grid_constant__ ndsr_config cfg) {
+field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcKernelArgs K,
+                const __grid_constant__ CallParams cp, const __grid_constant__ FieldArgs a,
+                const __grid_constant__ ndsr_config cfg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + OFF_CTRL);
@@ -212,13 +332,8 @@ field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = cfg.use_hyper_sheet ? cfg.hyper_num_dims : 0;
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
-    mbar_init(&ctl->a_ready, TM);
-    mbar_init(&ctl->d_ready, 1);
-    mbar_fence_init();
-  }
-  if (warp == 4) tmem_alloc(&ctl->tmem_base, 512);
+  if (threadIdx.x == 0) ctrl_init(ctl);
+  if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -227,29 +342,23 @@ field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ 
   const int64_t n_tiles = (a.n_samples_total + TM - 1) / TM;
   const TcLevel& L = K.lvl;
 
-  if (warp == 5) {
+  if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t cc = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int i = 0; i < L.n_ops; ++i) produce_op(L.ops[i], L.weights, smem, ctl, cc);
-    }
-  } else if (warp == 4) {
+    const bool leader = elect_one() != 0;
+    uint32_t sc = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) produce_tile(P, L.weights, smem, ctl, leader, sc);
+  } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t cc = 0, opc = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int i = 0; i < L.n_ops; ++i) {
-          mbar_wait(&ctl->a_ready, opc & 1u);
-          tc_fence_after_sync();
-          issue_op(L.ops[i], smem_base, ctl, cc);
-          ++opc;
-        }
-    }
+    const bool leader = elect_one() != 0;
+    uint32_t sc = 0, part_cnt = 0, glue_cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      issue_tile(P, smem_base, ctl, tmem_base, leader, sc, part_cnt, glue_cnt);
   } else {
-    // ===================== compute warps: one thread per sample =====================
-    const uint32_t row = threadIdx.x;
-    uint32_t opc = 0;
+    // ===================== compute warps =====================
+    const int q = warp & 3, sub = warp >> 2;
+    const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
+    const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
+    uint32_t dcnt0 = 0, dcnt1 = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t n = tile * TM + row;
       const bool valid = n < a.n_samples_total;
@@ -273,28 +382,37 @@ field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ 
         if (a.gt_mask) maskv = a.gt_mask[ray];
       }
       auto st_in = [&](int c, float v) { store_in(smem, row, (uint32_t)c, v); };
-      auto zero_in = [&](int from) { for (int c = from; c < 64; ++c) st_in(c, 0.f); };
-      // inputs of the first network of the chain
+      // columns [from, 64) of the IN block are zero (their weight rows are zero, but 0 x garbage could be NaN)
+      auto zero_in = [&](int from) { for (int c = from; c < 64; ++c) if ((c & (NSUB - 1)) == sub) st_in(c, 0.f); };
+      auto extras = [&](int o, const float* embed, int dims, bool with_mask) {
+        if (sub == 1) for (int e = 0; e < dims; ++e) st_in(o + e, __ldg(embed + (size_t)wid * dims + e));
+        o += dims;
+        if (with_mask) { if (sub == 2) st_in(o, maskv); ++o; }
+        return o;
+      };
+      // inputs of the networks of the chain
       auto prep_mask_in = [&]() {
-        int o = posenc_emit(x, 3, cp.pe_mask, st_in, 0);
-        for (int e = 0; e < cfg.mask_embed_dims; ++e) st_in(o++, __ldg(K.mask_embed + (size_t)wid * cfg.mask_embed_dims + e));
+        int pair = 0;
+        int o = posenc_emit_sub(x, 3, cp.pe_mask, st_in, 0, sub, pair);
+        o = extras(o, K.mask_embed, cfg.mask_embed_dims, false);
         zero_in(o);
       };
       auto prep_warp_in = [&]() {
-        int o = posenc_emit(x, 3, cp.pe_warp, st_in, 0);
-        for (int e = 0; e < cfg.warp_embed_dims; ++e) st_in(o++, __ldg(K.warp_embed + (size_t)wid * cfg.warp_embed_dims + e));
-        if (cfg.use_mask_in_warp) st_in(o++, maskv);
+        int pair = 0;
+        int o = posenc_emit_sub(x, 3, cp.pe_warp, st_in, 0, sub, pair);
+        o = extras(o, K.warp_embed, cfg.warp_embed_dims, cfg.use_mask_in_warp != 0);
         zero_in(o);
       };
       auto prep_hyper_in = [&]() {
-        int o = posenc_emit(x, 3, cp.pe_hsheet, st_in, 0);
-        for (int e = 0; e < cfg.warp_embed_dims; ++e) st_in(o++, __ldg(K.warp_embed + (size_t)wid * cfg.warp_embed_dims + e));
-        if (cfg.use_mask_in_hyper) st_in(o++, maskv);
+        int pair = 0;
+        int o = posenc_emit_sub(x, 3, cp.pe_hsheet, st_in, 0, sub, pair);
+        o = extras(o, K.warp_embed, cfg.warp_embed_dims, cfg.use_mask_in_hyper != 0);
         zero_in(o);
       };
       auto prep_trunk_in = [&]() {
-        int o = posenc_emit(xw, 3, cp.pe_spatial, st_in, 0);
-        if (H > 0) o = posenc_emit(om, H, cp.pe_hyperpt, st_in, o);
+        int pair = 0;
+        int o = posenc_emit_sub(xw, 3, cp.pe_spatial, st_in, 0, sub, pair);
+        if (H > 0) o = posenc_emit_sub(om, H, cp.pe_hyperpt, st_in, o, sub, pair);
         zero_in(o);
       };
       auto after_mask = [&]() { if (cfg.use_warp) prep_warp_in(); else prep_trunk_in(); };
@@ -302,17 +420,25 @@ field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ 
       if (cfg.use_predicted_mask) prep_mask_in();
       else if (cfg.use_warp) prep_warp_in();
       else { xw[0] = x[0]; xw[1] = x[1]; xw[2] = x[2]; prep_trunk_in(); }
+      warp_arrive(&ctl->in_ready, lane);
 
-      for (int i = 0; i < L.n_ops; ++i) {
-        const TcOp& op = L.ops[i];
-        fence_proxy_async_smem();          // my st.shared of A -> visible to tcgen05.mma
-        mbar_arrive(&ctl->a_ready);
-        mbar_wait(&ctl->d_ready, opc & 1u);
-        ++opc;
+      for (int i = 0; i < P.n_ops; ++i) {
+        const TcOp& op = P.ops[i];
+        if (op.out_kind != OUT_HEAD) {
+          for (int nc = 0; nc < op.n_nc; ++nc) {
+            if (nc == 0) { mbar_wait(&ctl->d_full[0], dcnt0 & 1u); ++dcnt0; }
+            else { mbar_wait(&ctl->d_full[1], dcnt1 & 1u); ++dcnt1; }
+            tc_fence_after_sync();
+            epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, nullptr, 0);
+            warp_arrive(&ctl->part_ready[nc], lane);
+          }
+          continue;
+        }
+        mbar_wait(&ctl->d_full[0], dcnt0 & 1u);
+        ++dcnt0;
         tc_fence_after_sync();
         float hv[16];
-        epilogue_op(op, L.bias, smem, tmem_base, row, hv, nullptr, 0);
-        tc_fence_before_sync();
+        epilogue_head(op, L.bias, tmem_lane, hv);
         switch (op.glue) {
           case GLUE_MASK: {            // models.py:967-975
             pmask = cfg.mask_output_relu ? fmaxf(hv[0], 0.f) : hv[0];
@@ -321,11 +447,11 @@ field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ 
           } break;
           case GLUE_WARP: {            // warping.py:217-232
             exp_se3<float>(hv, hv + 3, T);
-            for (int q = 0; q < 3; ++q) xw[q] = T.R[q * 3 + 0] * x[0] + T.R[q * 3 + 1] * x[1] + T.R[q * 3 + 2] * x[2] + T.p[q];
+            for (int c = 0; c < 3; ++c) xw[c] = T.R[c * 3 + 0] * x[0] + T.R[c * 3 + 1] * x[1] + T.R[c * 3 + 2] * x[2] + T.p[c];
             after_warp();
           } break;
           case GLUE_HYPER: {
-            for (int q = 0; q < H; ++q) om[q] = hv[q];
+            for (int c = 0; c < H; ++c) om[c] = hv[c];
             prep_trunk_in();
           } break;
           case GLUE_ALPHA: {
@@ -333,151 +459,220 @@ field_tc_kernel(const __grid_constant__ TcKernelArgs K, const __grid_constant__ 
             if (cfg.predict_norm) { nrm[0] = hv[1]; nrm[1] = hv[2]; nrm[2] = hv[3]; }
             if (!a.sigma_only) {
               // rgb branch side inputs: [viewdir feats | normal-input feats] in the IN block
-              int o = 0;
+              int o = 0, pair = 0;
               if (cfg.use_viewdirs) {
                 float vd[3] = {0.f, 0.f, 0.f};
                 if (valid) { vd[0] = a.viewdirs[ray * 3]; vd[1] = a.viewdirs[ray * 3 + 1]; vd[2] = a.viewdirs[ray * 3 + 2]; }
-                o = posenc_emit(vd, 3, cp.pe_view, st_in, 0);
+                o = posenc_emit_sub(vd, 3, cp.pe_view, st_in, 0, sub, pair);
               }
               if (cp.use_predicted_norm) {
                 float nh[3], ni[3];
                 normalize3(nrm, nh);
-                if (cfg.use_warp) { for (int q = 0; q < 3; ++q) ni[q] = T.R[0 * 3 + q] * nh[0] + T.R[1 * 3 + q] * nh[1] + T.R[2 * 3 + q] * nh[2]; }
+                if (cfg.use_warp) { for (int c = 0; c < 3; ++c) ni[c] = T.R[0 * 3 + c] * nh[0] + T.R[1 * 3 + c] * nh[1] + T.R[2 * 3 + c] * nh[2]; }
                 else { ni[0] = nh[0]; ni[1] = nh[1]; ni[2] = nh[2]; }
                 normalize3(ni, nh);
-                if (cfg.norm_input_posenc) o = posenc_emit(nh, 3, cp.pe_norm, st_in, o);
-                else { st_in(o++, nh[0]); st_in(o++, nh[1]); st_in(o++, nh[2]); }
+                if (cfg.norm_input_posenc) o = posenc_emit_sub(nh, 3, cp.pe_norm, st_in, o, sub, pair);
+                else { if (sub == 0) { st_in(o, nh[0]); st_in(o + 1, nh[1]); st_in(o + 2, nh[2]); } o += 3; }
               }
               zero_in(o);
             }
           } break;
           case GLUE_RGB: {
-            for (int q = 0; q < 3; ++q) rgb[q] = 1.f / (1.f + __expf(-hv[q]));
+            for (int c = 0; c < 3; ++c) rgb[c] = 1.f / (1.f + __expf(-hv[c]));
           } break;
           default: break;
         }
+        // the MMA issuer may overwrite the head accumulators / read the new inputs from here on
+        if (i != P.n_ops - 1) warp_arrive(&ctl->in_ready, lane);
       }
-      // ---- write planes ----
+      // ---- write planes (the warps sharing a sample take different planes) ----
       if (valid) {
         float* P = a.planes;
         const int64_t ps = a.plane_stride;
-        P[P_SIGMA_RAW * ps + n] = sigma_raw;
-        for (int q = 0; q < 3; ++q) {
-          P[(P_RGB + q) * ps + n] = rgb[q];
-          P[(P_NORM + q) * ps + n] = nrm[q];
-          P[(P_WARPED + q) * ps + n] = xw[q];
-        }
-        for (int q = 0; q < H; ++q) P[(P_WARPED + 3 + q) * ps + n] = om[q];
-        P[P_MASK * ps + n] = pmask;
-        if (cfg.use_warp) {
+        if (sub == 0) {
+          P[P_SIGMA_RAW * ps + n] = sigma_raw;
+          for (int c = 0; c < 3; ++c) P[(P_RGB + c) * ps + n] = rgb[c];
+        } else if (sub == 1) {
+          for (int c = 0; c < 3; ++c) P[(P_NORM + c) * ps + n] = nrm[c];
+          P[P_MASK * ps + n] = pmask;
+        } else if (sub == 2) {
+          for (int c = 0; c < 3; ++c) P[(P_WARPED + c) * ps + n] = xw[c];
+          for (int c = 0; c < H; ++c) P[(P_WARPED + 3 + c) * ps + n] = om[c];
+        } else if (cfg.use_warp) {
           const float r = 0.57735025882720947265625f;
           float rf[3], rn[3];
-          for (int q = 0; q < 3; ++q) rf[q] = T.R[q * 3 + 0] * r + T.R[q * 3 + 1] * r + T.R[q * 3 + 2] * r;
+          for (int c = 0; c < 3; ++c) rf[c] = T.R[c * 3 + 0] * r + T.R[c * 3 + 1] * r + T.R[c * 3 + 2] * r;
           normalize3(rf, rn);
-          for (int q = 0; q < 3; ++q) { P[(P_ROT + q) * ps + n] = rn[q]; P[(P_TRANS + q) * ps + n] = T.p[q]; }
+          for (int c = 0; c < 3; ++c) { P[(P_ROT + c) * ps + n] = rn[c]; P[(P_TRANS + c) * ps + n] = T.p[c]; }
         }
       }
+      tc_fence_before_sync();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------
-// self-test kernel: one op on caller-provided activations
+// self-test kernel: one op on caller-provided activations.  The activations
+// are written to the op's operand home (shared or tensor memory, per kc_src)
+// by the compute warps exactly as an upstream epilogue would.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_selftest_kernel(TcLevel L, const float* __restrict__ A, int k_hid, int k_in, float* out_f32, float* out_readback) {
+tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* __restrict__ A, int k_hid, int k_in,
+                   float* out_f32, float* out_readback) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + OFF_CTRL);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
-    mbar_init(&ctl->a_ready, TM);
-    mbar_init(&ctl->d_ready, 1);
-    mbar_fence_init();
-  }
-  if (warp == 4) tmem_alloc(&ctl->tmem_base, 512);
+  if (threadIdx.x == 0) ctrl_init(ctl);
+  if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
-  const TcOp& op = L.ops[0];
-  if (warp == 5) {
-    if (lane == 0) { uint32_t cc = 0; produce_op(op, L.weights, smem, ctl, cc); }
-  } else if (warp == 4) {
-    if (lane == 0) {
-      uint32_t cc = 0;
-      mbar_wait(&ctl->a_ready, 0);
-      tc_fence_after_sync();
-      issue_op(op, smem_base, ctl, cc);
-    }
+  const TcOp& op = P.ops[0];
+  if (warp == WARP_TMA) {
+    const bool leader = elect_one() != 0;
+    uint32_t sc = 0;
+    produce_tile(P, L.weights, smem, ctl, leader, sc);
+  } else if (warp == WARP_MMA) {
+    const bool leader = elect_one() != 0;
+    uint32_t sc = 0, pc = 0, gc = 0;
+    issue_tile(P, smem_base, ctl, tmem_base, leader, sc, pc, gc);
   } else {
-    const uint32_t row = threadIdx.x;
+    const int q = warp & 3, sub = warp >> 2;
+    const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
+    const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     const int ld = k_hid + k_in;
-    for (int c0 = 0; c0 < k_hid; c0 += 8) {
-      float v[8];
-      for (int i = 0; i < 8; ++i) v[i] = A[row * ld + c0 + i];
-      store8_split(smem, OFF_HID_HI, OFF_HID_LO, true, row, c0, v);
-    }
-    for (int c = 0; c < 64; ++c) store_in(smem, row, c, c < k_in ? A[row * ld + k_hid + c] : 0.f);
-    fence_proxy_async_smem();
-    mbar_arrive(&ctl->a_ready);
-    mbar_wait(&ctl->d_ready, 0);
-    tc_fence_after_sync();
-    float hv[16];
-    epilogue_op(op, L.bias, smem, tmem_base, row, hv, out_f32, op.N);
-    tc_fence_before_sync();
-    if (op.out_kind != OUT_HEAD && out_readback) {
-      const uint32_t off_hi = (op.out_kind == OUT_HIDDEN_LO_REGION) ? OFF_HID_LO : OFF_HID_HI;
-      for (uint32_t c = 0; c < op.N; ++c) {
-        const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
-        float v = __half2float(*reinterpret_cast<__half*>(smem + off_hi + o));
-        if (op.out_kind == OUT_HIDDEN) v += __half2float(*reinterpret_cast<__half*>(smem + OFF_HID_LO + o));
-        out_readback[row * op.N + c] = v;
+    bool a_tmem = false;
+    for (int k = 0; k < P.n_img; ++k) a_tmem = a_tmem || (P.img[k].flags & IMG_A_TMEM);
+    // hidden activations: this warp writes the 16-column groups g with g % NSUB == sub
+    for (int c0 = 0; c0 < k_hid; c0 += 16) {
+      if (((c0 >> 4) & (NSUB - 1)) != sub) continue;
+      uint32_t hi[8], lo[8];
+      for (int i = 0; i < 8; ++i) {
+        const float x0 = A[row * ld + c0 + 2 * i], x1 = A[row * ld + c0 + 2 * i + 1];
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
       }
+      if (a_tmem) {
+        tmem_st<8>(tmem_lane + TM_XT_HI + (c0 >> 1), hi);
+        tmem_st<8>(tmem_lane + TM_XT_LO + (c0 >> 1), lo);
+      } else {
+        for (int g = 0; g < 2; ++g) {
+          const uint32_t c = c0 + 8 * g;
+          const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
+          *reinterpret_cast<uint4*>(smem + OFF_XS_HI + o) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+          *reinterpret_cast<uint4*>(smem + OFF_XS_LO + o) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+        }
+      }
+    }
+    for (int c = 0; c < 64; ++c)
+      if ((c & (NSUB - 1)) == sub) store_in(smem, row, c, c < k_in ? A[row * ld + k_hid + c] : 0.f);
+    warp_arrive(&ctl->part_ready[0], lane);
+    warp_arrive(&ctl->part_ready[1], lane);
+    warp_arrive(&ctl->in_ready, lane);
+    if (op.out_kind == OUT_HEAD) {
+      mbar_wait(&ctl->d_full[0], 0);
+      tc_fence_after_sync();
+      float hv[16];
+      epilogue_head(op, L.bias, tmem_lane, hv);
+      if (sub == 0) for (int i = 0; i < 16 && i < op.N; ++i) out_f32[row * op.N + i] = hv[i];
+    } else {
+      for (int nc = 0; nc < op.n_nc; ++nc) {
+        mbar_wait(&ctl->d_full[nc], 0);
+        tc_fence_after_sync();
+        epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, out_f32, op.N);
+      }
+      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before_sync();
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 512);
+  tc_fence_after_sync();
+  // read the operand image the epilogue wrote back (hi + lo) -- what the next layer's MMA would see
+  if (warp < 4 && op.out_kind != OUT_HEAD && out_readback) {
+    const uint32_t row = (uint32_t)warp * 32u + (uint32_t)lane;
+    const uint32_t tmem_lane = tmem_base + (((uint32_t)warp * 32u) << 16);
+    const bool from_t = op.out_kind == OUT_XT || op.out_kind == OUT_XT_HI_ONLY;
+    const bool with_lo = op.out_kind == OUT_XS || op.out_kind == OUT_XT;
+    for (uint32_t c0 = 0; c0 < op.N; c0 += 16) {
+      float vals[16];
+      if (from_t) {
+        uint32_t h[8], l[8];
+        tmem_ld8(tmem_lane + TM_XT_HI + (c0 >> 1), h);
+        tmem_ld8(tmem_lane + TM_XT_LO + (c0 >> 1), l);
+        tmem_ld_wait();
+        for (int i = 0; i < 8; ++i) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+          vals[2 * i] = hf.x + (with_lo ? lf.x : 0.f);
+          vals[2 * i + 1] = hf.y + (with_lo ? lf.y : 0.f);
+        }
+      } else {
+        const uint32_t off_hi = (op.out_kind == OUT_XS_LO_AS_HI) ? OFF_XS_LO : OFF_XS_HI;
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t c = c0 + i;
+          const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
+          float v = __half2float(*reinterpret_cast<__half*>(smem + off_hi + o));
+          if (with_lo) v += __half2float(*reinterpret_cast<__half*>(smem + OFF_XS_LO + o));
+          vals[i] = v;
+        }
+      }
+      for (int i = 0; i < 16; ++i) out_readback[row * op.N + c0 + i] = vals[i];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------
 // host: packing
 // ---------------------------------------------------------------------------
-struct KChunkMap { uint8_t src; int rows[64]; };   // W row feeding each of the 64 A columns (-1 = zero pad)
+struct KChunkMap { uint8_t src; uint8_t wait; int rows[64]; };   // W row feeding each of the 64 A columns (-1 = zero pad)
 
 struct OpBuild {
-  const HostDense* dense;             // may be null when W2 (fused heads) is used
   std::vector<KChunkMap> kcs;
   int N_logical;                      // real output columns
-  int N;                              // padded (multiple of 16)
-  int terms, relu, out_kind, glue;
-  std::vector<float> W;               // [K_total][N_logical] gathered logical weights (row-major)
+  int N;                              // padded
+  int terms, relu, out_kind, glue, wait_glue;
+  std::vector<float> W;               // [K_total][N_logical] logical weights (row-major, Flax layout)
   std::vector<float> b;
 };
 
 struct Packed {
   std::vector<TcOp> ops;
+  std::vector<ImgEntry> imgs;
   std::vector<uint8_t> stream;
   std::vector<float> bias;
 };
+
+// operand address of K-chunk source `src` (hi, lo): shared byte offset or tensor-memory column
+static void src_address(uint8_t src, uint32_t& hi, uint32_t& lo, bool& tmem) {
+  tmem = src >= SRC_XT;
+  if (tmem) { hi = TM_XT_HI + (src - SRC_XT) * 32u; lo = hi + (TM_XT_LO - TM_XT_HI); }
+  else if (src == SRC_IN) { hi = OFF_IN_HI; lo = OFF_IN_LO; }
+  else if (src >= SRC_XS_LO) { hi = OFF_XS_LO + (src - SRC_XS_LO) * KBLK; lo = hi; }
+  else { hi = OFF_XS_HI + src * KBLK; lo = hi + (OFF_XS_LO - OFF_XS_HI); }
+}
 
 static void pack_op(const OpBuild& ob, Packed& out) {
   TcOp op;
   memset(&op, 0, sizeof op);
   op.N = (uint16_t)ob.N;
-  op.terms = (uint8_t)ob.terms;
   op.relu = (uint8_t)ob.relu;
   op.out_kind = (uint8_t)ob.out_kind;
   op.glue = (uint8_t)ob.glue;
-  op.n_kc = (uint8_t)ob.kcs.size();
-  const int max_rows = ob.terms == 3 ? 128 : 256;
-  op.n_nc = (uint8_t)((ob.N + max_rows - 1) / max_rows);
+  op.n_nc = (uint8_t)(ob.out_kind == OUT_HEAD ? 1 : 2);
   op.nc_rows = (uint16_t)(ob.N / op.n_nc);
   // power-of-two scale so that max |W| lands in [4, 8): keeps W_lo out of fp16 subnormals
   float mx = 0.f;
@@ -491,17 +686,18 @@ static void pack_op(const OpBuild& ob, Packed& out) {
   op.bias_off = (uint32_t)out.bias.size();
   for (int n = 0; n < ob.N; ++n) out.bias.push_back(n < ob.N_logical ? ob.b[n] : 0.f);
   while (out.bias.size() % 4) out.bias.push_back(0.f);
-  op.w_off = (uint32_t)out.stream.size();
-  for (size_t kc = 0; kc < ob.kcs.size(); ++kc) {
-    const KChunkMap& km = ob.kcs[kc];
-    op.kc_src[kc] = km.src;
-    int last = -1;
-    for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
-    op.kc_steps[kc] = (uint8_t)std::max(1, (last + 16) / 16);
-    for (int nc = 0; nc < op.n_nc; ++nc) {
-      const size_t img = (size_t)op.nc_rows * 128;
+  // stream order == issue order: N-chunk, K-chunk, image (hi, lo)
+  const size_t img = (size_t)op.nc_rows * 128;
+  const int n_img_per = ob.terms == 3 ? 2 : 1;
+  bool waited0 = false, waited1 = false, consumes = false;
+  for (int nc = 0; nc < op.n_nc; ++nc)
+    for (size_t kc = 0; kc < ob.kcs.size(); ++kc) {
+      const KChunkMap& km = ob.kcs[kc];
+      int last = -1;
+      for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
+      const int steps = std::max(1, (last + 16) / 16);
       const size_t base = out.stream.size();
-      out.stream.resize(base + img * (ob.terms == 3 ? 2 : 1), 0);
+      out.stream.resize(base + img * n_img_per, 0);
       for (int r = 0; r < op.nc_rows; ++r) {
         const int n = nc * op.nc_rows + r;
         for (int c = 0; c < 64; ++c) {
@@ -514,47 +710,82 @@ static void pack_op(const OpBuild& ob, Packed& out) {
           if (ob.terms == 3) memcpy(&out.stream[base + img + o], &lo, 2);
         }
       }
+      for (int im = 0; im < n_img_per; ++im) {
+        ImgEntry ie;
+        memset(&ie, 0, sizeof ie);
+        bool tmem;
+        src_address(km.src, ie.a_hi, ie.a_lo, tmem);
+        ie.rows = op.nc_rows;
+        ie.steps = (uint8_t)steps;
+        uint16_t fl = 0;
+        if (tmem) fl |= IMG_A_TMEM;
+        if (im == 0 && ob.terms == 3) fl |= IMG_TWO_TERMS;     // B_hi image: A_hi B_hi + A_lo B_hi
+        if (kc == 0 && im == 0) fl |= IMG_FIRST;
+        if (kc + 1 == ob.kcs.size() && im + 1 == n_img_per) fl |= IMG_LAST;
+        if (nc == 1) fl |= IMG_NC1;
+        if ((km.wait & 1) && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; consumes = true; }
+        if ((km.wait & 2) && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; consumes = true; }
+        if (nc == 0 && kc == 0 && im == 0 && ob.wait_glue) fl |= IMG_WAIT_GLUE;
+        ie.flags = fl;
+        out.imgs.push_back(ie);
+      }
     }
-  }
+  if (consumes) out.imgs.back().flags |= IMG_PART_NEXT;
   out.ops.push_back(op);
 }
 
-static KChunkMap kc_hidden(int block, int row0, int width_avail) {
+// which output part (N-chunk of the producing op) holds K-block `block` of a `width`-wide activation
+static uint8_t part_bits(int block, int width) {
+  if (width <= 64) return 3;
+  return (block * 64 < width / 2) ? 1 : 2;
+}
+// K-block `block` of the previous op's output, living in `home` (0 = XS shared, 1 = XT tensor memory)
+static KChunkMap kc_hidden(int block, int row0, int width, int home, bool wait) {
   KChunkMap k;
-  k.src = (uint8_t)block;
-  for (int c = 0; c < 64; ++c) k.rows[c] = (block * 64 + c < width_avail) ? row0 + block * 64 + c : -1;
+  k.src = (uint8_t)((home ? SRC_XT : 0) + block);
+  k.wait = wait ? part_bits(block, width) : 0;
+  for (int c = 0; c < 64; ++c) k.rows[c] = (block * 64 + c < width) ? row0 + block * 64 + c : -1;
   return k;
 }
 static KChunkMap kc_input(int row0, int in_dim) {
   KChunkMap k;
   k.src = SRC_IN;
+  k.wait = 0;
   for (int c = 0; c < 64; ++c) k.rows[c] = c < in_dim ? row0 + c : -1;
   return k;
 }
 
-// hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer]
-static void build_mlp_ops(const HostMlp& m, int terms, Packed& out) {
+// hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer]; outputs
+// alternate XT, XS, XT, ...  Returns the home of the last layer's output.
+static int build_mlp_ops(const HostMlp& m, int terms, Packed& out) {
+  int home = 1;
   for (int l = 0; l < m.depth; ++l) {
     OpBuild ob;
     ob.N_logical = ob.N = m.width;
-    ob.terms = terms; ob.relu = 1; ob.out_kind = OUT_HIDDEN; ob.glue = GLUE_NONE;
+    ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE;
+    ob.wait_glue = l == 0;
     ob.W = m.hidden[l].W; ob.b = m.hidden[l].b;
+    const int out_home = (l % 2 == 0) ? 1 : 0;
+    ob.out_kind = out_home ? OUT_XT : OUT_XS;
     if (l == 0) ob.kcs.push_back(kc_input(0, m.in_dim));
     else {
-      for (int j = 0; j < (m.width + 63) / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, m.width));
-      if (l == m.skip) ob.kcs.push_back(kc_input(m.width, m.in_dim));
+      if (l == m.skip) ob.kcs.push_back(kc_input(m.width, m.in_dim));   // ready long ago: issue it first
+      for (int j = 0; j < (m.width + 63) / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, m.width, home, true));
     }
     pack_op(ob, out);
+    home = out_home;
   }
+  return home;
 }
 
-static void build_head_op(const std::vector<const HostDense*>& heads, int width, int terms, int glue, Packed& out) {
+static void build_head_op(const std::vector<const HostDense*>& heads, int width, int home, int terms, int glue,
+                          Packed& out) {
   OpBuild ob;
   int n = 0;
   for (auto* h : heads) n += h->N;
   ob.N_logical = n;
   ob.N = 16;
-  ob.terms = terms; ob.relu = 0; ob.out_kind = OUT_HEAD; ob.glue = glue;
+  ob.terms = terms; ob.relu = 0; ob.out_kind = OUT_HEAD; ob.glue = glue; ob.wait_glue = 0;
   ob.W.assign((size_t)width * n, 0.f);
   int c0 = 0;
   for (auto* h : heads) {
@@ -562,27 +793,36 @@ static void build_head_op(const std::vector<const HostDense*>& heads, int width,
     for (int j = 0; j < h->N; ++j) ob.b.push_back(h->b[j]);
     c0 += h->N;
   }
-  for (int j = 0; j < (width + 63) / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, width));
+  for (int j = 0; j < (width + 63) / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, width, home, true));
   pack_op(ob, out);
 }
 
 struct TcEngine {
   Packed packed[2];
-  int n_ops_sigma[2] = {0, 0};
-  TcOp* d_ops[2] = {nullptr, nullptr};
+  TcProgram prog[2];
+  int n_ops_sigma[2] = {0, 0}, n_img_sigma[2] = {0, 0};
   uint8_t* d_stream[2] = {nullptr, nullptr};
   float* d_bias[2] = {nullptr, nullptr};
 };
 
+static bool make_program(const Packed& P, TcProgram& prog, std::string& err) {
+  if (P.ops.size() > (size_t)MAX_OPS || P.imgs.size() > (size_t)MAX_IMG) { err = "tensor-core engine: layer program too long"; return false; }
+  memset(&prog, 0, sizeof prog);
+  prog.n_ops = (int)P.ops.size();
+  prog.n_img = (int)P.imgs.size();
+  std::copy(P.ops.begin(), P.ops.end(), prog.ops);
+  std::copy(P.imgs.begin(), P.imgs.end(), prog.img);
+  return true;
+}
+
 std::string tc_engine_supports(const ndsr_config& c, int cc_major, int cc_minor) {
   if (cc_major != 10) return "needs an sm_100-class device (tcgen05)";
-  if (c.trunk_width != 256 && c.trunk_width != 128 && c.trunk_width != 64) return "trunk width must be 64/128/256";
   if (c.rgb_depth != 1) return "rgb branch depth must be 1";
-  if (c.rgb_width > 256 || c.rgb_width % 16) return "rgb width";
-  if (c.use_warp && c.warp_width > 256) return "warp width";
-  const int widths[] = {c.trunk_width, c.use_warp ? c.warp_width : 64, c.use_hyper_sheet ? c.hyper_sheet_width : 64,
-                        c.use_predicted_mask ? c.mask_width : 64};
-  for (int w : widths) if (w % 64) return "MLP widths must be multiples of 64";
+  if (!c.use_viewdirs) return "the rgb branch without viewdirs is not built";
+  if (c.trunk_depth % 2) return "trunk depth must be even (operand homes alternate)";
+  const int widths[] = {c.trunk_width, c.rgb_width, c.use_warp ? c.warp_width : 64,
+                        c.use_hyper_sheet ? c.hyper_sheet_width : 64, c.use_predicted_mask ? c.mask_width : 64};
+  for (int w : widths) if (w != 64 && w != 128 && w != 256) return "MLP widths must be 64, 128 or 256";
   (void)cc_minor;
   return "";
 }
@@ -592,64 +832,57 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
   const HostModel& HM = h->host_model;
   const int prec = c.precision;
   const int t_sigma = prec == NDSR_PREC_FP16 ? 1 : 3;
-  const int t_rgb = prec == NDSR_PREC_SPLIT3 ? 3 : 1;
+  if (prec == NDSR_PREC_SPLIT3) { h->err = "tensor-core engine: split3 precision on the rgb branch is not built (use mixed)"; return NDSR_ERR_UNSUPPORTED; }
   if (h->max_in > 64) { h->err = "tensor-core engine: MLP inputs wider than 64 features"; return NDSR_ERR_UNSUPPORTED; }
   if (h->dim_view + (c.predict_norm ? h->dim_norm : 0) > 64) { h->err = "tensor-core engine: rgb side inputs wider than 64"; return NDSR_ERR_UNSUPPORTED; }
   if (c.use_predicted_mask) {
-    build_mlp_ops(HM.mask, t_sigma, P);
-    build_head_op({&HM.mask.logit}, HM.mask.width, t_sigma, GLUE_MASK, P);
+    const int home = build_mlp_ops(HM.mask, t_sigma, P);
+    build_head_op({&HM.mask.logit}, HM.mask.width, home, t_sigma, GLUE_MASK, P);
   }
   if (c.use_warp) {
-    build_mlp_ops(HM.warp, t_sigma, P);
-    build_head_op({&HM.warp_w, &HM.warp_v}, HM.warp.width, t_sigma, GLUE_WARP, P);
+    const int home = build_mlp_ops(HM.warp, t_sigma, P);
+    build_head_op({&HM.warp_w, &HM.warp_v}, HM.warp.width, home, t_sigma, GLUE_WARP, P);
   }
   if (c.use_hyper_sheet) {
-    build_mlp_ops(HM.hyper, t_sigma, P);
-    build_head_op({&HM.hyper.logit}, HM.hyper.width, t_sigma, GLUE_HYPER, P);
+    const int home = build_mlp_ops(HM.hyper, t_sigma, P);
+    build_head_op({&HM.hyper.logit}, HM.hyper.width, home, t_sigma, GLUE_HYPER, P);
   }
-  build_mlp_ops(HM.trunk[lv], t_sigma, P);
-  build_head_op({&HM.alpha[lv]}, HM.trunk[lv].width, t_sigma, GLUE_ALPHA, P);
+  const int trunk_home = build_mlp_ops(HM.trunk[lv], t_sigma, P);
+  if (trunk_home != 0) { h->err = "tensor-core engine: trunk output must land in shared memory (even depth)"; return NDSR_ERR_UNSUPPORTED; }
+  build_head_op({&HM.alpha[lv]}, HM.trunk[lv].width, trunk_home, t_sigma, GLUE_ALPHA, P);
   n_sigma = (int)P.ops.size();
+  h->tc->n_img_sigma[lv] = (int)P.imgs.size();
   // ---- rgb branch (modules.py:288-313).  Flax input order:
-  //   [bottleneck|trunk_out (W) | viewdir feats | trunk_out (App. C-1) | norm feats]
+  //   [bottleneck (W) | viewdir feats | trunk_out (W, App. C-1) | norm feats]
+  // bottleneck: XS_hi (trunk_out) -> XT_hi, 1 term; rgb hidden: {XS_hi, IN, XT_hi} -> XS_lo region; head reads it.
   const int W = c.trunk_width;
-  const bool use_b = c.use_viewdirs != 0;
-  if (use_b) {
+  {
     OpBuild ob;
     ob.N_logical = ob.N = W;
-    ob.terms = t_rgb; ob.relu = 0; ob.out_kind = (t_rgb == 1) ? OUT_HIDDEN_LO_REGION : OUT_HIDDEN; ob.glue = GLUE_BOTTLENECK;
+    ob.terms = 1; ob.relu = 0; ob.out_kind = OUT_XT_HI_ONLY; ob.glue = GLUE_BOTTLENECK;
+    ob.wait_glue = 1;     // the sigma/normal head's accumulators must have been consumed
     ob.W = HM.bottleneck[lv].W; ob.b = HM.bottleneck[lv].b;
-    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, W));
-    if (t_rgb != 1) { h->err = "tensor-core engine: split3 precision on the rgb branch is not built (use mixed)"; return NDSR_ERR_UNSUPPORTED; }
+    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, W, 0, false));
     pack_op(ob, P);
   }
   {
     const HostMlp& R = HM.rgb[lv];
     OpBuild ob;
     ob.N_logical = ob.N = R.width;
-    ob.terms = 1; ob.relu = 1; ob.out_kind = OUT_HIDDEN; ob.glue = GLUE_NONE;
+    ob.terms = 1; ob.relu = 1; ob.out_kind = OUT_XS_LO_AS_HI; ob.glue = GLUE_NONE; ob.wait_glue = 0;
     ob.W = R.hidden[0].W; ob.b = R.hidden[0].b;
-    int row = 0;
-    // first segment: bottleneck (stored in the HID_LO region as a 1-term operand) or trunk_out
-    for (int j = 0; j < W / 64; ++j) {
-      KChunkMap k = kc_hidden(j, 0, W);
-      if (use_b) k.src = (uint8_t)(8 + j);
-      ob.kcs.push_back(k);
-    }
-    row += W;
+    int row = W;
     const int v0 = row;
     row += h->dim_view;
     int x0 = -1;
     if (c.use_x_in_rgb_condition) { x0 = row; row += W; }
     const int n0 = row;
     const int ndim = c.predict_norm ? h->dim_norm : 0;
-    if (x0 >= 0) {
-      if (!use_b) { h->err = "tensor-core engine: use_x_in_rgb_condition without viewdirs is not built"; return NDSR_ERR_UNSUPPORTED; }
-      for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, x0, W));
-    }
+    if (x0 >= 0) for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, x0, W, 0, false));   // trunk_out, ready
     if (h->dim_view + ndim > 0) {
       KChunkMap k;
       k.src = SRC_IN;
+      k.wait = 0;
       for (int cidx = 0; cidx < 64; ++cidx) {
         if (cidx < h->dim_view) k.rows[cidx] = v0 + cidx;
         else if (cidx < h->dim_view + ndim) k.rows[cidx] = n0 + (cidx - h->dim_view);
@@ -657,9 +890,21 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
       }
       ob.kcs.push_back(k);
     }
+    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, W, 1, true));                  // bottleneck
     if ((int)ob.kcs.size() > MAX_KC) { h->err = "tensor-core engine: rgb input too wide"; return NDSR_ERR_UNSUPPORTED; }
     pack_op(ob, P);
-    build_head_op({&R.logit}, R.width, 1, GLUE_RGB, P);
+    // head over the rgb hidden layer, which lives in the XS_lo region as a 1-term operand
+    OpBuild hb;
+    hb.N_logical = R.logit.N;
+    hb.N = 16;
+    hb.terms = 1; hb.relu = 0; hb.out_kind = OUT_HEAD; hb.glue = GLUE_RGB; hb.wait_glue = 0;
+    hb.W = R.logit.W; hb.b = R.logit.b;
+    for (int j = 0; j < (R.width + 63) / 64; ++j) {
+      KChunkMap k = kc_hidden(j, 0, R.width, 0, true);
+      k.src = (uint8_t)(SRC_XS_LO + j);
+      hb.kcs.push_back(k);
+    }
+    pack_op(hb, P);
   }
   return NDSR_OK;
 }
@@ -673,10 +918,9 @@ int tc_engine_load(ndsr_handle* h) {
     if (rc) return rc;
     Packed& P = E->packed[lv];
     cudaError_t e;
-    if ((e = cudaMalloc(&E->d_ops[lv], P.ops.size() * sizeof(TcOp))) != cudaSuccess ||
-        (e = cudaMalloc(&E->d_stream[lv], P.stream.size())) != cudaSuccess ||
+    if (!make_program(P, E->prog[lv], h->err)) return NDSR_ERR_UNSUPPORTED;
+    if ((e = cudaMalloc(&E->d_stream[lv], P.stream.size())) != cudaSuccess ||
         (e = cudaMalloc(&E->d_bias[lv], P.bias.size() * sizeof(float))) != cudaSuccess ||
-        (e = cudaMemcpy(E->d_ops[lv], P.ops.data(), P.ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(E->d_stream[lv], P.stream.data(), P.stream.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(E->d_bias[lv], P.bias.data(), P.bias.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
       h->err = std::string("tc_engine_load: ") + cudaGetErrorString(e);
@@ -691,7 +935,6 @@ int tc_engine_load(ndsr_handle* h) {
 void tc_engine_free(ndsr_handle* h) {
   if (!h->tc) return;
   for (int lv = 0; lv < 2; ++lv) {
-    if (h->tc->d_ops[lv]) cudaFree(h->tc->d_ops[lv]);
     if (h->tc->d_stream[lv]) cudaFree(h->tc->d_stream[lv]);
     if (h->tc->d_bias[lv]) cudaFree(h->tc->d_bias[lv]);
   }
@@ -703,16 +946,18 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
   TcEngine* E = h->tc;
   if (!E) { h->err = "tensor-core engine not loaded"; return NDSR_ERR_NOT_LOADED; }
   TcKernelArgs K;
-  K.lvl.ops = E->d_ops[fa.level];
-  K.lvl.n_ops = fa.sigma_only ? E->n_ops_sigma[fa.level] : (int)E->packed[fa.level].ops.size();
+  TcProgram& prog = E->prog[fa.level];
+  prog.n_ops = fa.sigma_only ? E->n_ops_sigma[fa.level] : (int)E->packed[fa.level].ops.size();
+  prog.n_img = fa.sigma_only ? E->n_img_sigma[fa.level] : (int)E->packed[fa.level].imgs.size();
   K.lvl.weights = E->d_stream[fa.level];
   K.lvl.bias = E->d_bias[fa.level];
   K.warp_embed = h->M.warp_embed;
   K.mask_embed = h->M.mask_embed;
   const int64_t tiles = (fa.n_samples_total + TM - 1) / TM;
   if (tiles == 0) return NDSR_OK;
-  const int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
-  field_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(K, cp, fa, h->cfg);
+  int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  if (const char* g = getenv("NDS_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // experiments
+  field_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(prog, K, cp, fa, h->cfg);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string("field_tc_kernel launch: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
   h->launches++;
@@ -728,33 +973,43 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
                                       const float* A, const float* W, const float* bias, float* out,
                                       float* out_readback) {
   using namespace nds;
+  // out_kind (public numbering): 0 = hidden layer written to shared memory (operands read from tensor memory),
+  // 1 = head (n_out <= 16, operands from shared memory), 2 = 1-term hidden written to the XS_lo region (operands
+  // from shared memory), 3 = hidden written to tensor memory (operands from shared memory), 4 = head with
+  // operands from tensor memory.
   if (k_hid % 64 || k_hid > 256 || k_in > 64 || k_in < 0 || n_out < 1 || n_out > 256 || (terms != 1 && terms != 3))
     return NDSR_ERR_INVALID;
   if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  const bool head = out_kind == 1 || out_kind == 4;
+  if (head && n_out > 16) return NDSR_ERR_INVALID;
+  if (out_kind == 2 && terms != 1) return NDSR_ERR_INVALID;
+  const int a_home = (out_kind == 0 || out_kind == 4) ? 1 : 0;
   OpBuild ob;
   ob.N_logical = n_out;
-  ob.N = out_kind == OUT_HEAD ? 16 : ((n_out + 63) / 64) * 64;
-  if (out_kind == OUT_HEAD && n_out > 16) return NDSR_ERR_INVALID;
-  ob.terms = terms; ob.relu = relu; ob.out_kind = out_kind; ob.glue = GLUE_SELFTEST;
+  ob.N = head ? 16 : (n_out <= 64 ? 64 : (n_out <= 128 ? 128 : 256));
+  ob.terms = terms; ob.relu = relu; ob.glue = GLUE_SELFTEST; ob.wait_glue = 1;
+  ob.out_kind = head ? OUT_HEAD : (out_kind == 0 ? OUT_XS : (out_kind == 2 ? OUT_XS_LO_AS_HI : OUT_XT));
   const int K = k_hid + k_in;
   ob.W.assign(W, W + (size_t)K * n_out);
   ob.b.assign(bias, bias + n_out);
-  for (int j = 0; j < k_hid / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, k_hid));
   if (k_in > 0) ob.kcs.push_back(kc_input(k_hid, k_in));
+  for (int j = 0; j < k_hid / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, k_hid, a_home, true));
   Packed P;
   pack_op(ob, P);
-  TcOp* d_ops; uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;
+  uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;
   const int N = P.ops[0].N;
-  cudaMalloc(&d_ops, sizeof(TcOp)); cudaMalloc(&d_stream, P.stream.size()); cudaMalloc(&d_bias, P.bias.size() * 4);
+  static TcProgram prog;
+  std::string perr;
+  if (!make_program(P, prog, perr)) return NDSR_ERR_INVALID;
+  cudaMalloc(&d_stream, P.stream.size()); cudaMalloc(&d_bias, P.bias.size() * 4);
   cudaMalloc(&d_A, (size_t)TM * K * 4); cudaMalloc(&d_out, (size_t)TM * N * 4); cudaMalloc(&d_rb, (size_t)TM * N * 4);
-  cudaMemcpy(d_ops, P.ops.data(), sizeof(TcOp), cudaMemcpyHostToDevice);
   cudaMemcpy(d_stream, P.stream.data(), P.stream.size(), cudaMemcpyHostToDevice);
   cudaMemcpy(d_bias, P.bias.data(), P.bias.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_A, A, (size_t)TM * K * 4, cudaMemcpyHostToDevice);
   cudaMemset(d_out, 0, (size_t)TM * N * 4); cudaMemset(d_rb, 0, (size_t)TM * N * 4);
   cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-  TcLevel L; L.ops = d_ops; L.n_ops = 1; L.weights = d_stream; L.bias = d_bias;
-  tc_selftest_kernel<<<1, TC_THREADS, TC_SMEM_BYTES>>>(L, d_A, k_hid, k_in, d_out, d_rb);
+  TcLevel L; L.weights = d_stream; L.bias = d_bias;
+  tc_selftest_kernel<<<1, TC_THREADS, TC_SMEM_BYTES>>>(prog, L, d_A, k_hid, k_in, d_out, d_rb);
   cudaError_t e = cudaDeviceSynchronize();
   int rc = NDSR_OK;
   if (e != cudaSuccess) { fprintf(stderr, "ndsr_selftest_tc_dense: %s\n", cudaGetErrorString(e)); rc = NDSR_ERR_CUDA; }
@@ -768,6 +1023,6 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
       if (out_readback) out_readback[(size_t)r * n_out + c] = tmp2[(size_t)r * N + c];
     }
   }
-  cudaFree(d_ops); cudaFree(d_stream); cudaFree(d_bias); cudaFree(d_A); cudaFree(d_out); cudaFree(d_rb);
+  cudaFree(d_stream); cudaFree(d_bias); cudaFree(d_A); cudaFree(d_out); cudaFree(d_rb);
   return rc;
 }
