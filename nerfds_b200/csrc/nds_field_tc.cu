@@ -81,9 +81,10 @@ struct TcOp {
 // (= one ring slot = up to 2 terms x 4 K-steps of tcgen05.mma).
 enum ImgFlags : uint16_t {
   IMG_A_TMEM = 1, IMG_TWO_TERMS = 2, IMG_FIRST = 4, IMG_LAST = 8, IMG_NC1 = 16, IMG_WAIT_P0 = 32, IMG_WAIT_P1 = 64,
-  IMG_WAIT_GLUE = 128, IMG_PART_NEXT = 256
+  IMG_WAIT_GLUE = 128,
+  IMG_PART_NEXT = 256    // the issuer has consumed one output phase of the previous op
 };
-struct ImgEntry {
+struct alignas(16) ImgEntry {
   uint32_t a_hi;         // shared: byte offset from the (1024-aligned) smem base; tensor memory: column
   uint32_t a_lo;
   uint16_t rows;         // rows of the image = N of its MMAs (bytes = rows * 128)
@@ -92,6 +93,7 @@ struct ImgEntry {
   uint16_t flags;
   uint16_t pad2;
 };
+static_assert(sizeof(ImgEntry) == 16, "ImgEntry is read as one uint4");
 
 constexpr int MAX_OPS = 48;
 constexpr int MAX_IMG = 448;
@@ -147,47 +149,74 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
-// MMA issuer: the whole warp walks the image program (uniform control flow and
-// address arithmetic); one elected lane issues the tcgen05 instructions.
+// MMA issuer.  The whole warp walks the image program in uniform control flow (so the operand arithmetic
+// runs on the uniform datapath); one elected lane issues the tcgen05 instructions.  A 3-term K-chunk (B_hi
+// image followed by its B_lo image, 12 tcgen05.mma) goes out as one asm burst.
 __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
-                                           bool leader, uint32_t& slot_ctr, uint32_t& part_cnt, uint32_t& glue_cnt) {
-  for (int i = 0; i < P.n_img; ++i) {
-    const ImgEntry e = P.img[i];
-    const uint32_t fl = e.flags;
+                                           uint32_t lead, uint32_t& slot_ctr, uint32_t& part_cnt, uint32_t& glue_cnt,
+                                           unsigned long long* trace) {
+  const int n_img = P.n_img;
+  const uint32_t empty0 = smem_u32(&ctl->empty[0]);
+  const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING);
+  uint4 raw = *reinterpret_cast<const uint4*>(&P.img[0]);
+  int i = 0;
+  while (i < n_img) {
+    const uint32_t a_hi = raw.x, a_lo = raw.y, rows = raw.z & 0xffffu, steps = (raw.z >> 16) & 0xffu, fl = raw.w & 0xffffu;
+    const bool two = (fl & IMG_TWO_TERMS) != 0;
+    const int adv = two ? 2 : 1;
+    uint32_t fl2 = fl;
+    if (two) fl2 = P.img[i + 1].flags;                 // IMG_LAST / IMG_PART_NEXT sit on the B_lo image
+    if (i + adv < n_img) raw = *reinterpret_cast<const uint4*>(&P.img[i + adv]);
     if (fl & IMG_WAIT_GLUE) { mbar_wait(&ctl->in_ready, glue_cnt & 1u); ++glue_cnt; }
     if (fl & IMG_WAIT_P0) mbar_wait(&ctl->part_ready[0], part_cnt & 1u);
     if (fl & IMG_WAIT_P1) mbar_wait(&ctl->part_ready[1], part_cnt & 1u);
-    const uint32_t slot = slot_ctr % NSLOT;
-    mbar_wait(&ctl->full[slot], (slot_ctr / NSLOT) & 1u);
+    const uint32_t s0 = slot_ctr % NSLOT, s1 = (slot_ctr + 1) % NSLOT;
+    mbar_wait(&ctl->full[s0], (slot_ctr / NSLOT) & 1u);
+    if (two) mbar_wait(&ctl->full[s1], ((slot_ctr + 1) / NSLOT) & 1u);
     tc_fence_after_sync();
+    if (trace && lead) trace[i] = clock64();
     const uint32_t d = tmem_base + TM_D + ((fl & IMG_NC1) ? 128u : 0u);
-    const uint32_t idesc = make_idesc_f16(e.rows);
-    const uint64_t bdesc = make_smem_desc(smem_base + OFF_RING + slot * SLOT_BYTES);
-    uint32_t acc = (fl & IMG_FIRST) ? 0u : 1u;
-    const int steps = e.steps;
-    const int nterm = (fl & IMG_TWO_TERMS) ? 2 : 1;
-    if (leader) {
+    const uint32_t idesc = make_idesc_f16(rows);
+    const uint32_t b0 = ring_lo32 + s0 * (SLOT_BYTES >> 4), b1 = ring_lo32 + s1 * (SLOT_BYTES >> 4);
+    const uint32_t acc = (fl & IMG_FIRST) ? 0u : 1u;
+    const uint32_t dbar = smem_u32(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0]);
+    const uint32_t last = (fl2 & IMG_LAST) ? 1u : 0u;
+    if (two && steps == 4) {
+      if (fl & IMG_A_TMEM)
+        umma_burst3_ts(d, tmem_base + a_hi, tmem_base + a_lo, b0, b1, idesc, acc, empty0 + 8 * s0, empty0 + 8 * s1, last, dbar, lead);
+      else
+        umma_burst3_ss(d, smem_desc_lo32(smem_base + a_hi), smem_desc_lo32(smem_base + a_lo), b0, b1, idesc, acc,
+                       empty0 + 8 * s0, empty0 + 8 * s1, last, dbar, lead);
+    } else {
+      // generic path: short K-chunks (network inputs) and 1-term layers
+      const uint64_t bd0 = ((uint64_t)NDS_DESC_HI << 32) | b0, bd1 = ((uint64_t)NDS_DESC_HI << 32) | b1;
+      const uint32_t lead2 = two ? lead : 0u;
       if (fl & IMG_A_TMEM) {
-        for (int t = 0; t < nterm; ++t) {
-          const uint32_t A = tmem_base + (t ? e.a_lo : e.a_hi);
+        const uint32_t A0 = tmem_base + a_hi, A1 = tmem_base + a_lo;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            if (ks < steps) { umma_f16_ts(d, A + ks * 8, bdesc + 2 * ks, idesc, acc); acc = 1u; }
-        }
+        for (int ks = 0; ks < 4; ++ks) umma_f16_ts_p(d, A0 + ks * 8, bd0 + 2 * ks, idesc, ks ? 1u : acc, ks < (int)steps ? lead : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16_ts_p(d, A1 + ks * 8, bd0 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
+        umma_commit_p(&ctl->empty[s0], lead);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16_ts_p(d, A0 + ks * 8, bd1 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
       } else {
-        for (int t = 0; t < nterm; ++t) {
-          const uint64_t adesc = make_smem_desc(smem_base + (t ? e.a_lo : e.a_hi));
+        const uint64_t ad0 = make_smem_desc(smem_base + a_hi), ad1 = make_smem_desc(smem_base + a_lo);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            if (ks < steps) { umma_f16(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, acc); acc = 1u; }
-        }
+        for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc, ks < (int)steps ? lead : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
+        umma_commit_p(&ctl->empty[s0], lead);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
       }
-      umma_commit(&ctl->empty[slot]);   // frees the ring slot when these MMAs retire
-      if (fl & IMG_LAST) umma_commit(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0]);
+      umma_commit_p(&ctl->empty[s1], lead2);
+      umma_commit_p(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0], last ? lead : 0u);
     }
-    __syncwarp();
-    ++slot_ctr;
-    if (fl & IMG_PART_NEXT) ++part_cnt;
+    if (trace && lead) trace[MAX_IMG + i] = clock64();
+    slot_ctr += adv;
+    if (fl2 & IMG_PART_NEXT) ++part_cnt;
+    i += adv;
   }
 }
 
@@ -319,7 +348,11 @@ struct TcKernelArgs {
   TcLevel lvl;
   const float* warp_embed;
   const float* mask_embed;
+  unsigned long long* trace;   // diagnostics (NDS_TC_TRACE): clock64 stamps of CTA 0's second tile, else null
 };
+// trace layout: [i] image i ready to issue | [MAX_IMG + i] image i issued | [2 MAX_IMG + 4 op + 2 nc] accumulators seen,
+// [.. + 1] operand written & signalled | [2 MAX_IMG + 4 MAX_OPS] tile start
+constexpr int TRACE_WORDS = 2 * MAX_IMG + 4 * MAX_OPS + 8;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcKernelArgs K,
@@ -349,10 +382,12 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) produce_tile(P, L.weights, smem, ctl, leader, sc);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
-    const bool leader = elect_one() != 0;
+    const uint32_t lead = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for the compiler
     uint32_t sc = 0, part_cnt = 0, glue_cnt = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      issue_tile(P, smem_base, ctl, tmem_base, leader, sc, part_cnt, glue_cnt);
+      issue_tile(P, smem_base, ctl, tb, lead, sc, part_cnt, glue_cnt,
+                 (K.trace && tile == (int64_t)gridDim.x) ? K.trace : nullptr);
   } else {
     // ===================== compute warps =====================
     const int q = warp & 3, sub = warp >> 2;
@@ -362,6 +397,8 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t n = tile * TM + row;
       const bool valid = n < a.n_samples_total;
+      unsigned long long* tr = (K.trace && tile == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 2 * MAX_IMG : nullptr;
+      if (tr) tr[4 * MAX_OPS] = clock64();
       float x[3] = {0.f, 0.f, 0.f}, xw[3] = {0.f, 0.f, 0.f}, om[2] = {0.f, 0.f};
       float maskv = 0.f, pmask = 0.f, sigma_raw = 0.f, nrm[3] = {0.f, 0.f, 0.f}, rgb[3] = {0.f, 0.f, 0.f};
       SE3<float> T;
@@ -429,14 +466,17 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
             if (nc == 0) { mbar_wait(&ctl->d_full[0], dcnt0 & 1u); ++dcnt0; }
             else { mbar_wait(&ctl->d_full[1], dcnt1 & 1u); ++dcnt1; }
             tc_fence_after_sync();
+            if (tr) tr[4 * i + 2 * nc] = clock64();
             epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, nullptr, 0);
             warp_arrive(&ctl->part_ready[nc], lane);
+            if (tr) tr[4 * i + 2 * nc + 1] = clock64();
           }
           continue;
         }
         mbar_wait(&ctl->d_full[0], dcnt0 & 1u);
         ++dcnt0;
         tc_fence_after_sync();
+        if (tr) tr[4 * i] = clock64();
         float hv[16];
         epilogue_head(op, L.bias, tmem_lane, hv);
         switch (op.glue) {
@@ -484,6 +524,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         }
         // the MMA issuer may overwrite the head accumulators / read the new inputs from here on
         if (i != P.n_ops - 1) warp_arrive(&ctl->in_ready, lane);
+        if (tr) tr[4 * i + 1] = clock64();
       }
       // ---- write planes (the warps sharing a sample take different planes) ----
       if (valid) {
@@ -539,9 +580,10 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
     uint32_t sc = 0;
     produce_tile(P, L.weights, smem, ctl, leader, sc);
   } else if (warp == WARP_MMA) {
-    const bool leader = elect_one() != 0;
+    const uint32_t lead = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t sc = 0, pc = 0, gc = 0;
-    issue_tile(P, smem_base, ctl, tmem_base, leader, sc, pc, gc);
+    issue_tile(P, smem_base, ctl, tb, lead, sc, pc, gc, nullptr);
   } else {
     const int q = warp & 3, sub = warp >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
@@ -645,6 +687,7 @@ struct OpBuild {
   int N_logical;                      // real output columns
   int N;                              // padded
   int terms, relu, out_kind, glue, wait_glue;
+  int prev_produces = 0;              // the op before this one is a hidden layer (its epilogue signals part_ready)
   std::vector<float> W;               // [K_total][N_logical] logical weights (row-major, Flax layout)
   std::vector<float> b;
 };
@@ -689,8 +732,12 @@ static void pack_op(const OpBuild& ob, Packed& out) {
   // stream order == issue order: N-chunk, K-chunk, image (hi, lo)
   const size_t img = (size_t)op.nc_rows * 128;
   const int n_img_per = ob.terms == 3 ? 2 : 1;
-  bool waited0 = false, waited1 = false, consumes = false;
-  for (int nc = 0; nc < op.n_nc; ++nc)
+  bool consumes = false;
+  for (size_t kc = 0; kc < ob.kcs.size(); ++kc) consumes = consumes || ob.kcs[kc].wait != 0;
+  bool waited0 = false, waited1 = false;
+  for (int nc = 0; nc < op.n_nc; ++nc) {
+    // the first image of chunk nc overwrites accumulator chunk nc, which the previous op's epilogue must have
+    // drained (= its part nc written) -- or, after a head, the per-sample stage must be done (wait_glue).
     for (size_t kc = 0; kc < ob.kcs.size(); ++kc) {
       const KChunkMap& km = ob.kcs[kc];
       int last = -1;
@@ -723,14 +770,19 @@ static void pack_op(const OpBuild& ob, Packed& out) {
         if (kc == 0 && im == 0) fl |= IMG_FIRST;
         if (kc + 1 == ob.kcs.size() && im + 1 == n_img_per) fl |= IMG_LAST;
         if (nc == 1) fl |= IMG_NC1;
-        if ((km.wait & 1) && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; consumes = true; }
-        if ((km.wait & 2) && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; consumes = true; }
-        if (nc == 0 && kc == 0 && im == 0 && ob.wait_glue) fl |= IMG_WAIT_GLUE;
+        const bool first = kc == 0 && im == 0;
+        if (first && ob.prev_produces && nc == 0 && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; }
+        if (first && ob.prev_produces && nc == 1 && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; }
+        if ((km.wait & 1) && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; }
+        if ((km.wait & 2) && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; }
+        if (first && nc == 0 && ob.wait_glue) fl |= IMG_WAIT_GLUE;
         ie.flags = fl;
         out.imgs.push_back(ie);
       }
     }
-  if (consumes) out.imgs.back().flags |= IMG_PART_NEXT;
+  }
+  if (ob.prev_produces) out.imgs.back().flags |= IMG_PART_NEXT;   // one output phase of the previous op consumed
+  (void)consumes;
   out.ops.push_back(op);
 }
 
@@ -764,6 +816,7 @@ static int build_mlp_ops(const HostMlp& m, int terms, Packed& out) {
     ob.N_logical = ob.N = m.width;
     ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE;
     ob.wait_glue = l == 0;
+    ob.prev_produces = l > 0;
     ob.W = m.hidden[l].W; ob.b = m.hidden[l].b;
     const int out_home = (l % 2 == 0) ? 1 : 0;
     ob.out_kind = out_home ? OUT_XT : OUT_XS;
@@ -785,7 +838,7 @@ static void build_head_op(const std::vector<const HostDense*>& heads, int width,
   for (auto* h : heads) n += h->N;
   ob.N_logical = n;
   ob.N = 16;
-  ob.terms = terms; ob.relu = 0; ob.out_kind = OUT_HEAD; ob.glue = glue; ob.wait_glue = 0;
+  ob.terms = terms; ob.relu = 0; ob.out_kind = OUT_HEAD; ob.glue = glue; ob.wait_glue = 0; ob.prev_produces = 1;
   ob.W.assign((size_t)width * n, 0.f);
   int c0 = 0;
   for (auto* h : heads) {
@@ -869,7 +922,7 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
     const HostMlp& R = HM.rgb[lv];
     OpBuild ob;
     ob.N_logical = ob.N = R.width;
-    ob.terms = 1; ob.relu = 1; ob.out_kind = OUT_XS_LO_AS_HI; ob.glue = GLUE_NONE; ob.wait_glue = 0;
+    ob.terms = 1; ob.relu = 1; ob.out_kind = OUT_XS_LO_AS_HI; ob.glue = GLUE_NONE; ob.wait_glue = 0; ob.prev_produces = 1;
     ob.W = R.hidden[0].W; ob.b = R.hidden[0].b;
     int row = W;
     const int v0 = row;
@@ -897,7 +950,7 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
     OpBuild hb;
     hb.N_logical = R.logit.N;
     hb.N = 16;
-    hb.terms = 1; hb.relu = 0; hb.out_kind = OUT_HEAD; hb.glue = GLUE_RGB; hb.wait_glue = 0;
+    hb.terms = 1; hb.relu = 0; hb.out_kind = OUT_HEAD; hb.glue = GLUE_RGB; hb.wait_glue = 0; hb.prev_produces = 1;
     hb.W = R.logit.W; hb.b = R.logit.b;
     for (int j = 0; j < (R.width + 63) / 64; ++j) {
       KChunkMap k = kc_hidden(j, 0, R.width, 0, true);
@@ -953,6 +1006,12 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
   K.lvl.bias = E->d_bias[fa.level];
   K.warp_embed = h->M.warp_embed;
   K.mask_embed = h->M.mask_embed;
+  K.trace = nullptr;
+  const char* trace_path = getenv("NDS_TC_TRACE");
+  if (trace_path && !fa.sigma_only) {
+    cudaMalloc(&K.trace, TRACE_WORDS * sizeof(unsigned long long));
+    cudaMemsetAsync(K.trace, 0, TRACE_WORDS * sizeof(unsigned long long), st);
+  }
   const int64_t tiles = (fa.n_samples_total + TM - 1) / TM;
   if (tiles == 0) return NDSR_OK;
   int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
@@ -960,6 +1019,24 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
   field_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(prog, K, cp, fa, h->cfg);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string("field_tc_kernel launch: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
+  if (K.trace) {   // diagnostics only: synchronous dump of the stamps, relative to the tile start
+    std::vector<unsigned long long> t(TRACE_WORDS);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(t.data(), K.trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(K.trace);
+    const unsigned long long t0 = t[2 * MAX_IMG + 4 * MAX_OPS];
+    if (FILE* f = fopen(trace_path, "w")) {
+      auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1LL; };
+      for (int i = 0; i < prog.n_img; ++i)
+        fprintf(f, "img %d rows %d steps %d flags %d ready %lld issued %lld\n", i, prog.img[i].rows, prog.img[i].steps,
+                prog.img[i].flags, rel(t[i]), rel(t[MAX_IMG + i]));
+      for (int i = 0; i < prog.n_ops; ++i)
+        fprintf(f, "op %d N %d kind %d glue %d c0_seen %lld c0_done %lld c1_seen %lld c1_done %lld\n", i, prog.ops[i].N,
+                prog.ops[i].out_kind, prog.ops[i].glue, rel(t[2 * MAX_IMG + 4 * i]), rel(t[2 * MAX_IMG + 4 * i + 1]),
+                rel(t[2 * MAX_IMG + 4 * i + 2]), rel(t[2 * MAX_IMG + 4 * i + 3]));
+      fclose(f);
+    }
+  }
   h->launches++;
   return NDSR_OK;
 }
@@ -987,7 +1064,7 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   OpBuild ob;
   ob.N_logical = n_out;
   ob.N = head ? 16 : (n_out <= 64 ? 64 : (n_out <= 128 ? 128 : 256));
-  ob.terms = terms; ob.relu = relu; ob.glue = GLUE_SELFTEST; ob.wait_glue = 1;
+  ob.terms = terms; ob.relu = relu; ob.glue = GLUE_SELFTEST; ob.wait_glue = 1; ob.prev_produces = 1;
   ob.out_kind = head ? OUT_HEAD : (out_kind == 0 ? OUT_XS : (out_kind == 2 ? OUT_XS_LO_AS_HI : OUT_XT));
   const int K = k_hid + k_in;
   ob.W.assign(W, W + (size_t)K * n_out);

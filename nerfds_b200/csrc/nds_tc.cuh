@@ -179,10 +179,84 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms: executed by the whole (converged) warp with `issue` true in exactly one lane, so that the
+// operand arithmetic stays warp-uniform (uniform datapath) and only the tcgen05 instruction is predicated.
+__device__ __forceinline__ void umma_f16_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue));
+}
+__device__ __forceinline__ void umma_f16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue));
+}
+__device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// ---- MMA bursts -------------------------------------------------------------
+// One K-chunk (4 K-steps of 16) of a split-fp16 Dense layer as ONE asm block:
+//   D (+)= A_hi B_hi ; D += A_lo B_hi ; commit(bar_hi) ; D += A_hi B_lo ; commit(bar_lo) ; [commit(bar_d)]
+// Descriptors differ only in their low word (start address >> 4, +2 per K-step), the high word is constant, so
+// the issuing thread spends ~3 instructions per tcgen05.mma.  `a*` are descriptor low words (shared-memory
+// operand) or tensor-memory addresses (TS form, +8 columns per K-step).
+#define NDS_DESC_HI 0x40004040u   /* SBO = 1024 B, version 1, SWIZZLE_128B */
+#define NDS_MMA_SS(AL, BL, PRED) \
+  "mov.b64 ad, {" AL ", %9};\n\tmov.b64 bd, {" BL ", %9};\n\t" \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, " PRED ";\n\t"
+#define NDS_MMA_TS(AL, BL, PRED) \
+  "mov.b64 bd, {" BL ", %9};\n\t" \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [" AL "], bd, %5, " PRED ";\n\t"
+#define NDS_BURST_BODY(MMA, STEP) \
+  "{\n\t.reg .pred p, t, l, q;\n\t.reg .b32 a1, a2, a3, b1, b2, b3, c1, c2, c3, e1, e2, e3;\n\t.reg .b64 ad, bd;\n\t" \
+  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\tand.pred l, l, q;\n\t" \
+  "add.u32 a1, %1, " STEP ";\n\tadd.u32 a2, %1, 2*" STEP ";\n\tadd.u32 a3, %1, 3*" STEP ";\n\t" \
+  "add.u32 c1, %2, " STEP ";\n\tadd.u32 c2, %2, 2*" STEP ";\n\tadd.u32 c3, %2, 3*" STEP ";\n\t" \
+  "add.u32 b1, %3, 2;\n\tadd.u32 b2, %3, 4;\n\tadd.u32 b3, %3, 6;\n\t" \
+  "add.u32 e1, %4, 2;\n\tadd.u32 e2, %4, 4;\n\tadd.u32 e3, %4, 6;\n\t" \
+  MMA("%1", "%3", "p") MMA("a1", "b1", "t") MMA("a2", "b2", "t") MMA("a3", "b3", "t") \
+  MMA("%2", "%3", "t") MMA("c1", "b1", "t") MMA("c2", "b2", "t") MMA("c3", "b3", "t") \
+  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
+  MMA("%1", "%4", "t") MMA("a1", "e1", "t") MMA("a2", "e2", "t") MMA("a3", "e3", "t") \
+  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t" \
+  "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t}"
+__device__ __forceinline__ void umma_burst3_ss(uint32_t d, uint32_t a_hi_lo32, uint32_t a_lo_lo32, uint32_t b_hi_lo32,
+                                               uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,
+                                               uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {
+  asm volatile(NDS_BURST_BODY(NDS_MMA_SS, "2")
+               ::"r"(d), "r"(a_hi_lo32), "r"(a_lo_lo32), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
+                 "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
+               : "memory");
+}
+__device__ __forceinline__ void umma_burst3_ts(uint32_t d, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi_lo32,
+                                               uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,
+                                               uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {
+  asm volatile(NDS_BURST_BODY(NDS_MMA_TS, "8")
+               ::"r"(d), "r"(a_hi_tmem), "r"(a_lo_tmem), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
+                 "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t smem_desc_lo32(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
 }
 
 // ---- split fp16 -------------------------------------------------------------
