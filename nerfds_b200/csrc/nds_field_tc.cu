@@ -82,7 +82,8 @@ struct TcOp {
 enum ImgFlags : uint16_t {
   IMG_A_TMEM = 1, IMG_TWO_TERMS = 2, IMG_FIRST = 4, IMG_LAST = 8, IMG_NC1 = 16, IMG_WAIT_P0 = 32, IMG_WAIT_P1 = 64,
   IMG_WAIT_GLUE = 128,
-  IMG_PART_NEXT = 256    // the issuer has consumed one output phase of the previous op
+  IMG_PART_NEXT = 256,   // the issuer has consumed one output phase of the previous op
+  IMG_PAIR_LAST = 1024, IMG_PAIR_PART_NEXT = 2048   // copies of the B_lo image's LAST / PART_NEXT on its B_hi image
 };
 struct alignas(16) ImgEntry {
   uint32_t a_hi;         // shared: byte offset from the (1024-aligned) smem base; tensor memory: column
@@ -160,35 +161,42 @@ __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_bas
   const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING);
   uint4 raw = *reinterpret_cast<const uint4*>(&P.img[0]);
   int i = 0;
+  bool ready0 = false, ready1 = false;      // full-barrier probes of the next burst's slots, taken before this burst
   while (i < n_img) {
     const uint32_t a_hi = raw.x, a_lo = raw.y, rows = raw.z & 0xffffu, steps = (raw.z >> 16) & 0xffu, fl = raw.w & 0xffffu;
     const bool two = (fl & IMG_TWO_TERMS) != 0;
     const int adv = two ? 2 : 1;
-    uint32_t fl2 = fl;
-    if (two) fl2 = P.img[i + 1].flags;                 // IMG_LAST / IMG_PART_NEXT sit on the B_lo image
     if (i + adv < n_img) raw = *reinterpret_cast<const uint4*>(&P.img[i + adv]);
     if (fl & IMG_WAIT_GLUE) { mbar_wait(&ctl->in_ready, glue_cnt & 1u); ++glue_cnt; }
     if (fl & IMG_WAIT_P0) mbar_wait(&ctl->part_ready[0], part_cnt & 1u);
     if (fl & IMG_WAIT_P1) mbar_wait(&ctl->part_ready[1], part_cnt & 1u);
     const uint32_t s0 = slot_ctr % NSLOT, s1 = (slot_ctr + 1) % NSLOT;
-    mbar_wait(&ctl->full[s0], (slot_ctr / NSLOT) & 1u);
-    if (two) mbar_wait(&ctl->full[s1], ((slot_ctr + 1) / NSLOT) & 1u);
+    if (!ready0) mbar_wait(&ctl->full[s0], (slot_ctr / NSLOT) & 1u);
+    if (two && !ready1) mbar_wait(&ctl->full[s1], ((slot_ctr + 1) / NSLOT) & 1u);
     tc_fence_after_sync();
     if (trace && lead) trace[i] = clock64();
+    {
+      const uint32_t n0 = slot_ctr + adv, n1 = n0 + 1;
+      ready0 = mbar_test_wait(&ctl->full[n0 % NSLOT], (n0 / NSLOT) & 1u);
+      ready1 = mbar_test_wait(&ctl->full[n1 % NSLOT], (n1 / NSLOT) & 1u);
+    }
     const uint32_t d = tmem_base + TM_D + ((fl & IMG_NC1) ? 128u : 0u);
     const uint32_t idesc = make_idesc_f16(rows);
     const uint32_t b0 = ring_lo32 + s0 * (SLOT_BYTES >> 4), b1 = ring_lo32 + s1 * (SLOT_BYTES >> 4);
     const uint32_t acc = (fl & IMG_FIRST) ? 0u : 1u;
     const uint32_t dbar = smem_u32(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0]);
-    const uint32_t last = (fl2 & IMG_LAST) ? 1u : 0u;
+    const uint32_t last = (fl & (two ? IMG_PAIR_LAST : IMG_LAST)) ? 1u : 0u;
     if (two && steps == 4) {
       if (fl & IMG_A_TMEM)
         umma_burst3_ts(d, tmem_base + a_hi, tmem_base + a_lo, b0, b1, idesc, acc, empty0 + 8 * s0, empty0 + 8 * s1, last, dbar, lead);
       else
         umma_burst3_ss(d, smem_desc_lo32(smem_base + a_hi), smem_desc_lo32(smem_base + a_lo), b0, b1, idesc, acc,
                        empty0 + 8 * s0, empty0 + 8 * s1, last, dbar, lead);
+    } else if (!two && steps == 4) {
+      if (fl & IMG_A_TMEM) umma_burst1_ts(d, tmem_base + a_hi, b0, idesc, acc, empty0 + 8 * s0, last, dbar, lead);
+      else umma_burst1_ss(d, smem_desc_lo32(smem_base + a_hi), b0, idesc, acc, empty0 + 8 * s0, last, dbar, lead);
     } else {
-      // generic path: short K-chunks (network inputs) and 1-term layers
+      // generic path: short K-chunks (network inputs, heads over narrow layers)
       const uint64_t bd0 = ((uint64_t)NDS_DESC_HI << 32) | b0, bd1 = ((uint64_t)NDS_DESC_HI << 32) | b1;
       const uint32_t lead2 = two ? lead : 0u;
       if (fl & IMG_A_TMEM) {
@@ -215,7 +223,7 @@ __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_bas
     }
     if (trace && lead) trace[MAX_IMG + i] = clock64();
     slot_ctr += adv;
-    if (fl2 & IMG_PART_NEXT) ++part_cnt;
+    if (fl & (two ? IMG_PAIR_PART_NEXT : IMG_PART_NEXT)) ++part_cnt;
     i += adv;
   }
 }
@@ -252,17 +260,19 @@ __device__ __forceinline__ void store_in(uint8_t* smem, uint32_t r, uint32_t c, 
 template <int CW>
 __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const float* __restrict__ bias_base,
                                                uint8_t* smem, uint32_t tmem_lane, uint32_t row, int sub,
-                                               float* dbg_out, int dbg_ld) {
-  uint32_t v[CW];
-  tmem_ld<CW>(tmem_lane + TM_D + (uint32_t)nc * 128u + (uint32_t)sub * CW, v);
+                                               float* dbg_out, int dbg_ld, uint64_t* bar, uint32_t parity) {
   const uint32_t oc0 = (uint32_t)nc * op.nc_rows + (uint32_t)sub * CW;   // first output column of this slice
   const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off + oc0);
   float b[CW];
 #pragma unroll
-  for (int i = 0; i < CW / 4; ++i) {
+  for (int i = 0; i < CW / 4; ++i) {     // issued before the accumulators are awaited: the latency hides in the wait
     const float4 t = __ldg(bias4 + i);
     b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
   }
+  mbar_wait(bar, parity);
+  tc_fence_after_sync();
+  uint32_t v[CW];
+  tmem_ld<CW>(tmem_lane + TM_D + (uint32_t)nc * 128u + (uint32_t)sub * CW, v);
   tmem_ld_wait();
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
@@ -297,12 +307,14 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   }
 }
 
+// waits for the chunk's accumulators (bar / parity) inside, after the bias prefetch
 __device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint8_t* smem,
-                                                  uint32_t tmem_lane, uint32_t row, int sub, float* dbg, int dbg_ld) {
+                                                  uint32_t tmem_lane, uint32_t row, int sub, float* dbg, int dbg_ld,
+                                                  uint64_t* bar, uint32_t parity) {
   switch (op.nc_rows) {
-    case 128: epilogue_chunk<32>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld); break;
-    case 64: epilogue_chunk<16>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld); break;
-    default: epilogue_chunk<8>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld); break;
+    case 128: epilogue_chunk<32>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld, bar, parity); break;
+    case 64: epilogue_chunk<16>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld, bar, parity); break;
+    default: epilogue_chunk<8>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld, bar, parity); break;
   }
 }
 
@@ -317,28 +329,48 @@ __device__ __forceinline__ void epilogue_head(const TcOp& op, const float* __res
   for (int i = 0; i < 16; ++i) hv[i] = fmaf(__uint_as_float(v[i]), op.inv_scale, __ldg(bias + i));
 }
 
-// positional encoding (model_utils.py:398-417) with the (sin, cos) pairs dealt round-robin to the NSUB warps
-// that share a sample; `pair` is the running pair counter, `o` the running feature offset.
+// sin(x) for the positional encodings (|x| <= 2^max_deg * scene extent, far below the 1e5 limit of the 3-term
+// Cody-Waite reduction): reduce by pi/2, then the cephes sinf / cosf minimax polynomials on [-pi/4, pi/4].
+// ~1 ulp; no slow path, so it stays inline and branch-free.
+__device__ __forceinline__ float pe_sin(float x) {
+  const float j = rintf(x * 0.636619772367581343f);
+  float r = fmaf(j, -1.57079601287841796875f, x);
+  r = fmaf(j, -3.1391647326017846e-07f, r);
+  r = fmaf(j, -5.390302529957764e-15f, r);
+  const int q = (int)j;
+  const float r2 = r * r;
+  float sn = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sn = fmaf(sn, r2, -1.6666654611e-1f);
+  sn = fmaf(sn * r2, r, r);
+  float cs = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cs = fmaf(cs, r2, 4.166664568298827e-2f);
+  cs = fmaf(cs * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const float v = (q & 1) ? cs : sn;
+  return (q & 2) ? -v : v;
+}
+
+// positional encoding (model_utils.py:398-417): feature layout (F, 2, C) flattened, identity first.  The
+// (sin, cos) pairs are dealt round-robin to the NSUB warps that share a sample: this warp evaluates the pairs p
+// with (pair + p) % NSUB == sub.  `pair` is the running pair counter, `o` the running feature offset.
 template <typename Store>
-__device__ __forceinline__ int posenc_emit_sub(const float* x, int C, const PosencSpec& pe, Store store, int o,
-                                               int sub, int& pair) {
+__device__ __forceinline__ int posenc_emit_sub(float x0, float x1, float x2, int C, const PosencSpec& pe, Store store,
+                                               int o, int sub, int& pair) {
   if (pe.identity) {
-    if (sub == 0) for (int c = 0; c < C; ++c) store(o + c, x[c]);
+    if (sub == 0) { store(o, x0); if (C > 1) store(o + 1, x1); if (C > 2) store(o + 2, x2); }
     o += C;
   }
-  for (int k = 0; k < pe.num_bands; ++k) {
-    const float s = exp2f((float)(pe.min_deg + k));
+  const int npair = pe.num_bands * C;
+  for (int p = (sub - pair) & (NSUB - 1); p < npair; p += NSUB) {
+    const int k = C == 3 ? p / 3 : (C == 2 ? p >> 1 : p);
+    const int c = p - k * C;
+    const float xv = c == 0 ? x0 : (c == 1 ? x1 : x2);
+    const float xb = xv * __int_as_float((127 + pe.min_deg + k) << 23);    // x * 2^(min_deg + k), exact
     const float w = pe.window[k];
-    for (int c = 0; c < C; ++c) {
-      if ((pair++ & (NSUB - 1)) == sub) {
-        const float xb = x[c] * s;
-        store(o + c, w * sinf(xb));
-        store(o + C + c, w * sinf(xb + NDS_HALF_PI_F));
-      }
-    }
-    o += 2 * C;
+    store(o + 2 * C * k + c, w * pe_sin(xb));
+    store(o + 2 * C * k + C + c, w * pe_sin(xb + NDS_HALF_PI_F));
   }
-  return o;
+  pair += npair;
+  return o + 2 * npair;
 }
 
 // ---------------------------------------------------------------------------
@@ -394,30 +426,41 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     uint32_t dcnt0 = 0, dcnt1 = 0;
+    // per-sample inputs are fetched one tile ahead, so their global-memory latency hides behind the previous tile
+    struct Sample { float x[3], vd[3], gt; int64_t ray; uint32_t wid; bool valid; };
+    auto load_sample = [&](int64_t tile_, Sample& s_) {
+      const int64_t n_ = tile_ * TM + row;
+      s_.valid = n_ < a.n_samples_total;
+      s_.x[0] = s_.x[1] = s_.x[2] = 0.f; s_.vd[0] = s_.vd[1] = s_.vd[2] = 0.f; s_.gt = 0.f; s_.ray = 0; s_.wid = 0;
+      if (!s_.valid) return;
+      s_.ray = n_ / a.S;
+      if (a.points) { s_.x[0] = a.points[n_ * 3]; s_.x[1] = a.points[n_ * 3 + 1]; s_.x[2] = a.points[n_ * 3 + 2]; }
+      else {
+        const float z = a.z[n_];
+        s_.x[0] = a.origins[s_.ray * 3 + 0] + z * a.dirs[s_.ray * 3 + 0];
+        s_.x[1] = a.origins[s_.ray * 3 + 1] + z * a.dirs[s_.ray * 3 + 1];
+        s_.x[2] = a.origins[s_.ray * 3 + 2] + z * a.dirs[s_.ray * 3 + 2];
+      }
+      s_.vd[0] = a.viewdirs[s_.ray * 3]; s_.vd[1] = a.viewdirs[s_.ray * 3 + 1]; s_.vd[2] = a.viewdirs[s_.ray * 3 + 2];
+      if (a.warp_id) s_.wid = a.warp_id[s_.ray];
+      if (a.gt_mask) s_.gt = a.gt_mask[s_.ray];
+    };
+    Sample nxt;
+    load_sample(blockIdx.x, nxt);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t n = tile * TM + row;
-      const bool valid = n < a.n_samples_total;
+      const Sample cur = nxt;
+      const bool valid = cur.valid;
       unsigned long long* tr = (K.trace && tile == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 2 * MAX_IMG : nullptr;
       if (tr) tr[4 * MAX_OPS] = clock64();
-      float x[3] = {0.f, 0.f, 0.f}, xw[3] = {0.f, 0.f, 0.f}, om[2] = {0.f, 0.f};
-      float maskv = 0.f, pmask = 0.f, sigma_raw = 0.f, nrm[3] = {0.f, 0.f, 0.f}, rgb[3] = {0.f, 0.f, 0.f};
+      const float x[3] = {cur.x[0], cur.x[1], cur.x[2]};
+      float xw[3] = {0.f, 0.f, 0.f}, om[2] = {0.f, 0.f};
+      float maskv = cur.gt, pmask = 0.f, sigma_raw = 0.f, nrm[3] = {0.f, 0.f, 0.f}, rgb[3] = {0.f, 0.f, 0.f};
       SE3<float> T;
       for (int i = 0; i < 9; ++i) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
       T.p[0] = T.p[1] = T.p[2] = 0.f;
-      int64_t ray = 0;
-      uint32_t wid = 0;
-      if (valid) {
-        ray = n / a.S;
-        if (a.points) { x[0] = a.points[n * 3]; x[1] = a.points[n * 3 + 1]; x[2] = a.points[n * 3 + 2]; }
-        else {
-          const float z = a.z[n];
-          x[0] = a.origins[ray * 3 + 0] + z * a.dirs[ray * 3 + 0];
-          x[1] = a.origins[ray * 3 + 1] + z * a.dirs[ray * 3 + 1];
-          x[2] = a.origins[ray * 3 + 2] + z * a.dirs[ray * 3 + 2];
-        }
-        if (a.warp_id) wid = a.warp_id[ray];
-        if (a.gt_mask) maskv = a.gt_mask[ray];
-      }
+      const int64_t ray = cur.ray;
+      const uint32_t wid = cur.wid;
       auto st_in = [&](int c, float v) { store_in(smem, row, (uint32_t)c, v); };
       // columns [from, 64) of the IN block are zero (their weight rows are zero, but 0 x garbage could be NaN)
       auto zero_in = [&](int from) { for (int c = from; c < 64; ++c) if ((c & (NSUB - 1)) == sub) st_in(c, 0.f); };
@@ -430,26 +473,26 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
       // inputs of the networks of the chain
       auto prep_mask_in = [&]() {
         int pair = 0;
-        int o = posenc_emit_sub(x, 3, cp.pe_mask, st_in, 0, sub, pair);
+        int o = posenc_emit_sub(x[0], x[1], x[2], 3, cp.pe_mask, st_in, 0, sub, pair);
         o = extras(o, K.mask_embed, cfg.mask_embed_dims, false);
         zero_in(o);
       };
       auto prep_warp_in = [&]() {
         int pair = 0;
-        int o = posenc_emit_sub(x, 3, cp.pe_warp, st_in, 0, sub, pair);
+        int o = posenc_emit_sub(x[0], x[1], x[2], 3, cp.pe_warp, st_in, 0, sub, pair);
         o = extras(o, K.warp_embed, cfg.warp_embed_dims, cfg.use_mask_in_warp != 0);
         zero_in(o);
       };
       auto prep_hyper_in = [&]() {
         int pair = 0;
-        int o = posenc_emit_sub(x, 3, cp.pe_hsheet, st_in, 0, sub, pair);
+        int o = posenc_emit_sub(x[0], x[1], x[2], 3, cp.pe_hsheet, st_in, 0, sub, pair);
         o = extras(o, K.warp_embed, cfg.warp_embed_dims, cfg.use_mask_in_hyper != 0);
         zero_in(o);
       };
       auto prep_trunk_in = [&]() {
         int pair = 0;
-        int o = posenc_emit_sub(xw, 3, cp.pe_spatial, st_in, 0, sub, pair);
-        if (H > 0) o = posenc_emit_sub(om, H, cp.pe_hyperpt, st_in, o, sub, pair);
+        int o = posenc_emit_sub(xw[0], xw[1], xw[2], 3, cp.pe_spatial, st_in, 0, sub, pair);
+        if (H > 0) o = posenc_emit_sub(om[0], om[1], 0.f, H, cp.pe_hyperpt, st_in, o, sub, pair);
         zero_in(o);
       };
       auto after_mask = [&]() { if (cfg.use_warp) prep_warp_in(); else prep_trunk_in(); };
@@ -458,16 +501,16 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
       else if (cfg.use_warp) prep_warp_in();
       else { xw[0] = x[0]; xw[1] = x[1]; xw[2] = x[2]; prep_trunk_in(); }
       warp_arrive(&ctl->in_ready, lane);
+      if (tile + gridDim.x < n_tiles) load_sample(tile + gridDim.x, nxt);
 
       for (int i = 0; i < P.n_ops; ++i) {
         const TcOp& op = P.ops[i];
         if (op.out_kind != OUT_HEAD) {
           for (int nc = 0; nc < op.n_nc; ++nc) {
-            if (nc == 0) { mbar_wait(&ctl->d_full[0], dcnt0 & 1u); ++dcnt0; }
-            else { mbar_wait(&ctl->d_full[1], dcnt1 & 1u); ++dcnt1; }
-            tc_fence_after_sync();
-            if (tr) tr[4 * i + 2 * nc] = clock64();
-            epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, nullptr, 0);
+            uint32_t par;
+            if (nc == 0) par = dcnt0++ & 1u; else par = dcnt1++ & 1u;
+            if (tr) { mbar_wait(&ctl->d_full[nc], par); tr[4 * i + 2 * nc] = clock64(); }
+            epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, nullptr, 0, &ctl->d_full[nc], par);
             warp_arrive(&ctl->part_ready[nc], lane);
             if (tr) tr[4 * i + 2 * nc + 1] = clock64();
           }
@@ -479,6 +522,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         if (tr) tr[4 * i] = clock64();
         float hv[16];
         epilogue_head(op, L.bias, tmem_lane, hv);
+        if (tr) tr[4 * i + 2] = clock64();
         switch (op.glue) {
           case GLUE_MASK: {            // models.py:967-975
             pmask = cfg.mask_output_relu ? fmaxf(hv[0], 0.f) : hv[0];
@@ -501,9 +545,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
               // rgb branch side inputs: [viewdir feats | normal-input feats] in the IN block
               int o = 0, pair = 0;
               if (cfg.use_viewdirs) {
-                float vd[3] = {0.f, 0.f, 0.f};
-                if (valid) { vd[0] = a.viewdirs[ray * 3]; vd[1] = a.viewdirs[ray * 3 + 1]; vd[2] = a.viewdirs[ray * 3 + 2]; }
-                o = posenc_emit_sub(vd, 3, cp.pe_view, st_in, 0, sub, pair);
+                o = posenc_emit_sub(cur.vd[0], cur.vd[1], cur.vd[2], 3, cp.pe_view, st_in, 0, sub, pair);
               }
               if (cp.use_predicted_norm) {
                 float nh[3], ni[3];
@@ -511,7 +553,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
                 if (cfg.use_warp) { for (int c = 0; c < 3; ++c) ni[c] = T.R[0 * 3 + c] * nh[0] + T.R[1 * 3 + c] * nh[1] + T.R[2 * 3 + c] * nh[2]; }
                 else { ni[0] = nh[0]; ni[1] = nh[1]; ni[2] = nh[2]; }
                 normalize3(ni, nh);
-                if (cfg.norm_input_posenc) o = posenc_emit_sub(nh, 3, cp.pe_norm, st_in, o, sub, pair);
+                if (cfg.norm_input_posenc) o = posenc_emit_sub(nh[0], nh[1], nh[2], 3, cp.pe_norm, st_in, o, sub, pair);
                 else { if (sub == 0) { st_in(o, nh[0]); st_in(o + 1, nh[1]); st_in(o + 2, nh[2]); } o += 3; }
               }
               zero_in(o);
@@ -627,11 +669,8 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
       epilogue_head(op, L.bias, tmem_lane, hv);
       if (sub == 0) for (int i = 0; i < 16 && i < op.N; ++i) out_f32[row * op.N + i] = hv[i];
     } else {
-      for (int nc = 0; nc < op.n_nc; ++nc) {
-        mbar_wait(&ctl->d_full[nc], 0);
-        tc_fence_after_sync();
-        epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, out_f32, op.N);
-      }
+      for (int nc = 0; nc < op.n_nc; ++nc)
+        epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, out_f32, op.N, &ctl->d_full[nc], 0);
       fence_proxy_async_smem();
       tmem_st_wait();
       tc_fence_before_sync();
@@ -865,6 +904,11 @@ static bool make_program(const Packed& P, TcProgram& prog, std::string& err) {
   prog.n_img = (int)P.imgs.size();
   std::copy(P.ops.begin(), P.ops.end(), prog.ops);
   std::copy(P.imgs.begin(), P.imgs.end(), prog.img);
+  for (int i = 0; i + 1 < prog.n_img; ++i)
+    if (prog.img[i].flags & IMG_TWO_TERMS) {
+      if (prog.img[i + 1].flags & IMG_LAST) prog.img[i].flags |= IMG_PAIR_LAST;
+      if (prog.img[i + 1].flags & IMG_PART_NEXT) prog.img[i].flags |= IMG_PAIR_PART_NEXT;
+    }
   return true;
 }
 

@@ -44,6 +44,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a while when the phase is still open)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
@@ -253,6 +265,31 @@ __device__ __forceinline__ void umma_burst3_ts(uint32_t d, uint32_t a_hi_tmem, u
   asm volatile(NDS_BURST_BODY(NDS_MMA_TS, "8")
                ::"r"(d), "r"(a_hi_tmem), "r"(a_lo_tmem), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
                  "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
+               : "memory");
+}
+// 1-term K-chunk (4 K-steps): D (+)= A_hi B_hi ; commit(bar_slot) ; [commit(bar_d)]
+#define NDS_BURST1_BODY(MMA, STEP) \
+  "{\n\t.reg .pred p, t, l, q;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 ad, bd;\n\t" \
+  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\tand.pred l, l, q;\n\t" \
+  "add.u32 a1, %1, " STEP ";\n\tadd.u32 a2, %1, 2*" STEP ";\n\tadd.u32 a3, %1, 3*" STEP ";\n\t" \
+  "add.u32 b1, %3, 2;\n\tadd.u32 b2, %3, 4;\n\tadd.u32 b3, %3, 6;\n\t" \
+  MMA("%1", "%3", "p") MMA("a1", "b1", "t") MMA("a2", "b2", "t") MMA("a3", "b3", "t") \
+  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
+  "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t}"
+__device__ __forceinline__ void umma_burst1_ss(uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
+                                               uint32_t issue) {
+  asm volatile(NDS_BURST1_BODY(NDS_MMA_SS, "2")
+               ::"r"(d), "r"(a_lo32), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
+                 "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
+               : "memory");
+}
+__device__ __forceinline__ void umma_burst1_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo32, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
+                                               uint32_t issue) {
+  asm volatile(NDS_BURST1_BODY(NDS_MMA_TS, "8")
+               ::"r"(d), "r"(a_tmem), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
+                 "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
 }
 __device__ __forceinline__ uint32_t smem_desc_lo32(uint32_t smem_addr) {
