@@ -104,6 +104,9 @@ struct TcProgram {       // passed by value as a __grid_constant__ kernel parame
   ImgEntry img[MAX_IMG];
 };
 
+constexpr int TRACE_X = 2 * MAX_IMG + 4 * MAX_OPS + 8;       // issuer loop-top / after-waits stamps
+constexpr int TRACE_WORDS = TRACE_X + 2 * MAX_IMG;
+
 struct TcLevel {
   const uint8_t* weights;
   const float* bias;
@@ -167,12 +170,14 @@ __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_bas
     const bool two = (fl & IMG_TWO_TERMS) != 0;
     const int adv = two ? 2 : 1;
     if (i + adv < n_img) raw = *reinterpret_cast<const uint4*>(&P.img[i + adv]);
+    if (trace && lead) trace[TRACE_X + i] = clock64();
     if (fl & IMG_WAIT_GLUE) { mbar_wait(&ctl->in_ready, glue_cnt & 1u); ++glue_cnt; }
     if (fl & IMG_WAIT_P0) mbar_wait(&ctl->part_ready[0], part_cnt & 1u);
     if (fl & IMG_WAIT_P1) mbar_wait(&ctl->part_ready[1], part_cnt & 1u);
     const uint32_t s0 = slot_ctr % NSLOT, s1 = (slot_ctr + 1) % NSLOT;
     if (!ready0) mbar_wait(&ctl->full[s0], (slot_ctr / NSLOT) & 1u);
     if (two && !ready1) mbar_wait(&ctl->full[s1], ((slot_ctr + 1) / NSLOT) & 1u);
+    if (trace && lead) trace[TRACE_X + MAX_IMG + i] = clock64();
     tc_fence_after_sync();
     if (trace && lead) trace[i] = clock64();
     {
@@ -384,7 +389,7 @@ struct TcKernelArgs {
 };
 // trace layout: [i] image i ready to issue | [MAX_IMG + i] image i issued | [2 MAX_IMG + 4 op + 2 nc] accumulators seen,
 // [.. + 1] operand written & signalled | [2 MAX_IMG + 4 MAX_OPS] tile start
-constexpr int TRACE_WORDS = 2 * MAX_IMG + 4 * MAX_OPS + 8;
+
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcKernelArgs K,
@@ -1072,8 +1077,9 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
     if (FILE* f = fopen(trace_path, "w")) {
       auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1LL; };
       for (int i = 0; i < prog.n_img; ++i)
-        fprintf(f, "img %d rows %d steps %d flags %d ready %lld issued %lld\n", i, prog.img[i].rows, prog.img[i].steps,
-                prog.img[i].flags, rel(t[i]), rel(t[MAX_IMG + i]));
+        fprintf(f, "img %d rows %d steps %d flags %d ready %lld issued %lld top %lld waited %lld\n", i, prog.img[i].rows,
+                prog.img[i].steps, prog.img[i].flags, rel(t[i]), rel(t[MAX_IMG + i]), rel(t[TRACE_X + i]),
+                rel(t[TRACE_X + MAX_IMG + i]));
       for (int i = 0; i < prog.n_ops; ++i)
         fprintf(f, "op %d N %d kind %d glue %d c0_seen %lld c0_done %lld c1_seen %lld c1_done %lld\n", i, prog.ops[i].N,
                 prog.ops[i].out_kind, prog.ops[i].glue, rel(t[2 * MAX_IMG + 4 * i]), rel(t[2 * MAX_IMG + 4 * i + 1]),

@@ -232,29 +232,46 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // the issuing thread spends ~3 instructions per tcgen05.mma.  `a*` are descriptor low words (shared-memory
 // operand) or tensor-memory addresses (TS form, +8 columns per K-step).
 #define NDS_DESC_HI 0x40004040u   /* SBO = 1024 B, version 1, SWIZZLE_128B */
-#define NDS_MMA_SS(AL, BL, PRED) \
-  "mov.b64 ad, {" AL ", %9};\n\tmov.b64 bd, {" BL ", %9};\n\t" \
-  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, " PRED ";\n\t"
-#define NDS_MMA_TS(AL, BL, PRED) \
-  "mov.b64 bd, {" BL ", %9};\n\t" \
-  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [" AL "], bd, %5, " PRED ";\n\t"
-#define NDS_BURST_BODY(MMA, STEP) \
-  "{\n\t.reg .pred p, t, l, q;\n\t.reg .b32 a1, a2, a3, b1, b2, b3, c1, c2, c3, e1, e2, e3;\n\t.reg .b64 ad, bd;\n\t" \
-  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\tand.pred l, l, q;\n\t" \
-  "add.u32 a1, %1, " STEP ";\n\tadd.u32 a2, %1, 2*" STEP ";\n\tadd.u32 a3, %1, 3*" STEP ";\n\t" \
-  "add.u32 c1, %2, " STEP ";\n\tadd.u32 c2, %2, 2*" STEP ";\n\tadd.u32 c3, %2, 3*" STEP ";\n\t" \
-  "add.u32 b1, %3, 2;\n\tadd.u32 b2, %3, 4;\n\tadd.u32 b3, %3, 6;\n\t" \
-  "add.u32 e1, %4, 2;\n\tadd.u32 e2, %4, 4;\n\tadd.u32 e3, %4, 6;\n\t" \
-  MMA("%1", "%3", "p") MMA("a1", "b1", "t") MMA("a2", "b2", "t") MMA("a3", "b3", "t") \
-  MMA("%2", "%3", "t") MMA("c1", "b1", "t") MMA("c2", "b2", "t") MMA("c3", "b3", "t") \
-  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
-  MMA("%1", "%4", "t") MMA("a1", "e1", "t") MMA("a2", "e2", "t") MMA("a3", "e3", "t") \
-  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t" \
-  "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t}"
+// operand setup first (all descriptors / addresses into their own registers), then the tcgen05 instructions
+// back to back inside one branch taken by the elected lane only.
+#define NDS_SETUP_SS \
+  ".reg .b64 A0, A1, A2, A3, L0, L1, L2, L3, H0, H1, H2, H3, G0, G1, G2, G3;\n\t.reg .b32 w;\n\t" \
+  "mov.b64 A0, {%1, %9};\n\tadd.u32 w, %1, 2;\n\tmov.b64 A1, {w, %9};\n\tadd.u32 w, %1, 4;\n\tmov.b64 A2, {w, %9};\n\tadd.u32 w, %1, 6;\n\tmov.b64 A3, {w, %9};\n\t" \
+  "mov.b64 L0, {%2, %9};\n\tadd.u32 w, %2, 2;\n\tmov.b64 L1, {w, %9};\n\tadd.u32 w, %2, 4;\n\tmov.b64 L2, {w, %9};\n\tadd.u32 w, %2, 6;\n\tmov.b64 L3, {w, %9};\n\t"
+#define NDS_SETUP_TS \
+  ".reg .b32 A0, A1, A2, A3, L0, L1, L2, L3, w;\n\t.reg .b64 H0, H1, H2, H3, G0, G1, G2, G3;\n\t" \
+  "mov.b32 A0, %1;\n\tadd.u32 A1, %1, 8;\n\tadd.u32 A2, %1, 16;\n\tadd.u32 A3, %1, 24;\n\t" \
+  "mov.b32 L0, %2;\n\tadd.u32 L1, %2, 8;\n\tadd.u32 L2, %2, 16;\n\tadd.u32 L3, %2, 24;\n\t"
+#define NDS_SETUP_B \
+  "mov.b64 H0, {%3, %9};\n\tadd.u32 w, %3, 2;\n\tmov.b64 H1, {w, %9};\n\tadd.u32 w, %3, 4;\n\tmov.b64 H2, {w, %9};\n\tadd.u32 w, %3, 6;\n\tmov.b64 H3, {w, %9};\n\t" \
+  "mov.b64 G0, {%4, %9};\n\tadd.u32 w, %4, 2;\n\tmov.b64 G1, {w, %9};\n\tadd.u32 w, %4, 4;\n\tmov.b64 G2, {w, %9};\n\tadd.u32 w, %4, 6;\n\tmov.b64 G3, {w, %9};\n\t"
+#define NDS_MMA_SS(A, B, PRED) "tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %5, " PRED ";\n\t"
+#define NDS_MMA_TS(A, B, PRED) "tcgen05.mma.cta_group::1.kind::f16 [%0], [" A "], " B ", %5, " PRED ";\n\t"
+#define NDS_COMMIT(BAR) "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [" BAR "];\n\t"
+#define NDS_BURST_BODY(SETUP_A, MMA) \
+  "{\n\t.reg .pred p, t, l, q;\n\t" SETUP_A NDS_SETUP_B \
+  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\t" \
+  "@!q bra NDS_DONE;\n\t" \
+  MMA("A0", "H0", "p") MMA("A1", "H1", "t") MMA("A2", "H2", "t") MMA("A3", "H3", "t") \
+  MMA("L0", "H0", "t") MMA("L1", "H1", "t") MMA("L2", "H2", "t") MMA("L3", "H3", "t") \
+  NDS_COMMIT("%7") \
+  MMA("A0", "G0", "t") MMA("A1", "G1", "t") MMA("A2", "G2", "t") MMA("A3", "G3", "t") \
+  NDS_COMMIT("%8") \
+  "@l " NDS_COMMIT("%11") \
+  "NDS_DONE:\n\t}"
+// 1-term K-chunk (4 K-steps): D (+)= A_hi B_hi ; commit(bar_slot) ; [commit(bar_d)]
+#define NDS_BURST1_BODY(SETUP_A, MMA) \
+  "{\n\t.reg .pred p, t, l, q;\n\t" SETUP_A NDS_SETUP_B \
+  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\t" \
+  "@!q bra NDS_DONE;\n\t" \
+  MMA("A0", "H0", "p") MMA("A1", "H1", "t") MMA("A2", "H2", "t") MMA("A3", "H3", "t") \
+  NDS_COMMIT("%7") \
+  "@l " NDS_COMMIT("%11") \
+  "NDS_DONE:\n\t}"
 __device__ __forceinline__ void umma_burst3_ss(uint32_t d, uint32_t a_hi_lo32, uint32_t a_lo_lo32, uint32_t b_hi_lo32,
                                                uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,
                                                uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {
-  asm volatile(NDS_BURST_BODY(NDS_MMA_SS, "2")
+  asm volatile(NDS_BURST_BODY(NDS_SETUP_SS, NDS_MMA_SS)
                ::"r"(d), "r"(a_hi_lo32), "r"(a_lo_lo32), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
                  "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
@@ -262,24 +279,15 @@ __device__ __forceinline__ void umma_burst3_ss(uint32_t d, uint32_t a_hi_lo32, u
 __device__ __forceinline__ void umma_burst3_ts(uint32_t d, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi_lo32,
                                                uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,
                                                uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {
-  asm volatile(NDS_BURST_BODY(NDS_MMA_TS, "8")
+  asm volatile(NDS_BURST_BODY(NDS_SETUP_TS, NDS_MMA_TS)
                ::"r"(d), "r"(a_hi_tmem), "r"(a_lo_tmem), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
                  "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
 }
-// 1-term K-chunk (4 K-steps): D (+)= A_hi B_hi ; commit(bar_slot) ; [commit(bar_d)]
-#define NDS_BURST1_BODY(MMA, STEP) \
-  "{\n\t.reg .pred p, t, l, q;\n\t.reg .b32 a1, a2, a3, b1, b2, b3;\n\t.reg .b64 ad, bd;\n\t" \
-  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\tand.pred l, l, q;\n\t" \
-  "add.u32 a1, %1, " STEP ";\n\tadd.u32 a2, %1, 2*" STEP ";\n\tadd.u32 a3, %1, 3*" STEP ";\n\t" \
-  "add.u32 b1, %3, 2;\n\tadd.u32 b2, %3, 4;\n\tadd.u32 b3, %3, 6;\n\t" \
-  MMA("%1", "%3", "p") MMA("a1", "b1", "t") MMA("a2", "b2", "t") MMA("a3", "b3", "t") \
-  "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t" \
-  "@l tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%11];\n\t}"
 __device__ __forceinline__ void umma_burst1_ss(uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
                                                uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
                                                uint32_t issue) {
-  asm volatile(NDS_BURST1_BODY(NDS_MMA_SS, "2")
+  asm volatile(NDS_BURST1_BODY(NDS_SETUP_SS, NDS_MMA_SS)
                ::"r"(d), "r"(a_lo32), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
                  "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
@@ -287,7 +295,7 @@ __device__ __forceinline__ void umma_burst1_ss(uint32_t d, uint32_t a_lo32, uint
 __device__ __forceinline__ void umma_burst1_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo32, uint32_t idesc,
                                                uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
                                                uint32_t issue) {
-  asm volatile(NDS_BURST1_BODY(NDS_MMA_TS, "8")
+  asm volatile(NDS_BURST1_BODY(NDS_SETUP_TS, NDS_MMA_TS)
                ::"r"(d), "r"(a_tmem), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
                  "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
