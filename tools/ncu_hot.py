@@ -5,13 +5,18 @@ rep = sys.argv[1]; top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
-want = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active_realtime.avg.pct', 'sm__pipe_tensor_subpipe_hmma_cycles_active',
-        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'sm__warps_active.avg.pct', 'launch__registers_per_thread',
-        'smsp__inst_executed.sum', 'sm__inst_executed_pipe_uniform', 'lts__throughput.avg.pct', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ',
-        'smsp__issue_active.avg.pct', 'sm__cycles_elapsed.max', 'lts__t_sectors_srcunit_tex_op_read.sum', 'sm__sass_inst_executed_op_shared']
+want = ['gpu__time_duration.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
+        'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max',
+        'smsp__mem_tensor_reads_op_ldt.sum.pct_of_peak_sustained_elapsed',
+        'smsp__mem_tensor_writes_op_stt.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']
 for h, u, v in zip(hdr, units, vals):
-  if any(h.startswith(w) or w in h for w in want) and 'TriageCompute' not in h or 'tensor' in h and 'pct' in h:
-    print(f'{h:90s} {u:12s} {v}')
+  if h in want:
+    print(f'{h:100s} {u:16s} {v}')
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 hdr, data = rows[1], rows[2:]
