@@ -2,26 +2,28 @@
 //
 // One persistent CTA per SM processes tiles of 128 samples.  Every Dense layer
 // of the path (hypernerf/modules.py:57-83) is a [128 x K] x [K x N] GEMM issued
-// as tcgen05.mma (kind::f16, fp32 accumulators in TMEM) by ONE thread:
-//   * A = the tile's activations as split fp16 (hi + lo).  Successive layers
-//     ALTERNATE between two homes -- tensor memory (TS-mode MMA, written with
-//     tcgen05.st) and shared memory (canonical K-major SWIZZLE_128B K-blocks) --
-//     so the epilogue of layer l never overwrites what layer l's MMAs still read;
+// as tcgen05.mma (kind::f16, fp32 accumulators in TMEM):
+//   * A = the tile's activations as split fp16 (hi + lo), kept IN TENSOR MEMORY
+//     for the whole chain (TS-mode MMA).  The 512 TMEM columns form two regions
+//     of 256: layer l reads its operand from one region and accumulates into the
+//     other; the epilogue converts the accumulators IN PLACE (tcgen05.ld ->
+//     bias/ReLU -> split -> tcgen05.st over the columns it just read) into the
+//     operand of layer l+1, which accumulates back into the first region.
+//     Network inputs (posenc features, embeddings, mask) are the only shared-
+//     memory operands (canonical K-major SWIZZLE_128B block, SS-mode MMA);
 //   * B = the layer's weights, pre-packed on the host into the exact
 //     shared-memory image (scaled by a power of two, split hi + lo, swizzled)
-//     and streamed image by image through a 4-slot bulk-TMA (cp.async.bulk) ring;
+//     and streamed image by image through a 12-slot bulk-TMA (cp.async.bulk) ring;
 //   * "3-term" layers issue A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (~fp32 accuracy,
 //     needed on the sigma path for the 1e-3 RGB bound -- tools/precision_study.py),
 //     "1-term" layers issue A_hi*B_hi only (bottleneck, rgb branch).
-// Every layer is split into two N-chunks with separate accumulators and
+// Wide layers are split into two N-chunks with separate accumulators and
 // barriers: while the tensor core works on chunk 1, the 16 compute warps drain
-// chunk 0 (tcgen05.ld -> bias/ReLU -> split -> next layer's operand), and the
-// next layer's MMAs start on the K-range chunk 0 produced before chunk 1's
-// epilogue has finished.
+// chunk 0, and the next layer's MMAs start on the K-range chunk 0 produced
+// before chunk 1's epilogue has finished.
 // Warp roles: warps 0-15 = compute (TMEM lane quarter = warp % 4 -> 32 samples,
 // column slice / feature slice = warp / 4): positional encodings, SE(3)
-// exponential, epilogues; warp 16 lane 0 = MMA issuer; warp 17 lane 0 = TMA
-// producer.
+// exponential, epilogues; warp 16 = MMA issuer; warp 17 = TMA producer.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -46,27 +48,28 @@ constexpr int WARP_MMA = N_CWARPS, WARP_TMA = N_CWARPS + 1;
 constexpr int TC_THREADS = (N_CWARPS + 2) * 32;
 constexpr uint32_t KBLK = 16384;        // one 128-row K-block (64 fp16 columns)
 // shared memory map
-constexpr uint32_t OFF_XS_HI = 0;
-constexpr uint32_t OFF_XS_LO = 4 * KBLK;
-constexpr uint32_t OFF_IN_HI = 8 * KBLK;
-constexpr uint32_t OFF_IN_LO = 9 * KBLK;
-constexpr uint32_t OFF_RING = 10 * KBLK;
+constexpr uint32_t OFF_IN_HI = 0;
+constexpr uint32_t OFF_IN_LO = KBLK;
+constexpr uint32_t OFF_RING = 2 * KBLK;
 constexpr uint32_t SLOT_BYTES = 16384;  // one weight image: <= 128 rows x 64 fp16
-constexpr int NSLOT = 4;
+constexpr int NSLOT = 12;
 constexpr uint32_t OFF_CTRL = OFF_RING + NSLOT * SLOT_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 256 + 1024;   // + manual 1024-byte alignment slack
-// tensor memory map (512 columns): accumulators | activations hi | activations lo
-constexpr uint32_t TM_D = 0;            // N-chunk c accumulates at column 128 c
-constexpr uint32_t TM_XT_HI = 256;      // K-block j at column 32 j (two fp16 per column)
-constexpr uint32_t TM_XT_LO = 384;
+constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 512 + 1024;   // + manual 1024-byte alignment slack
+// tensor memory: two regions of 256 columns; accumulator chunk c of an op sits at region + 128 c
+constexpr uint32_t TM_REGION = 256;
 constexpr int MAX_KC = 10;
 
-enum OutKind : uint8_t { OUT_XS = 0, OUT_XT = 1, OUT_XS_LO_AS_HI = 2, OUT_XT_HI_ONLY = 3, OUT_HEAD = 4 };
+enum EpiKind : uint8_t {
+  EPI_INPLACE = 0,      // slice of CW accumulator columns -> hi (CW/2 columns) | lo (CW/2 columns) over the same slice
+  EPI_INPLACE_HI = 1,   // hi only (consumer is a 1-term layer)
+  EPI_COMPACT_HI = 2,   // hi only, compacted to the first half of the chunk (frees the second half for accumulators)
+  EPI_HEAD = 4          // <= 16 outputs consumed by the per-sample stage
+};
 enum Glue : uint8_t { GLUE_NONE = 0, GLUE_MASK = 1, GLUE_WARP = 2, GLUE_HYPER = 3, GLUE_ALPHA = 4, GLUE_BOTTLENECK = 5,
                       GLUE_RGB = 6, GLUE_SELFTEST = 7 };
-// A-operand source of a K-chunk: 0..3 XS block j (shared) | 4 IN block (shared) | 8+j XS_LO block j used as a
-// 1-term operand | 16+j XT block j (tensor memory)
-constexpr uint8_t SRC_IN = 4, SRC_XS_LO = 8, SRC_XT = 16;
+// A-operand addressing pattern of an image: 0 = shared memory (IN block), else tensor memory with the K-step
+// column offsets of nds_tc.cuh (32 / 16 / 8)
+enum APattern : uint8_t { PAT_SS = 0, PAT_32 = 1, PAT_16 = 2, PAT_8 = 3 };
 
 // What the compute warps need to know about one Dense layer.
 struct TcOp {
@@ -74,25 +77,26 @@ struct TcOp {
   float inv_scale;       // accumulators hold (scale * W) x; multiply back
   uint16_t N;            // output columns (padded)
   uint16_t nc_rows;      // output columns per N-chunk
-  uint8_t n_nc, relu, out_kind, glue;
+  uint8_t n_nc, relu, epi_kind, glue;
+  uint16_t d_col[2];     // tensor-memory column of accumulator chunk c
 };
 
 // What the MMA issuer / TMA producer need to know about one weight image
 // (= one ring slot = up to 2 terms x 4 K-steps of tcgen05.mma).
 enum ImgFlags : uint16_t {
-  IMG_A_TMEM = 1, IMG_TWO_TERMS = 2, IMG_FIRST = 4, IMG_LAST = 8, IMG_NC1 = 16, IMG_WAIT_P0 = 32, IMG_WAIT_P1 = 64,
+  IMG_TWO_TERMS = 2, IMG_FIRST = 4, IMG_LAST = 8, IMG_NC1 = 16, IMG_WAIT_P0 = 32, IMG_WAIT_P1 = 64,
   IMG_WAIT_GLUE = 128,
   IMG_PART_NEXT = 256,   // the issuer has consumed one output phase of the previous op
   IMG_PAIR_LAST = 1024, IMG_PAIR_PART_NEXT = 2048   // copies of the B_lo image's LAST / PART_NEXT on its B_hi image
 };
 struct alignas(16) ImgEntry {
-  uint32_t a_hi;         // shared: byte offset from the (1024-aligned) smem base; tensor memory: column
+  uint32_t a_hi;         // PAT_SS: byte offset from the (1024-aligned) smem base; else tensor-memory column
   uint32_t a_lo;
   uint16_t rows;         // rows of the image = N of its MMAs (bytes = rows * 128)
   uint8_t steps;         // K-steps, 1..4
-  uint8_t pad;
+  uint8_t pat;           // APattern
   uint16_t flags;
-  uint16_t pad2;
+  uint16_t d_col;        // accumulator column
 };
 static_assert(sizeof(ImgEntry) == 16, "ImgEntry is read as one uint4");
 
@@ -157,16 +161,16 @@ __device__ __forceinline__ uint32_t elect_one() {
 // runs on the uniform datapath); one elected lane issues the tcgen05 instructions.  A 3-term K-chunk (B_hi
 // image followed by its B_lo image, 12 tcgen05.mma) goes out as one asm burst.
 __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
-                                           uint32_t lead, uint32_t& slot_ctr, uint32_t& part_cnt, uint32_t& glue_cnt,
-                                           unsigned long long* trace) {
+                                           uint32_t lead, uint32_t& slot, uint32_t& phase, uint32_t& part_cnt,
+                                           uint32_t& glue_cnt, unsigned long long* trace) {
   const int n_img = P.n_img;
   const uint32_t empty0 = smem_u32(&ctl->empty[0]);
   const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING);
   uint4 raw = *reinterpret_cast<const uint4*>(&P.img[0]);
   int i = 0;
-  bool ready0 = false, ready1 = false;      // full-barrier probes of the next burst's slots, taken before this burst
   while (i < n_img) {
-    const uint32_t a_hi = raw.x, a_lo = raw.y, rows = raw.z & 0xffffu, steps = (raw.z >> 16) & 0xffu, fl = raw.w & 0xffffu;
+    const uint32_t a_hi = raw.x, a_lo = raw.y, rows = raw.z & 0xffffu, steps = (raw.z >> 16) & 0xffu, pat = raw.z >> 24;
+    const uint32_t fl = raw.w & 0xffffu, d = tmem_base + (raw.w >> 16);
     const bool two = (fl & IMG_TWO_TERMS) != 0;
     const int adv = two ? 2 : 1;
     if (i + adv < n_img) raw = *reinterpret_cast<const uint4*>(&P.img[i + adv]);
@@ -174,60 +178,51 @@ __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_bas
     if (fl & IMG_WAIT_GLUE) { mbar_wait(&ctl->in_ready, glue_cnt & 1u); ++glue_cnt; }
     if (fl & IMG_WAIT_P0) mbar_wait(&ctl->part_ready[0], part_cnt & 1u);
     if (fl & IMG_WAIT_P1) mbar_wait(&ctl->part_ready[1], part_cnt & 1u);
-    const uint32_t s0 = slot_ctr % NSLOT, s1 = (slot_ctr + 1) % NSLOT;
-    if (!ready0) mbar_wait(&ctl->full[s0], (slot_ctr / NSLOT) & 1u);
-    if (two && !ready1) mbar_wait(&ctl->full[s1], ((slot_ctr + 1) / NSLOT) & 1u);
+    const uint32_t s0 = slot, p0 = phase;
+    uint32_t s1 = slot + 1, p1 = phase;
+    if (s1 == NSLOT) { s1 = 0; p1 ^= 1u; }
+    mbar_wait(&ctl->full[s0], p0);
+    if (two) mbar_wait(&ctl->full[s1], p1);
     if (trace && lead) trace[TRACE_X + MAX_IMG + i] = clock64();
     tc_fence_after_sync();
     if (trace && lead) trace[i] = clock64();
-    {
-      const uint32_t n0 = slot_ctr + adv, n1 = n0 + 1;
-      ready0 = mbar_test_wait(&ctl->full[n0 % NSLOT], (n0 / NSLOT) & 1u);
-      ready1 = mbar_test_wait(&ctl->full[n1 % NSLOT], (n1 / NSLOT) & 1u);
-    }
-    const uint32_t d = tmem_base + TM_D + ((fl & IMG_NC1) ? 128u : 0u);
     const uint32_t idesc = make_idesc_f16(rows);
     const uint32_t b0 = ring_lo32 + s0 * (SLOT_BYTES >> 4), b1 = ring_lo32 + s1 * (SLOT_BYTES >> 4);
     const uint32_t acc = (fl & IMG_FIRST) ? 0u : 1u;
     const uint32_t dbar = smem_u32(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0]);
     const uint32_t last = (fl & (two ? IMG_PAIR_LAST : IMG_LAST)) ? 1u : 0u;
-    if (two && steps == 4) {
-      if (fl & IMG_A_TMEM)
-        umma_burst3_ts(d, tmem_base + a_hi, tmem_base + a_lo, b0, b1, idesc, acc, empty0 + 8 * s0, empty0 + 8 * s1, last, dbar, lead);
-      else
-        umma_burst3_ss(d, smem_desc_lo32(smem_base + a_hi), smem_desc_lo32(smem_base + a_lo), b0, b1, idesc, acc,
-                       empty0 + 8 * s0, empty0 + 8 * s1, last, dbar, lead);
-    } else if (!two && steps == 4) {
-      if (fl & IMG_A_TMEM) umma_burst1_ts(d, tmem_base + a_hi, b0, idesc, acc, empty0 + 8 * s0, last, dbar, lead);
-      else umma_burst1_ss(d, smem_desc_lo32(smem_base + a_hi), b0, idesc, acc, empty0 + 8 * s0, last, dbar, lead);
+    const uint32_t e0 = empty0 + 8 * s0, e1 = empty0 + 8 * s1;
+    if (steps == 4 && two) {
+      const uint32_t A0 = tmem_base + a_hi, A1 = tmem_base + a_lo;
+      if (pat == PAT_32) umma_burst3_ts32(d, A0, A1, b0, b1, idesc, acc, e0, e1, last, dbar, lead);
+      else if (pat == PAT_16) umma_burst3_ts16(d, A0, A1, b0, b1, idesc, acc, e0, e1, last, dbar, lead);
+      else if (pat == PAT_8) umma_burst3_ts8(d, A0, A1, b0, b1, idesc, acc, e0, e1, last, dbar, lead);
+      else umma_burst3_ss(d, smem_desc_lo32(smem_base + a_hi), smem_desc_lo32(smem_base + a_lo), b0, b1, idesc, acc, e0,
+                          e1, last, dbar, lead);
+    } else if (steps == 4) {
+      const uint32_t A0 = tmem_base + a_hi;
+      if (pat == PAT_32) umma_burst1_ts32(d, A0, b0, idesc, acc, e0, last, dbar, lead);
+      else if (pat == PAT_16) umma_burst1_ts16(d, A0, b0, idesc, acc, e0, last, dbar, lead);
+      else if (pat == PAT_8) umma_burst1_ts8(d, A0, b0, idesc, acc, e0, last, dbar, lead);
+      else umma_burst1_ss(d, smem_desc_lo32(smem_base + a_hi), b0, idesc, acc, e0, last, dbar, lead);
     } else {
-      // generic path: short K-chunks (network inputs, heads over narrow layers)
+      // short K-chunks: network inputs in shared memory (the host packer only emits PAT_SS here)
       const uint64_t bd0 = ((uint64_t)NDS_DESC_HI << 32) | b0, bd1 = ((uint64_t)NDS_DESC_HI << 32) | b1;
       const uint32_t lead2 = two ? lead : 0u;
-      if (fl & IMG_A_TMEM) {
-        const uint32_t A0 = tmem_base + a_hi, A1 = tmem_base + a_lo;
+      const uint64_t ad0 = make_smem_desc(smem_base + a_hi), ad1 = make_smem_desc(smem_base + a_lo);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_f16_ts_p(d, A0 + ks * 8, bd0 + 2 * ks, idesc, ks ? 1u : acc, ks < (int)steps ? lead : 0u);
+      for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc, ks < (int)steps ? lead : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_f16_ts_p(d, A1 + ks * 8, bd0 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
-        umma_commit_p(&ctl->empty[s0], lead);
+      for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
+      umma_commit_p(&ctl->empty[s0], lead);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_f16_ts_p(d, A0 + ks * 8, bd1 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
-      } else {
-        const uint64_t ad0 = make_smem_desc(smem_base + a_hi), ad1 = make_smem_desc(smem_base + a_lo);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc, ks < (int)steps ? lead : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
-        umma_commit_p(&ctl->empty[s0], lead);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
-      }
+      for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
       umma_commit_p(&ctl->empty[s1], lead2);
       umma_commit_p(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0], last ? lead : 0u);
     }
     if (trace && lead) trace[MAX_IMG + i] = clock64();
-    slot_ctr += adv;
+    if (two) { slot = s1; phase = p1; }
+    if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
     if (fl & (two ? IMG_PAIR_PART_NEXT : IMG_PART_NEXT)) ++part_cnt;
     i += adv;
   }
@@ -235,19 +230,18 @@ __device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_bas
 
 // TMA producer: streams every image of the program into the ring
 __device__ __forceinline__ void produce_tile(const TcProgram& P, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
-                                             bool leader, uint32_t& slot_ctr) {
+                                             bool leader, uint32_t& slot, uint32_t& phase, bool& wrapped) {
   const uint8_t* src = wstream;
   for (int i = 0; i < P.n_img; ++i) {
     const uint32_t bytes = (uint32_t)P.img[i].rows * 128u;
-    const uint32_t slot = slot_ctr % NSLOT;
-    if (slot_ctr >= NSLOT) mbar_wait(&ctl->empty[slot], ((slot_ctr / NSLOT) - 1u) & 1u);
+    if (wrapped) mbar_wait(&ctl->empty[slot], phase ^ 1u);     // the previous fill of this slot has been consumed
     if (leader) {
       mbar_arrive_expect_tx(&ctl->full[slot], bytes);
       tma_bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &ctl->full[slot]);
     }
     __syncwarp();
     src += bytes;
-    ++slot_ctr;
+    if (++slot == NSLOT) { slot = 0; phase ^= 1u; wrapped = true; }
   }
 }
 
@@ -260,12 +254,12 @@ __device__ __forceinline__ void store_in(uint8_t* smem, uint32_t r, uint32_t c, 
   *reinterpret_cast<__half*>(smem + OFF_IN_LO + o) = l;
 }
 
-// Epilogue of one N-chunk for this thread's row and its CW-column slice:
-// D -> scale/bias/ReLU -> split fp16 -> the next layer's operand home.
+// Epilogue of one N-chunk for this thread's row and its CW-column slice: accumulators -> scale/bias/ReLU ->
+// split fp16 -> written over the very columns just read (hi | lo), the operand of the next layer.
 template <int CW>
 __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const float* __restrict__ bias_base,
-                                               uint8_t* smem, uint32_t tmem_lane, uint32_t row, int sub,
-                                               float* dbg_out, int dbg_ld, uint64_t* bar, uint32_t parity) {
+                                               uint32_t tmem_lane, uint32_t row, int sub, int q, float* dbg_out,
+                                               int dbg_ld, uint64_t* bar, uint32_t parity) {
   const uint32_t oc0 = (uint32_t)nc * op.nc_rows + (uint32_t)sub * CW;   // first output column of this slice
   const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off + oc0);
   float b[CW];
@@ -276,8 +270,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   }
   mbar_wait(bar, parity);
   tc_fence_after_sync();
+  const uint32_t chunk = tmem_lane + op.d_col[nc];
+  const uint32_t col = chunk + (uint32_t)sub * CW;
   uint32_t v[CW];
-  tmem_ld<CW>(tmem_lane + TM_D + (uint32_t)nc * 128u + (uint32_t)sub * CW, v);
+  tmem_ld<CW>(col, v);
   tmem_ld_wait();
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
@@ -294,40 +290,32 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
     hi[i] = *reinterpret_cast<const uint32_t*>(&h);
     lo[i] = *reinterpret_cast<const uint32_t*>(&l);
   }
-  const uint8_t kind = op.out_kind;
-  if (kind == OUT_XT || kind == OUT_XT_HI_ONLY) {
-    uint32_t (&hi_ref)[CW / 2] = hi;
-    tmem_st<CW / 2>(tmem_lane + TM_XT_HI + (oc0 >> 1), hi_ref);
-    if (kind == OUT_XT) tmem_st<CW / 2>(tmem_lane + TM_XT_LO + (oc0 >> 1), lo);
+  const uint8_t kind = op.epi_kind;
+  if (kind == EPI_COMPACT_HI) {
+    // the compacted slice overlaps columns other warps of this lane quarter are still reading
+    tc_fence_before_sync();
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+    tc_fence_after_sync();
+    tmem_st<CW / 2>(chunk + (uint32_t)sub * (CW / 2), hi);
   } else {
-    const uint32_t off_hi = (kind == OUT_XS_LO_AS_HI) ? OFF_XS_LO : OFF_XS_HI;
-#pragma unroll
-    for (int g = 0; g < CW / 8; ++g) {
-      const uint32_t c = oc0 + 8 * g;
-      const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
-      *reinterpret_cast<uint4*>(smem + off_hi + o) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-      if (kind == OUT_XS)
-        *reinterpret_cast<uint4*>(smem + OFF_XS_LO + o) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
-    }
+    tmem_st<CW / 2>(col, hi);
+    if (kind == EPI_INPLACE) tmem_st<CW / 2>(col + CW / 2, lo);
   }
 }
 
 // waits for the chunk's accumulators (bar / parity) inside, after the bias prefetch
-__device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint8_t* smem,
-                                                  uint32_t tmem_lane, uint32_t row, int sub, float* dbg, int dbg_ld,
-                                                  uint64_t* bar, uint32_t parity) {
-  switch (op.nc_rows) {
-    case 128: epilogue_chunk<32>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld, bar, parity); break;
-    case 64: epilogue_chunk<16>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld, bar, parity); break;
-    default: epilogue_chunk<8>(op, nc, bias_base, smem, tmem_lane, row, sub, dbg, dbg_ld, bar, parity); break;
-  }
+__device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint32_t tmem_lane,
+                                                  uint32_t row, int sub, int q, float* dbg, int dbg_ld, uint64_t* bar,
+                                                  uint32_t parity) {
+  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity);
+  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity);
 }
 
 // head (<= 16 outputs): every compute warp of the lane quarter reads all of them
 __device__ __forceinline__ void epilogue_head(const TcOp& op, const float* __restrict__ bias_base, uint32_t tmem_lane,
                                               float* hv) {
   uint32_t v[16];
-  tmem_ld16(tmem_lane + TM_D, v);
+  tmem_ld16(tmem_lane + op.d_col[0], v);
   tmem_ld_wait();
   const float* bias = bias_base + op.bias_off;
 #pragma unroll
@@ -415,15 +403,17 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
     const bool leader = elect_one() != 0;
-    uint32_t sc = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) produce_tile(P, L.weights, smem, ctl, leader, sc);
+    uint32_t slot = 0, phase = 0;
+    bool wrapped = false;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      produce_tile(P, L.weights, smem, ctl, leader, slot, phase, wrapped);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
     const uint32_t lead = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for the compiler
-    uint32_t sc = 0, part_cnt = 0, glue_cnt = 0;
+    uint32_t slot = 0, phase = 0, part_cnt = 0, glue_cnt = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      issue_tile(P, smem_base, ctl, tb, lead, sc, part_cnt, glue_cnt,
+      issue_tile(P, smem_base, ctl, tb, lead, slot, phase, part_cnt, glue_cnt,
                  (K.trace && tile == (int64_t)gridDim.x) ? K.trace : nullptr);
   } else {
     // ===================== compute warps =====================
@@ -510,13 +500,14 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
 
       for (int i = 0; i < P.n_ops; ++i) {
         const TcOp& op = P.ops[i];
-        if (op.out_kind != OUT_HEAD) {
+        if (op.epi_kind != EPI_HEAD) {
           for (int nc = 0; nc < op.n_nc; ++nc) {
             uint32_t par;
             if (nc == 0) par = dcnt0++ & 1u; else par = dcnt1++ & 1u;
             if (tr) { mbar_wait(&ctl->d_full[nc], par); tr[4 * i + 2 * nc] = clock64(); }
-            epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, nullptr, 0, &ctl->d_full[nc], par);
+            epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[nc], par);
             warp_arrive(&ctl->part_ready[nc], lane);
+            if (op.n_nc == 1) warp_arrive(&ctl->part_ready[1], lane);   // keeps both barriers on one phase per op
             if (tr) tr[4 * i + 2 * nc + 1] = clock64();
           }
           continue;
@@ -603,9 +594,9 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
 }
 
 // ---------------------------------------------------------------------------
-// self-test kernel: one op on caller-provided activations.  The activations
-// are written to the op's operand home (shared or tensor memory, per kc_src)
-// by the compute warps exactly as an upstream epilogue would.
+// self-test kernel: one op on caller-provided activations.  The k_hid hidden
+// activations are written to tensor-memory region 0 in the layout an upstream
+// epilogue of that width produces, the k_in inputs to the IN block.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* __restrict__ A, int k_hid, int k_in,
@@ -624,42 +615,36 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   const TcOp& op = P.ops[0];
   if (warp == WARP_TMA) {
     const bool leader = elect_one() != 0;
-    uint32_t sc = 0;
-    produce_tile(P, L.weights, smem, ctl, leader, sc);
+    uint32_t slot = 0, phase = 0;
+    bool wrapped = false;
+    produce_tile(P, L.weights, smem, ctl, leader, slot, phase, wrapped);
   } else if (warp == WARP_MMA) {
     const uint32_t lead = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    uint32_t sc = 0, pc = 0, gc = 0;
-    issue_tile(P, smem_base, ctl, tb, lead, sc, pc, gc, nullptr);
+    uint32_t slot = 0, phase = 0, pc = 0, gc = 0;
+    issue_tile(P, smem_base, ctl, tb, lead, slot, phase, pc, gc, nullptr);
   } else {
     const int q = warp & 3, sub = warp >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     const int ld = k_hid + k_in;
-    bool a_tmem = false;
-    for (int k = 0; k < P.n_img; ++k) a_tmem = a_tmem || (P.img[k].flags & IMG_A_TMEM);
-    // hidden activations: this warp writes the 16-column groups g with g % NSUB == sub
-    for (int c0 = 0; c0 < k_hid; c0 += 16) {
-      if (((c0 >> 4) & (NSUB - 1)) != sub) continue;
-      uint32_t hi[8], lo[8];
-      for (int i = 0; i < 8; ++i) {
-        const float x0 = A[row * ld + c0 + 2 * i], x1 = A[row * ld + c0 + 2 * i + 1];
-        const __half2 h = __floats2half2_rn(x0, x1);
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-      }
-      if (a_tmem) {
-        tmem_st<8>(tmem_lane + TM_XT_HI + (c0 >> 1), hi);
-        tmem_st<8>(tmem_lane + TM_XT_LO + (c0 >> 1), lo);
-      } else {
-        for (int g = 0; g < 2; ++g) {
-          const uint32_t c = c0 + 8 * g;
-          const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
-          *reinterpret_cast<uint4*>(smem + OFF_XS_HI + o) = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
-          *reinterpret_cast<uint4*>(smem + OFF_XS_LO + o) = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+    // producer layout of a k_hid-wide layer: chunks of nc_rows columns at region 0 + 128 c, slices of CW per warp
+    const int p_nc = k_hid >= 128 ? 2 : 1, p_rows = k_hid / (p_nc ? p_nc : 1), p_cw = p_rows / NSUB;
+    for (int c = 0; c < p_nc && k_hid > 0; ++c) {
+      const uint32_t col = tmem_lane + 128u * c + (uint32_t)sub * p_cw;
+      for (int g = 0; g < p_cw; g += 16) {
+        uint32_t hi[8], lo[8];
+        for (int i = 0; i < 8; ++i) {
+          const int f = c * p_rows + sub * p_cw + g + 2 * i;
+          const float x0 = A[row * ld + f], x1 = A[row * ld + f + 1];
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+          lo[i] = *reinterpret_cast<const uint32_t*>(&l);
         }
+        tmem_st<8>(col + g / 2, hi);
+        tmem_st<8>(col + p_cw / 2 + g / 2, lo);
       }
     }
     for (int c = 0; c < 64; ++c)
@@ -667,7 +652,7 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
     warp_arrive(&ctl->part_ready[0], lane);
     warp_arrive(&ctl->part_ready[1], lane);
     warp_arrive(&ctl->in_ready, lane);
-    if (op.out_kind == OUT_HEAD) {
+    if (op.epi_kind == EPI_HEAD) {
       mbar_wait(&ctl->d_full[0], 0);
       tc_fence_after_sync();
       float hv[16];
@@ -675,8 +660,7 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
       if (sub == 0) for (int i = 0; i < 16 && i < op.N; ++i) out_f32[row * op.N + i] = hv[i];
     } else {
       for (int nc = 0; nc < op.n_nc; ++nc)
-        epilogue_dispatch(op, nc, L.bias, smem, tmem_lane, row, sub, out_f32, op.N, &ctl->d_full[nc], 0);
-      fence_proxy_async_smem();
+        epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, out_f32, op.N, &ctl->d_full[nc], 0);
       tmem_st_wait();
       tc_fence_before_sync();
     }
@@ -684,36 +668,29 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  // read the operand image the epilogue wrote back (hi + lo) -- what the next layer's MMA would see
-  if (warp < 4 && op.out_kind != OUT_HEAD && out_readback) {
-    const uint32_t row = (uint32_t)warp * 32u + (uint32_t)lane;
-    const uint32_t tmem_lane = tmem_base + (((uint32_t)warp * 32u) << 16);
-    const bool from_t = op.out_kind == OUT_XT || op.out_kind == OUT_XT_HI_ONLY;
-    const bool with_lo = op.out_kind == OUT_XS || op.out_kind == OUT_XT;
-    for (uint32_t c0 = 0; c0 < op.N; c0 += 16) {
-      float vals[16];
-      if (from_t) {
+  // read back the operand image the epilogue left in tensor memory -- what the next layer's MMA would see
+  if (warp < N_CWARPS && op.epi_kind != EPI_HEAD && out_readback) {
+    const int q = warp & 3, sub = warp >> 2;
+    const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
+    const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
+    const int cw = op.nc_rows / NSUB;
+    for (int nc = 0; nc < op.n_nc; ++nc) {
+      const uint32_t chunk = tmem_lane + op.d_col[nc];
+      const uint32_t hcol = op.epi_kind == EPI_COMPACT_HI ? chunk + sub * (cw / 2) : chunk + sub * cw;
+      for (int g = 0; g < cw / 2; g += 8) {
         uint32_t h[8], l[8];
-        tmem_ld8(tmem_lane + TM_XT_HI + (c0 >> 1), h);
-        tmem_ld8(tmem_lane + TM_XT_LO + (c0 >> 1), l);
+        tmem_ld8(hcol + g, h);
+        tmem_ld8(hcol + cw / 2 + g, l);        // only meaningful for EPI_INPLACE
         tmem_ld_wait();
         for (int i = 0; i < 8; ++i) {
           const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
           const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
-          vals[2 * i] = hf.x + (with_lo ? lf.x : 0.f);
-          vals[2 * i + 1] = hf.y + (with_lo ? lf.y : 0.f);
-        }
-      } else {
-        const uint32_t off_hi = (op.out_kind == OUT_XS_LO_AS_HI) ? OFF_XS_LO : OFF_XS_HI;
-        for (int i = 0; i < 16; ++i) {
-          const uint32_t c = c0 + i;
-          const uint32_t o = (c >> 6) * KBLK + kblock_offset(row, c & 63u);
-          float v = __half2float(*reinterpret_cast<__half*>(smem + off_hi + o));
-          if (with_lo) v += __half2float(*reinterpret_cast<__half*>(smem + OFF_XS_LO + o));
-          vals[i] = v;
+          const bool wl = op.epi_kind == EPI_INPLACE;
+          const int oc = nc * op.nc_rows + sub * cw + 2 * (g + i);
+          out_readback[row * op.N + oc] = hf.x + (wl ? lf.x : 0.f);
+          out_readback[row * op.N + oc + 1] = hf.y + (wl ? lf.y : 0.f);
         }
       }
-      for (int i = 0; i < 16; ++i) out_readback[row * op.N + c0 + i] = vals[i];
     }
   }
   tc_fence_before_sync();
@@ -724,13 +701,21 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
 // ---------------------------------------------------------------------------
 // host: packing
 // ---------------------------------------------------------------------------
-struct KChunkMap { uint8_t src; uint8_t wait; int rows[64]; };   // W row feeding each of the 64 A columns (-1 = zero pad)
+// One K-chunk (64 operand columns) of an op: where the operand lives and which weight rows multiply it.
+struct KChunkMap {
+  uint8_t pat;          // APattern
+  uint8_t wait;         // bit c: needs output chunk c of the previous op
+  uint32_t a_hi, a_lo;  // PAT_SS: shared byte offsets; else tensor-memory columns
+  int rows[64];         // W row feeding each of the 64 operand columns (-1 = zero pad)
+};
 
 struct OpBuild {
   std::vector<KChunkMap> kcs;
   int N_logical;                      // real output columns
   int N;                              // padded
-  int terms, relu, out_kind, glue, wait_glue;
+  int n_nc;                           // N-chunks (accumulators); nc_rows = N / n_nc
+  int d_col[2];                       // tensor-memory column of accumulator chunk c
+  int terms, relu, epi_kind, glue, wait_glue;
   int prev_produces = 0;              // the op before this one is a hidden layer (its epilogue signals part_ready)
   std::vector<float> W;               // [K_total][N_logical] logical weights (row-major, Flax layout)
   std::vector<float> b;
@@ -743,13 +728,35 @@ struct Packed {
   std::vector<float> bias;
 };
 
-// operand address of K-chunk source `src` (hi, lo): shared byte offset or tensor-memory column
-static void src_address(uint8_t src, uint32_t& hi, uint32_t& lo, bool& tmem) {
-  tmem = src >= SRC_XT;
-  if (tmem) { hi = TM_XT_HI + (src - SRC_XT) * 32u; lo = hi + (TM_XT_LO - TM_XT_HI); }
-  else if (src == SRC_IN) { hi = OFF_IN_HI; lo = OFF_IN_LO; }
-  else if (src >= SRC_XS_LO) { hi = OFF_XS_LO + (src - SRC_XS_LO) * KBLK; lo = hi; }
-  else { hi = OFF_XS_HI + src * KBLK; lo = hi + (OFF_XS_LO - OFF_XS_HI); }
+// Layout an in-place epilogue leaves behind (see epilogue_chunk): N output features in n_nc chunks at
+// region + 128 c; inside a chunk, warp slice s holds features [s CW, (s+1) CW) as hi (CW/2 columns) | lo (CW/2).
+struct ActLayout {
+  int region, N, n_nc, compact_hi;    // compact_hi: EPI_COMPACT_HI (hi only, contiguous from the chunk start)
+  int d_col[2];
+  int nc_rows() const { return N / n_nc; }
+  int cw() const { return nc_rows() / NSUB; }
+};
+static int chunks_for(int N) { return N >= 128 ? 2 : 1; }
+
+// operand K-block j (features 64 j ...) of a layer output with layout L
+static KChunkMap kc_hidden(const ActLayout& L, int j, int row0, bool wait) {
+  KChunkMap k;
+  const int f0 = 64 * j, c = f0 / L.nc_rows(), g = f0 % L.nc_rows();
+  if (L.compact_hi) { k.pat = PAT_8; k.a_hi = L.d_col[c] + g / 2; k.a_lo = k.a_hi; }
+  else {
+    k.pat = L.cw() == 32 ? PAT_32 : PAT_16;
+    k.a_hi = L.d_col[c] + g;            // g is a multiple of 64 = whole warp slices
+    k.a_lo = k.a_hi + L.cw() / 2;
+  }
+  k.wait = wait ? (uint8_t)(1u << c) : 0;
+  for (int cidx = 0; cidx < 64; ++cidx) k.rows[cidx] = (f0 + cidx < L.N) ? row0 + f0 + cidx : -1;
+  return k;
+}
+static KChunkMap kc_input(int row0, int in_dim) {
+  KChunkMap k;
+  k.pat = PAT_SS; k.wait = 0; k.a_hi = OFF_IN_HI; k.a_lo = OFF_IN_LO;
+  for (int c = 0; c < 64; ++c) k.rows[c] = c < in_dim ? row0 + c : -1;
+  return k;
 }
 
 static void pack_op(const OpBuild& ob, Packed& out) {
@@ -757,10 +764,12 @@ static void pack_op(const OpBuild& ob, Packed& out) {
   memset(&op, 0, sizeof op);
   op.N = (uint16_t)ob.N;
   op.relu = (uint8_t)ob.relu;
-  op.out_kind = (uint8_t)ob.out_kind;
+  op.epi_kind = (uint8_t)ob.epi_kind;
   op.glue = (uint8_t)ob.glue;
-  op.n_nc = (uint8_t)(ob.out_kind == OUT_HEAD ? 1 : 2);
-  op.nc_rows = (uint16_t)(ob.N / op.n_nc);
+  op.n_nc = (uint8_t)ob.n_nc;
+  op.nc_rows = (uint16_t)(ob.N / ob.n_nc);
+  op.d_col[0] = (uint16_t)ob.d_col[0];
+  op.d_col[1] = (uint16_t)ob.d_col[1];
   // power-of-two scale so that max |W| lands in [4, 8): keeps W_lo out of fp16 subnormals
   float mx = 0.f;
   for (float v : ob.W) mx = std::max(mx, std::fabs(v));
@@ -776,8 +785,6 @@ static void pack_op(const OpBuild& ob, Packed& out) {
   // stream order == issue order: N-chunk, K-chunk, image (hi, lo)
   const size_t img = (size_t)op.nc_rows * 128;
   const int n_img_per = ob.terms == 3 ? 2 : 1;
-  bool consumes = false;
-  for (size_t kc = 0; kc < ob.kcs.size(); ++kc) consumes = consumes || ob.kcs[kc].wait != 0;
   bool waited0 = false, waited1 = false;
   for (int nc = 0; nc < op.n_nc; ++nc) {
     // the first image of chunk nc overwrites accumulator chunk nc, which the previous op's epilogue must have
@@ -786,7 +793,7 @@ static void pack_op(const OpBuild& ob, Packed& out) {
       const KChunkMap& km = ob.kcs[kc];
       int last = -1;
       for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
-      const int steps = std::max(1, (last + 16) / 16);
+      const int steps = km.pat == PAT_SS ? std::max(1, (last + 16) / 16) : 4;
       const size_t base = out.stream.size();
       out.stream.resize(base + img * n_img_per, 0);
       for (int r = 0; r < op.nc_rows; ++r) {
@@ -804,17 +811,17 @@ static void pack_op(const OpBuild& ob, Packed& out) {
       for (int im = 0; im < n_img_per; ++im) {
         ImgEntry ie;
         memset(&ie, 0, sizeof ie);
-        bool tmem;
-        src_address(km.src, ie.a_hi, ie.a_lo, tmem);
+        ie.a_hi = km.a_hi; ie.a_lo = km.a_lo; ie.pat = km.pat;
         ie.rows = op.nc_rows;
         ie.steps = (uint8_t)steps;
+        ie.d_col = op.d_col[nc];
         uint16_t fl = 0;
-        if (tmem) fl |= IMG_A_TMEM;
         if (im == 0 && ob.terms == 3) fl |= IMG_TWO_TERMS;     // B_hi image: A_hi B_hi + A_lo B_hi
         if (kc == 0 && im == 0) fl |= IMG_FIRST;
         if (kc + 1 == ob.kcs.size() && im + 1 == n_img_per) fl |= IMG_LAST;
         if (nc == 1) fl |= IMG_NC1;
         const bool first = kc == 0 && im == 0;
+        // a single-chunk producer signals both part barriers; wait on the one matching the accumulator index
         if (first && ob.prev_produces && nc == 0 && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; }
         if (first && ob.prev_produces && nc == 1 && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; }
         if ((km.wait & 1) && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; }
@@ -826,71 +833,55 @@ static void pack_op(const OpBuild& ob, Packed& out) {
     }
   }
   if (ob.prev_produces) out.imgs.back().flags |= IMG_PART_NEXT;   // one output phase of the previous op consumed
-  (void)consumes;
   out.ops.push_back(op);
 }
 
-// which output part (N-chunk of the producing op) holds K-block `block` of a `width`-wide activation
-static uint8_t part_bits(int block, int width) {
-  if (width <= 64) return 3;
-  return (block * 64 < width / 2) ? 1 : 2;
-}
-// K-block `block` of the previous op's output, living in `home` (0 = XS shared, 1 = XT tensor memory)
-static KChunkMap kc_hidden(int block, int row0, int width, int home, bool wait) {
-  KChunkMap k;
-  k.src = (uint8_t)((home ? SRC_XT : 0) + block);
-  k.wait = wait ? part_bits(block, width) : 0;
-  for (int c = 0; c < 64; ++c) k.rows[c] = (block * 64 + c < width) ? row0 + block * 64 + c : -1;
-  return k;
-}
-static KChunkMap kc_input(int row0, int in_dim) {
-  KChunkMap k;
-  k.src = SRC_IN;
-  k.wait = 0;
-  for (int c = 0; c < 64; ++c) k.rows[c] = c < in_dim ? row0 + c : -1;
-  return k;
-}
-
-// hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer]; outputs
-// alternate XT, XS, XT, ...  Returns the home of the last layer's output.
-static int build_mlp_ops(const HostMlp& m, int terms, Packed& out) {
-  int home = 1;
+// hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer].  Layer l
+// accumulates into region (l even ? 1 : 0) and leaves its activations there.  Returns the last layer's layout.
+static ActLayout build_mlp_ops(const HostMlp& m, int terms, Packed& out) {
+  ActLayout prev{};
   for (int l = 0; l < m.depth; ++l) {
     OpBuild ob;
     ob.N_logical = ob.N = m.width;
-    ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE;
+    ob.n_nc = chunks_for(m.width);
+    const int region = (l % 2 == 0) ? 1 : 0;
+    ob.d_col[0] = region * (int)TM_REGION;
+    ob.d_col[1] = ob.d_col[0] + 128;
+    ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE; ob.epi_kind = EPI_INPLACE;
     ob.wait_glue = l == 0;
     ob.prev_produces = l > 0;
     ob.W = m.hidden[l].W; ob.b = m.hidden[l].b;
-    const int out_home = (l % 2 == 0) ? 1 : 0;
-    ob.out_kind = out_home ? OUT_XT : OUT_XS;
     if (l == 0) ob.kcs.push_back(kc_input(0, m.in_dim));
     else {
       if (l == m.skip) ob.kcs.push_back(kc_input(m.width, m.in_dim));   // ready long ago: issue it first
-      for (int j = 0; j < (m.width + 63) / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, m.width, home, true));
+      for (int j = 0; j < m.width / 64; ++j) ob.kcs.push_back(kc_hidden(prev, j, 0, true));
     }
     pack_op(ob, out);
-    home = out_home;
+    prev = ActLayout{region, m.width, ob.n_nc, 0, {ob.d_col[0], ob.d_col[1]}};
   }
-  return home;
+  return prev;
 }
 
-static void build_head_op(const std::vector<const HostDense*>& heads, int width, int home, int terms, int glue,
+// head over the layer output `in`; accumulators in the other region
+static void build_head_op(const std::vector<const HostDense*>& heads, const ActLayout& in, int terms, int glue,
                           Packed& out) {
   OpBuild ob;
   int n = 0;
   for (auto* h : heads) n += h->N;
   ob.N_logical = n;
   ob.N = 16;
-  ob.terms = terms; ob.relu = 0; ob.out_kind = OUT_HEAD; ob.glue = glue; ob.wait_glue = 0; ob.prev_produces = 1;
-  ob.W.assign((size_t)width * n, 0.f);
+  ob.n_nc = 1;
+  ob.d_col[0] = (1 - in.region) * (int)TM_REGION;
+  ob.d_col[1] = ob.d_col[0];
+  ob.terms = terms; ob.relu = 0; ob.epi_kind = EPI_HEAD; ob.glue = glue; ob.wait_glue = 0; ob.prev_produces = 1;
+  ob.W.assign((size_t)in.N * n, 0.f);
   int c0 = 0;
   for (auto* h : heads) {
-    for (int k = 0; k < width; ++k) for (int j = 0; j < h->N; ++j) ob.W[(size_t)k * n + c0 + j] = h->W[(size_t)k * h->N + j];
+    for (int k = 0; k < in.N; ++k) for (int j = 0; j < h->N; ++j) ob.W[(size_t)k * n + c0 + j] = h->W[(size_t)k * h->N + j];
     for (int j = 0; j < h->N; ++j) ob.b.push_back(h->b[j]);
     c0 += h->N;
   }
-  for (int j = 0; j < (width + 63) / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, width, home, true));
+  for (int j = 0; j < in.N / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, true));
   pack_op(ob, out);
 }
 
@@ -921,7 +912,7 @@ std::string tc_engine_supports(const ndsr_config& c, int cc_major, int cc_minor)
   if (cc_major != 10) return "needs an sm_100-class device (tcgen05)";
   if (c.rgb_depth != 1) return "rgb branch depth must be 1";
   if (!c.use_viewdirs) return "the rgb branch without viewdirs is not built";
-  if (c.trunk_depth % 2) return "trunk depth must be even (operand homes alternate)";
+  if (c.trunk_width != 256 || c.rgb_width != 128) return "the tensor-core rgb branch is built for trunk width 256 / rgb width 128";
   const int widths[] = {c.trunk_width, c.rgb_width, c.use_warp ? c.warp_width : 64,
                         c.use_hyper_sheet ? c.hyper_sheet_width : 64, c.use_predicted_mask ? c.mask_width : 64};
   for (int w : widths) if (w != 64 && w != 128 && w != 256) return "MLP widths must be 64, 128 or 256";
@@ -937,41 +928,42 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
   if (prec == NDSR_PREC_SPLIT3) { h->err = "tensor-core engine: split3 precision on the rgb branch is not built (use mixed)"; return NDSR_ERR_UNSUPPORTED; }
   if (h->max_in > 64) { h->err = "tensor-core engine: MLP inputs wider than 64 features"; return NDSR_ERR_UNSUPPORTED; }
   if (h->dim_view + (c.predict_norm ? h->dim_norm : 0) > 64) { h->err = "tensor-core engine: rgb side inputs wider than 64"; return NDSR_ERR_UNSUPPORTED; }
-  if (c.use_predicted_mask) {
-    const int home = build_mlp_ops(HM.mask, t_sigma, P);
-    build_head_op({&HM.mask.logit}, HM.mask.width, home, t_sigma, GLUE_MASK, P);
-  }
-  if (c.use_warp) {
-    const int home = build_mlp_ops(HM.warp, t_sigma, P);
-    build_head_op({&HM.warp_w, &HM.warp_v}, HM.warp.width, home, t_sigma, GLUE_WARP, P);
-  }
-  if (c.use_hyper_sheet) {
-    const int home = build_mlp_ops(HM.hyper, t_sigma, P);
-    build_head_op({&HM.hyper.logit}, HM.hyper.width, home, t_sigma, GLUE_HYPER, P);
-  }
-  const int trunk_home = build_mlp_ops(HM.trunk[lv], t_sigma, P);
-  if (trunk_home != 0) { h->err = "tensor-core engine: trunk output must land in shared memory (even depth)"; return NDSR_ERR_UNSUPPORTED; }
-  build_head_op({&HM.alpha[lv]}, HM.trunk[lv].width, trunk_home, t_sigma, GLUE_ALPHA, P);
+  if (c.use_predicted_mask) build_head_op({&HM.mask.logit}, build_mlp_ops(HM.mask, t_sigma, P), t_sigma, GLUE_MASK, P);
+  if (c.use_warp) build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, P), t_sigma, GLUE_WARP, P);
+  if (c.use_hyper_sheet) build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, P), t_sigma, GLUE_HYPER, P);
+  const ActLayout trunk = build_mlp_ops(HM.trunk[lv], t_sigma, P);
+  build_head_op({&HM.alpha[lv]}, trunk, t_sigma, GLUE_ALPHA, P);
   n_sigma = (int)P.ops.size();
   h->tc->n_img_sigma[lv] = (int)P.imgs.size();
   // ---- rgb branch (modules.py:288-313).  Flax input order:
   //   [bottleneck (W) | viewdir feats | trunk_out (W, App. C-1) | norm feats]
-  // bottleneck: XS_hi (trunk_out) -> XT_hi, 1 term; rgb hidden: {XS_hi, IN, XT_hi} -> XS_lo region; head reads it.
+  // trunk_out stays in its region T; everything else happens in the other region B (256 columns):
+  //   bottleneck   accumulates into B (two chunks of 128 columns), epilogue compacts its hi halves to the first
+  //                64 columns of each chunk;
+  //   rgb hidden   accumulates into the freed second halves (two chunks of 64 columns), hi-only in place;
+  //   rgb head     accumulates into the first columns of T (trunk_out is dead by then: in-order MMA pipe).
   const int W = c.trunk_width;
+  if (W != 256 || HM.rgb[lv].width != 128) { h->err = "tensor-core engine: the rgb branch is built for trunk 256 / rgb 128"; return NDSR_ERR_UNSUPPORTED; }
+  const int Tcol = trunk.region * (int)TM_REGION, Bcol = (1 - trunk.region) * (int)TM_REGION;
+  ActLayout bott{1 - trunk.region, W, 2, 1, {Bcol, Bcol + 128}};
   {
     OpBuild ob;
     ob.N_logical = ob.N = W;
-    ob.terms = 1; ob.relu = 0; ob.out_kind = OUT_XT_HI_ONLY; ob.glue = GLUE_BOTTLENECK;
-    ob.wait_glue = 1;     // the sigma/normal head's accumulators must have been consumed
+    ob.n_nc = 2; ob.d_col[0] = Bcol; ob.d_col[1] = Bcol + 128;
+    ob.terms = 1; ob.relu = 0; ob.epi_kind = EPI_COMPACT_HI; ob.glue = GLUE_BOTTLENECK;
+    ob.wait_glue = 1;     // the sigma/normal head's accumulators (in B) must have been consumed
+    ob.prev_produces = 0;
     ob.W = HM.bottleneck[lv].W; ob.b = HM.bottleneck[lv].b;
-    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, W, 0, false));
+    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, 0, false));
     pack_op(ob, P);
   }
+  ActLayout rgbh{1 - trunk.region, 128, 2, 0, {Bcol + 64, Bcol + 192}};
   {
     const HostMlp& R = HM.rgb[lv];
     OpBuild ob;
     ob.N_logical = ob.N = R.width;
-    ob.terms = 1; ob.relu = 1; ob.out_kind = OUT_XS_LO_AS_HI; ob.glue = GLUE_NONE; ob.wait_glue = 0; ob.prev_produces = 1;
+    ob.n_nc = 2; ob.d_col[0] = rgbh.d_col[0]; ob.d_col[1] = rgbh.d_col[1];
+    ob.terms = 1; ob.relu = 1; ob.epi_kind = EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.wait_glue = 0; ob.prev_produces = 1;
     ob.W = R.hidden[0].W; ob.b = R.hidden[0].b;
     int row = W;
     const int v0 = row;
@@ -980,11 +972,10 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
     if (c.use_x_in_rgb_condition) { x0 = row; row += W; }
     const int n0 = row;
     const int ndim = c.predict_norm ? h->dim_norm : 0;
-    if (x0 >= 0) for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, x0, W, 0, false));   // trunk_out, ready
+    // the accumulators overwrite the second halves of the bottleneck chunks: every image waits for the compaction
+    if (x0 >= 0) for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, x0, false));   // trunk_out
     if (h->dim_view + ndim > 0) {
-      KChunkMap k;
-      k.src = SRC_IN;
-      k.wait = 0;
+      KChunkMap k = kc_input(0, 0);
       for (int cidx = 0; cidx < 64; ++cidx) {
         if (cidx < h->dim_view) k.rows[cidx] = v0 + cidx;
         else if (cidx < h->dim_view + ndim) k.rows[cidx] = n0 + (cidx - h->dim_view);
@@ -992,20 +983,16 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
       }
       ob.kcs.push_back(k);
     }
-    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, W, 1, true));                  // bottleneck
+    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(bott, j, 0, true));                   // bottleneck
     if ((int)ob.kcs.size() > MAX_KC) { h->err = "tensor-core engine: rgb input too wide"; return NDSR_ERR_UNSUPPORTED; }
     pack_op(ob, P);
-    // head over the rgb hidden layer, which lives in the XS_lo region as a 1-term operand
+    // head over the rgb hidden layer; accumulators at the start of T
     OpBuild hb;
     hb.N_logical = R.logit.N;
-    hb.N = 16;
-    hb.terms = 1; hb.relu = 0; hb.out_kind = OUT_HEAD; hb.glue = GLUE_RGB; hb.wait_glue = 0; hb.prev_produces = 1;
+    hb.N = 16; hb.n_nc = 1; hb.d_col[0] = hb.d_col[1] = Tcol;
+    hb.terms = 1; hb.relu = 0; hb.epi_kind = EPI_HEAD; hb.glue = GLUE_RGB; hb.wait_glue = 0; hb.prev_produces = 1;
     hb.W = R.logit.W; hb.b = R.logit.b;
-    for (int j = 0; j < (R.width + 63) / 64; ++j) {
-      KChunkMap k = kc_hidden(j, 0, R.width, 0, true);
-      k.src = (uint8_t)(SRC_XS_LO + j);
-      hb.kcs.push_back(k);
-    }
+    for (int j = 0; j < R.width / 64; ++j) hb.kcs.push_back(kc_hidden(rgbh, j, 0, true));
     pack_op(hb, P);
   }
   return NDSR_OK;
@@ -1082,7 +1069,7 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
                 rel(t[TRACE_X + MAX_IMG + i]));
       for (int i = 0; i < prog.n_ops; ++i)
         fprintf(f, "op %d N %d kind %d glue %d c0_seen %lld c0_done %lld c1_seen %lld c1_done %lld\n", i, prog.ops[i].N,
-                prog.ops[i].out_kind, prog.ops[i].glue, rel(t[2 * MAX_IMG + 4 * i]), rel(t[2 * MAX_IMG + 4 * i + 1]),
+                prog.ops[i].epi_kind, prog.ops[i].glue, rel(t[2 * MAX_IMG + 4 * i]), rel(t[2 * MAX_IMG + 4 * i + 1]),
                 rel(t[2 * MAX_IMG + 4 * i + 2]), rel(t[2 * MAX_IMG + 4 * i + 3]));
       fclose(f);
     }
@@ -1100,27 +1087,30 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
                                       const float* A, const float* W, const float* bias, float* out,
                                       float* out_readback) {
   using namespace nds;
-  // out_kind (public numbering): 0 = hidden layer written to shared memory (operands read from tensor memory),
-  // 1 = head (n_out <= 16, operands from shared memory), 2 = 1-term hidden written to the XS_lo region (operands
-  // from shared memory), 3 = hidden written to tensor memory (operands from shared memory), 4 = head with
-  // operands from tensor memory.
+  // out_kind: 0 = hidden layer (in-place hi + lo), 1 = head (n_out <= 16), 2 = hidden layer, hi only (1-term
+  // consumer), 5 = hidden layer compacted hi (the bottleneck's epilogue; n_out = 256).  The k_hid activations are
+  // read from tensor memory in the layout a k_hid-wide layer leaves, the k_in inputs from the shared IN block.
   if (k_hid % 64 || k_hid > 256 || k_in > 64 || k_in < 0 || n_out < 1 || n_out > 256 || (terms != 1 && terms != 3))
     return NDSR_ERR_INVALID;
   if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
-  const bool head = out_kind == 1 || out_kind == 4;
+  const bool head = out_kind == 1;
   if (head && n_out > 16) return NDSR_ERR_INVALID;
-  if (out_kind == 2 && terms != 1) return NDSR_ERR_INVALID;
-  const int a_home = (out_kind == 0 || out_kind == 4) ? 1 : 0;
+  if (out_kind == 5 && n_out != 256) return NDSR_ERR_INVALID;
   OpBuild ob;
   ob.N_logical = n_out;
   ob.N = head ? 16 : (n_out <= 64 ? 64 : (n_out <= 128 ? 128 : 256));
+  ob.n_nc = head ? 1 : chunks_for(ob.N);
+  ob.d_col[0] = (int)TM_REGION; ob.d_col[1] = (int)TM_REGION + (head ? 0 : 128);
   ob.terms = terms; ob.relu = relu; ob.glue = GLUE_SELFTEST; ob.wait_glue = 1; ob.prev_produces = 1;
-  ob.out_kind = head ? OUT_HEAD : (out_kind == 0 ? OUT_XS : (out_kind == 2 ? OUT_XS_LO_AS_HI : OUT_XT));
+  ob.epi_kind = head ? EPI_HEAD : (out_kind == 2 ? EPI_INPLACE_HI : (out_kind == 5 ? EPI_COMPACT_HI : EPI_INPLACE));
   const int K = k_hid + k_in;
   ob.W.assign(W, W + (size_t)K * n_out);
   ob.b.assign(bias, bias + n_out);
   if (k_in > 0) ob.kcs.push_back(kc_input(k_hid, k_in));
-  for (int j = 0; j < k_hid / 64; ++j) ob.kcs.push_back(kc_hidden(j, 0, k_hid, a_home, true));
+  if (k_hid > 0) {
+    const ActLayout in{0, k_hid, chunks_for(k_hid), 0, {0, 128}};
+    for (int j = 0; j < k_hid / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, true));
+  }
   Packed P;
   pack_op(ob, P);
   uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;

@@ -238,10 +238,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   ".reg .b64 A0, A1, A2, A3, L0, L1, L2, L3, H0, H1, H2, H3, G0, G1, G2, G3;\n\t.reg .b32 w;\n\t" \
   "mov.b64 A0, {%1, %9};\n\tadd.u32 w, %1, 2;\n\tmov.b64 A1, {w, %9};\n\tadd.u32 w, %1, 4;\n\tmov.b64 A2, {w, %9};\n\tadd.u32 w, %1, 6;\n\tmov.b64 A3, {w, %9};\n\t" \
   "mov.b64 L0, {%2, %9};\n\tadd.u32 w, %2, 2;\n\tmov.b64 L1, {w, %9};\n\tadd.u32 w, %2, 4;\n\tmov.b64 L2, {w, %9};\n\tadd.u32 w, %2, 6;\n\tmov.b64 L3, {w, %9};\n\t"
-#define NDS_SETUP_TS \
+// tensor-memory A operand: K-step t lives at column (base + S_t); the lo image at the same offsets from its base
+#define NDS_SETUP_TS(S1, S2, S3) \
   ".reg .b32 A0, A1, A2, A3, L0, L1, L2, L3, w;\n\t.reg .b64 H0, H1, H2, H3, G0, G1, G2, G3;\n\t" \
-  "mov.b32 A0, %1;\n\tadd.u32 A1, %1, 8;\n\tadd.u32 A2, %1, 16;\n\tadd.u32 A3, %1, 24;\n\t" \
-  "mov.b32 L0, %2;\n\tadd.u32 L1, %2, 8;\n\tadd.u32 L2, %2, 16;\n\tadd.u32 L3, %2, 24;\n\t"
+  "mov.b32 A0, %1;\n\tadd.u32 A1, %1, " S1 ";\n\tadd.u32 A2, %1, " S2 ";\n\tadd.u32 A3, %1, " S3 ";\n\t" \
+  "mov.b32 L0, %2;\n\tadd.u32 L1, %2, " S1 ";\n\tadd.u32 L2, %2, " S2 ";\n\tadd.u32 L3, %2, " S3 ";\n\t"
 #define NDS_SETUP_B \
   "mov.b64 H0, {%3, %9};\n\tadd.u32 w, %3, 2;\n\tmov.b64 H1, {w, %9};\n\tadd.u32 w, %3, 4;\n\tmov.b64 H2, {w, %9};\n\tadd.u32 w, %3, 6;\n\tmov.b64 H3, {w, %9};\n\t" \
   "mov.b64 G0, {%4, %9};\n\tadd.u32 w, %4, 2;\n\tmov.b64 G1, {w, %9};\n\tadd.u32 w, %4, 4;\n\tmov.b64 G2, {w, %9};\n\tadd.u32 w, %4, 6;\n\tmov.b64 G3, {w, %9};\n\t"
@@ -276,27 +277,39 @@ __device__ __forceinline__ void umma_burst3_ss(uint32_t d, uint32_t a_hi_lo32, u
                  "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
 }
-__device__ __forceinline__ void umma_burst3_ts(uint32_t d, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi_lo32,
-                                               uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,
-                                               uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {
-  asm volatile(NDS_BURST_BODY(NDS_SETUP_TS, NDS_MMA_TS)
-               ::"r"(d), "r"(a_hi_tmem), "r"(a_lo_tmem), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
-                 "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
-               : "memory");
-}
+// PAT: column offsets of K-steps 1..3 inside one 64-feature K-block of a tensor-memory operand
+//   32: {8, 32, 40}  epilogue slices of 32 features (hi 16 columns | lo 16 columns)
+//   16: {16, 32, 48} epilogue slices of 16 features (hi 8 | lo 8)
+//    8: {8, 16, 24}  compacted hi-only activations
+#define NDS_DEFINE_BURST3_TS(NAME, S1, S2, S3)                                                                        \
+  __device__ __forceinline__ void NAME(uint32_t d, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi_lo32,        \
+                                       uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,      \
+                                       uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {              \
+    asm volatile(NDS_BURST_BODY(NDS_SETUP_TS(S1, S2, S3), NDS_MMA_TS)                                                 \
+                 ::"r"(d), "r"(a_hi_tmem), "r"(a_lo_tmem), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate), \
+                   "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)                      \
+                 : "memory");                                                                                         \
+  }
+NDS_DEFINE_BURST3_TS(umma_burst3_ts32, "8", "32", "40")
+NDS_DEFINE_BURST3_TS(umma_burst3_ts16, "16", "32", "48")
+NDS_DEFINE_BURST3_TS(umma_burst3_ts8, "8", "16", "24")
+#define NDS_DEFINE_BURST1_TS(NAME, S1, S2, S3)                                                                        \
+  __device__ __forceinline__ void NAME(uint32_t d, uint32_t a_tmem, uint32_t b_lo32, uint32_t idesc,                  \
+                                       uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,         \
+                                       uint32_t issue) {                                                              \
+    asm volatile(NDS_BURST1_BODY(NDS_SETUP_TS(S1, S2, S3), NDS_MMA_TS)                                                \
+                 ::"r"(d), "r"(a_tmem), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot),    \
+                   "r"(0u), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)                                       \
+                 : "memory");                                                                                         \
+  }
+NDS_DEFINE_BURST1_TS(umma_burst1_ts32, "8", "32", "40")
+NDS_DEFINE_BURST1_TS(umma_burst1_ts16, "16", "32", "48")
+NDS_DEFINE_BURST1_TS(umma_burst1_ts8, "8", "16", "24")
 __device__ __forceinline__ void umma_burst1_ss(uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
                                                uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
                                                uint32_t issue) {
   asm volatile(NDS_BURST1_BODY(NDS_SETUP_SS, NDS_MMA_SS)
                ::"r"(d), "r"(a_lo32), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
-                 "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
-               : "memory");
-}
-__device__ __forceinline__ void umma_burst1_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo32, uint32_t idesc,
-                                               uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
-                                               uint32_t issue) {
-  asm volatile(NDS_BURST1_BODY(NDS_SETUP_TS, NDS_MMA_TS)
-               ::"r"(d), "r"(a_tmem), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
                  "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
                : "memory");
 }

@@ -28,35 +28,34 @@ def _run(k_hid, k_in, n_out, terms, relu, out_kind, seed=0, scale_w=0.1):
   return out, rb, ref
 
 
-# out_kind: 0 = operands in tensor memory (TS-mode MMA) -> hidden layer written to shared memory;
-#           3 = operands in shared memory -> hidden layer written to tensor memory (tcgen05.st);
-#           2 = 1-term hidden layer written to the XS_lo region; 1 / 4 = head, operands in shared / tensor memory.
-SHAPES = [(0, 52, 256), (256, 0, 256), (256, 52, 256), (128, 33, 128), (64, 45, 64), (128, 0, 128), (256, 48, 128)]
+# out_kind: 0 = hidden layer (accumulators converted in place to hi + lo operands in tensor memory);
+#           2 = hidden layer, hi only; 5 = hidden layer, compacted hi (n_out = 256); 1 = head (n_out <= 16).
+# k_hid activations come from tensor memory (TS-mode MMA, layout of a k_hid-wide layer), k_in from shared memory.
+SHAPES = [(0, 52, 256), (256, 0, 256), (256, 52, 256), (128, 33, 128), (64, 45, 64), (128, 0, 128), (256, 48, 128),
+          (64, 0, 64), (128, 0, 64), (64, 0, 128)]
 
 
-@pytest.mark.parametrize('kind', [0, 3])
 @pytest.mark.parametrize('k_hid,k_in,n_out', SHAPES)
-def test_dense_split3_matches_fp64(cuda_device, k_hid, k_in, n_out, kind):
-  out, rb, ref = _run(k_hid, k_in, n_out, 3, 1, kind)
+def test_dense_split3_matches_fp64(cuda_device, k_hid, k_in, n_out):
+  out, rb, ref = _run(k_hid, k_in, n_out, 3, 1, 0)
   scale = np.abs(ref).max()
   assert np.abs(out - ref).max() <= 2e-5 * scale, np.abs(out - ref).max() / scale
   # the operand image written for the next layer reproduces the activations to ~2^-21
   assert np.abs(rb - out).max() <= 2e-6 * scale
 
 
-@pytest.mark.parametrize('k_hid,k_in,n_out,kind', [(256, 0, 256, 3), (256, 48, 128, 2), (128, 0, 3, 1), (256, 0, 256, 0)])
+@pytest.mark.parametrize('k_hid,k_in,n_out,kind', [(256, 0, 256, 5), (256, 48, 128, 2), (128, 0, 3, 1), (256, 0, 256, 0)])
 def test_dense_fp16_single_term(cuda_device, k_hid, k_in, n_out, kind):
   out, rb, ref = _run(k_hid, k_in, n_out, 1, 0, kind)
   scale = np.abs(ref).max()
   assert np.abs(out - ref).max() <= 3e-3 * scale
-  if kind == 2:
+  if kind in (2, 5):
     assert np.abs(rb - out).max() <= 1e-3 * scale   # hi-only image keeps 11 bits
 
 
-@pytest.mark.parametrize('kind', [1, 4])
 @pytest.mark.parametrize('k_hid,n_out', [(256, 4), (128, 6), (64, 2), (128, 1)])
-def test_heads_split3(cuda_device, k_hid, n_out, kind):
-  out, rb, ref = _run(k_hid, 0, n_out, 3, 0, kind, seed=3)
+def test_heads_split3(cuda_device, k_hid, n_out):
+  out, rb, ref = _run(k_hid, 0, n_out, 3, 0, 1, seed=3)
   scale = max(1.0, np.abs(ref).max())
   assert np.abs(out - ref).max() <= 2e-5 * scale
 
