@@ -1,29 +1,30 @@
-// tcgen05 tensor-core field engine (sm_100a).
+// tcgen05 tensor-core field engine (sm_100a), "pair" schedule.
 //
-// One persistent CTA per SM processes tiles of 128 samples.  Every Dense layer
-// of the path (hypernerf/modules.py:57-83) is a [128 x K] x [K x N] GEMM issued
-// as tcgen05.mma (kind::f16, fp32 accumulators in TMEM):
-//   * A = the tile's activations as split fp16 (hi + lo), kept IN TENSOR MEMORY
-//     for the whole chain (TS-mode MMA).  The 512 TMEM columns form two regions
-//     of 256: layer l reads its operand from one region and accumulates into the
-//     other; the epilogue converts the accumulators IN PLACE (tcgen05.ld ->
-//     bias/ReLU -> split -> tcgen05.st over the columns it just read) into the
-//     operand of layer l+1, which accumulates back into the first region.
-//     Network inputs (posenc features, embeddings, mask) are the only shared-
-//     memory operands (canonical K-major SWIZZLE_128B block, SS-mode MMA);
-//   * B = the layer's weights, pre-packed on the host into the exact
-//     shared-memory image (scaled by a power of two, split hi + lo, swizzled)
-//     and streamed image by image through a 12-slot bulk-TMA (cp.async.bulk) ring;
-//   * "3-term" layers issue A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (~fp32 accuracy,
-//     needed on the sigma path for the 1e-3 RGB bound -- tools/precision_study.py),
-//     "1-term" layers issue A_hi*B_hi only (bottleneck, rgb branch).
-// Wide layers are split into two N-chunks with separate accumulators and
-// barriers: while the tensor core works on chunk 1, the 16 compute warps drain
-// chunk 0, and the next layer's MMAs start on the K-range chunk 0 produced
-// before chunk 1's epilogue has finished.
-// Warp roles: warps 0-15 = compute (TMEM lane quarter = warp % 4 -> 32 samples,
-// column slice / feature slice = warp / 4): positional encodings, SE(3)
-// exponential, epilogues; warp 16 = MMA issuer; warp 17 = TMA producer.
+// One persistent CTA per SM processes PAIRS of 128-sample tiles (tile slots A and B).  Every Dense layer of the
+// path (hypernerf/modules.py:57-83) is a [128 x K] x [K x N] GEMM issued as tcgen05.mma (kind::f16, fp32
+// accumulators in TMEM):
+//   * A = the tile's activations as split fp16 (hi + lo), kept IN TENSOR MEMORY for the whole chain (TS-mode MMA):
+//     layer l reads its operand from one TMEM region and accumulates into the other; the epilogue converts the
+//     accumulators IN PLACE (tcgen05.ld -> bias/ReLU -> split -> tcgen05.st over the columns it just read) into
+//     the operand of layer l+1.  Network inputs (posenc features, embeddings, mask) are the only shared-memory
+//     operands (canonical K-major SWIZZLE_128B block, SS-mode MMA);
+//   * B = the layer's weights, pre-packed on the host into the exact shared-memory image (scaled by a power of
+//     two, split hi + lo, swizzled) and streamed through a ring of 4 x 32 KB units by bulk TMA (cp.async.bulk);
+//   * "3-term" layers issue A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (~fp32 accuracy, needed on the sigma path for the
+//     1e-3 RGB bound -- tools/precision_study.py), "1-term" layers A_hi*B_hi only (bottleneck, rgb branch).
+//
+// Schedule of one pair (static, built on the host: TcProgram):
+//   N phase  the narrow networks (mask MLP -> hyper sheet -> SE(3) warp field; width <= 128) of BOTH tiles,
+//            interleaved op by op: each tile owns 256 TMEM columns (two regions of 128), the tensor core works on
+//            one tile while the compute warps run the other tile's epilogue / per-sample stage, and every weight
+//            image loaded into the ring is used by both tiles before it is released;
+//   T phase  the template NeRF (trunk 8 x 256, sigma/normal head, bottleneck, rgb branch) needs all 512 columns
+//            (two regions of 256), so tile A then tile B run it alone, each layer split into two N-chunks whose
+//            K-ranges are ordered so that the tensor core never waits for the second chunk's epilogue.
+//   The three narrow networks read ONE shared feature block per tile ([sin/cos bands of x | embeddings | mask],
+//   posenc windows folded into the first-layer weights on the host), written one pair ahead during the T phase.
+// Warp roles: warps 0-15 = compute (TMEM lane quarter = warp % 4 -> 32 samples, column slice = warp / 4):
+// positional encodings, SE(3) exponential, epilogues; warp 16 = MMA issuer; warp 17 = TMA producer.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -48,16 +49,15 @@ constexpr int WARP_MMA = N_CWARPS, WARP_TMA = N_CWARPS + 1;
 constexpr int TC_THREADS = (N_CWARPS + 2) * 32;
 constexpr uint32_t KBLK = 16384;        // one 128-row K-block (64 fp16 columns)
 // shared memory map
-constexpr uint32_t OFF_IN_HI = 0;
-constexpr uint32_t OFF_IN_LO = KBLK;
-constexpr uint32_t OFF_RING = 2 * KBLK;
-constexpr uint32_t SLOT_BYTES = 16384;  // one weight image: <= 128 rows x 64 fp16
-constexpr int NSLOT = 12;
-constexpr uint32_t OFF_CTRL = OFF_RING + NSLOT * SLOT_BYTES;
+constexpr uint32_t OFF_IN = 0;          // IN[tile slot]: hi block at slot * 2 KBLK, lo block right after
+constexpr uint32_t OFF_IN2 = 4 * KBLK;  // rgb-branch side inputs [viewdir feats | normal feats], hi only
+constexpr uint32_t OFF_RING = 5 * KBLK;
+constexpr uint32_t UNIT_BYTES = 32768;  // one ring unit: a B_hi image followed by its B_lo image (<= 2 x 16 KB)
+constexpr int NUNIT = 4;
+constexpr uint32_t OFF_CTRL = OFF_RING + NUNIT * UNIT_BYTES;
 constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 512 + 1024;   // + manual 1024-byte alignment slack
-// tensor memory: two regions of 256 columns; accumulator chunk c of an op sits at region + 128 c
-constexpr uint32_t TM_REGION = 256;
 constexpr int MAX_KC = 10;
+constexpr int NPREP = 3;                // the shared feature block of the next pair is written in 3 parts
 
 enum EpiKind : uint8_t {
   EPI_INPLACE = 0,      // slice of CW accumulator columns -> hi (CW/2 columns) | lo (CW/2 columns) over the same slice
@@ -67,11 +67,11 @@ enum EpiKind : uint8_t {
 };
 enum Glue : uint8_t { GLUE_NONE = 0, GLUE_MASK = 1, GLUE_WARP = 2, GLUE_HYPER = 3, GLUE_ALPHA = 4, GLUE_BOTTLENECK = 5,
                       GLUE_RGB = 6, GLUE_SELFTEST = 7 };
-// A-operand addressing pattern of an image: 0 = shared memory (IN block), else tensor memory with the K-step
-// column offsets of nds_tc.cuh (32 / 16 / 8)
+// A-operand addressing pattern of a burst: 0 = shared memory (IN block), else tensor memory with the K-step
+// column offsets {0,8,32,40} / {0,16,32,48} / {0,8,16,24}
 enum APattern : uint8_t { PAT_SS = 0, PAT_32 = 1, PAT_16 = 2, PAT_8 = 3 };
 
-// What the compute warps need to know about one Dense layer.
+// What the compute warps need to know about one Dense layer of one tile slot.
 struct TcOp {
   uint32_t bias_off;     // float offset into the bias array
   float inv_scale;       // accumulators hold (scale * W) x; multiply back
@@ -79,37 +79,55 @@ struct TcOp {
   uint16_t nc_rows;      // output columns per N-chunk
   uint8_t n_nc, relu, epi_kind, glue;
   uint16_t d_col[2];     // tensor-memory column of accumulator chunk c
+  uint8_t signal_glue;   // the per-sample stage after this head arrives on glue[tile slot]
+  uint8_t pad[3];
 };
 
-// What the MMA issuer / TMA producer need to know about one weight image
-// (= one ring slot = up to 2 terms x 4 K-steps of tcgen05.mma).
-enum ImgFlags : uint16_t {
-  IMG_TWO_TERMS = 2, IMG_FIRST = 4, IMG_LAST = 8, IMG_NC1 = 16, IMG_WAIT_P0 = 32, IMG_WAIT_P1 = 64,
-  IMG_WAIT_GLUE = 128,
-  IMG_PART_NEXT = 256,   // the issuer has consumed one output phase of the previous op
-  IMG_PAIR_LAST = 1024, IMG_PAIR_PART_NEXT = 2048   // copies of the B_lo image's LAST / PART_NEXT on its B_hi image
+// One burst of the MMA issuer = one K-chunk (<= 4 K-steps) of one N-chunk of one op of one tile slot:
+// 12 tcgen05.mma for a 3-term layer (B_hi and B_lo images), 4 for a 1-term layer.
+enum BurstFlags : uint16_t {
+  B_TWO = 1, B_FIRST = 2, B_LAST = 4, B_NC1 = 8, B_WAIT_P0 = 16, B_WAIT_P1 = 32,
+  B_WAIT_GLUE = 64,          // the tile slot's previous per-sample stage is done (head consumed, inputs written)
+  B_PEEK_GLUE_OTHER = 128,   // ... of the OTHER tile slot, without consuming the phase
+  B_WAIT_PREP = 256,         // the shared feature block of this tile slot is written
+  B_WAIT_DONE_OTHER = 512,   // the other tile slot has left the T phase (its TMEM columns are free)
+  B_PART_NEXT = 1024,        // last burst of an op that consumed one output phase of the previous op
+  B_ACQUIRE = 2048,          // first use of a ring unit: wait for the TMA
+  B_RELEASE = 4096           // last use: commit to the unit's empty barrier
 };
-struct alignas(16) ImgEntry {
-  uint32_t a_hi;         // PAT_SS: byte offset from the (1024-aligned) smem base; else tensor-memory column
-  uint32_t a_lo;
-  uint16_t rows;         // rows of the image = N of its MMAs (bytes = rows * 128)
+struct alignas(16) Burst {
+  uint32_t a_hi, a_lo;   // PAT_SS: byte offset from the (1024-aligned) smem base; else tensor-memory column
+  uint32_t src;          // weight stream offset of the unit's images, in 128-byte rows
+  uint16_t d_col;        // accumulator column
+  uint16_t rows;         // rows of the weight image = N of its MMAs (image bytes = rows * 128)
   uint8_t steps;         // K-steps, 1..4
   uint8_t pat;           // APattern
+  uint8_t unit;          // ring unit
+  uint8_t tslot;         // tile slot (barrier set)
   uint16_t flags;
-  uint16_t d_col;        // accumulator column
+  uint16_t rows128;      // 128-byte rows to load on B_ACQUIRE (rows, or 2 x rows for a 3-term burst)
+  uint32_t pad;
 };
-static_assert(sizeof(ImgEntry) == 16, "ImgEntry is read as one uint4");
+static_assert(sizeof(Burst) == 32, "Burst is read as two uint4");
 
-constexpr int MAX_OPS = 48;
-constexpr int MAX_IMG = 448;
+enum StepKind : uint8_t { STEP_EPI = 0, STEP_HEAD = 1, STEP_VIEW = 2, STEP_PREP = 3, STEP_OUT = 4 };
+struct Step { uint8_t kind, tslot, op, arg; };
+
+constexpr int MAX_OPS = 80;
+constexpr int MAX_STEPS = 128;
+constexpr int MAX_BURST = 300;
 struct TcProgram {       // passed by value as a __grid_constant__ kernel parameter (constant bank)
-  int n_ops, n_img;
+  int n_ops, n_burst, n_steps, full;     // full: rgb branch present (else sigma-only)
+  // shared feature block: [identity x (3)] [sin/cos of bands f_kmin .. f_kmin + f_nb) (6 each)] [warp embed]
+  // [mask embed] [mask]; t_cols = width of the trunk input that later overwrites it
+  int f_col_ident, f_col_bands, f_kmin, f_nb, f_col_wembed, f_col_membed, f_col_mask, f_cols, t_cols;
   TcOp ops[MAX_OPS];
-  ImgEntry img[MAX_IMG];
+  Step steps[MAX_STEPS];
+  Burst burst[MAX_BURST];
 };
+static_assert(sizeof(TcProgram) < 16384, "kernel parameter budget");
 
-constexpr int TRACE_X = 2 * MAX_IMG + 4 * MAX_OPS + 8;       // issuer loop-top / after-waits stamps
-constexpr int TRACE_WORDS = TRACE_X + 2 * MAX_IMG;
+constexpr int TRACE_WORDS = 3 * MAX_BURST + 2 * MAX_STEPS + 8;
 
 struct TcLevel {
   const uint8_t* weights;
@@ -120,21 +138,24 @@ struct TcLevel {
 // device helpers
 // ---------------------------------------------------------------------------
 struct Ctrl {
-  uint64_t full[NSLOT];
-  uint64_t empty[NSLOT];
-  uint64_t in_ready;        // compute -> MMA: inputs of the next network written, previous head consumed
-  uint64_t part_ready[2];   // compute -> MMA: N-chunk c of the current op drained and re-written as operand
-  uint64_t d_full[2];       // MMA -> compute: accumulators of N-chunk c complete
+  uint64_t full[NUNIT];
+  uint64_t empty[NUNIT];
+  uint64_t prep[2];         // compute -> MMA: shared feature block of tile slot s written
+  uint64_t glue[2];         // compute -> MMA: per-sample stage after a head done (head consumed, inputs written)
+  uint64_t done[2];         // compute -> MMA: tile slot s finished its T phase (every TMEM read done)
+  uint64_t part[2][2];      // compute -> MMA: N-chunk c of the current op drained and re-written as operand
+  uint64_t d_full[2][2];    // MMA -> compute: accumulators of N-chunk c complete
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void ctrl_init(Ctrl* ctl) {
-  for (int i = 0; i < NSLOT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
-  mbar_init(&ctl->in_ready, N_CWARPS);
-  mbar_init(&ctl->part_ready[0], N_CWARPS);
-  mbar_init(&ctl->part_ready[1], N_CWARPS);
-  mbar_init(&ctl->d_full[0], 1);
-  mbar_init(&ctl->d_full[1], 1);
+  for (int i = 0; i < NUNIT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
+  for (int s = 0; s < 2; ++s) {
+    mbar_init(&ctl->prep[s], N_CWARPS);
+    mbar_init(&ctl->glue[s], N_CWARPS);
+    mbar_init(&ctl->done[s], N_CWARPS);
+    for (int c = 0; c < 2; ++c) { mbar_init(&ctl->part[s][c], N_CWARPS); mbar_init(&ctl->d_full[s][c], 1); }
+  }
   mbar_fence_init();
 }
 
@@ -147,111 +168,180 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred = 0;
+// elect.sync in the form ptxas recognises as "exactly one thread runs the guarded region": the tcgen05
+// instructions inside `if (elect_one_sync())` are then emitted back to back on the uniform datapath.  (Guarding
+// them with any other predicate -- threadIdx.x == 0, a selp'd flag -- makes ptxas wrap EVERY UTCHMMA in an
+// ELECT / BRA.U.ANY serialisation loop: tools/mma_bench.cu.)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
   return pred;
 }
 
-// MMA issuer.  The whole warp walks the image program in uniform control flow (so the operand arithmetic
-// runs on the uniform datapath); one elected lane issues the tcgen05 instructions.  A 3-term K-chunk (B_hi
-// image followed by its B_lo image, 12 tcgen05.mma) goes out as one asm burst.
-__device__ __forceinline__ void issue_tile(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
-                                           uint32_t lead, uint32_t& slot, uint32_t& phase, uint32_t& part_cnt,
-                                           uint32_t& glue_cnt, unsigned long long* trace) {
-  const int n_img = P.n_img;
-  const uint32_t empty0 = smem_u32(&ctl->empty[0]);
-  const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING);
-  uint4 raw = *reinterpret_cast<const uint4*>(&P.img[0]);
-  int i = 0;
-  while (i < n_img) {
-    const uint32_t a_hi = raw.x, a_lo = raw.y, rows = raw.z & 0xffffu, steps = (raw.z >> 16) & 0xffu, pat = raw.z >> 24;
-    const uint32_t fl = raw.w & 0xffffu, d = tmem_base + (raw.w >> 16);
-    const bool two = (fl & IMG_TWO_TERMS) != 0;
-    const int adv = two ? 2 : 1;
-    if (i + adv < n_img) raw = *reinterpret_cast<const uint4*>(&P.img[i + adv]);
-    if (trace && lead) trace[TRACE_X + i] = clock64();
-    if (fl & IMG_WAIT_GLUE) { mbar_wait(&ctl->in_ready, glue_cnt & 1u); ++glue_cnt; }
-    if (fl & IMG_WAIT_P0) mbar_wait(&ctl->part_ready[0], part_cnt & 1u);
-    if (fl & IMG_WAIT_P1) mbar_wait(&ctl->part_ready[1], part_cnt & 1u);
-    const uint32_t s0 = slot, p0 = phase;
-    uint32_t s1 = slot + 1, p1 = phase;
-    if (s1 == NSLOT) { s1 = 0; p1 ^= 1u; }
-    mbar_wait(&ctl->full[s0], p0);
-    if (two) mbar_wait(&ctl->full[s1], p1);
-    if (trace && lead) trace[TRACE_X + MAX_IMG + i] = clock64();
-    tc_fence_after_sync();
-    if (trace && lead) trace[i] = clock64();
-    const uint32_t idesc = make_idesc_f16(rows);
-    const uint32_t b0 = ring_lo32 + s0 * (SLOT_BYTES >> 4), b1 = ring_lo32 + s1 * (SLOT_BYTES >> 4);
-    const uint32_t acc = (fl & IMG_FIRST) ? 0u : 1u;
-    const uint32_t dbar = smem_u32(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0]);
-    const uint32_t last = (fl & (two ? IMG_PAIR_LAST : IMG_LAST)) ? 1u : 0u;
-    const uint32_t e0 = empty0 + 8 * s0, e1 = empty0 + 8 * s1;
-    if (steps == 4 && two) {
-      const uint32_t A0 = tmem_base + a_hi, A1 = tmem_base + a_lo;
-      if (pat == PAT_32) umma_burst3_ts32(d, A0, A1, b0, b1, idesc, acc, e0, e1, last, dbar, lead);
-      else if (pat == PAT_16) umma_burst3_ts16(d, A0, A1, b0, b1, idesc, acc, e0, e1, last, dbar, lead);
-      else if (pat == PAT_8) umma_burst3_ts8(d, A0, A1, b0, b1, idesc, acc, e0, e1, last, dbar, lead);
-      else umma_burst3_ss(d, smem_desc_lo32(smem_base + a_hi), smem_desc_lo32(smem_base + a_lo), b0, b1, idesc, acc, e0,
-                          e1, last, dbar, lead);
-    } else if (steps == 4) {
-      const uint32_t A0 = tmem_base + a_hi;
-      if (pat == PAT_32) umma_burst1_ts32(d, A0, b0, idesc, acc, e0, last, dbar, lead);
-      else if (pat == PAT_16) umma_burst1_ts16(d, A0, b0, idesc, acc, e0, last, dbar, lead);
-      else if (pat == PAT_8) umma_burst1_ts8(d, A0, b0, idesc, acc, e0, last, dbar, lead);
-      else umma_burst1_ss(d, smem_desc_lo32(smem_base + a_hi), b0, idesc, acc, e0, last, dbar, lead);
+// One burst, issued by the elected thread in two halves so that the issuer can wait for the NEXT burst's weights
+// in between (tcgen05.mma issue blocks while the tensor core's queue, ~3 instructions deep, is full; whatever the
+// issuer does between two bursts must fit under that cover or the pipe drains):
+//   half 0   D (+)= A_hi B_hi [; D += A_lo B_hi]           (1-term: K-steps 0, 1)
+//   half 1   [D += A_hi B_lo]                               (1-term: K-steps 2, 3)
+// a_hi / a_lo: tensor-memory addresses (pat != PAT_SS, K-step column offsets per pattern) or the low words of
+// shared-memory descriptors; b0 / b1: low descriptor words of the B_hi / B_lo images in the ring.
+__device__ __forceinline__ void issue_half(int half, bool two, uint32_t pat, uint32_t steps, uint32_t d, uint32_t a_hi,
+                                           uint32_t a_lo, uint32_t b0, uint32_t b1, uint32_t idesc, uint32_t acc) {
+  const uint64_t hi = (uint64_t)NDS_DESC_HI << 32;
+  const uint64_t bd0 = hi | b0, bd1 = hi | b1;
+  if (pat != PAT_SS) {
+    // PAT_32: {0, 8, 32, 40}; PAT_16: {0, 16, 32, 48}; PAT_8: {0, 8, 16, 24}
+    const uint32_t s1 = pat == PAT_16 ? 16u : 8u, s2 = pat == PAT_8 ? 16u : 32u;
+    const uint32_t s3 = pat == PAT_32 ? 40u : (pat == PAT_16 ? 48u : 24u);
+    if (two) {
+      if (half == 0) {
+        umma_f16_ts(d, a_hi, bd0, idesc, acc);
+        umma_f16_ts(d, a_hi + s1, bd0 + 2, idesc, 1u);
+        umma_f16_ts(d, a_hi + s2, bd0 + 4, idesc, 1u);
+        umma_f16_ts(d, a_hi + s3, bd0 + 6, idesc, 1u);
+        umma_f16_ts(d, a_lo, bd0, idesc, 1u);
+        umma_f16_ts(d, a_lo + s1, bd0 + 2, idesc, 1u);
+        umma_f16_ts(d, a_lo + s2, bd0 + 4, idesc, 1u);
+        umma_f16_ts(d, a_lo + s3, bd0 + 6, idesc, 1u);
+      } else {
+        umma_f16_ts(d, a_hi, bd1, idesc, 1u);
+        umma_f16_ts(d, a_hi + s1, bd1 + 2, idesc, 1u);
+        umma_f16_ts(d, a_hi + s2, bd1 + 4, idesc, 1u);
+        umma_f16_ts(d, a_hi + s3, bd1 + 6, idesc, 1u);
+      }
+    } else if (half == 0) {
+      umma_f16_ts(d, a_hi, bd0, idesc, acc);
+      umma_f16_ts(d, a_hi + s1, bd0 + 2, idesc, 1u);
     } else {
-      // short K-chunks: network inputs in shared memory (the host packer only emits PAT_SS here)
-      const uint64_t bd0 = ((uint64_t)NDS_DESC_HI << 32) | b0, bd1 = ((uint64_t)NDS_DESC_HI << 32) | b1;
-      const uint32_t lead2 = two ? lead : 0u;
-      const uint64_t ad0 = make_smem_desc(smem_base + a_hi), ad1 = make_smem_desc(smem_base + a_lo);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc, ks < (int)steps ? lead : 0u);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
-      umma_commit_p(&ctl->empty[s0], lead);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) umma_f16_p(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u, ks < (int)steps ? lead2 : 0u);
-      umma_commit_p(&ctl->empty[s1], lead2);
-      umma_commit_p(&ctl->d_full[(fl & IMG_NC1) ? 1 : 0], last ? lead : 0u);
+      umma_f16_ts(d, a_hi + s2, bd0 + 4, idesc, 1u);
+      umma_f16_ts(d, a_hi + s3, bd0 + 6, idesc, 1u);
     }
-    if (trace && lead) trace[MAX_IMG + i] = clock64();
-    if (two) { slot = s1; phase = p1; }
-    if (++slot == NSLOT) { slot = 0; phase ^= 1u; }
-    if (fl & (two ? IMG_PAIR_PART_NEXT : IMG_PART_NEXT)) ++part_cnt;
-    i += adv;
+  } else {
+    const uint64_t ad0 = hi | a_hi, ad1 = hi | a_lo;
+    if (two) {
+      if (half == 0) {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc);
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u);
+      } else {
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u);
+      }
+    } else if (half == 0) {
+      umma_f16(d, ad0, bd0, idesc, acc);
+      if (steps > 1) umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+    } else {
+      if (steps > 2) umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
+      if (steps > 3) umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+    }
   }
 }
 
-// TMA producer: streams every image of the program into the ring
-__device__ __forceinline__ void produce_tile(const TcProgram& P, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
-                                             bool leader, uint32_t& slot, uint32_t& phase, bool& wrapped) {
-  const uint8_t* src = wstream;
-  for (int i = 0; i < P.n_img; ++i) {
-    const uint32_t bytes = (uint32_t)P.img[i].rows * 128u;
-    if (wrapped) mbar_wait(&ctl->empty[slot], phase ^ 1u);     // the previous fill of this slot has been consumed
-    if (leader) {
-      mbar_arrive_expect_tx(&ctl->full[slot], bytes);
-      tma_bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &ctl->full[slot]);
+__device__ __forceinline__ Burst load_burst(const TcProgram& P, int i) {
+  union { Burst b; uint4 q[2]; } u;
+  const uint4* src = reinterpret_cast<const uint4*>(&P.burst[i]);
+  u.q[0] = src[0];
+  u.q[1] = src[1];
+  return u.b;
+}
+
+// Issuer state: one parity bit per barrier it waits on.  bit s: part[s][*]; 2+s: glue[s]; 4+s: prep[s];
+// 6+s: done[s]; 8+u: full[u].
+struct IssuerState { uint32_t bits; bool primed; };
+
+// MMA issuer: the whole warp walks the burst program of one pair in uniform control flow (operand arithmetic on
+// the uniform datapath); inside `if (elect_one_sync())` one thread issues the tcgen05 instructions.
+__device__ __forceinline__ void issue_program(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
+                                              uint32_t lane, IssuerState& st, bool more, unsigned long long* trace) {
+  const int n = P.n_burst;
+  const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING);
+  const bool tr = trace != nullptr && lane == 0;
+  uint32_t bits = st.bits;
+  Burst e = load_burst(P, 0);
+  if (!st.primed) {        // the very first burst of the kernel: nobody waited for its weights yet
+    if (e.flags & B_ACQUIRE) { mbar_wait(&ctl->full[e.unit], (bits >> (8 + e.unit)) & 1u); bits ^= 1u << (8 + e.unit); }
+    st.primed = true;
+  }
+  for (int i = 0; i < n; ++i) {
+    const bool has_next = (i + 1 < n) || more;
+    const Burst nx = load_burst(P, (i + 1 < n) ? i + 1 : 0);
+    const uint32_t fl = e.flags, s = e.tslot, o = s ^ 1u;
+    if (tr) trace[i] = clock64();
+    if (fl & B_WAIT_PREP) { mbar_wait(&ctl->prep[s], (bits >> (4 + s)) & 1u); bits ^= 1u << (4 + s); }
+    if (fl & B_WAIT_DONE_OTHER) { mbar_wait(&ctl->done[o], (bits >> (6 + o)) & 1u); bits ^= 1u << (6 + o); }
+    if (fl & B_WAIT_GLUE) { mbar_wait(&ctl->glue[s], (bits >> (2 + s)) & 1u); bits ^= 1u << (2 + s); }
+    if (fl & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
+    if (fl & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
+    if (fl & B_WAIT_P1) mbar_wait(&ctl->part[s][1], (bits >> s) & 1u);
+    tc_fence_after_sync();
+    if (tr) trace[MAX_BURST + i] = clock64();
+    const bool two = (fl & B_TWO) != 0;
+    const bool ss = e.pat == PAT_SS;
+    const uint32_t b0 = ring_lo32 + (uint32_t)e.unit * (UNIT_BYTES >> 4), b1 = b0 + (uint32_t)e.rows * 8u;
+    const uint32_t a_hi = ss ? smem_desc_lo32(smem_base + e.a_hi) : tmem_base + e.a_hi;
+    const uint32_t a_lo = ss ? smem_desc_lo32(smem_base + e.a_lo) : tmem_base + e.a_lo;
+    const uint32_t d = tmem_base + e.d_col, idesc = make_idesc_f16(e.rows), acc = (fl & B_FIRST) ? 0u : 1u;
+    if (elect_one_sync()) issue_half(0, two, e.pat, e.steps, d, a_hi, a_lo, b0, b1, idesc, acc);
+    __syncwarp();
+    // the next burst's weights (in the ring long ago in steady state): waiting here, with the tensor core busy on
+    // half 0, keeps the ~90-cycle barrier round trip off the critical path.  Only ring waits may be hoisted:
+    // the producer never depends on anything this warp still has to issue.
+    if (has_next && (nx.flags & B_ACQUIRE)) {
+      mbar_wait(&ctl->full[nx.unit], (bits >> (8 + nx.unit)) & 1u);
+      bits ^= 1u << (8 + nx.unit);
+      tc_fence_after_sync();
+    }
+    if (elect_one_sync()) {
+      issue_half(1, two, e.pat, e.steps, d, a_hi, a_lo, b0, b1, idesc, acc);
+      if (fl & B_RELEASE) umma_commit(&ctl->empty[e.unit]);
+      if (fl & B_LAST) umma_commit(&ctl->d_full[s][(fl & B_NC1) ? 1 : 0]);
     }
     __syncwarp();
-    src += bytes;
-    if (++slot == NSLOT) { slot = 0; phase ^= 1u; wrapped = true; }
+    if (tr) trace[2 * MAX_BURST + i] = clock64();
+    if (fl & B_PART_NEXT) bits ^= 1u << s;
+    e = nx;
+  }
+  st.bits = bits;
+}
+
+// TMA producer: streams the weight images of every acquiring burst of the program into the ring
+struct ProducerState { uint32_t ebits, filled; };
+__device__ __forceinline__ void produce_program(const TcProgram& P, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
+                                                bool leader, ProducerState& st) {
+  for (int i = 0; i < P.n_burst; ++i) {
+    const Burst e = load_burst(P, i);
+    if (!(e.flags & B_ACQUIRE)) continue;
+    const uint32_t u = e.unit, bytes = (uint32_t)e.rows128 * 128u;
+    if ((st.filled >> u) & 1u) {       // the previous fill of this unit has been consumed
+      mbar_wait(&ctl->empty[u], (st.ebits >> u) & 1u);
+      st.ebits ^= 1u << u;
+    }
+    st.filled |= 1u << u;
+    if (leader) {
+      mbar_arrive_expect_tx(&ctl->full[u], bytes);
+      tma_bulk_g2s(smem + OFF_RING + u * UNIT_BYTES, wstream + (size_t)e.src * 128u, bytes, &ctl->full[u]);
+    }
+    __syncwarp();
   }
 }
 
-// write one feature (col c of the IN block) of row r, split
-__device__ __forceinline__ void store_in(uint8_t* smem, uint32_t r, uint32_t c, float v) {
+// write one feature (col c of a hi | lo input block at `blk`) of row r, split
+__device__ __forceinline__ void store_in(uint8_t* blk, uint32_t r, uint32_t c, float v) {
   __half h, l;
   split_h(v, h, l);
   const uint32_t o = kblock_offset(r, c);
-  *reinterpret_cast<__half*>(smem + OFF_IN_HI + o) = h;
-  *reinterpret_cast<__half*>(smem + OFF_IN_LO + o) = l;
+  *reinterpret_cast<__half*>(blk + o) = h;
+  *reinterpret_cast<__half*>(blk + KBLK + o) = l;
+}
+__device__ __forceinline__ void store_in_hi(uint8_t* blk, uint32_t r, uint32_t c, float v) {
+  *reinterpret_cast<__half*>(blk + kblock_offset(r, c)) = __float2half_rn(v);
 }
 
 // Epilogue of one N-chunk for this thread's row and its CW-column slice: accumulators -> scale/bias/ReLU ->
@@ -366,6 +456,7 @@ __device__ __forceinline__ int posenc_emit_sub(float x0, float x1, float x2, int
   return o + 2 * npair;
 }
 
+
 // ---------------------------------------------------------------------------
 // the field kernel
 // ---------------------------------------------------------------------------
@@ -373,11 +464,24 @@ struct TcKernelArgs {
   TcLevel lvl;
   const float* warp_embed;
   const float* mask_embed;
-  unsigned long long* trace;   // diagnostics (NDS_TC_TRACE): clock64 stamps of CTA 0's second tile, else null
+  unsigned long long* trace;   // diagnostics (NDS_TC_TRACE): clock64 stamps of CTA 0's second pair, else null
 };
-// trace layout: [i] image i ready to issue | [MAX_IMG + i] image i issued | [2 MAX_IMG + 4 op + 2 nc] accumulators seen,
-// [.. + 1] operand written & signalled | [2 MAX_IMG + 4 MAX_OPS] tile start
+// trace layout: [i] burst i reached | [MAX_BURST + i] its dependencies satisfied | [2 MAX_BURST + i] issued |
+// [3 MAX_BURST + 2 s] compute step s started, [.. + 1] finished | [3 MAX_BURST + 2 MAX_STEPS] pair start
 
+// per-sample state of one tile slot (lives in local memory: it is touched only by the per-sample stages)
+struct TileState {
+  float x[3], vd[3], gt;
+  uint32_t wid;
+  int valid;
+  float xw[3], om[2], maskv, pmask, sigma_raw, nrm[3], rgb[3];
+  float R[9], p[3];
+};
+struct NextSample {
+  float x[3], vd[3], gt;
+  uint32_t wid;
+  int valid;
+};
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcKernelArgs K,
@@ -390,202 +494,214 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = cfg.use_hyper_sheet ? cfg.hyper_num_dims : 0;
 
+  // input blocks start as zeros: columns beyond the written features multiply zero weight rows, but 0 x garbage
+  // could be NaN
+  for (uint32_t i = threadIdx.x; i < OFF_RING / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) ctrl_init(ctl);
   if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
 
   const int64_t n_tiles = (a.n_samples_total + TM - 1) / TM;
+  const int64_t n_pairs = (n_tiles + 1) / 2;
   const TcLevel& L = K.lvl;
 
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
-    const bool leader = elect_one() != 0;
-    uint32_t slot = 0, phase = 0;
-    bool wrapped = false;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      produce_tile(P, L.weights, smem, ctl, leader, slot, phase, wrapped);
+    ProducerState ps{0u, 0u};
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+      produce_program(P, L.weights, smem, ctl, lane == 0, ps);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
-    const uint32_t lead = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for the compiler
-    uint32_t slot = 0, phase = 0, part_cnt = 0, glue_cnt = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-      issue_tile(P, smem_base, ctl, tb, lead, slot, phase, part_cnt, glue_cnt,
-                 (K.trace && tile == (int64_t)gridDim.x) ? K.trace : nullptr);
+    IssuerState is{0u, false};
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+      issue_program(P, smem_base, ctl, tb, (uint32_t)lane, is, pair + gridDim.x < n_pairs,
+                    (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
   } else {
     // ===================== compute warps =====================
     const int q = warp & 3, sub = warp >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
-    uint32_t dcnt0 = 0, dcnt1 = 0;
-    // per-sample inputs are fetched one tile ahead, so their global-memory latency hides behind the previous tile
-    struct Sample { float x[3], vd[3], gt; int64_t ray; uint32_t wid; bool valid; };
-    auto load_sample = [&](int64_t tile_, Sample& s_) {
-      const int64_t n_ = tile_ * TM + row;
-      s_.valid = n_ < a.n_samples_total;
-      s_.x[0] = s_.x[1] = s_.x[2] = 0.f; s_.vd[0] = s_.vd[1] = s_.vd[2] = 0.f; s_.gt = 0.f; s_.ray = 0; s_.wid = 0;
-      if (!s_.valid) return;
-      s_.ray = n_ / a.S;
-      if (a.points) { s_.x[0] = a.points[n_ * 3]; s_.x[1] = a.points[n_ * 3 + 1]; s_.x[2] = a.points[n_ * 3 + 2]; }
+    uint32_t dc = 0;      // parity of d_full[s][c]: bit 2 s + c
+    TileState cur[2];
+    NextSample nxt[2];
+    // per-sample inputs are fetched one pair ahead, so their global-memory latency hides behind the T phase
+    auto load_next = [&](int64_t pair_, int s_) {
+      NextSample& ns = nxt[s_];
+      const int64_t n_ = (2 * pair_ + s_) * TM + row;
+      ns.valid = (pair_ < n_pairs && n_ < a.n_samples_total) ? 1 : 0;
+      ns.x[0] = ns.x[1] = ns.x[2] = 0.f; ns.vd[0] = ns.vd[1] = ns.vd[2] = 0.f; ns.gt = 0.f; ns.wid = 0;
+      if (!ns.valid) return;
+      const int64_t ray = n_ / a.S;
+      if (a.points) { ns.x[0] = a.points[n_ * 3]; ns.x[1] = a.points[n_ * 3 + 1]; ns.x[2] = a.points[n_ * 3 + 2]; }
       else {
         const float z = a.z[n_];
-        s_.x[0] = a.origins[s_.ray * 3 + 0] + z * a.dirs[s_.ray * 3 + 0];
-        s_.x[1] = a.origins[s_.ray * 3 + 1] + z * a.dirs[s_.ray * 3 + 1];
-        s_.x[2] = a.origins[s_.ray * 3 + 2] + z * a.dirs[s_.ray * 3 + 2];
+        ns.x[0] = a.origins[ray * 3 + 0] + z * a.dirs[ray * 3 + 0];
+        ns.x[1] = a.origins[ray * 3 + 1] + z * a.dirs[ray * 3 + 1];
+        ns.x[2] = a.origins[ray * 3 + 2] + z * a.dirs[ray * 3 + 2];
       }
-      s_.vd[0] = a.viewdirs[s_.ray * 3]; s_.vd[1] = a.viewdirs[s_.ray * 3 + 1]; s_.vd[2] = a.viewdirs[s_.ray * 3 + 2];
-      if (a.warp_id) s_.wid = a.warp_id[s_.ray];
-      if (a.gt_mask) s_.gt = a.gt_mask[s_.ray];
+      ns.vd[0] = a.viewdirs[ray * 3]; ns.vd[1] = a.viewdirs[ray * 3 + 1]; ns.vd[2] = a.viewdirs[ray * 3 + 2];
+      if (a.warp_id) ns.wid = a.warp_id[ray];
+      if (a.gt_mask) ns.gt = a.gt_mask[ray];
     };
-    Sample nxt;
-    load_sample(blockIdx.x, nxt);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t n = tile * TM + row;
-      const Sample cur = nxt;
-      const bool valid = cur.valid;
-      unsigned long long* tr = (K.trace && tile == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 2 * MAX_IMG : nullptr;
-      if (tr) tr[4 * MAX_OPS] = clock64();
-      const float x[3] = {cur.x[0], cur.x[1], cur.x[2]};
-      float xw[3] = {0.f, 0.f, 0.f}, om[2] = {0.f, 0.f};
-      float maskv = cur.gt, pmask = 0.f, sigma_raw = 0.f, nrm[3] = {0.f, 0.f, 0.f}, rgb[3] = {0.f, 0.f, 0.f};
-      SE3<float> T;
-      for (int i = 0; i < 9; ++i) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
-      T.p[0] = T.p[1] = T.p[2] = 0.f;
-      const int64_t ray = cur.ray;
-      const uint32_t wid = cur.wid;
-      auto st_in = [&](int c, float v) { store_in(smem, row, (uint32_t)c, v); };
-      // columns [from, 64) of the IN block are zero (their weight rows are zero, but 0 x garbage could be NaN)
-      auto zero_in = [&](int from) { for (int c = from; c < 64; ++c) if ((c & (NSUB - 1)) == sub) st_in(c, 0.f); };
-      auto extras = [&](int o, const float* embed, int dims, bool with_mask) {
-        if (sub == 1) for (int e = 0; e < dims; ++e) st_in(o + e, __ldg(embed + (size_t)wid * dims + e));
-        o += dims;
-        if (with_mask) { if (sub == 2) st_in(o, maskv); ++o; }
-        return o;
-      };
-      // inputs of the networks of the chain
-      auto prep_mask_in = [&]() {
-        int pair = 0;
-        int o = posenc_emit_sub(x[0], x[1], x[2], 3, cp.pe_mask, st_in, 0, sub, pair);
-        o = extras(o, K.mask_embed, cfg.mask_embed_dims, false);
-        zero_in(o);
-      };
-      auto prep_warp_in = [&]() {
-        int pair = 0;
-        int o = posenc_emit_sub(x[0], x[1], x[2], 3, cp.pe_warp, st_in, 0, sub, pair);
-        o = extras(o, K.warp_embed, cfg.warp_embed_dims, cfg.use_mask_in_warp != 0);
-        zero_in(o);
-      };
-      auto prep_hyper_in = [&]() {
-        int pair = 0;
-        int o = posenc_emit_sub(x[0], x[1], x[2], 3, cp.pe_hsheet, st_in, 0, sub, pair);
-        o = extras(o, K.warp_embed, cfg.warp_embed_dims, cfg.use_mask_in_hyper != 0);
-        zero_in(o);
-      };
-      auto prep_trunk_in = [&]() {
-        int pair = 0;
-        int o = posenc_emit_sub(xw[0], xw[1], xw[2], 3, cp.pe_spatial, st_in, 0, sub, pair);
-        if (H > 0) o = posenc_emit_sub(om[0], om[1], 0.f, H, cp.pe_hyperpt, st_in, o, sub, pair);
-        zero_in(o);
-      };
-      auto after_mask = [&]() { if (cfg.use_warp) prep_warp_in(); else prep_trunk_in(); };
-      auto after_warp = [&]() { if (cfg.use_hyper_sheet) prep_hyper_in(); else prep_trunk_in(); };
-      if (cfg.use_predicted_mask) prep_mask_in();
-      else if (cfg.use_warp) prep_warp_in();
-      else { xw[0] = x[0]; xw[1] = x[1]; xw[2] = x[2]; prep_trunk_in(); }
-      warp_arrive(&ctl->in_ready, lane);
-      if (tile + gridDim.x < n_tiles) load_sample(tile + gridDim.x, nxt);
-
-      for (int i = 0; i < P.n_ops; ++i) {
-        const TcOp& op = P.ops[i];
-        if (op.epi_kind != EPI_HEAD) {
-          for (int nc = 0; nc < op.n_nc; ++nc) {
-            uint32_t par;
-            if (nc == 0) par = dcnt0++ & 1u; else par = dcnt1++ & 1u;
-            if (tr) { mbar_wait(&ctl->d_full[nc], par); tr[4 * i + 2 * nc] = clock64(); }
-            epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[nc], par);
-            warp_arrive(&ctl->part_ready[nc], lane);
-            if (op.n_nc == 1) warp_arrive(&ctl->part_ready[1], lane);   // keeps both barriers on one phase per op
-            if (tr) tr[4 * i + 2 * nc + 1] = clock64();
-          }
-          continue;
+    // Part `part` of the shared feature block of the NEXT tile of slot s_ (model_utils.py:398-417 without the
+    // window, which is folded into the weights): the (sin, cos) pairs are dealt to the 4 warps sharing a sample
+    // and to the NPREP parts; part 0 also writes the embeddings.
+    auto prep_part = [&](int s_, int part) {
+      const NextSample& ns = nxt[s_];
+      uint8_t* blk = smem + OFF_IN + (uint32_t)s_ * 2u * KBLK;
+      const int npair = P.f_nb * 3;
+      for (int pi = sub; pi < npair; pi += NSUB) {
+        if (((pi >> 2) % NPREP) != part) continue;
+        const int k = pi / 3, c = pi - 3 * k;
+        const float xv = c == 0 ? ns.x[0] : (c == 1 ? ns.x[1] : ns.x[2]);
+        const float xb = xv * __int_as_float((127 + P.f_kmin + k) << 23);    // x * 2^band, exact
+        const int col = P.f_col_bands + 6 * k + c;
+        store_in(blk, row, (uint32_t)col, pe_sin(xb));
+        store_in(blk, row, (uint32_t)(col + 3), pe_sin(xb + NDS_HALF_PI_F));
+      }
+      if (part == 0) {
+        if (sub == 0 && P.f_col_ident >= 0) for (int c = 0; c < 3; ++c) store_in(blk, row, (uint32_t)(P.f_col_ident + c), ns.x[c]);
+        if (sub == 1 && P.f_col_wembed >= 0)
+          for (int e = 0; e < cfg.warp_embed_dims; ++e)
+            store_in(blk, row, (uint32_t)(P.f_col_wembed + e), __ldg(K.warp_embed + (size_t)ns.wid * cfg.warp_embed_dims + e));
+        if (sub == 2 && P.f_col_membed >= 0)
+          for (int e = 0; e < cfg.mask_embed_dims; ++e)
+            store_in(blk, row, (uint32_t)(P.f_col_membed + e), __ldg(K.mask_embed + (size_t)ns.wid * cfg.mask_embed_dims + e));
+        if (sub == 3) {
+          // without a predicted mask the mask feature is the ground-truth mask (models.py:975 with mask_ratio 0)
+          if (P.f_col_mask >= 0 && !cfg.use_predicted_mask) store_in(blk, row, (uint32_t)P.f_col_mask, ns.gt);
+          for (int c = P.f_cols; c < P.t_cols; ++c) store_in(blk, row, (uint32_t)c, 0.f);   // left by the trunk input
         }
-        mbar_wait(&ctl->d_full[0], dcnt0 & 1u);
-        ++dcnt0;
-        tc_fence_after_sync();
-        if (tr) tr[4 * i] = clock64();
-        float hv[16];
-        epilogue_head(op, L.bias, tmem_lane, hv);
-        if (tr) tr[4 * i + 2] = clock64();
-        switch (op.glue) {
-          case GLUE_MASK: {            // models.py:967-975
-            pmask = cfg.mask_output_relu ? fmaxf(hv[0], 0.f) : hv[0];
-            maskv = a.gt_mask ? (pmask * cp.mask_ratio + maskv * (1.f - cp.mask_ratio)) : pmask * cp.mask_ratio;
-            after_mask();
-          } break;
-          case GLUE_WARP: {            // warping.py:217-232
-            exp_se3<float>(hv, hv + 3, T);
-            for (int c = 0; c < 3; ++c) xw[c] = T.R[c * 3 + 0] * x[0] + T.R[c * 3 + 1] * x[1] + T.R[c * 3 + 2] * x[2] + T.p[c];
-            after_warp();
-          } break;
-          case GLUE_HYPER: {
-            for (int c = 0; c < H; ++c) om[c] = hv[c];
-            prep_trunk_in();
-          } break;
-          case GLUE_ALPHA: {
-            sigma_raw = hv[0];
-            if (cfg.predict_norm) { nrm[0] = hv[1]; nrm[1] = hv[2]; nrm[2] = hv[3]; }
-            if (!a.sigma_only) {
-              // rgb branch side inputs: [viewdir feats | normal-input feats] in the IN block
-              int o = 0, pair = 0;
-              if (cfg.use_viewdirs) {
-                o = posenc_emit_sub(cur.vd[0], cur.vd[1], cur.vd[2], 3, cp.pe_view, st_in, 0, sub, pair);
-              }
-              if (cp.use_predicted_norm) {
+      }
+      if (part == NPREP - 1) warp_arrive(&ctl->prep[s_], lane);
+    };
+
+    load_next(blockIdx.x, 0);
+    load_next(blockIdx.x, 1);
+    for (int s = 0; s < 2; ++s) for (int part = 0; part < NPREP; ++part) prep_part(s, part);
+    warp_arrive(&ctl->done[1], lane);     // nothing occupies tensor memory before the first pair
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+      for (int s = 0; s < 2; ++s) {
+        TileState& T = cur[s];
+        const NextSample& ns = nxt[s];
+        for (int c = 0; c < 3; ++c) { T.x[c] = ns.x[c]; T.vd[c] = ns.vd[c]; T.xw[c] = 0.f; T.nrm[c] = 0.f; T.rgb[c] = 0.f; T.p[c] = 0.f; }
+        for (int i = 0; i < 9; ++i) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+        T.gt = ns.gt; T.wid = ns.wid; T.valid = ns.valid;
+        T.om[0] = T.om[1] = 0.f; T.maskv = ns.gt; T.pmask = 0.f; T.sigma_raw = 0.f;
+      }
+      unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 3 * MAX_BURST : nullptr;
+      if (tr) tr[2 * MAX_STEPS] = clock64();
+      for (int si = 0; si < P.n_steps; ++si) {
+        const Step sp = P.steps[si];
+        const int s = sp.tslot;
+        TileState& T = cur[s];
+        uint8_t* blk = smem + OFF_IN + (uint32_t)s * 2u * KBLK;
+        auto st_in = [&](int c, float v) { store_in(blk, row, (uint32_t)c, v); };
+        auto st_in2 = [&](int c, float v) { store_in_hi(smem + OFF_IN2, row, (uint32_t)c, v); };
+        if (tr) tr[2 * si] = clock64();
+        if (sp.kind == STEP_EPI) {
+          const TcOp& op = P.ops[sp.op];
+          for (int nc = 0; nc < op.n_nc; ++nc) {
+            const uint32_t par = (dc >> (2 * s + nc)) & 1u;
+            dc ^= 1u << (2 * s + nc);
+            epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par);
+            warp_arrive(&ctl->part[s][nc], lane);
+            if (op.n_nc == 1) warp_arrive(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
+          }
+        } else if (sp.kind == STEP_HEAD) {
+          const TcOp& op = P.ops[sp.op];
+          mbar_wait(&ctl->d_full[s][0], (dc >> (2 * s)) & 1u);
+          dc ^= 1u << (2 * s);
+          tc_fence_after_sync();
+          float hv[16];
+          epilogue_head(op, L.bias, tmem_lane, hv);
+          switch (op.glue) {
+            case GLUE_MASK: {            // models.py:967-975
+              T.pmask = cfg.mask_output_relu ? fmaxf(hv[0], 0.f) : hv[0];
+              T.maskv = a.gt_mask ? (T.pmask * cp.mask_ratio + T.gt * (1.f - cp.mask_ratio)) : T.pmask * cp.mask_ratio;
+              if (P.f_col_mask >= 0 && sub == 2) st_in(P.f_col_mask, T.maskv);
+            } break;
+            case GLUE_HYPER: {
+              for (int c = 0; c < H; ++c) T.om[c] = hv[c];
+            } break;
+            case GLUE_WARP: {            // warping.py:217-232
+              SE3<float> se;
+              exp_se3<float>(hv, hv + 3, se);
+              float xw[3];
+              for (int c = 0; c < 3; ++c) xw[c] = se.R[c * 3 + 0] * T.x[0] + se.R[c * 3 + 1] * T.x[1] + se.R[c * 3 + 2] * T.x[2] + se.p[c];
+              for (int i = 0; i < 9; ++i) T.R[i] = se.R[i];
+              for (int c = 0; c < 3; ++c) { T.p[c] = se.p[c]; T.xw[c] = xw[c]; }
+              // trunk input (models.py:493-523) over the feature block, which the narrow networks are done with
+              int pr = 0;
+              int o = posenc_emit_sub(xw[0], xw[1], xw[2], 3, cp.pe_spatial, st_in, 0, sub, pr);
+              if (H > 0) o = posenc_emit_sub(T.om[0], T.om[1], 0.f, H, cp.pe_hyperpt, st_in, o, sub, pr);
+              for (int c = o + sub; c < P.f_cols; c += NSUB) st_in(c, 0.f);
+            } break;
+            case GLUE_ALPHA: {
+              T.sigma_raw = hv[0];
+              if (cfg.predict_norm) { T.nrm[0] = hv[1]; T.nrm[1] = hv[2]; T.nrm[2] = hv[3]; }
+              if (P.full && cp.use_predicted_norm) {
+                // rgb branch side input: normal in the observation frame (models.py:1117-1148), after the viewdir feats
                 float nh[3], ni[3];
-                normalize3(nrm, nh);
+                const float nr[3] = {T.nrm[0], T.nrm[1], T.nrm[2]};
+                normalize3(nr, nh);
                 if (cfg.use_warp) { for (int c = 0; c < 3; ++c) ni[c] = T.R[0 * 3 + c] * nh[0] + T.R[1 * 3 + c] * nh[1] + T.R[2 * 3 + c] * nh[2]; }
                 else { ni[0] = nh[0]; ni[1] = nh[1]; ni[2] = nh[2]; }
                 normalize3(ni, nh);
-                if (cfg.norm_input_posenc) o = posenc_emit_sub(nh[0], nh[1], nh[2], 3, cp.pe_norm, st_in, o, sub, pair);
-                else { if (sub == 0) { st_in(o, nh[0]); st_in(o + 1, nh[1]); st_in(o + 2, nh[2]); } o += 3; }
+                const int o = cfg.use_viewdirs ? cp.pe_view.dim(3) : 0;
+                int pr = 0;
+                if (cfg.norm_input_posenc) posenc_emit_sub(nh[0], nh[1], nh[2], 3, cp.pe_norm, st_in2, o, sub, pr);
+                else if (sub == 0) { st_in2(o, nh[0]); st_in2(o + 1, nh[1]); st_in2(o + 2, nh[2]); }
               }
-              zero_in(o);
+            } break;
+            case GLUE_RGB: {
+              for (int c = 0; c < 3; ++c) T.rgb[c] = 1.f / (1.f + __expf(-hv[c]));
+            } break;
+            default: break;
+          }
+          // the MMA issuer may overwrite the head accumulators / read the new inputs from here on
+          if (op.signal_glue) warp_arrive(&ctl->glue[s], lane);
+        } else if (sp.kind == STEP_VIEW) {
+          load_next(pair + gridDim.x, s);
+          if (P.full && cfg.use_viewdirs) {
+            int pr = 0;
+            posenc_emit_sub(T.vd[0], T.vd[1], T.vd[2], 3, cp.pe_view, st_in2, 0, sub, pr);
+          }
+        } else if (sp.kind == STEP_PREP) {
+          prep_part(s, sp.arg);
+        } else {
+          // ---- STEP_OUT: write planes (the warps sharing a sample take different planes) ----
+          const int64_t n = (2 * pair + s) * TM + row;
+          if (T.valid) {
+            float* PL = a.planes;
+            const int64_t ps = a.plane_stride;
+            if (sub == 0) {
+              PL[P_SIGMA_RAW * ps + n] = T.sigma_raw;
+              for (int c = 0; c < 3; ++c) PL[(P_RGB + c) * ps + n] = T.rgb[c];
+            } else if (sub == 1) {
+              for (int c = 0; c < 3; ++c) PL[(P_NORM + c) * ps + n] = T.nrm[c];
+              PL[P_MASK * ps + n] = T.pmask;
+            } else if (sub == 2) {
+              for (int c = 0; c < 3; ++c) PL[(P_WARPED + c) * ps + n] = T.xw[c];
+              for (int c = 0; c < H; ++c) PL[(P_WARPED + 3 + c) * ps + n] = T.om[c];
+            } else if (cfg.use_warp) {
+              const float r = 0.57735025882720947265625f;
+              float rf[3], rn[3];
+              for (int c = 0; c < 3; ++c) rf[c] = T.R[c * 3 + 0] * r + T.R[c * 3 + 1] * r + T.R[c * 3 + 2] * r;
+              normalize3(rf, rn);
+              for (int c = 0; c < 3; ++c) { PL[(P_ROT + c) * ps + n] = rn[c]; PL[(P_TRANS + c) * ps + n] = T.p[c]; }
             }
-          } break;
-          case GLUE_RGB: {
-            for (int c = 0; c < 3; ++c) rgb[c] = 1.f / (1.f + __expf(-hv[c]));
-          } break;
-          default: break;
+          }
+          warp_arrive(&ctl->done[s], lane);
         }
-        // the MMA issuer may overwrite the head accumulators / read the new inputs from here on
-        if (i != P.n_ops - 1) warp_arrive(&ctl->in_ready, lane);
-        if (tr) tr[4 * i + 1] = clock64();
+        if (tr) tr[2 * si + 1] = clock64();
       }
-      // ---- write planes (the warps sharing a sample take different planes) ----
-      if (valid) {
-        float* P = a.planes;
-        const int64_t ps = a.plane_stride;
-        if (sub == 0) {
-          P[P_SIGMA_RAW * ps + n] = sigma_raw;
-          for (int c = 0; c < 3; ++c) P[(P_RGB + c) * ps + n] = rgb[c];
-        } else if (sub == 1) {
-          for (int c = 0; c < 3; ++c) P[(P_NORM + c) * ps + n] = nrm[c];
-          P[P_MASK * ps + n] = pmask;
-        } else if (sub == 2) {
-          for (int c = 0; c < 3; ++c) P[(P_WARPED + c) * ps + n] = xw[c];
-          for (int c = 0; c < H; ++c) P[(P_WARPED + 3 + c) * ps + n] = om[c];
-        } else if (cfg.use_warp) {
-          const float r = 0.57735025882720947265625f;
-          float rf[3], rn[3];
-          for (int c = 0; c < 3; ++c) rf[c] = T.R[c * 3 + 0] * r + T.R[c * 3 + 1] * r + T.R[c * 3 + 2] * r;
-          normalize3(rf, rn);
-          for (int c = 0; c < 3; ++c) { P[(P_ROT + c) * ps + n] = rn[c]; P[(P_TRANS + c) * ps + n] = T.p[c]; }
-        }
-      }
-      tc_fence_before_sync();
     }
   }
   tc_fence_before_sync();
@@ -595,8 +711,8 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
 
 // ---------------------------------------------------------------------------
 // self-test kernel: one op on caller-provided activations.  The k_hid hidden
-// activations are written to tensor-memory region 0 in the layout an upstream
-// epilogue of that width produces, the k_in inputs to the IN block.
+// activations are written to tensor-memory columns [0, 256) in the layout an
+// upstream epilogue of that width produces, the k_in inputs to IN[0].
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* __restrict__ A, int k_hid, int k_in,
@@ -614,22 +730,19 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   const uint32_t tmem_base = ctl->tmem_base;
   const TcOp& op = P.ops[0];
   if (warp == WARP_TMA) {
-    const bool leader = elect_one() != 0;
-    uint32_t slot = 0, phase = 0;
-    bool wrapped = false;
-    produce_tile(P, L.weights, smem, ctl, leader, slot, phase, wrapped);
+    ProducerState ps{0u, 0u};
+    produce_program(P, L.weights, smem, ctl, lane == 0, ps);
   } else if (warp == WARP_MMA) {
-    const uint32_t lead = elect_one();
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    uint32_t slot = 0, phase = 0, pc = 0, gc = 0;
-    issue_tile(P, smem_base, ctl, tb, lead, slot, phase, pc, gc, nullptr);
+    IssuerState is{0u, false};
+    issue_program(P, smem_base, ctl, tb, (uint32_t)lane, is, false, nullptr);
   } else {
     const int q = warp & 3, sub = warp >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     const int ld = k_hid + k_in;
-    // producer layout of a k_hid-wide layer: chunks of nc_rows columns at region 0 + 128 c, slices of CW per warp
-    const int p_nc = k_hid >= 128 ? 2 : 1, p_rows = k_hid / (p_nc ? p_nc : 1), p_cw = p_rows / NSUB;
+    // producer layout of a k_hid-wide layer: chunks of nc_rows columns at 128 c, slices of CW per warp
+    const int p_nc = k_hid >= 256 ? 2 : 1, p_rows = k_hid / p_nc, p_cw = p_rows / NSUB;
     for (int c = 0; c < p_nc && k_hid > 0; ++c) {
       const uint32_t col = tmem_lane + 128u * c + (uint32_t)sub * p_cw;
       for (int g = 0; g < p_cw; g += 16) {
@@ -648,19 +761,19 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
       }
     }
     for (int c = 0; c < 64; ++c)
-      if ((c & (NSUB - 1)) == sub) store_in(smem, row, c, c < k_in ? A[row * ld + k_hid + c] : 0.f);
-    warp_arrive(&ctl->part_ready[0], lane);
-    warp_arrive(&ctl->part_ready[1], lane);
-    warp_arrive(&ctl->in_ready, lane);
+      if ((c & (NSUB - 1)) == sub) store_in(smem + OFF_IN, row, c, c < k_in ? A[row * ld + k_hid + c] : 0.f);
+    warp_arrive(&ctl->part[0][0], lane);
+    warp_arrive(&ctl->part[0][1], lane);
+    warp_arrive(&ctl->glue[0], lane);
     if (op.epi_kind == EPI_HEAD) {
-      mbar_wait(&ctl->d_full[0], 0);
+      mbar_wait(&ctl->d_full[0][0], 0);
       tc_fence_after_sync();
       float hv[16];
       epilogue_head(op, L.bias, tmem_lane, hv);
       if (sub == 0) for (int i = 0; i < 16 && i < op.N; ++i) out_f32[row * op.N + i] = hv[i];
     } else {
       for (int nc = 0; nc < op.n_nc; ++nc)
-        epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, out_f32, op.N, &ctl->d_full[nc], 0);
+        epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, out_f32, op.N, &ctl->d_full[0][nc], 0);
       tmem_st_wait();
       tc_fence_before_sync();
     }
@@ -703,40 +816,56 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
 // ---------------------------------------------------------------------------
 // One K-chunk (64 operand columns) of an op: where the operand lives and which weight rows multiply it.
 struct KChunkMap {
-  uint8_t pat;          // APattern
-  uint8_t wait;         // bit c: needs output chunk c of the previous op
-  uint32_t a_hi, a_lo;  // PAT_SS: shared byte offsets; else tensor-memory columns
-  int rows[64];         // W row feeding each of the 64 operand columns (-1 = zero pad)
+  uint8_t pat = PAT_SS;    // APattern
+  uint8_t wait = 0;        // bit c: needs output chunk c of the previous op
+  uint8_t wait_glue = 0;   // needs the per-sample stage (rgb side inputs)
+  uint32_t a_hi = 0, a_lo = 0;   // PAT_SS: shared byte offsets; else tensor-memory columns
+  int rows[64];            // W row feeding each of the 64 operand columns (-1 = zero pad)
+  int band[64];            // >= 0: the column is a posenc feature of that band; its weights carry the window
+  int pe = -1;             // which window: 0 mask, 1 warp, 2 hyper sheet
 };
 
 struct OpBuild {
   std::vector<KChunkMap> kcs;
-  int N_logical;                      // real output columns
-  int N;                              // padded
-  int n_nc;                           // N-chunks (accumulators); nc_rows = N / n_nc
-  int d_col[2];                       // tensor-memory column of accumulator chunk c
-  int terms, relu, epi_kind, glue, wait_glue;
-  int prev_produces = 0;              // the op before this one is a hidden layer (its epilogue signals part_ready)
-  std::vector<float> W;               // [K_total][N_logical] logical weights (row-major, Flax layout)
-  std::vector<float> b;
+  int N_logical = 0;                  // real output columns
+  int N = 0;                          // padded
+  int n_nc = 1;                       // N-chunks (accumulators); nc_rows = N / n_nc
+  int d_col[2] = {0, 0};              // tensor-memory column of accumulator chunk c
+  int terms = 3, relu = 0, epi_kind = EPI_INPLACE, glue = GLUE_NONE;
+  int prev_produces = 0;              // the op before this one is a hidden layer (its epilogue signals part)
+  int interleave = 0;                 // order the bursts K-range-major so that chunk 1's epilogue stays hidden
+  uint16_t first_flags = 0;           // B_WAIT_* of the first burst
+  uint16_t first_part_waits = 0;      // bit c: the first burst waits for part c of the previous op
+  int signal_glue = 0;
+  int tslot = 0;
+  const std::vector<float>* W = nullptr;   // [K_total][N_logical] logical weights (row-major, Flax layout)
+  const std::vector<float>* b = nullptr;
+  std::vector<float> W_own, b_own;    // fused heads own their matrices
+};
+
+// weight images of one input K-chunk whose columns carry posenc windows: re-packed when the windows change
+struct WindowedImage {
+  size_t stream_off;                  // byte offset of the B_hi image (B_lo follows when terms == 3)
+  int rows, terms, pe;
+  std::vector<float> w;               // [rows][64] scaled weights without the window
+  int band[64];
 };
 
 struct Packed {
-  std::vector<TcOp> ops;
-  std::vector<ImgEntry> imgs;
   std::vector<uint8_t> stream;
   std::vector<float> bias;
+  std::vector<WindowedImage> windowed;
 };
 
-// Layout an in-place epilogue leaves behind (see epilogue_chunk): N output features in n_nc chunks at
-// region + 128 c; inside a chunk, warp slice s holds features [s CW, (s+1) CW) as hi (CW/2 columns) | lo (CW/2).
+// Layout an in-place epilogue leaves behind (see epilogue_chunk): N output features in n_nc chunks at d_col[c];
+// inside a chunk, warp slice s holds features [s CW, (s+1) CW) as hi (CW/2 columns) | lo (CW/2).
 struct ActLayout {
-  int region, N, n_nc, compact_hi;    // compact_hi: EPI_COMPACT_HI (hi only, contiguous from the chunk start)
-  int d_col[2];
+  int N = 0, n_nc = 1, compact_hi = 0;   // compact_hi: EPI_COMPACT_HI (hi only, contiguous from the chunk start)
+  int d_col[2] = {0, 0};
+  int region = 0;                        // which of the two ping-pong regions holds it
   int nc_rows() const { return N / n_nc; }
   int cw() const { return nc_rows() / NSUB; }
 };
-static int chunks_for(int N) { return N >= 128 ? 2 : 1; }
 
 // operand K-block j (features 64 j ...) of a layer output with layout L
 static KChunkMap kc_hidden(const ActLayout& L, int j, int row0, bool wait) {
@@ -749,178 +878,373 @@ static KChunkMap kc_hidden(const ActLayout& L, int j, int row0, bool wait) {
     k.a_lo = k.a_hi + L.cw() / 2;
   }
   k.wait = wait ? (uint8_t)(1u << c) : 0;
-  for (int cidx = 0; cidx < 64; ++cidx) k.rows[cidx] = (f0 + cidx < L.N) ? row0 + f0 + cidx : -1;
+  for (int cidx = 0; cidx < 64; ++cidx) { k.rows[cidx] = (f0 + cidx < L.N) ? row0 + f0 + cidx : -1; k.band[cidx] = -1; }
   return k;
 }
-static KChunkMap kc_input(int row0, int in_dim) {
+// inputs in a shared-memory block (hi at `off`, lo one K-block later), identity column map
+static KChunkMap kc_input(uint32_t off, int row0, int in_dim) {
   KChunkMap k;
-  k.pat = PAT_SS; k.wait = 0; k.a_hi = OFF_IN_HI; k.a_lo = OFF_IN_LO;
-  for (int c = 0; c < 64; ++c) k.rows[c] = c < in_dim ? row0 + c : -1;
+  k.pat = PAT_SS; k.a_hi = off; k.a_lo = off + KBLK;
+  for (int c = 0; c < 64; ++c) { k.rows[c] = c < in_dim ? row0 + c : -1; k.band[c] = -1; }
   return k;
 }
 
-static void pack_op(const OpBuild& ob, Packed& out) {
-  TcOp op;
-  memset(&op, 0, sizeof op);
-  op.N = (uint16_t)ob.N;
-  op.relu = (uint8_t)ob.relu;
-  op.epi_kind = (uint8_t)ob.epi_kind;
-  op.glue = (uint8_t)ob.glue;
-  op.n_nc = (uint8_t)ob.n_nc;
-  op.nc_rows = (uint16_t)(ob.N / ob.n_nc);
-  op.d_col[0] = (uint16_t)ob.d_col[0];
-  op.d_col[1] = (uint16_t)ob.d_col[1];
+// shared feature block layout (TcProgram::f_*)
+struct FLayout {
+  int col_ident = -1, col_bands = 0, kmin = 0, nb = 0, col_wembed = -1, col_membed = -1, col_mask = -1, cols = 0;
+};
+// inputs of narrow network `pe` (0 mask, 1 warp, 2 hyper sheet) gathered from the shared feature block.
+// Reference input order: [identity x][band k: sin(3) cos(3)]...[embedding][mask]  (modules.py:394-434,
+// warping.py:200-215, modules.py:351-392)
+static KChunkMap kc_features(const FLayout& F, uint32_t off, int row0, int pe, int min_deg, int max_deg, int identity,
+                             int embed_col, int embed_dims, bool with_mask) {
+  KChunkMap k;
+  k.pat = PAT_SS; k.a_hi = off; k.a_lo = off + KBLK; k.pe = pe;
+  for (int c = 0; c < 64; ++c) { k.rows[c] = -1; k.band[c] = -1; }
+  int j = row0;
+  if (identity) for (int c = 0; c < 3; ++c) k.rows[F.col_ident + c] = j++;
+  for (int d = min_deg; d < max_deg; ++d)
+    for (int r = 0; r < 6; ++r) {
+      const int col = F.col_bands + 6 * (d - F.kmin) + r;
+      k.rows[col] = j++;
+      k.band[col] = d - min_deg;
+    }
+  for (int e = 0; e < embed_dims; ++e) k.rows[embed_col + e] = j++;
+  if (with_mask) k.rows[F.col_mask] = j++;
+  return k;
+}
+
+static float op_scale(const OpBuild& ob, int& e_out) {
   // power-of-two scale so that max |W| lands in [4, 8): keeps W_lo out of fp16 subnormals
   float mx = 0.f;
-  for (float v : ob.W) mx = std::max(mx, std::fabs(v));
+  for (float v : *ob.W) mx = std::max(mx, std::fabs(v));
   int e = 0;
   if (mx > 0.f) { std::frexp(mx, &e); e = 3 - e; }
   if (e > 14) e = 14;
   if (e < -14) e = -14;
-  const float scale = std::ldexp(1.f, e);
-  op.inv_scale = std::ldexp(1.f, -e);
-  op.bias_off = (uint32_t)out.bias.size();
-  for (int n = 0; n < ob.N; ++n) out.bias.push_back(n < ob.N_logical ? ob.b[n] : 0.f);
-  while (out.bias.size() % 4) out.bias.push_back(0.f);
-  // stream order == issue order: N-chunk, K-chunk, image (hi, lo)
-  const size_t img = (size_t)op.nc_rows * 128;
-  const int n_img_per = ob.terms == 3 ? 2 : 1;
-  bool waited0 = false, waited1 = false;
-  for (int nc = 0; nc < op.n_nc; ++nc) {
-    // the first image of chunk nc overwrites accumulator chunk nc, which the previous op's epilogue must have
-    // drained (= its part nc written) -- or, after a head, the per-sample stage must be done (wait_glue).
-    for (size_t kc = 0; kc < ob.kcs.size(); ++kc) {
-      const KChunkMap& km = ob.kcs[kc];
-      int last = -1;
-      for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
-      const int steps = km.pat == PAT_SS ? std::max(1, (last + 16) / 16) : 4;
-      const size_t base = out.stream.size();
-      out.stream.resize(base + img * n_img_per, 0);
-      for (int r = 0; r < op.nc_rows; ++r) {
-        const int n = nc * op.nc_rows + r;
-        for (int c = 0; c < 64; ++c) {
-          float w = 0.f;
-          if (n < ob.N_logical && km.rows[c] >= 0) w = ob.W[(size_t)km.rows[c] * ob.N_logical + n] * scale;
-          const __half hi = __float2half_rn(w);
-          const __half lo = __float2half_rn(w - __half2float(hi));
-          const uint32_t o = kblock_offset((uint32_t)r, (uint32_t)c);
-          memcpy(&out.stream[base + o], &hi, 2);
-          if (ob.terms == 3) memcpy(&out.stream[base + img + o], &lo, 2);
-        }
-      }
-      for (int im = 0; im < n_img_per; ++im) {
-        ImgEntry ie;
-        memset(&ie, 0, sizeof ie);
-        ie.a_hi = km.a_hi; ie.a_lo = km.a_lo; ie.pat = km.pat;
-        ie.rows = op.nc_rows;
-        ie.steps = (uint8_t)steps;
-        ie.d_col = op.d_col[nc];
-        uint16_t fl = 0;
-        if (im == 0 && ob.terms == 3) fl |= IMG_TWO_TERMS;     // B_hi image: A_hi B_hi + A_lo B_hi
-        if (kc == 0 && im == 0) fl |= IMG_FIRST;
-        if (kc + 1 == ob.kcs.size() && im + 1 == n_img_per) fl |= IMG_LAST;
-        if (nc == 1) fl |= IMG_NC1;
-        const bool first = kc == 0 && im == 0;
-        // a single-chunk producer signals both part barriers; wait on the one matching the accumulator index
-        if (first && ob.prev_produces && nc == 0 && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; }
-        if (first && ob.prev_produces && nc == 1 && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; }
-        if ((km.wait & 1) && !waited0) { fl |= IMG_WAIT_P0; waited0 = true; }
-        if ((km.wait & 2) && !waited1) { fl |= IMG_WAIT_P1; waited1 = true; }
-        if (first && nc == 0 && ob.wait_glue) fl |= IMG_WAIT_GLUE;
-        ie.flags = fl;
-        out.imgs.push_back(ie);
-      }
-    }
-  }
-  if (ob.prev_produces) out.imgs.back().flags |= IMG_PART_NEXT;   // one output phase of the previous op consumed
-  out.ops.push_back(op);
+  e_out = e;
+  return std::ldexp(1.f, e);
 }
 
-// hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer].  Layer l
-// accumulates into region (l even ? 1 : 0) and leaves its activations there.  Returns the last layer's layout.
-static ActLayout build_mlp_ops(const HostMlp& m, int terms, Packed& out) {
-  ActLayout prev{};
+static void write_image(uint8_t* dst, const float* w /*[rows][64]*/, const float* colscale, int rows, int terms) {
+  const size_t img = (size_t)rows * 128;
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < 64; ++c) {
+      const float v = w[(size_t)r * 64 + c] * (colscale ? colscale[c] : 1.f);
+      const __half hi = __float2half_rn(v);
+      const __half lo = __float2half_rn(v - __half2float(hi));
+      const uint32_t o = kblock_offset((uint32_t)r, (uint32_t)c);
+      memcpy(dst + o, &hi, 2);
+      if (terms == 3) memcpy(dst + img + o, &lo, 2);
+    }
+}
+
+// Weight images of one op (shared by both tile slots): src[nc][kc] = stream offset in 128-byte rows.
+struct OpWeights {
+  uint32_t bias_off = 0;
+  float inv_scale = 1.f;
+  std::vector<uint32_t> src;          // [nc * n_kc + kc]
+};
+static OpWeights pack_weights(const OpBuild& ob, Packed& out) {
+  OpWeights ow;
+  int e = 0;
+  const float scale = op_scale(ob, e);
+  ow.inv_scale = std::ldexp(1.f, -e);
+  ow.bias_off = (uint32_t)out.bias.size();
+  for (int n = 0; n < ob.N; ++n) out.bias.push_back(n < ob.N_logical ? (*ob.b)[n] : 0.f);
+  while (out.bias.size() % 4) out.bias.push_back(0.f);
+  const int nc_rows = ob.N / ob.n_nc;
+  const size_t img = (size_t)nc_rows * 128;
+  std::vector<float> w((size_t)nc_rows * 64);
+  for (int nc = 0; nc < ob.n_nc; ++nc)
+    for (size_t kc = 0; kc < ob.kcs.size(); ++kc) {
+      const KChunkMap& km = ob.kcs[kc];
+      bool windowed = false;
+      for (int r = 0; r < nc_rows; ++r) {
+        const int n = nc * nc_rows + r;
+        for (int c = 0; c < 64; ++c) {
+          float v = 0.f;
+          if (n < ob.N_logical && km.rows[c] >= 0) v = (*ob.W)[(size_t)km.rows[c] * ob.N_logical + n] * scale;
+          w[(size_t)r * 64 + c] = v;
+          if (km.band[c] >= 0) windowed = true;
+        }
+      }
+      const size_t base = out.stream.size();
+      out.stream.resize(base + img * (ob.terms == 3 ? 2 : 1), 0);
+      write_image(&out.stream[base], w.data(), nullptr, nc_rows, ob.terms);
+      ow.src.push_back((uint32_t)(base / 128));
+      if (windowed) {
+        WindowedImage wi;
+        wi.stream_off = base; wi.rows = nc_rows; wi.terms = ob.terms; wi.pe = km.pe; wi.w = w;
+        memcpy(wi.band, km.band, sizeof wi.band);
+        out.windowed.push_back(std::move(wi));
+      }
+    }
+  return ow;
+}
+
+static TcOp make_tcop(const OpBuild& ob, const OpWeights& ow) {
+  TcOp op;
+  memset(&op, 0, sizeof op);
+  op.bias_off = ow.bias_off;
+  op.inv_scale = ow.inv_scale;
+  op.N = (uint16_t)ob.N;
+  op.nc_rows = (uint16_t)(ob.N / ob.n_nc);
+  op.n_nc = (uint8_t)ob.n_nc;
+  op.relu = (uint8_t)ob.relu;
+  op.epi_kind = (uint8_t)ob.epi_kind;
+  op.glue = (uint8_t)ob.glue;
+  op.d_col[0] = (uint16_t)ob.d_col[0];
+  op.d_col[1] = (uint16_t)ob.d_col[1];
+  op.signal_glue = (uint8_t)ob.signal_glue;
+  return op;
+}
+
+// bursts of one op of one tile slot, in issue order (ring flags / units are assigned by the assembler)
+static std::vector<Burst> make_bursts(const OpBuild& ob, const OpWeights& ow) {
+  const int nc_rows = ob.N / ob.n_nc;
+  const int n_kc = (int)ob.kcs.size();
+  std::vector<std::pair<int, int>> order;
+  if (ob.n_nc == 2 && ob.interleave) {
+    for (int late = 0; late < 2; ++late)
+      for (int nc = 0; nc < 2; ++nc)
+        for (int kc = 0; kc < n_kc; ++kc)
+          if (((ob.kcs[kc].wait & 2) != 0 || ob.kcs[kc].wait_glue) == (late != 0)) order.push_back({nc, kc});
+  } else {
+    for (int nc = 0; nc < ob.n_nc; ++nc) for (int kc = 0; kc < n_kc; ++kc) order.push_back({nc, kc});
+  }
+  std::vector<Burst> out;
+  int waited = 0;    // bit 0 / 1: part c, bit 2: glue (of the per-sample stage feeding a K-chunk)
+  int seen[2] = {0, 0};
+  int left[2] = {n_kc, n_kc};
+  for (size_t i = 0; i < order.size(); ++i) {
+    const int nc = order[i].first, kc = order[i].second;
+    const KChunkMap& km = ob.kcs[kc];
+    Burst e;
+    memset(&e, 0, sizeof e);
+    e.a_hi = km.a_hi; e.a_lo = km.a_lo; e.pat = km.pat;
+    e.rows = (uint16_t)nc_rows;
+    int last = -1;
+    for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
+    e.steps = (uint8_t)(km.pat == PAT_SS ? std::max(1, (last + 16) / 16) : 4);
+    e.d_col = (uint16_t)ob.d_col[nc];
+    e.tslot = (uint8_t)ob.tslot;
+    e.src = ow.src[(size_t)nc * n_kc + kc];
+    e.rows128 = (uint16_t)(nc_rows * (ob.terms == 3 ? 2 : 1));
+    uint16_t fl = 0;
+    if (ob.terms == 3) fl |= B_TWO;
+    if (!seen[nc]) { fl |= B_FIRST; seen[nc] = 1; }
+    if (--left[nc] == 0) fl |= B_LAST;
+    if (nc == 1) fl |= B_NC1;
+    int need = km.wait | (km.wait_glue ? 4 : 0);
+    if (i == 0) { fl |= ob.first_flags; need |= ob.first_part_waits; if (ob.first_flags & B_WAIT_GLUE) waited |= 4; }
+    need &= ~waited;
+    if (need & 1) fl |= B_WAIT_P0;
+    if (need & 2) fl |= B_WAIT_P1;
+    if (need & 4) fl |= B_WAIT_GLUE;
+    waited |= need;
+    if (i + 1 == order.size() && ob.prev_produces) fl |= B_PART_NEXT;
+    e.flags = fl;
+    out.push_back(e);
+  }
+  return out;
+}
+
+// hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer].
+//   narrow (N phase): regions of 128 columns at 256 tslot + {0, 128}; layer l accumulates into region (l even ? 1 : 0)
+//   wide   (T phase): regions of 256 columns at {0, 256}, two N-chunks; layer l accumulates into region (l even ? 0 : 1)
+// Returns the last layer's layout.
+static ActLayout build_mlp_ops(const HostMlp& m, int terms, bool wide, int tslot, const KChunkMap& in0,
+                               const KChunkMap& in_skip, uint16_t first_flags, std::vector<OpBuild>& ops) {
+  ActLayout prev;
   for (int l = 0; l < m.depth; ++l) {
     OpBuild ob;
     ob.N_logical = ob.N = m.width;
-    ob.n_nc = chunks_for(m.width);
-    const int region = (l % 2 == 0) ? 1 : 0;
-    ob.d_col[0] = region * (int)TM_REGION;
-    ob.d_col[1] = ob.d_col[0] + 128;
+    ob.tslot = tslot;
+    int region;
+    if (wide) {
+      region = (l % 2 == 0) ? 0 : 1;
+      ob.n_nc = 2;
+      ob.d_col[0] = region * 256; ob.d_col[1] = ob.d_col[0] + 128;
+      ob.interleave = 1;
+    } else {
+      region = (l % 2 == 0) ? 1 : 0;
+      ob.n_nc = 1;
+      ob.d_col[0] = ob.d_col[1] = 256 * tslot + 128 * region;
+    }
     ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE; ob.epi_kind = EPI_INPLACE;
-    ob.wait_glue = l == 0;
     ob.prev_produces = l > 0;
-    ob.W = m.hidden[l].W; ob.b = m.hidden[l].b;
-    if (l == 0) ob.kcs.push_back(kc_input(0, m.in_dim));
+    if (l == 0) ob.first_flags = first_flags;
+    // the second trunk layer of tile slot 0 accumulates over the columns of tile slot 1's narrow networks
+    if (wide && l == 1 && tslot == 0) ob.first_flags |= B_PEEK_GLUE_OTHER;
+    ob.W = &m.hidden[l].W; ob.b = &m.hidden[l].b;
+    if (l == 0) ob.kcs.push_back(in0);
     else {
-      if (l == m.skip) ob.kcs.push_back(kc_input(m.width, m.in_dim));   // ready long ago: issue it first
+      if (l == m.skip) ob.kcs.push_back(in_skip);          // ready long ago: issue it first
       for (int j = 0; j < m.width / 64; ++j) ob.kcs.push_back(kc_hidden(prev, j, 0, true));
     }
-    pack_op(ob, out);
-    prev = ActLayout{region, m.width, ob.n_nc, 0, {ob.d_col[0], ob.d_col[1]}};
+    ops.push_back(ob);
+    prev = ActLayout();
+    prev.N = m.width; prev.n_nc = ob.n_nc; prev.d_col[0] = ob.d_col[0]; prev.d_col[1] = ob.d_col[1]; prev.region = region;
   }
   return prev;
 }
 
-// head over the layer output `in`; accumulators in the other region
+// head over the layer output `in`; accumulators at the start of the other region
 static void build_head_op(const std::vector<const HostDense*>& heads, const ActLayout& in, int terms, int glue,
-                          Packed& out) {
+                          bool wide, int tslot, int signal_glue, std::vector<OpBuild>& ops) {
   OpBuild ob;
   int n = 0;
   for (auto* h : heads) n += h->N;
   ob.N_logical = n;
   ob.N = 16;
   ob.n_nc = 1;
-  ob.d_col[0] = (1 - in.region) * (int)TM_REGION;
-  ob.d_col[1] = ob.d_col[0];
-  ob.terms = terms; ob.relu = 0; ob.epi_kind = EPI_HEAD; ob.glue = glue; ob.wait_glue = 0; ob.prev_produces = 1;
-  ob.W.assign((size_t)in.N * n, 0.f);
+  ob.tslot = tslot;
+  ob.d_col[0] = ob.d_col[1] = wide ? (1 - in.region) * 256 : 256 * tslot + 128 * (1 - in.region);
+  ob.terms = terms; ob.relu = 0; ob.epi_kind = EPI_HEAD; ob.glue = glue; ob.prev_produces = 1;
+  ob.signal_glue = signal_glue;
+  ob.W_own.assign((size_t)in.N * n, 0.f);
   int c0 = 0;
   for (auto* h : heads) {
-    for (int k = 0; k < in.N; ++k) for (int j = 0; j < h->N; ++j) ob.W[(size_t)k * n + c0 + j] = h->W[(size_t)k * h->N + j];
-    for (int j = 0; j < h->N; ++j) ob.b.push_back(h->b[j]);
+    for (int k = 0; k < in.N; ++k) for (int j = 0; j < h->N; ++j) ob.W_own[(size_t)k * n + c0 + j] = h->W[(size_t)k * h->N + j];
+    for (int j = 0; j < h->N; ++j) ob.b_own.push_back(h->b[j]);
     c0 += h->N;
   }
   for (int j = 0; j < in.N / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, true));
-  pack_op(ob, out);
+  ops.push_back(ob);
 }
+static void fix_own(std::vector<OpBuild>& ops) {
+  for (auto& ob : ops) if (!ob.W) { ob.W = &ob.W_own; ob.b = &ob.b_own; }
+}
+
+struct LevelBuild {
+  std::vector<OpBuild> ops[2];        // per tile slot, same length
+  std::vector<OpWeights> weights;     // per op (shared by the tile slots)
+  int n_narrow = 0, n_sigma = 0;      // ops of the N phase; ops up to and including the sigma/normal head
+  int trunk_first = 0, trunk_skip_op = -1;
+  FLayout F;
+  int t_cols = 0;
+};
 
 struct TcEngine {
   Packed packed[2];
-  TcProgram prog[2];
-  int n_ops_sigma[2] = {0, 0}, n_img_sigma[2] = {0, 0};
+  LevelBuild lb[2];
+  TcProgram prog[2][2];               // [level][full]
   uint8_t* d_stream[2] = {nullptr, nullptr};
   float* d_bias[2] = {nullptr, nullptr};
+  float win[2][3][NDSR_MAX_BANDS];    // windows currently folded into the streams, per level
+  bool win_valid[2] = {false, false};
 };
 
-static bool make_program(const Packed& P, TcProgram& prog, std::string& err) {
-  if (P.ops.size() > (size_t)MAX_OPS || P.imgs.size() > (size_t)MAX_IMG) { err = "tensor-core engine: layer program too long"; return false; }
+// Merges the per-slot op lists into the pair program: bursts (issuer / producer) and steps (compute warps).
+static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::string& err) {
   memset(&prog, 0, sizeof prog);
-  prog.n_ops = (int)P.ops.size();
-  prog.n_img = (int)P.imgs.size();
-  std::copy(P.ops.begin(), P.ops.end(), prog.ops);
-  std::copy(P.imgs.begin(), P.imgs.end(), prog.img);
-  for (int i = 0; i + 1 < prog.n_img; ++i)
-    if (prog.img[i].flags & IMG_TWO_TERMS) {
-      if (prog.img[i + 1].flags & IMG_LAST) prog.img[i].flags |= IMG_PAIR_LAST;
-      if (prog.img[i + 1].flags & IMG_PART_NEXT) prog.img[i].flags |= IMG_PAIR_PART_NEXT;
+  const int n_ops = full ? (int)LB.ops[0].size() : LB.n_sigma;
+  if (2 * n_ops > MAX_OPS) { err = "tensor-core engine: too many layers"; return false; }
+  prog.n_ops = 2 * n_ops;
+  prog.full = full ? 1 : 0;
+  prog.f_col_ident = LB.F.col_ident; prog.f_col_bands = LB.F.col_bands; prog.f_kmin = LB.F.kmin; prog.f_nb = LB.F.nb;
+  prog.f_col_wembed = LB.F.col_wembed; prog.f_col_membed = LB.F.col_membed; prog.f_col_mask = LB.F.col_mask;
+  prog.f_cols = LB.F.cols; prog.t_cols = LB.t_cols;
+  std::vector<Burst> bursts;
+  std::vector<Step> steps;
+  auto op_index = [&](int s, int i) { return s * n_ops + i; };
+  for (int s = 0; s < 2; ++s)
+    for (int i = 0; i < n_ops; ++i) {
+      OpBuild ob = LB.ops[s][i];
+      if (!full && i == n_ops - 1) ob.signal_glue = 0;      // nothing follows the sigma head
+      prog.ops[op_index(s, i)] = make_tcop(ob, LB.weights[i]);
     }
+  auto step_of = [&](int s, int i) {
+    Step st;
+    st.kind = LB.ops[s][i].epi_kind == EPI_HEAD ? STEP_HEAD : STEP_EPI;
+    st.tslot = (uint8_t)s; st.op = (uint8_t)op_index(s, i); st.arg = 0;
+    return st;
+  };
+  // ---- N phase: both tile slots op by op; slot 0 acquires the weights, slot 1 releases them
+  int cursor = 0;
+  for (int i = 0; i < LB.n_narrow; ++i) {
+    std::vector<Burst> b0 = make_bursts(LB.ops[0][i], LB.weights[i]);
+    std::vector<Burst> b1 = make_bursts(LB.ops[1][i], LB.weights[i]);
+    if ((int)b0.size() > NUNIT - 1) { err = "tensor-core engine: narrow layer with too many K-chunks for the weight ring"; return false; }
+    for (size_t j = 0; j < b0.size(); ++j) {
+      b0[j].unit = b1[j].unit = (uint8_t)cursor;
+      cursor = (cursor + 1) % NUNIT;
+      b0[j].flags |= B_ACQUIRE;
+      b1[j].flags |= B_RELEASE;
+    }
+    bursts.insert(bursts.end(), b0.begin(), b0.end());
+    bursts.insert(bursts.end(), b1.begin(), b1.end());
+    steps.push_back(step_of(0, i));
+    steps.push_back(step_of(1, i));
+  }
+  // ---- T phase: tile slot 0, then tile slot 1
+  for (int s = 0; s < 2; ++s) {
+    Step v; v.kind = STEP_VIEW; v.tslot = (uint8_t)s; v.op = 0; v.arg = 0;
+    steps.push_back(v);
+    int prep_next = 0;
+    for (int i = LB.n_narrow; i < n_ops; ++i) {
+      std::vector<Burst> b = make_bursts(LB.ops[s][i], LB.weights[i]);
+      for (auto& e : b) {
+        e.unit = (uint8_t)cursor;
+        cursor = (cursor + 1) % NUNIT;
+        e.flags |= B_ACQUIRE | B_RELEASE;
+      }
+      bursts.insert(bursts.end(), b.begin(), b.end());
+      steps.push_back(step_of(s, i));
+      // the input block of this tile slot is free once the skip layer (or layer 0) has consumed it: write the
+      // next pair's features into it, one part per following layer
+      if (i >= LB.trunk_skip_op && prep_next < NPREP) {
+        Step p; p.kind = STEP_PREP; p.tslot = (uint8_t)s; p.op = 0; p.arg = (uint8_t)prep_next++;
+        steps.push_back(p);
+      }
+    }
+    for (; prep_next < NPREP; ++prep_next) {
+      Step p; p.kind = STEP_PREP; p.tslot = (uint8_t)s; p.op = 0; p.arg = (uint8_t)prep_next;
+      steps.push_back(p);
+    }
+    Step o; o.kind = STEP_OUT; o.tslot = (uint8_t)s; o.op = 0; o.arg = 0;
+    steps.push_back(o);
+  }
+  if ((int)bursts.size() > MAX_BURST || (int)steps.size() > MAX_STEPS) { err = "tensor-core engine: layer program too long"; return false; }
+  // ring safety: a unit is re-acquired only if its previous occupant was released at least two bursts earlier
+  // (the issuer waits for burst i + 1's weights in the middle of burst i)
+  {
+    const int n = (int)bursts.size();
+    std::vector<int> released(NUNIT, -1000000);
+    std::vector<int> held(NUNIT, 0);
+    for (int it = 0; it < 2; ++it)
+      for (int i = 0; i < n; ++i) {
+        const Burst& e = bursts[i];
+        const int gi = it * n + i;
+        if (e.flags & B_ACQUIRE) {
+          if (held[e.unit] || released[e.unit] > gi - 2) { err = "tensor-core engine: weight ring too small for this layer program"; return false; }
+          held[e.unit] = 1;
+        } else if (!held[e.unit]) { err = "tensor-core engine: internal ring schedule error"; return false; }
+        if (e.flags & B_RELEASE) { held[e.unit] = 0; released[e.unit] = gi; }
+      }
+  }
+  prog.n_burst = (int)bursts.size();
+  prog.n_steps = (int)steps.size();
+  std::copy(bursts.begin(), bursts.end(), prog.burst);
+  std::copy(steps.begin(), steps.end(), prog.steps);
   return true;
 }
 
 std::string tc_engine_supports(const ndsr_config& c, int cc_major, int cc_minor) {
   if (cc_major != 10) return "needs an sm_100-class device (tcgen05)";
+  if (!c.use_warp) return "the tensor-core engine is built for models with an SE(3) warp field";
   if (c.rgb_depth != 1) return "rgb branch depth must be 1";
   if (!c.use_viewdirs) return "the rgb branch without viewdirs is not built";
   if (c.trunk_width != 256 || c.rgb_width != 128) return "the tensor-core rgb branch is built for trunk width 256 / rgb width 128";
-  const int widths[] = {c.trunk_width, c.rgb_width, c.use_warp ? c.warp_width : 64,
-                        c.use_hyper_sheet ? c.hyper_sheet_width : 64, c.use_predicted_mask ? c.mask_width : 64};
-  for (int w : widths) if (w != 64 && w != 128 && w != 256) return "MLP widths must be 64, 128 or 256";
+  if (c.trunk_depth < 2) return "trunk depth must be >= 2";
+  const int widths[] = {c.warp_width, c.use_hyper_sheet ? c.hyper_sheet_width : 64, c.use_predicted_mask ? c.mask_width : 64};
+  for (int w : widths) if (w != 64 && w != 128) return "warp / hyper-sheet / mask MLP widths must be 64 or 128";
   (void)cc_minor;
   return "";
 }
 
-static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
+static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
   const ndsr_config& c = h->cfg;
   const HostModel& HM = h->host_model;
   const int prec = c.precision;
@@ -928,73 +1252,129 @@ static int build_level(ndsr_handle* h, int lv, Packed& P, int& n_sigma) {
   if (prec == NDSR_PREC_SPLIT3) { h->err = "tensor-core engine: split3 precision on the rgb branch is not built (use mixed)"; return NDSR_ERR_UNSUPPORTED; }
   if (h->max_in > 64) { h->err = "tensor-core engine: MLP inputs wider than 64 features"; return NDSR_ERR_UNSUPPORTED; }
   if (h->dim_view + (c.predict_norm ? h->dim_norm : 0) > 64) { h->err = "tensor-core engine: rgb side inputs wider than 64"; return NDSR_ERR_UNSUPPORTED; }
-  if (c.use_predicted_mask) build_head_op({&HM.mask.logit}, build_mlp_ops(HM.mask, t_sigma, P), t_sigma, GLUE_MASK, P);
-  if (c.use_warp) build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, P), t_sigma, GLUE_WARP, P);
-  if (c.use_hyper_sheet) build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, P), t_sigma, GLUE_HYPER, P);
-  const ActLayout trunk = build_mlp_ops(HM.trunk[lv], t_sigma, P);
-  build_head_op({&HM.alpha[lv]}, trunk, t_sigma, GLUE_ALPHA, P);
-  n_sigma = (int)P.ops.size();
-  h->tc->n_img_sigma[lv] = (int)P.imgs.size();
-  // ---- rgb branch (modules.py:288-313).  Flax input order:
-  //   [bottleneck (W) | viewdir feats | trunk_out (W, App. C-1) | norm feats]
-  // trunk_out stays in its region T; everything else happens in the other region B (256 columns):
-  //   bottleneck   accumulates into B (two chunks of 128 columns), epilogue compacts its hi halves to the first
-  //                64 columns of each chunk;
-  //   rgb hidden   accumulates into the freed second halves (two chunks of 64 columns), hi-only in place;
-  //   rgb head     accumulates into the first columns of T (trunk_out is dead by then: in-order MMA pipe).
-  const int W = c.trunk_width;
-  if (W != 256 || HM.rgb[lv].width != 128) { h->err = "tensor-core engine: the rgb branch is built for trunk 256 / rgb 128"; return NDSR_ERR_UNSUPPORTED; }
-  const int Tcol = trunk.region * (int)TM_REGION, Bcol = (1 - trunk.region) * (int)TM_REGION;
-  ActLayout bott{1 - trunk.region, W, 2, 1, {Bcol, Bcol + 128}};
+  // ---- shared feature block of the narrow networks
+  FLayout& F = LB.F;
   {
-    OpBuild ob;
-    ob.N_logical = ob.N = W;
-    ob.n_nc = 2; ob.d_col[0] = Bcol; ob.d_col[1] = Bcol + 128;
-    ob.terms = 1; ob.relu = 0; ob.epi_kind = EPI_COMPACT_HI; ob.glue = GLUE_BOTTLENECK;
-    ob.wait_glue = 1;     // the sigma/normal head's accumulators (in B) must have been consumed
-    ob.prev_produces = 0;
-    ob.W = HM.bottleneck[lv].W; ob.b = HM.bottleneck[lv].b;
-    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, 0, false));
-    pack_op(ob, P);
+    int kmin = c.warp_min_deg, kmax = c.warp_max_deg;
+    if (c.use_hyper_sheet) { kmin = std::min(kmin, c.hyper_sheet_min_deg); kmax = std::max(kmax, c.hyper_sheet_max_deg); }
+    if (c.use_predicted_mask) { kmin = std::min(kmin, c.mask_min_deg); kmax = std::max(kmax, c.mask_max_deg); }
+    int col = 0;
+    if (c.warp_use_posenc_identity) { F.col_ident = col; col += 3; }
+    F.col_bands = col; F.kmin = kmin; F.nb = kmax - kmin; col += 6 * F.nb;
+    F.col_wembed = col; col += c.warp_embed_dims;
+    if (c.use_predicted_mask) { F.col_membed = col; col += c.mask_embed_dims; }
+    if ((c.use_mask_in_warp) || (c.use_hyper_sheet && c.use_mask_in_hyper)) { F.col_mask = col; col += 1; }
+    F.cols = col;
+    if (col > 64) { h->err = "tensor-core engine: shared feature block wider than 64 columns"; return NDSR_ERR_UNSUPPORTED; }
   }
-  ActLayout rgbh{1 - trunk.region, 128, 2, 0, {Bcol + 64, Bcol + 192}};
-  {
-    const HostMlp& R = HM.rgb[lv];
-    OpBuild ob;
-    ob.N_logical = ob.N = R.width;
-    ob.n_nc = 2; ob.d_col[0] = rgbh.d_col[0]; ob.d_col[1] = rgbh.d_col[1];
-    ob.terms = 1; ob.relu = 1; ob.epi_kind = EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.wait_glue = 0; ob.prev_produces = 1;
-    ob.W = R.hidden[0].W; ob.b = R.hidden[0].b;
-    int row = W;
-    const int v0 = row;
-    row += h->dim_view;
-    int x0 = -1;
-    if (c.use_x_in_rgb_condition) { x0 = row; row += W; }
-    const int n0 = row;
-    const int ndim = c.predict_norm ? h->dim_norm : 0;
-    // the accumulators overwrite the second halves of the bottleneck chunks: every image waits for the compaction
-    if (x0 >= 0) for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, x0, false));   // trunk_out
-    if (h->dim_view + ndim > 0) {
-      KChunkMap k = kc_input(0, 0);
-      for (int cidx = 0; cidx < 64; ++cidx) {
-        if (cidx < h->dim_view) k.rows[cidx] = v0 + cidx;
-        else if (cidx < h->dim_view + ndim) k.rows[cidx] = n0 + (cidx - h->dim_view);
-        else k.rows[cidx] = -1;
-      }
-      ob.kcs.push_back(k);
+  LB.t_cols = h->dim_trunk_in;
+  for (int s = 0; s < 2; ++s) {
+    std::vector<OpBuild>& ops = LB.ops[s];
+    const uint32_t in_off = OFF_IN + (uint32_t)s * 2u * KBLK;
+    bool first_net = true;
+    auto first_flags = [&]() {
+      uint16_t f = first_net ? (uint16_t)(B_WAIT_PREP | (s == 0 ? B_WAIT_DONE_OTHER : 0)) : (uint16_t)B_WAIT_GLUE;
+      first_net = false;
+      return f;
+    };
+    if (c.use_predicted_mask) {
+      const KChunkMap k0 = kc_features(F, in_off, 0, 0, c.mask_min_deg, c.mask_max_deg, 0, F.col_membed, c.mask_embed_dims, false);
+      const KChunkMap ks = kc_features(F, in_off, HM.mask.width, 0, c.mask_min_deg, c.mask_max_deg, 0, F.col_membed, c.mask_embed_dims, false);
+      build_head_op({&HM.mask.logit}, build_mlp_ops(HM.mask, t_sigma, false, s, k0, ks, first_flags(), ops), t_sigma, GLUE_MASK, false, s, 1, ops);
     }
-    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(bott, j, 0, true));                   // bottleneck
-    if ((int)ob.kcs.size() > MAX_KC) { h->err = "tensor-core engine: rgb input too wide"; return NDSR_ERR_UNSUPPORTED; }
-    pack_op(ob, P);
-    // head over the rgb hidden layer; accumulators at the start of T
-    OpBuild hb;
-    hb.N_logical = R.logit.N;
-    hb.N = 16; hb.n_nc = 1; hb.d_col[0] = hb.d_col[1] = Tcol;
-    hb.terms = 1; hb.relu = 0; hb.epi_kind = EPI_HEAD; hb.glue = GLUE_RGB; hb.wait_glue = 0; hb.prev_produces = 1;
-    hb.W = R.logit.W; hb.b = R.logit.b;
-    for (int j = 0; j < R.width / 64; ++j) hb.kcs.push_back(kc_hidden(rgbh, j, 0, true));
-    pack_op(hb, P);
+    if (c.use_hyper_sheet) {
+      const bool wm = c.use_mask_in_hyper != 0;
+      const KChunkMap k0 = kc_features(F, in_off, 0, 2, c.hyper_sheet_min_deg, c.hyper_sheet_max_deg, 0, F.col_wembed, c.warp_embed_dims, wm);
+      const KChunkMap ks = kc_features(F, in_off, HM.hyper.width, 2, c.hyper_sheet_min_deg, c.hyper_sheet_max_deg, 0, F.col_wembed, c.warp_embed_dims, wm);
+      build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, false, s, k0, ks, first_flags(), ops), t_sigma, GLUE_HYPER, false, s, 1, ops);
+    }
+    {
+      const bool wm = c.use_mask_in_warp != 0;
+      const KChunkMap k0 = kc_features(F, in_off, 0, 1, c.warp_min_deg, c.warp_max_deg, c.warp_use_posenc_identity, F.col_wembed, c.warp_embed_dims, wm);
+      const KChunkMap ks = kc_features(F, in_off, HM.warp.width, 1, c.warp_min_deg, c.warp_max_deg, c.warp_use_posenc_identity, F.col_wembed, c.warp_embed_dims, wm);
+      build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, false, s, k0, ks, first_flags(), ops), t_sigma, GLUE_WARP, false, s, 1, ops);
+    }
+    LB.n_narrow = (int)ops.size();
+    // ---- template NeRF
+    LB.trunk_first = (int)ops.size();
+    const HostMlp& TR = HM.trunk[lv];
+    LB.trunk_skip_op = LB.trunk_first + (TR.skip > 0 ? TR.skip : 0);
+    const KChunkMap t0 = kc_input(in_off, 0, TR.in_dim), tsk = kc_input(in_off, TR.width, TR.in_dim);
+    const uint16_t tflags = (uint16_t)(B_WAIT_GLUE | (s == 1 ? B_WAIT_DONE_OTHER : 0));
+    const ActLayout trunk = build_mlp_ops(TR, t_sigma, true, s, t0, tsk, tflags, ops);
+    build_head_op({&HM.alpha[lv]}, trunk, t_sigma, GLUE_ALPHA, true, s, 1, ops);
+    LB.n_sigma = (int)ops.size();
+    // ---- rgb branch (modules.py:288-313).  Flax input order:
+    //   [bottleneck (W) | viewdir feats | trunk_out (W, App. C-1) | norm feats]
+    // trunk_out stays in its region T; everything else happens in the other region B (256 columns):
+    //   bottleneck   accumulates into B (two chunks of 128 columns), epilogue compacts its hi halves to the first
+    //                64 columns of each chunk;
+    //   rgb hidden   accumulates into the freed second halves (two chunks of 64 columns), hi-only in place;
+    //   rgb head     accumulates into the first columns of T (trunk_out is dead by then: in-order MMA pipe).
+    const int W = c.trunk_width;
+    if (W != 256 || HM.rgb[lv].width != 128) { h->err = "tensor-core engine: the rgb branch is built for trunk 256 / rgb 128"; return NDSR_ERR_UNSUPPORTED; }
+    const int Tcol = trunk.region * 256, Bcol = (1 - trunk.region) * 256;
+    ActLayout bott;
+    bott.N = W; bott.n_nc = 2; bott.compact_hi = 1; bott.d_col[0] = Bcol; bott.d_col[1] = Bcol + 128; bott.region = 1 - trunk.region;
+    {
+      OpBuild ob;
+      ob.N_logical = ob.N = W;
+      ob.tslot = s;
+      ob.n_nc = 2; ob.d_col[0] = Bcol; ob.d_col[1] = Bcol + 128;
+      ob.terms = 1; ob.relu = 0; ob.epi_kind = EPI_COMPACT_HI; ob.glue = GLUE_BOTTLENECK;
+      ob.first_flags = B_WAIT_GLUE;     // the sigma/normal head's accumulators (in B) must have been consumed
+      ob.prev_produces = 0;
+      ob.W = &HM.bottleneck[lv].W; ob.b = &HM.bottleneck[lv].b;
+      for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, 0, false));
+      ops.push_back(ob);
+    }
+    ActLayout rgbh;
+    rgbh.N = 128; rgbh.n_nc = 2; rgbh.d_col[0] = Bcol + 64; rgbh.d_col[1] = Bcol + 192; rgbh.region = 1 - trunk.region;
+    {
+      const HostMlp& R = HM.rgb[lv];
+      OpBuild ob;
+      ob.N_logical = ob.N = R.width;
+      ob.tslot = s;
+      ob.n_nc = 2; ob.d_col[0] = rgbh.d_col[0]; ob.d_col[1] = rgbh.d_col[1];
+      ob.terms = 1; ob.relu = 1; ob.epi_kind = EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.prev_produces = 1;
+      // the accumulators overwrite the second halves of both bottleneck chunks: wait for the compaction
+      ob.first_part_waits = 3;
+      ob.W = &R.hidden[0].W; ob.b = &R.hidden[0].b;
+      int row = W;
+      const int v0 = row;
+      row += h->dim_view;
+      int x0 = -1;
+      if (c.use_x_in_rgb_condition) { x0 = row; row += W; }
+      const int n0 = row;
+      const int ndim = c.predict_norm ? h->dim_norm : 0;
+      if (x0 >= 0) for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, x0, false));   // trunk_out
+      for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(bott, j, 0, true));                   // bottleneck
+      if (h->dim_view + ndim > 0) {                      // side inputs last: the normal features arrive late
+        KChunkMap k = kc_input(OFF_IN2, 0, 0);
+        for (int cidx = 0; cidx < 64; ++cidx) {
+          if (cidx < h->dim_view) k.rows[cidx] = v0 + cidx;
+          else if (cidx < h->dim_view + ndim) k.rows[cidx] = n0 + (cidx - h->dim_view);
+          else k.rows[cidx] = -1;
+        }
+        ob.kcs.push_back(k);
+      }
+      if ((int)ob.kcs.size() > MAX_KC) { h->err = "tensor-core engine: rgb input too wide"; return NDSR_ERR_UNSUPPORTED; }
+      ops.push_back(ob);
+      // head over the rgb hidden layer; accumulators at the start of T
+      OpBuild hb;
+      hb.N_logical = R.logit.N;
+      hb.tslot = s;
+      hb.N = 16; hb.n_nc = 1; hb.d_col[0] = hb.d_col[1] = Tcol;
+      hb.terms = 1; hb.relu = 0; hb.epi_kind = EPI_HEAD; hb.glue = GLUE_RGB; hb.prev_produces = 1; hb.signal_glue = 0;
+      hb.W = &R.logit.W; hb.b = &R.logit.b;
+      for (int j = 0; j < R.width / 64; ++j) hb.kcs.push_back(kc_hidden(rgbh, j, 0, true));
+      ops.push_back(hb);
+    }
+    fix_own(ops);
   }
+  // (the rgb hidden layer's side-input K-chunk needs no wait of its own: the bottleneck's first burst, issued
+  // before it, already consumed the glue phase of the sigma/normal head)
+  for (size_t i = 0; i < LB.ops[0].size(); ++i) LB.weights.push_back(pack_weights(LB.ops[0][i], P));
   return NDSR_OK;
 }
 
@@ -1003,11 +1383,12 @@ int tc_engine_load(ndsr_handle* h) {
   TcEngine* E = new TcEngine();
   h->tc = E;
   for (int lv = 0; lv < 2; ++lv) {
-    int rc = build_level(h, lv, E->packed[lv], E->n_ops_sigma[lv]);
+    int rc = build_level(h, lv, E->lb[lv], E->packed[lv]);
     if (rc) return rc;
     Packed& P = E->packed[lv];
+    for (int full = 0; full < 2; ++full)
+      if (!assemble(E->lb[lv], full != 0, E->prog[lv][full], h->err)) return NDSR_ERR_UNSUPPORTED;
     cudaError_t e;
-    if (!make_program(P, E->prog[lv], h->err)) return NDSR_ERR_UNSUPPORTED;
     if ((e = cudaMalloc(&E->d_stream[lv], P.stream.size())) != cudaSuccess ||
         (e = cudaMalloc(&E->d_bias[lv], P.bias.size() * sizeof(float))) != cudaSuccess ||
         (e = cudaMemcpy(E->d_stream[lv], P.stream.data(), P.stream.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -1015,6 +1396,9 @@ int tc_engine_load(ndsr_handle* h) {
       h->err = std::string("tc_engine_load: ") + cudaGetErrorString(e);
       return NDSR_ERR_CUDA;
     }
+    // the streams were packed with unit windows
+    for (int p = 0; p < 3; ++p) for (int k = 0; k < NDSR_MAX_BANDS; ++k) E->win[lv][p][k] = 1.f;
+    E->win_valid[lv] = true;
   }
   cudaError_t e = cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
   if (e != cudaSuccess) { h->err = std::string("tc smem attribute: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
@@ -1031,13 +1415,39 @@ void tc_engine_free(ndsr_handle* h) {
   h->tc = nullptr;
 }
 
+// The posenc windows of the narrow networks (model_utils.py:419-436) scale features of the shared block, which
+// all three networks read: they are folded into the first-layer / skip-layer weight images instead.  Re-packs
+// those images (a few 16 KB tiles) when the windows of this call differ from the ones in the stream.
+static int fold_windows(ndsr_handle* h, int lv, const CallParams& cp, cudaStream_t st) {
+  TcEngine* E = h->tc;
+  const PosencSpec* pes[3] = {&cp.pe_mask, &cp.pe_warp, &cp.pe_hsheet};
+  bool same = E->win_valid[lv];
+  for (int p = 0; p < 3 && same; ++p)
+    for (int k = 0; k < NDSR_MAX_BANDS; ++k) if (E->win[lv][p][k] != pes[p]->window[k]) { same = false; break; }
+  if (same) return NDSR_OK;
+  Packed& P = E->packed[lv];
+  for (const WindowedImage& wi : P.windowed) {
+    float colscale[64];
+    for (int c = 0; c < 64; ++c) colscale[c] = wi.band[c] >= 0 ? pes[wi.pe]->window[wi.band[c]] : 1.f;
+    const size_t bytes = (size_t)wi.rows * 128 * (wi.terms == 3 ? 2 : 1);
+    write_image(&P.stream[wi.stream_off], wi.w.data(), colscale, wi.rows, wi.terms);
+    cudaError_t e = cudaMemcpyAsync(E->d_stream[lv] + wi.stream_off, &P.stream[wi.stream_off], bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { h->err = std::string("fold_windows: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
+  }
+  for (int p = 0; p < 3; ++p) for (int k = 0; k < NDSR_MAX_BANDS; ++k) E->win[lv][p][k] = pes[p]->window[k];
+  E->win_valid[lv] = true;
+  return NDSR_OK;
+}
+
 int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, cudaStream_t st) {
   TcEngine* E = h->tc;
   if (!E) { h->err = "tensor-core engine not loaded"; return NDSR_ERR_NOT_LOADED; }
+  const int64_t tiles = (fa.n_samples_total + TM - 1) / TM;
+  if (tiles == 0) return NDSR_OK;
+  int rc = fold_windows(h, fa.level, cp, st);
+  if (rc) return rc;
   TcKernelArgs K;
-  TcProgram& prog = E->prog[fa.level];
-  prog.n_ops = fa.sigma_only ? E->n_ops_sigma[fa.level] : (int)E->packed[fa.level].ops.size();
-  prog.n_img = fa.sigma_only ? E->n_img_sigma[fa.level] : (int)E->packed[fa.level].imgs.size();
+  const TcProgram& prog = E->prog[fa.level][fa.sigma_only ? 0 : 1];
   K.lvl.weights = E->d_stream[fa.level];
   K.lvl.bias = E->d_bias[fa.level];
   K.warp_embed = h->M.warp_embed;
@@ -1048,29 +1458,33 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
     cudaMalloc(&K.trace, TRACE_WORDS * sizeof(unsigned long long));
     cudaMemsetAsync(K.trace, 0, TRACE_WORDS * sizeof(unsigned long long), st);
   }
-  const int64_t tiles = (fa.n_samples_total + TM - 1) / TM;
-  if (tiles == 0) return NDSR_OK;
-  int grid = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  const int64_t pairs = (tiles + 1) / 2;
+  int grid = (int)(pairs < h->num_sms ? pairs : h->num_sms);
   if (const char* g = getenv("NDS_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // experiments
   field_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(prog, K, cp, fa, h->cfg);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string("field_tc_kernel launch: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
-  if (K.trace) {   // diagnostics only: synchronous dump of the stamps, relative to the tile start
+  if (K.trace) {   // diagnostics only: synchronous dump of the stamps, relative to the pair start
     std::vector<unsigned long long> t(TRACE_WORDS);
     cudaStreamSynchronize(st);
     cudaMemcpy(t.data(), K.trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(K.trace);
-    const unsigned long long t0 = t[2 * MAX_IMG + 4 * MAX_OPS];
+    const unsigned long long t0 = t[3 * MAX_BURST + 2 * MAX_STEPS];
     if (FILE* f = fopen(trace_path, "w")) {
       auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1LL; };
-      for (int i = 0; i < prog.n_img; ++i)
-        fprintf(f, "img %d rows %d steps %d flags %d ready %lld issued %lld top %lld waited %lld\n", i, prog.img[i].rows,
-                prog.img[i].steps, prog.img[i].flags, rel(t[i]), rel(t[MAX_IMG + i]), rel(t[TRACE_X + i]),
-                rel(t[TRACE_X + MAX_IMG + i]));
-      for (int i = 0; i < prog.n_ops; ++i)
-        fprintf(f, "op %d N %d kind %d glue %d c0_seen %lld c0_done %lld c1_seen %lld c1_done %lld\n", i, prog.ops[i].N,
-                prog.ops[i].epi_kind, prog.ops[i].glue, rel(t[2 * MAX_IMG + 4 * i]), rel(t[2 * MAX_IMG + 4 * i + 1]),
-                rel(t[2 * MAX_IMG + 4 * i + 2]), rel(t[2 * MAX_IMG + 4 * i + 3]));
+      for (int i = 0; i < prog.n_burst; ++i) {
+        const Burst& b = prog.burst[i];
+        fprintf(f, "burst %d slot %d rows %d steps %d pat %d flags %d unit %d dcol %d top %lld ready %lld issued %lld\n", i,
+                b.tslot, b.rows, b.steps, b.pat, b.flags, b.unit, b.d_col, rel(t[i]), rel(t[MAX_BURST + i]),
+                rel(t[2 * MAX_BURST + i]));
+      }
+      for (int i = 0; i < prog.n_steps; ++i) {
+        const Step& s = prog.steps[i];
+        const TcOp& op = prog.ops[s.op];
+        fprintf(f, "step %d kind %d slot %d op %d N %d glue %d arg %d start %lld end %lld\n", i, s.kind, s.tslot, s.op,
+                (s.kind <= STEP_HEAD) ? op.N : 0, (s.kind <= STEP_HEAD) ? op.glue : 0, s.arg,
+                rel(t[3 * MAX_BURST + 2 * i]), rel(t[3 * MAX_BURST + 2 * i + 1]));
+      }
       fclose(f);
     }
   }
@@ -1096,28 +1510,36 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   const bool head = out_kind == 1;
   if (head && n_out > 16) return NDSR_ERR_INVALID;
   if (out_kind == 5 && n_out != 256) return NDSR_ERR_INVALID;
+  std::vector<float> Wv(W, W + (size_t)(k_hid + k_in) * n_out), bv(bias, bias + n_out);
   OpBuild ob;
   ob.N_logical = n_out;
   ob.N = head ? 16 : (n_out <= 64 ? 64 : (n_out <= 128 ? 128 : 256));
-  ob.n_nc = head ? 1 : chunks_for(ob.N);
-  ob.d_col[0] = (int)TM_REGION; ob.d_col[1] = (int)TM_REGION + (head ? 0 : 128);
-  ob.terms = terms; ob.relu = relu; ob.glue = GLUE_SELFTEST; ob.wait_glue = 1; ob.prev_produces = 1;
+  ob.n_nc = head ? 1 : (ob.N >= 256 ? 2 : 1);
+  ob.interleave = 1;
+  ob.d_col[0] = 256; ob.d_col[1] = 256 + (ob.n_nc == 2 ? 128 : 0);
+  ob.terms = terms; ob.relu = relu; ob.glue = GLUE_SELFTEST; ob.first_flags = B_WAIT_GLUE; ob.prev_produces = 1;
   ob.epi_kind = head ? EPI_HEAD : (out_kind == 2 ? EPI_INPLACE_HI : (out_kind == 5 ? EPI_COMPACT_HI : EPI_INPLACE));
-  const int K = k_hid + k_in;
-  ob.W.assign(W, W + (size_t)K * n_out);
-  ob.b.assign(bias, bias + n_out);
-  if (k_in > 0) ob.kcs.push_back(kc_input(k_hid, k_in));
+  ob.W = &Wv; ob.b = &bv;
+  if (k_in > 0) ob.kcs.push_back(kc_input(OFF_IN, k_hid, k_in));
   if (k_hid > 0) {
-    const ActLayout in{0, k_hid, chunks_for(k_hid), 0, {0, 128}};
+    ActLayout in;
+    in.N = k_hid; in.n_nc = k_hid >= 256 ? 2 : 1; in.d_col[0] = 0; in.d_col[1] = 128;
     for (int j = 0; j < k_hid / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, true));
   }
   Packed P;
-  pack_op(ob, P);
-  uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;
-  const int N = P.ops[0].N;
+  const OpWeights ow = pack_weights(ob, P);
+  std::vector<Burst> bursts = make_bursts(ob, ow);
   static TcProgram prog;
-  std::string perr;
-  if (!make_program(P, prog, perr)) return NDSR_ERR_INVALID;
+  memset(&prog, 0, sizeof prog);
+  prog.n_ops = 1;
+  prog.ops[0] = make_tcop(ob, ow);
+  int cursor = 0;
+  for (auto& e : bursts) { e.unit = (uint8_t)cursor; cursor = (cursor + 1) % NUNIT; e.flags |= B_ACQUIRE | B_RELEASE; }
+  prog.n_burst = (int)bursts.size();
+  std::copy(bursts.begin(), bursts.end(), prog.burst);
+  uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;
+  const int N = prog.ops[0].N;
+  const int K = k_hid + k_in;
   cudaMalloc(&d_stream, P.stream.size()); cudaMalloc(&d_bias, P.bias.size() * 4);
   cudaMalloc(&d_A, (size_t)TM * K * 4); cudaMalloc(&d_out, (size_t)TM * N * 4); cudaMalloc(&d_rb, (size_t)TM * N * 4);
   cudaMemcpy(d_stream, P.stream.data(), P.stream.size(), cudaMemcpyHostToDevice);
