@@ -55,7 +55,7 @@ constexpr uint32_t OFF_RING = 5 * KBLK;
 constexpr uint32_t UNIT_BYTES = 32768;  // one ring unit: a B_hi image followed by its B_lo image (<= 2 x 16 KB)
 constexpr int NUNIT = 4;
 constexpr uint32_t OFF_CTRL = OFF_RING + NUNIT * UNIT_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 512 + 1024;   // + manual 1024-byte alignment slack
+constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 3072 + 1024;  // Ctrl + manual 1024-byte alignment slack
 constexpr int MAX_KC = 10;
 constexpr int NPREP = 3;                // the shared feature block of the next pair is written in 3 parts
 
@@ -95,20 +95,24 @@ enum BurstFlags : uint16_t {
   B_ACQUIRE = 2048,          // first use of a ring unit: wait for the TMA
   B_RELEASE = 4096           // last use: commit to the unit's empty barrier
 };
+constexpr uint16_t B_WAIT_ANY = B_WAIT_P0 | B_WAIT_P1 | B_WAIT_GLUE | B_PEEK_GLUE_OTHER | B_WAIT_PREP | B_WAIT_DONE_OTHER;
+// Device encoding, everything the issuer needs pre-computed (it is read as two uint4 from the constant bank):
 struct alignas(16) Burst {
-  uint32_t a_hi, a_lo;   // PAT_SS: byte offset from the (1024-aligned) smem base; else tensor-memory column
-  uint32_t src;          // weight stream offset of the unit's images, in 128-byte rows
-  uint16_t d_col;        // accumulator column
-  uint16_t rows;         // rows of the weight image = N of its MMAs (image bytes = rows * 128)
-  uint8_t steps;         // K-steps, 1..4
-  uint8_t pat;           // APattern
-  uint8_t unit;          // ring unit
-  uint8_t tslot;         // tile slot (barrier set)
-  uint16_t flags;
-  uint16_t rows128;      // 128-byte rows to load on B_ACQUIRE (rows, or 2 x rows for a 3-term burst)
-  uint32_t pad;
+  uint32_t a_hi, a_lo;   // PAT_SS: (byte offset from the 1024-aligned smem base) >> 4 | 1 << 16; else tensor-memory column
+  uint32_t d_col;        // accumulator column
+  uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = rows)
+  uint32_t b0, b1;       // B_hi / B_lo image: 16-byte units from the ring base
+  uint32_t ctl;          // [0,13) BurstFlags | [13,15) pat | [15,18) steps | [18] tile slot | [19,21) ring unit |
+                         // [21,24) 1 + ring unit the NEXT burst acquires (0: none) | [24] that next burst is burst 0
+  uint32_t src;          // [0,22) weight stream offset in 128-byte rows | [22,31) rows to load on B_ACQUIRE
 };
 static_assert(sizeof(Burst) == 32, "Burst is read as two uint4");
+// host-side description of a burst (encode_burst() makes the device form)
+struct BurstH {
+  uint32_t a_hi = 0, a_lo = 0, src = 0;
+  uint16_t d_col = 0, rows = 0, flags = 0, rows128 = 0;
+  uint8_t steps = 4, pat = 0, unit = 0, tslot = 0;
+};
 
 enum StepKind : uint8_t { STEP_EPI = 0, STEP_HEAD = 1, STEP_VIEW = 2, STEP_PREP = 3, STEP_OUT = 4 };
 struct Step { uint8_t kind, tslot, op, arg; };
@@ -146,6 +150,11 @@ struct Ctrl {
   uint64_t part[2][2];      // compute -> MMA: N-chunk c of the current op drained and re-written as operand
   uint64_t d_full[2][2];    // MMA -> compute: accumulators of N-chunk c complete
   uint32_t tmem_base;
+  uint32_t pad[3];
+  // the compute warps' view of the program, copied here once: a dynamically indexed constant-bank read costs a
+  // few hundred cycles, a shared-memory read ~30
+  TcOp ops[MAX_OPS];
+  Step steps[MAX_STEPS];
 };
 
 __device__ __forceinline__ void ctrl_init(Ctrl* ctl) {
@@ -184,151 +193,146 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
   return pred;
 }
 
-// One burst, issued by the elected thread in two halves so that the issuer can wait for the NEXT burst's weights
-// in between (tcgen05.mma issue blocks while the tensor core's queue, ~3 instructions deep, is full; whatever the
-// issuer does between two bursts must fit under that cover or the pipe drains):
+// K-step column offsets of a tensor-memory operand K-block, per pattern
+template <int PAT> struct KSteps;
+template <> struct KSteps<PAT_32> { static constexpr uint32_t s1 = 8, s2 = 32, s3 = 40; };
+template <> struct KSteps<PAT_16> { static constexpr uint32_t s1 = 16, s2 = 32, s3 = 48; };
+template <> struct KSteps<PAT_8> { static constexpr uint32_t s1 = 8, s2 = 16, s3 = 24; };
+
+// One burst is issued in two halves so that the issuer can wait for the NEXT burst's weights in between
+// (tcgen05.mma issue blocks while the tensor core's queue, ~3 instructions deep, is full; whatever the issuer
+// does between two bursts must fit under that cover or the pipe drains):
 //   half 0   D (+)= A_hi B_hi [; D += A_lo B_hi]           (1-term: K-steps 0, 1)
 //   half 1   [D += A_hi B_lo]                               (1-term: K-steps 2, 3)
-// a_hi / a_lo: tensor-memory addresses (pat != PAT_SS, K-step column offsets per pattern) or the low words of
-// shared-memory descriptors; b0 / b1: low descriptor words of the B_hi / B_lo images in the ring.
-__device__ __forceinline__ void issue_half(int half, bool two, uint32_t pat, uint32_t steps, uint32_t d, uint32_t a_hi,
+template <int PAT>
+__device__ __forceinline__ void issue_half_ts(int half, bool two, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t bd0,
+                                              uint64_t bd1, uint32_t idesc, uint32_t acc) {
+  using S = KSteps<PAT>;
+  if (two) {
+    if (half == 0) {
+      umma_f16_ts(d, a_hi, bd0, idesc, acc);
+      umma_f16_ts(d, a_hi + S::s1, bd0 + 2, idesc, 1u);
+      umma_f16_ts(d, a_hi + S::s2, bd0 + 4, idesc, 1u);
+      umma_f16_ts(d, a_hi + S::s3, bd0 + 6, idesc, 1u);
+      umma_f16_ts(d, a_lo, bd0, idesc, 1u);
+      umma_f16_ts(d, a_lo + S::s1, bd0 + 2, idesc, 1u);
+      umma_f16_ts(d, a_lo + S::s2, bd0 + 4, idesc, 1u);
+      umma_f16_ts(d, a_lo + S::s3, bd0 + 6, idesc, 1u);
+    } else {
+      umma_f16_ts(d, a_hi, bd1, idesc, 1u);
+      umma_f16_ts(d, a_hi + S::s1, bd1 + 2, idesc, 1u);
+      umma_f16_ts(d, a_hi + S::s2, bd1 + 4, idesc, 1u);
+      umma_f16_ts(d, a_hi + S::s3, bd1 + 6, idesc, 1u);
+    }
+  } else if (half == 0) {
+    umma_f16_ts(d, a_hi, bd0, idesc, acc);
+    umma_f16_ts(d, a_hi + S::s1, bd0 + 2, idesc, 1u);
+  } else {
+    umma_f16_ts(d, a_hi + S::s2, bd0 + 4, idesc, 1u);
+    umma_f16_ts(d, a_hi + S::s3, bd0 + 6, idesc, 1u);
+  }
+}
+__device__ __forceinline__ void issue_half_ss(int half, bool two, uint32_t steps, uint32_t d, uint64_t ad0, uint64_t ad1,
+                                              uint64_t bd0, uint64_t bd1, uint32_t idesc, uint32_t acc) {
+  if (two) {
+    if (half == 0) {
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc);
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u);
+    } else {
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u);
+    }
+  } else if (half == 0) {
+    umma_f16(d, ad0, bd0, idesc, acc);
+    if (steps > 1) umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
+  } else {
+    if (steps > 2) umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
+    if (steps > 3) umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+  }
+}
+__device__ __forceinline__ void issue_half(int half, uint32_t pat, bool two, uint32_t steps, uint32_t d, uint32_t a_hi,
                                            uint32_t a_lo, uint32_t b0, uint32_t b1, uint32_t idesc, uint32_t acc) {
   const uint64_t hi = (uint64_t)NDS_DESC_HI << 32;
   const uint64_t bd0 = hi | b0, bd1 = hi | b1;
-  if (pat != PAT_SS) {
-    // PAT_32: {0, 8, 32, 40}; PAT_16: {0, 16, 32, 48}; PAT_8: {0, 8, 16, 24}
-    const uint32_t s1 = pat == PAT_16 ? 16u : 8u, s2 = pat == PAT_8 ? 16u : 32u;
-    const uint32_t s3 = pat == PAT_32 ? 40u : (pat == PAT_16 ? 48u : 24u);
-    if (two) {
-      if (half == 0) {
-        umma_f16_ts(d, a_hi, bd0, idesc, acc);
-        umma_f16_ts(d, a_hi + s1, bd0 + 2, idesc, 1u);
-        umma_f16_ts(d, a_hi + s2, bd0 + 4, idesc, 1u);
-        umma_f16_ts(d, a_hi + s3, bd0 + 6, idesc, 1u);
-        umma_f16_ts(d, a_lo, bd0, idesc, 1u);
-        umma_f16_ts(d, a_lo + s1, bd0 + 2, idesc, 1u);
-        umma_f16_ts(d, a_lo + s2, bd0 + 4, idesc, 1u);
-        umma_f16_ts(d, a_lo + s3, bd0 + 6, idesc, 1u);
-      } else {
-        umma_f16_ts(d, a_hi, bd1, idesc, 1u);
-        umma_f16_ts(d, a_hi + s1, bd1 + 2, idesc, 1u);
-        umma_f16_ts(d, a_hi + s2, bd1 + 4, idesc, 1u);
-        umma_f16_ts(d, a_hi + s3, bd1 + 6, idesc, 1u);
-      }
-    } else if (half == 0) {
-      umma_f16_ts(d, a_hi, bd0, idesc, acc);
-      umma_f16_ts(d, a_hi + s1, bd0 + 2, idesc, 1u);
-    } else {
-      umma_f16_ts(d, a_hi + s2, bd0 + 4, idesc, 1u);
-      umma_f16_ts(d, a_hi + s3, bd0 + 6, idesc, 1u);
-    }
-  } else {
-    const uint64_t ad0 = hi | a_hi, ad1 = hi | a_lo;
-    if (two) {
-      if (half == 0) {
-#pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc);
-#pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u);
-      } else {
-#pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u);
-      }
-    } else if (half == 0) {
-      umma_f16(d, ad0, bd0, idesc, acc);
-      if (steps > 1) umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
-    } else {
-      if (steps > 2) umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
-      if (steps > 3) umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
-    }
-  }
+  if (pat == PAT_32) issue_half_ts<PAT_32>(half, two, d, a_hi, a_lo, bd0, bd1, idesc, acc);
+  else if (pat == PAT_16) issue_half_ts<PAT_16>(half, two, d, a_hi, a_lo, bd0, bd1, idesc, acc);
+  else if (pat == PAT_8) issue_half_ts<PAT_8>(half, two, d, a_hi, a_lo, bd0, bd1, idesc, acc);
+  else issue_half_ss(half, two, steps, d, hi | a_hi, hi | a_lo, bd0, bd1, idesc, acc);
 }
 
-__device__ __forceinline__ Burst load_burst(const TcProgram& P, int i) {
-  union { Burst b; uint4 q[2]; } u;
-  const uint4* src = reinterpret_cast<const uint4*>(&P.burst[i]);
-  u.q[0] = src[0];
-  u.q[1] = src[1];
-  return u.b;
-}
-
-// Issuer state: one parity bit per barrier it waits on.  bit s: part[s][*]; 2+s: glue[s]; 4+s: prep[s];
+// MMA issuer, run by ONE elected thread (the caller guards it with elect_one_sync(), which is what lets ptxas keep
+// the whole loop -- program decode, barrier waits, tcgen05 instructions -- on the uniform datapath).
+// `bits`: one parity bit per barrier the issuer waits on.  bit s: part[s][*]; 2+s: glue[s]; 4+s: prep[s];
 // 6+s: done[s]; 8+u: full[u].
-struct IssuerState { uint32_t bits; bool primed; };
-
-// MMA issuer: the whole warp walks the burst program of one pair in uniform control flow (operand arithmetic on
-// the uniform datapath); inside `if (elect_one_sync())` one thread issues the tcgen05 instructions.
 __device__ __forceinline__ void issue_program(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
-                                              uint32_t lane, IssuerState& st, bool more, unsigned long long* trace) {
+                                              uint32_t& bits_io, bool more, unsigned long long* trace) {
   const int n = P.n_burst;
-  const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING);
-  const bool tr = trace != nullptr && lane == 0;
-  uint32_t bits = st.bits;
-  Burst e = load_burst(P, 0);
-  if (!st.primed) {        // the very first burst of the kernel: nobody waited for its weights yet
-    if (e.flags & B_ACQUIRE) { mbar_wait(&ctl->full[e.unit], (bits >> (8 + e.unit)) & 1u); bits ^= 1u << (8 + e.unit); }
-    st.primed = true;
-  }
+  const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING), ss_base = smem_base >> 4;
+  uint32_t bits = bits_io;
+  // program entries are fetched one burst ahead: a constant-bank load with a dynamic index misses the small
+  // immediate-constant cache and costs a few hundred cycles, which must not sit between two bursts
+  uint4 q0 = *reinterpret_cast<const uint4*>(&P.burst[0]);
+  uint4 q1 = *(reinterpret_cast<const uint4*>(&P.burst[0]) + 1);
   for (int i = 0; i < n; ++i) {
-    const bool has_next = (i + 1 < n) || more;
-    const Burst nx = load_burst(P, (i + 1 < n) ? i + 1 : 0);
-    const uint32_t fl = e.flags, s = e.tslot, o = s ^ 1u;
-    if (tr) trace[i] = clock64();
-    if (fl & B_WAIT_PREP) { mbar_wait(&ctl->prep[s], (bits >> (4 + s)) & 1u); bits ^= 1u << (4 + s); }
-    if (fl & B_WAIT_DONE_OTHER) { mbar_wait(&ctl->done[o], (bits >> (6 + o)) & 1u); bits ^= 1u << (6 + o); }
-    if (fl & B_WAIT_GLUE) { mbar_wait(&ctl->glue[s], (bits >> (2 + s)) & 1u); bits ^= 1u << (2 + s); }
-    if (fl & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
-    if (fl & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
-    if (fl & B_WAIT_P1) mbar_wait(&ctl->part[s][1], (bits >> s) & 1u);
-    tc_fence_after_sync();
-    if (tr) trace[MAX_BURST + i] = clock64();
-    const bool two = (fl & B_TWO) != 0;
-    const bool ss = e.pat == PAT_SS;
-    const uint32_t b0 = ring_lo32 + (uint32_t)e.unit * (UNIT_BYTES >> 4), b1 = b0 + (uint32_t)e.rows * 8u;
-    const uint32_t a_hi = ss ? smem_desc_lo32(smem_base + e.a_hi) : tmem_base + e.a_hi;
-    const uint32_t a_lo = ss ? smem_desc_lo32(smem_base + e.a_lo) : tmem_base + e.a_lo;
-    const uint32_t d = tmem_base + e.d_col, idesc = make_idesc_f16(e.rows), acc = (fl & B_FIRST) ? 0u : 1u;
-    if (elect_one_sync()) issue_half(0, two, e.pat, e.steps, d, a_hi, a_lo, b0, b1, idesc, acc);
-    __syncwarp();
-    // the next burst's weights (in the ring long ago in steady state): waiting here, with the tensor core busy on
-    // half 0, keeps the ~90-cycle barrier round trip off the critical path.  Only ring waits may be hoisted:
-    // the producer never depends on anything this warp still has to issue.
-    if (has_next && (nx.flags & B_ACQUIRE)) {
-      mbar_wait(&ctl->full[nx.unit], (bits >> (8 + nx.unit)) & 1u);
-      bits ^= 1u << (8 + nx.unit);
+    const int ni = (i + 1 < n) ? i + 1 : 0;
+    const uint4 n0 = *reinterpret_cast<const uint4*>(&P.burst[ni]);
+    const uint4 n1 = *(reinterpret_cast<const uint4*>(&P.burst[ni]) + 1);
+    const uint32_t c = q1.z, fl = c & 0x1fffu, pat = (c >> 13) & 3u, steps = (c >> 15) & 7u, s = (c >> 18) & 1u;
+    const uint32_t unit = (c >> 19) & 3u, nu = (c >> 21) & 7u, wrap = (c >> 24) & 1u;
+    if (trace) trace[i] = clock64();
+    if (fl & B_WAIT_ANY) {
+      const uint32_t o = s ^ 1u;
+      if (fl & B_WAIT_PREP) { mbar_wait(&ctl->prep[s], (bits >> (4 + s)) & 1u); bits ^= 1u << (4 + s); }
+      if (fl & B_WAIT_DONE_OTHER) { mbar_wait(&ctl->done[o], (bits >> (6 + o)) & 1u); bits ^= 1u << (6 + o); }
+      if (fl & B_WAIT_GLUE) { mbar_wait(&ctl->glue[s], (bits >> (2 + s)) & 1u); bits ^= 1u << (2 + s); }
+      if (fl & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
+      if (fl & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
+      if (fl & B_WAIT_P1) mbar_wait(&ctl->part[s][1], (bits >> s) & 1u);
       tc_fence_after_sync();
     }
-    if (elect_one_sync()) {
-      issue_half(1, two, e.pat, e.steps, d, a_hi, a_lo, b0, b1, idesc, acc);
-      if (fl & B_RELEASE) umma_commit(&ctl->empty[e.unit]);
-      if (fl & B_LAST) umma_commit(&ctl->d_full[s][(fl & B_NC1) ? 1 : 0]);
+    if (trace) trace[MAX_BURST + i] = clock64();
+    const bool two = (fl & B_TWO) != 0;
+    const uint32_t abase = pat == PAT_SS ? ss_base : tmem_base;
+    const uint32_t a_hi = abase + q0.x, a_lo = abase + q0.y, d = tmem_base + q0.z, idesc = q0.w;
+    const uint32_t b0 = ring_lo32 + q1.x, b1 = ring_lo32 + q1.y, acc = (fl & B_FIRST) ? 0u : 1u;
+    issue_half(0, pat, two, steps, d, a_hi, a_lo, b0, b1, idesc, acc);
+    // the next burst's weights (in the ring long ago in steady state): waiting here, with the tensor core busy on
+    // half 0, keeps the barrier round trip off the critical path.  Only ring waits may be hoisted: the producer
+    // never depends on anything this thread still has to issue.
+    if (nu && (!wrap || more)) {
+      mbar_wait(&ctl->full[nu - 1], (bits >> (7 + nu)) & 1u);
+      bits ^= 1u << (7 + nu);
+      tc_fence_after_sync();
     }
-    __syncwarp();
-    if (tr) trace[2 * MAX_BURST + i] = clock64();
+    issue_half(1, pat, two, steps, d, a_hi, a_lo, b0, b1, idesc, acc);
+    if (fl & B_RELEASE) umma_commit(&ctl->empty[unit]);
+    if (fl & B_LAST) umma_commit(&ctl->d_full[s][(fl & B_NC1) ? 1 : 0]);
+    if (trace) trace[2 * MAX_BURST + i] = clock64();
     if (fl & B_PART_NEXT) bits ^= 1u << s;
-    e = nx;
+    q0 = n0;
+    q1 = n1;
   }
-  st.bits = bits;
+  bits_io = bits;
 }
 
-// TMA producer: streams the weight images of every acquiring burst of the program into the ring
+// TMA producer (one thread): streams the weight images of every acquiring burst of the program into the ring
 struct ProducerState { uint32_t ebits, filled; };
 __device__ __forceinline__ void produce_program(const TcProgram& P, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
-                                                bool leader, ProducerState& st) {
+                                                ProducerState& st) {
   for (int i = 0; i < P.n_burst; ++i) {
-    const Burst e = load_burst(P, i);
-    if (!(e.flags & B_ACQUIRE)) continue;
-    const uint32_t u = e.unit, bytes = (uint32_t)e.rows128 * 128u;
+    const uint32_t c = P.burst[i].ctl;
+    if (!(c & B_ACQUIRE)) continue;
+    const uint32_t sw = P.burst[i].src;
+    const uint32_t u = (c >> 19) & 3u, bytes = (sw >> 22) * 128u;
     if ((st.filled >> u) & 1u) {       // the previous fill of this unit has been consumed
       mbar_wait(&ctl->empty[u], (st.ebits >> u) & 1u);
       st.ebits ^= 1u << u;
     }
     st.filled |= 1u << u;
-    if (leader) {
-      mbar_arrive_expect_tx(&ctl->full[u], bytes);
-      tma_bulk_g2s(smem + OFF_RING + u * UNIT_BYTES, wstream + (size_t)e.src * 128u, bytes, &ctl->full[u]);
-    }
-    __syncwarp();
+    mbar_arrive_expect_tx(&ctl->full[u], bytes);
+    tma_bulk_g2s(smem + OFF_RING + u * UNIT_BYTES, wstream + (size_t)(sw & 0x3fffffu) * 128u, bytes, &ctl->full[u]);
   }
 }
 
@@ -497,6 +501,10 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
   // input blocks start as zeros: columns beyond the written features multiply zero weight rows, but 0 x garbage
   // could be NaN
   for (uint32_t i = threadIdx.x; i < OFF_RING / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < P.n_ops * (int)(sizeof(TcOp) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ctl->ops)[i] = reinterpret_cast<const uint32_t*>(P.ops)[i];
+  for (int i = threadIdx.x; i < P.n_steps; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ctl->steps)[i] = reinterpret_cast<const uint32_t*>(P.steps)[i];
   if (threadIdx.x == 0) ctrl_init(ctl);
   if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   fence_proxy_async_smem();
@@ -511,16 +519,24 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
 
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
-    ProducerState ps{0u, 0u};
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-      produce_program(P, L.weights, smem, ctl, lane == 0, ps);
+    if (lane == 0) {
+      ProducerState ps{0u, 0u};
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) produce_program(P, L.weights, smem, ctl, ps);
+    }
+    __syncwarp();
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
-    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);      // warp-uniform for the compiler
-    IssuerState is{0u, false};
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-      issue_program(P, smem_base, ctl, tb, (uint32_t)lane, is, pair + gridDim.x < n_pairs,
-                    (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
+    if (elect_one_sync()) {
+      uint32_t bits = 0;
+      {   // the very first burst of the kernel: nobody waited for its weights yet
+        const uint32_t c0 = P.burst[0].ctl, u0 = (c0 >> 19) & 3u;
+        if (c0 & B_ACQUIRE) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
+      }
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+        issue_program(P, smem_base, ctl, tmem_base, bits, pair + gridDim.x < n_pairs,
+                      (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
+    }
+    __syncwarp();
   } else {
     // ===================== compute warps =====================
     const int q = warp & 3, sub = warp >> 2;
@@ -598,7 +614,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
       unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 3 * MAX_BURST : nullptr;
       if (tr) tr[2 * MAX_STEPS] = clock64();
       for (int si = 0; si < P.n_steps; ++si) {
-        const Step sp = P.steps[si];
+        const Step sp = ctl->steps[si];
         const int s = sp.tslot;
         TileState& T = cur[s];
         uint8_t* blk = smem + OFF_IN + (uint32_t)s * 2u * KBLK;
@@ -606,7 +622,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         auto st_in2 = [&](int c, float v) { store_in_hi(smem + OFF_IN2, row, (uint32_t)c, v); };
         if (tr) tr[2 * si] = clock64();
         if (sp.kind == STEP_EPI) {
-          const TcOp& op = P.ops[sp.op];
+          const TcOp& op = ctl->ops[sp.op];
           for (int nc = 0; nc < op.n_nc; ++nc) {
             const uint32_t par = (dc >> (2 * s + nc)) & 1u;
             dc ^= 1u << (2 * s + nc);
@@ -615,7 +631,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
             if (op.n_nc == 1) warp_arrive(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
           }
         } else if (sp.kind == STEP_HEAD) {
-          const TcOp& op = P.ops[sp.op];
+          const TcOp& op = ctl->ops[sp.op];
           mbar_wait(&ctl->d_full[s][0], (dc >> (2 * s)) & 1u);
           dc ^= 1u << (2 * s);
           tc_fence_after_sync();
@@ -730,12 +746,19 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   const uint32_t tmem_base = ctl->tmem_base;
   const TcOp& op = P.ops[0];
   if (warp == WARP_TMA) {
-    ProducerState ps{0u, 0u};
-    produce_program(P, L.weights, smem, ctl, lane == 0, ps);
+    if (lane == 0) {
+      ProducerState ps{0u, 0u};
+      produce_program(P, L.weights, smem, ctl, ps);
+    }
+    __syncwarp();
   } else if (warp == WARP_MMA) {
-    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    IssuerState is{0u, false};
-    issue_program(P, smem_base, ctl, tb, (uint32_t)lane, is, false, nullptr);
+    if (elect_one_sync()) {
+      uint32_t bits = 0;
+      const uint32_t c0 = P.burst[0].ctl, u0 = (c0 >> 19) & 3u;
+      if (c0 & B_ACQUIRE) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
+      issue_program(P, smem_base, ctl, tmem_base, bits, false, nullptr);
+    }
+    __syncwarp();
   } else {
     const int q = warp & 3, sub = warp >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
@@ -1001,7 +1024,7 @@ static TcOp make_tcop(const OpBuild& ob, const OpWeights& ow) {
 }
 
 // bursts of one op of one tile slot, in issue order (ring flags / units are assigned by the assembler)
-static std::vector<Burst> make_bursts(const OpBuild& ob, const OpWeights& ow) {
+static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
   const int nc_rows = ob.N / ob.n_nc;
   const int n_kc = (int)ob.kcs.size();
   std::vector<std::pair<int, int>> order;
@@ -1013,15 +1036,14 @@ static std::vector<Burst> make_bursts(const OpBuild& ob, const OpWeights& ow) {
   } else {
     for (int nc = 0; nc < ob.n_nc; ++nc) for (int kc = 0; kc < n_kc; ++kc) order.push_back({nc, kc});
   }
-  std::vector<Burst> out;
+  std::vector<BurstH> out;
   int waited = 0;    // bit 0 / 1: part c, bit 2: glue (of the per-sample stage feeding a K-chunk)
   int seen[2] = {0, 0};
   int left[2] = {n_kc, n_kc};
   for (size_t i = 0; i < order.size(); ++i) {
     const int nc = order[i].first, kc = order[i].second;
     const KChunkMap& km = ob.kcs[kc];
-    Burst e;
-    memset(&e, 0, sizeof e);
+    BurstH e;
     e.a_hi = km.a_hi; e.a_lo = km.a_lo; e.pat = km.pat;
     e.rows = (uint16_t)nc_rows;
     int last = -1;
@@ -1048,6 +1070,29 @@ static std::vector<Burst> make_bursts(const OpBuild& ob, const OpWeights& ow) {
     out.push_back(e);
   }
   return out;
+}
+
+// device form of the bursts of a program; `next` links implement the issuer's mid-burst weight wait
+static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, Burst* out) {
+  const int n = (int)hb.size();
+  for (int i = 0; i < n; ++i) {
+    const BurstH& e = hb[i];
+    Burst b;
+    const bool ss = e.pat == PAT_SS;
+    b.a_hi = ss ? ((e.a_hi >> 4) | (1u << 16)) : e.a_hi;
+    b.a_lo = ss ? ((e.a_lo >> 4) | (1u << 16)) : e.a_lo;
+    b.d_col = e.d_col;
+    b.idesc = make_idesc_f16(e.rows);
+    b.b0 = (uint32_t)e.unit * (UNIT_BYTES >> 4);
+    b.b1 = b.b0 + (uint32_t)e.rows * 8u;
+    uint32_t nu = 0, wrap = 0;
+    if (i + 1 < n) { if (hb[i + 1].flags & B_ACQUIRE) nu = 1u + hb[i + 1].unit; }
+    else if (cyclic && (hb[0].flags & B_ACQUIRE)) { nu = 1u + hb[0].unit; wrap = 1; }
+    b.ctl = (uint32_t)(e.flags & 0x1fffu) | ((uint32_t)e.pat << 13) | ((uint32_t)e.steps << 15) | ((uint32_t)e.tslot << 18) |
+            ((uint32_t)e.unit << 19) | (nu << 21) | (wrap << 24);
+    b.src = (e.src & 0x3fffffu) | ((uint32_t)e.rows128 << 22);
+    out[i] = b;
+  }
 }
 
 // hidden stack of a modules.MLP: layer l reads [h (width) | inputs (in_dim) at the skip layer].
@@ -1146,7 +1191,7 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
   prog.f_col_ident = LB.F.col_ident; prog.f_col_bands = LB.F.col_bands; prog.f_kmin = LB.F.kmin; prog.f_nb = LB.F.nb;
   prog.f_col_wembed = LB.F.col_wembed; prog.f_col_membed = LB.F.col_membed; prog.f_col_mask = LB.F.col_mask;
   prog.f_cols = LB.F.cols; prog.t_cols = LB.t_cols;
-  std::vector<Burst> bursts;
+  std::vector<BurstH> bursts;
   std::vector<Step> steps;
   auto op_index = [&](int s, int i) { return s * n_ops + i; };
   for (int s = 0; s < 2; ++s)
@@ -1164,8 +1209,8 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
   // ---- N phase: both tile slots op by op; slot 0 acquires the weights, slot 1 releases them
   int cursor = 0;
   for (int i = 0; i < LB.n_narrow; ++i) {
-    std::vector<Burst> b0 = make_bursts(LB.ops[0][i], LB.weights[i]);
-    std::vector<Burst> b1 = make_bursts(LB.ops[1][i], LB.weights[i]);
+    std::vector<BurstH> b0 = make_bursts(LB.ops[0][i], LB.weights[i]);
+    std::vector<BurstH> b1 = make_bursts(LB.ops[1][i], LB.weights[i]);
     if ((int)b0.size() > NUNIT - 1) { err = "tensor-core engine: narrow layer with too many K-chunks for the weight ring"; return false; }
     for (size_t j = 0; j < b0.size(); ++j) {
       b0[j].unit = b1[j].unit = (uint8_t)cursor;
@@ -1184,7 +1229,7 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
     steps.push_back(v);
     int prep_next = 0;
     for (int i = LB.n_narrow; i < n_ops; ++i) {
-      std::vector<Burst> b = make_bursts(LB.ops[s][i], LB.weights[i]);
+      std::vector<BurstH> b = make_bursts(LB.ops[s][i], LB.weights[i]);
       for (auto& e : b) {
         e.unit = (uint8_t)cursor;
         cursor = (cursor + 1) % NUNIT;
@@ -1215,7 +1260,7 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
     std::vector<int> held(NUNIT, 0);
     for (int it = 0; it < 2; ++it)
       for (int i = 0; i < n; ++i) {
-        const Burst& e = bursts[i];
+        const BurstH& e = bursts[i];
         const int gi = it * n + i;
         if (e.flags & B_ACQUIRE) {
           if (held[e.unit] || released[e.unit] > gi - 2) { err = "tensor-core engine: weight ring too small for this layer program"; return false; }
@@ -1226,7 +1271,7 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
   }
   prog.n_burst = (int)bursts.size();
   prog.n_steps = (int)steps.size();
-  std::copy(bursts.begin(), bursts.end(), prog.burst);
+  encode_bursts(bursts, true, prog.burst);
   std::copy(steps.begin(), steps.end(), prog.steps);
   return true;
 }
@@ -1304,42 +1349,29 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
     const ActLayout trunk = build_mlp_ops(TR, t_sigma, true, s, t0, tsk, tflags, ops);
     build_head_op({&HM.alpha[lv]}, trunk, t_sigma, GLUE_ALPHA, true, s, 1, ops);
     LB.n_sigma = (int)ops.size();
-    // ---- rgb branch (modules.py:288-313).  Flax input order:
+    // ---- rgb branch (modules.py:288-313).  Flax input order of its Dense(560 -> 128):
     //   [bottleneck (W) | viewdir feats | trunk_out (W, App. C-1) | norm feats]
-    // trunk_out stays in its region T; everything else happens in the other region B (256 columns):
-    //   bottleneck   accumulates into B (two chunks of 128 columns), epilogue compacts its hi halves to the first
-    //                64 columns of each chunk;
-    //   rgb hidden   accumulates into the freed second halves (two chunks of 64 columns), hi-only in place;
-    //   rgb head     accumulates into the first columns of T (trunk_out is dead by then: in-order MMA pipe).
+    // The bottleneck is a Dense WITHOUT activation (modules.py:283-286), so it is folded into this layer on the
+    // host:  W_fold = W_bott W_rgb[bottleneck rows] + W_rgb[trunk_out rows],  b_fold = b_rgb + b_bott W_rgb[...]:
+    // one GEMM over trunk_out (K = 256) plus the side-input K-chunk instead of two layers with K = 256 + 560.
+    // trunk_out stays in its region T; in the other region B the sigma/normal head accumulates into columns
+    // [0, 16) and this layer into [128, 256), so neither waits for the other; only the side-input K-chunk (the
+    // normal features come out of the head's per-sample stage) is issued after the glue barrier.
     const int W = c.trunk_width;
     if (W != 256 || HM.rgb[lv].width != 128) { h->err = "tensor-core engine: the rgb branch is built for trunk 256 / rgb 128"; return NDSR_ERR_UNSUPPORTED; }
     const int Tcol = trunk.region * 256, Bcol = (1 - trunk.region) * 256;
-    ActLayout bott;
-    bott.N = W; bott.n_nc = 2; bott.compact_hi = 1; bott.d_col[0] = Bcol; bott.d_col[1] = Bcol + 128; bott.region = 1 - trunk.region;
-    {
-      OpBuild ob;
-      ob.N_logical = ob.N = W;
-      ob.tslot = s;
-      ob.n_nc = 2; ob.d_col[0] = Bcol; ob.d_col[1] = Bcol + 128;
-      ob.terms = 1; ob.relu = 0; ob.epi_kind = EPI_COMPACT_HI; ob.glue = GLUE_BOTTLENECK;
-      ob.first_flags = B_WAIT_GLUE;     // the sigma/normal head's accumulators (in B) must have been consumed
-      ob.prev_produces = 0;
-      ob.W = &HM.bottleneck[lv].W; ob.b = &HM.bottleneck[lv].b;
-      for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, 0, false));
-      ops.push_back(ob);
-    }
     ActLayout rgbh;
-    rgbh.N = 128; rgbh.n_nc = 2; rgbh.d_col[0] = Bcol + 64; rgbh.d_col[1] = Bcol + 192; rgbh.region = 1 - trunk.region;
+    rgbh.N = 128; rgbh.n_nc = 1; rgbh.d_col[0] = rgbh.d_col[1] = Bcol + 128; rgbh.region = 1 - trunk.region;
     {
       const HostMlp& R = HM.rgb[lv];
+      const HostDense& BT = HM.bottleneck[lv];
       OpBuild ob;
-      ob.N_logical = ob.N = R.width;
+      const int NR = R.width;
+      ob.N_logical = ob.N = NR;
       ob.tslot = s;
-      ob.n_nc = 2; ob.d_col[0] = rgbh.d_col[0]; ob.d_col[1] = rgbh.d_col[1];
-      ob.terms = 1; ob.relu = 1; ob.epi_kind = EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.prev_produces = 1;
-      // the accumulators overwrite the second halves of both bottleneck chunks: wait for the compaction
-      ob.first_part_waits = 3;
-      ob.W = &R.hidden[0].W; ob.b = &R.hidden[0].b;
+      ob.n_nc = 1; ob.d_col[0] = ob.d_col[1] = rgbh.d_col[0];
+      ob.terms = 1; ob.relu = 1; ob.epi_kind = EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.prev_produces = 0;
+      const std::vector<float>& WR = R.hidden[0].W;     // [560][NR]
       int row = W;
       const int v0 = row;
       row += h->dim_view;
@@ -1347,20 +1379,37 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
       if (c.use_x_in_rgb_condition) { x0 = row; row += W; }
       const int n0 = row;
       const int ndim = c.predict_norm ? h->dim_norm : 0;
-      if (x0 >= 0) for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, x0, false));   // trunk_out
-      for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(bott, j, 0, true));                   // bottleneck
-      if (h->dim_view + ndim > 0) {                      // side inputs last: the normal features arrive late
-        KChunkMap k = kc_input(OFF_IN2, 0, 0);
-        for (int cidx = 0; cidx < 64; ++cidx) {
-          if (cidx < h->dim_view) k.rows[cidx] = v0 + cidx;
-          else if (cidx < h->dim_view + ndim) k.rows[cidx] = n0 + (cidx - h->dim_view);
-          else k.rows[cidx] = -1;
+      const int side = h->dim_view + ndim;
+      // folded logical weights: rows [0, W) over trunk_out, then the side inputs [viewdir feats | norm feats]
+      ob.W_own.assign((size_t)(W + side) * NR, 0.f);
+      ob.b_own.assign(NR, 0.f);
+      for (int n = 0; n < NR; ++n) {
+        double bacc = R.hidden[0].b[n];
+        for (int j = 0; j < W; ++j) bacc += (double)BT.b[j] * WR[(size_t)j * NR + n];
+        ob.b_own[n] = (float)bacc;
+      }
+      {
+        std::vector<double> acc((size_t)NR);
+        for (int k = 0; k < W; ++k) {
+          for (int n = 0; n < NR; ++n) acc[n] = x0 >= 0 ? (double)WR[(size_t)(x0 + k) * NR + n] : 0.0;
+          for (int j = 0; j < W; ++j) {
+            const double bkj = BT.W[(size_t)k * W + j];
+            const float* wr = &WR[(size_t)j * NR];
+            for (int n = 0; n < NR; ++n) acc[n] += bkj * wr[n];
+          }
+          for (int n = 0; n < NR; ++n) ob.W_own[(size_t)k * NR + n] = (float)acc[n];
         }
+      }
+      for (int i = 0; i < h->dim_view; ++i) for (int n = 0; n < NR; ++n) ob.W_own[(size_t)(W + i) * NR + n] = WR[(size_t)(v0 + i) * NR + n];
+      for (int i = 0; i < ndim; ++i) for (int n = 0; n < NR; ++n) ob.W_own[(size_t)(W + h->dim_view + i) * NR + n] = WR[(size_t)(n0 + i) * NR + n];
+      for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(trunk, j, 0, false));   // trunk_out (the head before it waited)
+      if (side > 0) {                                    // side inputs last: the normal features arrive late
+        KChunkMap k = kc_input(OFF_IN2, W, side);
+        k.wait_glue = 1;
         ob.kcs.push_back(k);
       }
-      if ((int)ob.kcs.size() > MAX_KC) { h->err = "tensor-core engine: rgb input too wide"; return NDSR_ERR_UNSUPPORTED; }
       ops.push_back(ob);
-      // head over the rgb hidden layer; accumulators at the start of T
+      // head over the rgb hidden layer; accumulators at the start of T (trunk_out is dead: in-order MMA pipe)
       OpBuild hb;
       hb.N_logical = R.logit.N;
       hb.tslot = s;
@@ -1372,8 +1421,6 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
     }
     fix_own(ops);
   }
-  // (the rgb hidden layer's side-input K-chunk needs no wait of its own: the bottleneck's first burst, issued
-  // before it, already consumed the glue phase of the sigma/normal head)
   for (size_t i = 0; i < LB.ops[0].size(); ++i) LB.weights.push_back(pack_weights(LB.ops[0][i], P));
   return NDSR_OK;
 }
@@ -1475,8 +1522,8 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
       for (int i = 0; i < prog.n_burst; ++i) {
         const Burst& b = prog.burst[i];
         fprintf(f, "burst %d slot %d rows %d steps %d pat %d flags %d unit %d dcol %d top %lld ready %lld issued %lld\n", i,
-                b.tslot, b.rows, b.steps, b.pat, b.flags, b.unit, b.d_col, rel(t[i]), rel(t[MAX_BURST + i]),
-                rel(t[2 * MAX_BURST + i]));
+                (b.ctl >> 18) & 1, ((b.idesc >> 17) & 63) * 8, (b.ctl >> 15) & 7, (b.ctl >> 13) & 3, b.ctl & 0x1fff,
+                (b.ctl >> 19) & 3, b.d_col, rel(t[i]), rel(t[MAX_BURST + i]), rel(t[2 * MAX_BURST + i]));
       }
       for (int i = 0; i < prog.n_steps; ++i) {
         const Step& s = prog.steps[i];
@@ -1528,7 +1575,7 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   }
   Packed P;
   const OpWeights ow = pack_weights(ob, P);
-  std::vector<Burst> bursts = make_bursts(ob, ow);
+  std::vector<BurstH> bursts = make_bursts(ob, ow);
   static TcProgram prog;
   memset(&prog, 0, sizeof prog);
   prog.n_ops = 1;
@@ -1536,7 +1583,7 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   int cursor = 0;
   for (auto& e : bursts) { e.unit = (uint8_t)cursor; cursor = (cursor + 1) % NUNIT; e.flags |= B_ACQUIRE | B_RELEASE; }
   prog.n_burst = (int)bursts.size();
-  std::copy(bursts.begin(), bursts.end(), prog.burst);
+  encode_bursts(bursts, false, prog.burst);
   uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;
   const int N = prog.ops[0].N;
   const int K = k_hid + k_in;

@@ -125,6 +125,49 @@ __global__ void __launch_bounds__(512, 1) tmem_bench_kernel(int mode, int iters,
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// cost of tcgen05.commit / mbarrier waits for the issuing thread: bursts of 12 MMAs (N=128) followed by `ncommit`
+// commits and `nwait` waits on an already-complete barrier
+__global__ void __launch_bounds__(128, 1) commit_bench_kernel(int ncommit, int nwait, int test, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar, dummy[4], done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); for (int i = 0; i < 4; ++i) mbar_init(&dummy[i], 1); mbar_init(&done, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tb = tmem_base_s;
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive(&done);            // phase 0 of `done` complete: waits with parity 0 succeed at once
+      const uint32_t idesc = make_idesc_f16(128);
+      const uint64_t bd = ((uint64_t)NDS_DESC_HI << 32) | smem_desc_lo32(smem_u32(smem) + 16384);
+      const unsigned long long t0 = clock64();
+      for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) umma_f16_ts(tb, tb + 256 + 8 * (k & 3), bd + 2 * (k & 3), idesc, 1u);
+        for (int c = 0; c < ncommit; ++c) umma_commit(&dummy[c]);
+        for (int w = 0; w < nwait; ++w) {
+          if (test) { while (!mbar_test_wait(&done, 0)) {} } else mbar_wait(&done, 0);
+        }
+      }
+      const unsigned long long t1 = clock64();
+      umma_commit(&bar);
+      mbar_wait(&bar, 0);
+      const unsigned long long t2 = clock64();
+      out[0] = t1 - t0; out[1] = t2 - t0;
+    }
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 int main() {
   unsigned long long* d_out;
   cudaMalloc(&d_out, 1024);
@@ -151,6 +194,17 @@ int main() {
     cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
     printf("tmem mode %d (0 ld32, 1 st 2x16, 2 both) 16 warps x 64 iters: %llu cycles -> %.1f cyc/iter (16 KB per iter per direction)\n",
            mode, h[0], (double)h[0] / 64);
+  }
+  cudaFuncSetAttribute(commit_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  for (int cfg = 0; cfg < 8; ++cfg) {
+    const int nc[] = {0, 1, 2, 0, 0, 0, 0, 1}, nw[] = {0, 0, 0, 1, 2, 1, 2, 1}, ts[] = {0, 0, 0, 0, 0, 1, 1, 0};
+    commit_bench_kernel<<<1, 128, 100 * 1024>>>(nc[cfg], nw[cfg], ts[cfg], d_out);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+    unsigned long long h[2];
+    cudaMemcpy(h, d_out, sizeof h, cudaMemcpyDeviceToHost);
+    printf("16 bursts of 12 MMAs N=128 + %d commits + %d %s waits per burst: issue %llu total %llu -> %.0f cycles per burst\n", nc[cfg], nw[cfg],
+           ts[cfg] ? "test" : "try", h[0], h[1], (double)h[1] / 16);
   }
   // many CTAs at once (whole chip): does the pacing change under chip-wide load?
   {
