@@ -199,67 +199,33 @@ template <> struct KSteps<PAT_32> { static constexpr uint32_t s1 = 8, s2 = 32, s
 template <> struct KSteps<PAT_16> { static constexpr uint32_t s1 = 16, s2 = 32, s3 = 48; };
 template <> struct KSteps<PAT_8> { static constexpr uint32_t s1 = 8, s2 = 16, s3 = 24; };
 
-// One burst is issued in two halves so that the issuer can wait for the NEXT burst's weights in between
-// (tcgen05.mma issue blocks while the tensor core's queue, ~3 instructions deep, is full; whatever the issuer
-// does between two bursts must fit under that cover or the pipe drains):
-//   half 0   D (+)= A_hi B_hi [; D += A_lo B_hi]           (1-term: K-steps 0, 1)
-//   half 1   [D += A_hi B_lo]                               (1-term: K-steps 2, 3)
+// One burst: the first group of four MMAs carries a probe of the NEXT burst's weight barrier (see mma4_ts), read
+// back only after the whole burst has been issued.
+//   D (+)= A_hi B_hi [; D += A_lo B_hi ; D += A_hi B_lo]
 template <int PAT>
-__device__ __forceinline__ void issue_half_ts(int half, bool two, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t bd0,
-                                              uint64_t bd1, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ uint32_t issue_burst_ts(bool two, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b0,
+                                                   uint32_t b1, uint32_t idesc, uint32_t acc, uint32_t pbar, uint32_t ppar,
+                                                   uint32_t do_probe) {
   using S = KSteps<PAT>;
+  const uint32_t ok = mma4_ts(d, a_hi, a_hi + S::s1, a_hi + S::s2, a_hi + S::s3, b0, idesc, acc, 4u, pbar, ppar, do_probe);
   if (two) {
-    if (half == 0) {
-      umma_f16_ts(d, a_hi, bd0, idesc, acc);
-      umma_f16_ts(d, a_hi + S::s1, bd0 + 2, idesc, 1u);
-      umma_f16_ts(d, a_hi + S::s2, bd0 + 4, idesc, 1u);
-      umma_f16_ts(d, a_hi + S::s3, bd0 + 6, idesc, 1u);
-      umma_f16_ts(d, a_lo, bd0, idesc, 1u);
-      umma_f16_ts(d, a_lo + S::s1, bd0 + 2, idesc, 1u);
-      umma_f16_ts(d, a_lo + S::s2, bd0 + 4, idesc, 1u);
-      umma_f16_ts(d, a_lo + S::s3, bd0 + 6, idesc, 1u);
-    } else {
-      umma_f16_ts(d, a_hi, bd1, idesc, 1u);
-      umma_f16_ts(d, a_hi + S::s1, bd1 + 2, idesc, 1u);
-      umma_f16_ts(d, a_hi + S::s2, bd1 + 4, idesc, 1u);
-      umma_f16_ts(d, a_hi + S::s3, bd1 + 6, idesc, 1u);
-    }
-  } else if (half == 0) {
-    umma_f16_ts(d, a_hi, bd0, idesc, acc);
-    umma_f16_ts(d, a_hi + S::s1, bd0 + 2, idesc, 1u);
-  } else {
-    umma_f16_ts(d, a_hi + S::s2, bd0 + 4, idesc, 1u);
-    umma_f16_ts(d, a_hi + S::s3, bd0 + 6, idesc, 1u);
+    mma4_ts(d, a_lo, a_lo + S::s1, a_lo + S::s2, a_lo + S::s3, b0, idesc, 1u, 4u, 0u, 0u, 0u);
+    mma4_ts(d, a_hi, a_hi + S::s1, a_hi + S::s2, a_hi + S::s3, b1, idesc, 1u, 4u, 0u, 0u, 0u);
   }
+  return ok;
 }
-__device__ __forceinline__ void issue_half_ss(int half, bool two, uint32_t steps, uint32_t d, uint64_t ad0, uint64_t ad1,
-                                              uint64_t bd0, uint64_t bd1, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ uint32_t issue_burst(uint32_t pat, bool two, uint32_t steps, uint32_t d, uint32_t a_hi,
+                                                uint32_t a_lo, uint32_t b0, uint32_t b1, uint32_t idesc, uint32_t acc,
+                                                uint32_t pbar, uint32_t ppar, uint32_t do_probe) {
+  if (pat == PAT_32) return issue_burst_ts<PAT_32>(two, d, a_hi, a_lo, b0, b1, idesc, acc, pbar, ppar, do_probe);
+  if (pat == PAT_16) return issue_burst_ts<PAT_16>(two, d, a_hi, a_lo, b0, b1, idesc, acc, pbar, ppar, do_probe);
+  if (pat == PAT_8) return issue_burst_ts<PAT_8>(two, d, a_hi, a_lo, b0, b1, idesc, acc, pbar, ppar, do_probe);
+  const uint32_t ok = mma4_ss(d, a_hi, b0, idesc, acc, steps, pbar, ppar, do_probe);
   if (two) {
-    if (half == 0) {
-#pragma unroll
-      for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd0 + 2 * ks, idesc, ks ? 1u : acc);
-#pragma unroll
-      for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad1 + 2 * ks, bd0 + 2 * ks, idesc, 1u);
-    } else {
-#pragma unroll
-      for (uint32_t ks = 0; ks < 4; ++ks) if (ks < steps) umma_f16(d, ad0 + 2 * ks, bd1 + 2 * ks, idesc, 1u);
-    }
-  } else if (half == 0) {
-    umma_f16(d, ad0, bd0, idesc, acc);
-    if (steps > 1) umma_f16(d, ad0 + 2, bd0 + 2, idesc, 1u);
-  } else {
-    if (steps > 2) umma_f16(d, ad0 + 4, bd0 + 4, idesc, 1u);
-    if (steps > 3) umma_f16(d, ad0 + 6, bd0 + 6, idesc, 1u);
+    mma4_ss(d, a_lo, b0, idesc, 1u, steps, 0u, 0u, 0u);
+    mma4_ss(d, a_hi, b1, idesc, 1u, steps, 0u, 0u, 0u);
   }
-}
-__device__ __forceinline__ void issue_half(int half, uint32_t pat, bool two, uint32_t steps, uint32_t d, uint32_t a_hi,
-                                           uint32_t a_lo, uint32_t b0, uint32_t b1, uint32_t idesc, uint32_t acc) {
-  const uint64_t hi = (uint64_t)NDS_DESC_HI << 32;
-  const uint64_t bd0 = hi | b0, bd1 = hi | b1;
-  if (pat == PAT_32) issue_half_ts<PAT_32>(half, two, d, a_hi, a_lo, bd0, bd1, idesc, acc);
-  else if (pat == PAT_16) issue_half_ts<PAT_16>(half, two, d, a_hi, a_lo, bd0, bd1, idesc, acc);
-  else if (pat == PAT_8) issue_half_ts<PAT_8>(half, two, d, a_hi, a_lo, bd0, bd1, idesc, acc);
-  else issue_half_ss(half, two, steps, d, hi | a_hi, hi | a_lo, bd0, bd1, idesc, acc);
+  return ok;
 }
 
 // MMA issuer, run by ONE elected thread (the caller guards it with elect_one_sync(), which is what lets ptxas keep
@@ -290,25 +256,25 @@ __device__ __forceinline__ void issue_program(const TcProgram& P, uint32_t smem_
       if (fl & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
       if (fl & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
       if (fl & B_WAIT_P1) mbar_wait(&ctl->part[s][1], (bits >> s) & 1u);
-      tc_fence_after_sync();
     }
+    tc_fence_after_sync();
     if (trace) trace[MAX_BURST + i] = clock64();
     const bool two = (fl & B_TWO) != 0;
     const uint32_t abase = pat == PAT_SS ? ss_base : tmem_base;
     const uint32_t a_hi = abase + q0.x, a_lo = abase + q0.y, d = tmem_base + q0.z, idesc = q0.w;
     const uint32_t b0 = ring_lo32 + q1.x, b1 = ring_lo32 + q1.y, acc = (fl & B_FIRST) ? 0u : 1u;
-    issue_half(0, pat, two, steps, d, a_hi, a_lo, b0, b1, idesc, acc);
-    // the next burst's weights (in the ring long ago in steady state): waiting here, with the tensor core busy on
-    // half 0, keeps the barrier round trip off the critical path.  Only ring waits may be hoisted: the producer
-    // never depends on anything this thread still has to issue.
-    if (nu && (!wrap || more)) {
-      mbar_wait(&ctl->full[nu - 1], (bits >> (7 + nu)) & 1u);
-      bits ^= 1u << (7 + nu);
-      tc_fence_after_sync();
-    }
-    issue_half(1, pat, two, steps, d, a_hi, a_lo, b0, b1, idesc, acc);
+    // the next burst's weights (in the ring long ago in steady state) are probed while this burst is issued.
+    // Only ring waits may be hoisted: the producer never depends on anything this thread still has to issue.
+    const uint32_t do_probe = (nu && (!wrap || more)) ? 1u : 0u;
+    uint64_t* nbar = &ctl->full[nu ? nu - 1 : 0];
+    const uint32_t ppar = (bits >> (7 + nu)) & 1u;
+    const uint32_t ok = issue_burst(pat, two, steps, d, a_hi, a_lo, b0, b1, idesc, acc, smem_u32(nbar), ppar, do_probe);
     if (fl & B_RELEASE) umma_commit(&ctl->empty[unit]);
     if (fl & B_LAST) umma_commit(&ctl->d_full[s][(fl & B_NC1) ? 1 : 0]);
+    if (do_probe) {
+      if (!ok) mbar_wait(nbar, ppar);
+      bits ^= 1u << (7 + nu);
+    }
     if (trace) trace[2 * MAX_BURST + i] = clock64();
     if (fl & B_PART_NEXT) bits ^= 1u << s;
     q0 = n0;
@@ -372,17 +338,33 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
   uint32_t hi[CW / 2], lo[CW / 2];
+  if (relu && !dbg_out) {
+    // ReLU folded into the conversions: hi = relu(x) truncated to fp16 (round toward zero, so the residual of a
+    // positive x is never negative), lo = relu(x - hi) -- for x < 0 both come out 0.  hi + lo still carries 21+ bits.
 #pragma unroll
-  for (int i = 0; i < CW / 2; ++i) {
-    float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
-    float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
-    if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-    if (dbg_out) { dbg_out[row * dbg_ld + oc0 + 2 * i] = x0; dbg_out[row * dbg_ld + oc0 + 2 * i + 1] = x1; }
-    const __half2 h = __floats2half2_rn(x0, x1);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
-    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    for (int i = 0; i < CW / 2; ++i) {
+      const float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
+      const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
+      uint32_t h, l;
+      asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+      asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+      hi[i] = h;
+      lo[i] = l;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) {
+      float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
+      float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
+      if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      if (dbg_out) { dbg_out[row * dbg_ld + oc0 + 2 * i] = x0; dbg_out[row * dbg_ld + oc0 + 2 * i + 1] = x1; }
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+      hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
   }
   const uint8_t kind = op.epi_kind;
   if (kind == EPI_COMPACT_HI) {

@@ -225,93 +225,56 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// ---- MMA bursts -------------------------------------------------------------
-// One K-chunk (4 K-steps of 16) of a split-fp16 Dense layer as ONE asm block:
-//   D (+)= A_hi B_hi ; D += A_lo B_hi ; commit(bar_hi) ; D += A_hi B_lo ; commit(bar_lo) ; [commit(bar_d)]
-// Descriptors differ only in their low word (start address >> 4, +2 per K-step), the high word is constant, so
-// the issuing thread spends ~3 instructions per tcgen05.mma.  `a*` are descriptor low words (shared-memory
-// operand) or tensor-memory addresses (TS form, +8 columns per K-step).
+// ---- MMA groups ---------------------------------------------------------------
+// Four tcgen05.mma (one K-chunk: K-steps 0..3, B descriptor low word + 2 per step) as ONE asm block, optionally
+// preceded by a non-consuming probe of an mbarrier (mbarrier.try_wait whose predicate is read only AFTER the four
+// MMAs): the issuing thread blocks on tcgen05.mma while the tensor core's short queue is full, so the barrier
+// round trip (~100-150 cycles) hides behind the issue instead of sitting between two bursts.
+// `nmma`: how many of the 4 K-steps exist (1..4).  Returns 1 when the probed phase had completed (or no probe).
 #define NDS_DESC_HI 0x40004040u   /* SBO = 1024 B, version 1, SWIZZLE_128B */
-// operand setup first (all descriptors / addresses into their own registers), then the tcgen05 instructions
-// back to back inside one branch taken by the elected lane only.
-#define NDS_SETUP_SS \
-  ".reg .b64 A0, A1, A2, A3, L0, L1, L2, L3, H0, H1, H2, H3, G0, G1, G2, G3;\n\t.reg .b32 w;\n\t" \
-  "mov.b64 A0, {%1, %9};\n\tadd.u32 w, %1, 2;\n\tmov.b64 A1, {w, %9};\n\tadd.u32 w, %1, 4;\n\tmov.b64 A2, {w, %9};\n\tadd.u32 w, %1, 6;\n\tmov.b64 A3, {w, %9};\n\t" \
-  "mov.b64 L0, {%2, %9};\n\tadd.u32 w, %2, 2;\n\tmov.b64 L1, {w, %9};\n\tadd.u32 w, %2, 4;\n\tmov.b64 L2, {w, %9};\n\tadd.u32 w, %2, 6;\n\tmov.b64 L3, {w, %9};\n\t"
-// tensor-memory A operand: K-step t lives at column (base + S_t); the lo image at the same offsets from its base
-#define NDS_SETUP_TS(S1, S2, S3) \
-  ".reg .b32 A0, A1, A2, A3, L0, L1, L2, L3, w;\n\t.reg .b64 H0, H1, H2, H3, G0, G1, G2, G3;\n\t" \
-  "mov.b32 A0, %1;\n\tadd.u32 A1, %1, " S1 ";\n\tadd.u32 A2, %1, " S2 ";\n\tadd.u32 A3, %1, " S3 ";\n\t" \
-  "mov.b32 L0, %2;\n\tadd.u32 L1, %2, " S1 ";\n\tadd.u32 L2, %2, " S2 ";\n\tadd.u32 L3, %2, " S3 ";\n\t"
-#define NDS_SETUP_B \
-  "mov.b64 H0, {%3, %9};\n\tadd.u32 w, %3, 2;\n\tmov.b64 H1, {w, %9};\n\tadd.u32 w, %3, 4;\n\tmov.b64 H2, {w, %9};\n\tadd.u32 w, %3, 6;\n\tmov.b64 H3, {w, %9};\n\t" \
-  "mov.b64 G0, {%4, %9};\n\tadd.u32 w, %4, 2;\n\tmov.b64 G1, {w, %9};\n\tadd.u32 w, %4, 4;\n\tmov.b64 G2, {w, %9};\n\tadd.u32 w, %4, 6;\n\tmov.b64 G3, {w, %9};\n\t"
-#define NDS_MMA_SS(A, B, PRED) "tcgen05.mma.cta_group::1.kind::f16 [%0], " A ", " B ", %5, " PRED ";\n\t"
-#define NDS_MMA_TS(A, B, PRED) "tcgen05.mma.cta_group::1.kind::f16 [%0], [" A "], " B ", %5, " PRED ";\n\t"
-#define NDS_COMMIT(BAR) "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [" BAR "];\n\t"
-#define NDS_BURST_BODY(SETUP_A, MMA) \
-  "{\n\t.reg .pred p, t, l, q;\n\t" SETUP_A NDS_SETUP_B \
-  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\t" \
-  "@!q bra NDS_DONE;\n\t" \
-  MMA("A0", "H0", "p") MMA("A1", "H1", "t") MMA("A2", "H2", "t") MMA("A3", "H3", "t") \
-  MMA("L0", "H0", "t") MMA("L1", "H1", "t") MMA("L2", "H2", "t") MMA("L3", "H3", "t") \
-  NDS_COMMIT("%7") \
-  MMA("A0", "G0", "t") MMA("A1", "G1", "t") MMA("A2", "G2", "t") MMA("A3", "G3", "t") \
-  NDS_COMMIT("%8") \
-  "@l " NDS_COMMIT("%11") \
-  "NDS_DONE:\n\t}"
-// 1-term K-chunk (4 K-steps): D (+)= A_hi B_hi ; commit(bar_slot) ; [commit(bar_d)]
-#define NDS_BURST1_BODY(SETUP_A, MMA) \
-  "{\n\t.reg .pred p, t, l, q;\n\t" SETUP_A NDS_SETUP_B \
-  "setp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 t, 0, 0;\n\tsetp.ne.b32 q, %12, 0;\n\tsetp.ne.b32 l, %10, 0;\n\t" \
-  "@!q bra NDS_DONE;\n\t" \
-  MMA("A0", "H0", "p") MMA("A1", "H1", "t") MMA("A2", "H2", "t") MMA("A3", "H3", "t") \
-  NDS_COMMIT("%7") \
-  "@l " NDS_COMMIT("%11") \
-  "NDS_DONE:\n\t}"
-__device__ __forceinline__ void umma_burst3_ss(uint32_t d, uint32_t a_hi_lo32, uint32_t a_lo_lo32, uint32_t b_hi_lo32,
-                                               uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,
-                                               uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {
-  asm volatile(NDS_BURST_BODY(NDS_SETUP_SS, NDS_MMA_SS)
-               ::"r"(d), "r"(a_hi_lo32), "r"(a_lo_lo32), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate),
-                 "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
+#define NDS_MMA4_PROLOGUE \
+  "{\n\t.reg .pred p, t, e1, e2, e3, pq, ok;\n\t.reg .b64 B0, B1, B2, B3;\n\t.reg .b32 w;\n\t" \
+  "setp.ne.b32 p, %7, 0;\n\tsetp.gt.u32 e1, %8, 1;\n\tsetp.gt.u32 e2, %8, 2;\n\tsetp.gt.u32 e3, %8, 3;\n\t" \
+  "setp.ne.b32 pq, %11, 0;\n\tsetp.eq.u32 ok, 0, 0;\n\tsetp.eq.u32 t, 0, 0;\n\t" \
+  "mov.b64 B0, {%5, %12};\n\tadd.u32 w, %5, 2;\n\tmov.b64 B1, {w, %12};\n\tadd.u32 w, %5, 4;\n\tmov.b64 B2, {w, %12};\n\t" \
+  "add.u32 w, %5, 6;\n\tmov.b64 B3, {w, %12};\n\t" \
+  "@pq mbarrier.try_wait.parity.shared::cta.b64 ok, [%9], %10;\n\t"
+// tensor-memory A operand: a0..a3 are the tensor-memory addresses of the four K-steps
+__device__ __forceinline__ uint32_t mma4_ts(uint32_t d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b_lo32,
+                                            uint32_t idesc, uint32_t accumulate, uint32_t nmma, uint32_t probe_bar,
+                                            uint32_t probe_parity, uint32_t do_probe) {
+  uint32_t ok;
+  asm volatile(NDS_MMA4_PROLOGUE
+               "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], B0, %6, p;\n\t"
+               "@e1 tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], B1, %6, t;\n\t"
+               "@e2 tcgen05.mma.cta_group::1.kind::f16 [%1], [%4], B2, %6, t;\n\t"
+               "@e3 tcgen05.mma.cta_group::1.kind::f16 [%1], [%13], B3, %6, t;\n\t"
+               "selp.u32 %0, 1, 0, ok;\n\t}"
+               : "=r"(ok)
+               : "r"(d), "r"(a0), "r"(a1), "r"(a2), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(nmma), "r"(probe_bar),
+                 "r"(probe_parity), "r"(do_probe), "r"(NDS_DESC_HI), "r"(a3)
                : "memory");
+  return ok;
 }
-// PAT: column offsets of K-steps 1..3 inside one 64-feature K-block of a tensor-memory operand
-//   32: {8, 32, 40}  epilogue slices of 32 features (hi 16 columns | lo 16 columns)
-//   16: {16, 32, 48} epilogue slices of 16 features (hi 8 | lo 8)
-//    8: {8, 16, 24}  compacted hi-only activations
-#define NDS_DEFINE_BURST3_TS(NAME, S1, S2, S3)                                                                        \
-  __device__ __forceinline__ void NAME(uint32_t d, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi_lo32,        \
-                                       uint32_t b_lo_lo32, uint32_t idesc, uint32_t accumulate, uint32_t bar_hi,      \
-                                       uint32_t bar_lo, uint32_t last, uint32_t bar_d, uint32_t issue) {              \
-    asm volatile(NDS_BURST_BODY(NDS_SETUP_TS(S1, S2, S3), NDS_MMA_TS)                                                 \
-                 ::"r"(d), "r"(a_hi_tmem), "r"(a_lo_tmem), "r"(b_hi_lo32), "r"(b_lo_lo32), "r"(idesc), "r"(accumulate), \
-                   "r"(bar_hi), "r"(bar_lo), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)                      \
-                 : "memory");                                                                                         \
-  }
-NDS_DEFINE_BURST3_TS(umma_burst3_ts32, "8", "32", "40")
-NDS_DEFINE_BURST3_TS(umma_burst3_ts16, "16", "32", "48")
-NDS_DEFINE_BURST3_TS(umma_burst3_ts8, "8", "16", "24")
-#define NDS_DEFINE_BURST1_TS(NAME, S1, S2, S3)                                                                        \
-  __device__ __forceinline__ void NAME(uint32_t d, uint32_t a_tmem, uint32_t b_lo32, uint32_t idesc,                  \
-                                       uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,         \
-                                       uint32_t issue) {                                                              \
-    asm volatile(NDS_BURST1_BODY(NDS_SETUP_TS(S1, S2, S3), NDS_MMA_TS)                                                \
-                 ::"r"(d), "r"(a_tmem), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot),    \
-                   "r"(0u), "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)                                       \
-                 : "memory");                                                                                         \
-  }
-NDS_DEFINE_BURST1_TS(umma_burst1_ts32, "8", "32", "40")
-NDS_DEFINE_BURST1_TS(umma_burst1_ts16, "16", "32", "48")
-NDS_DEFINE_BURST1_TS(umma_burst1_ts8, "8", "16", "24")
-__device__ __forceinline__ void umma_burst1_ss(uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
-                                               uint32_t accumulate, uint32_t bar_slot, uint32_t last, uint32_t bar_d,
-                                               uint32_t issue) {
-  asm volatile(NDS_BURST1_BODY(NDS_SETUP_SS, NDS_MMA_SS)
-               ::"r"(d), "r"(a_lo32), "r"(0u), "r"(b_lo32), "r"(0u), "r"(idesc), "r"(accumulate), "r"(bar_slot), "r"(0u),
-                 "r"(NDS_DESC_HI), "r"(last), "r"(bar_d), "r"(issue)
+// shared-memory A operand: a_lo32 is the descriptor low word of K-step 0 (+ 2 per step)
+__device__ __forceinline__ uint32_t mma4_ss(uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t nmma, uint32_t probe_bar, uint32_t probe_parity,
+                                            uint32_t do_probe) {
+  uint32_t ok;
+  asm volatile(NDS_MMA4_PROLOGUE
+               ".reg .b64 A0, A1, A2, A3;\n\t"
+               "mov.b64 A0, {%2, %12};\n\tadd.u32 w, %2, 2;\n\tmov.b64 A1, {w, %12};\n\tadd.u32 w, %2, 4;\n\tmov.b64 A2, {w, %12};\n\t"
+               "add.u32 w, %2, 6;\n\tmov.b64 A3, {w, %12};\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%1], A0, B0, %6, p;\n\t"
+               "@e1 tcgen05.mma.cta_group::1.kind::f16 [%1], A1, B1, %6, t;\n\t"
+               "@e2 tcgen05.mma.cta_group::1.kind::f16 [%1], A2, B2, %6, t;\n\t"
+               "@e3 tcgen05.mma.cta_group::1.kind::f16 [%1], A3, B3, %6, t;\n\t"
+               "selp.u32 %0, 1, 0, ok;\n\t}"
+               : "=r"(ok)
+               : "r"(d), "r"(a_lo32), "r"(0u), "r"(0u), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(nmma), "r"(probe_bar),
+                 "r"(probe_parity), "r"(do_probe), "r"(NDS_DESC_HI), "r"(0u)
                : "memory");
+  return ok;
 }
 __device__ __forceinline__ uint32_t smem_desc_lo32(uint32_t smem_addr) {
   return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);

@@ -237,7 +237,7 @@ def test_tc_end_to_end_matches_simt(cuda_device):
                 keys=('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'med_points'), coarse_keys=('rgb', 'weights'))
     outs[eng] = {k: _np(v) for k, v in o.items()}
   assert linf(outs['tc']['coarse']['rgb'], outs['simt']['coarse']['rgb']) <= RGB_TOL
-  assert linf(outs['tc']['coarse']['weights'], outs['simt']['coarse']['weights']) <= 2e-4
+  assert linf(outs["tc"]["coarse"]["weights"], outs["simt"]["coarse"]["weights"]) <= 3e-4   # split-fp16 (2^-22 rel.) vs fp32 weights
   err = np.abs(outs['tc']['fine']['rgb'] - outs['simt']['fine']['rgb']).max(-1)
   # (the fp32 and fp64 ORACLES disagree on a comparable fraction of rays after resampling)
   assert np.mean(err <= RGB_TOL) >= 0.97, np.sort(err)[-5:]
