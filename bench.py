@@ -356,7 +356,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--engine', default='auto', choices=['auto', 'tc', 'simt'])
-  ap.add_argument('--precision', default='mixed', choices=['mixed', 'fp16', 'split3'])
+  ap.add_argument('--precision', default='split3', choices=['mixed', 'fp16', 'split3'])
   ap.add_argument('--image', type=int, default=800)
   ap.add_argument('--coarse', type=int, default=128)
   ap.add_argument('--fine', type=int, default=128)

@@ -42,9 +42,10 @@ typedef enum ndsr_engine {
 /* Tensor-core operand precision (NDSR_ENGINE_TC only). */
 typedef enum ndsr_precision {
   NDSR_PREC_MIXED = 0,    /* 3-term split fp16 on the sigma path (mask, warp, hyper-sheet,
-                             trunk, sigma/normal head), 1-term fp16 on bottleneck + rgb */
+                             trunk, sigma/normal head), 1-term fp16 on the rgb branch
+                             (median rgb error ~2e-4) */
   NDSR_PREC_FP16 = 1,     /* 1-term fp16 everywhere (fast; misses 1e-3 RGB) */
-  NDSR_PREC_SPLIT3 = 2    /* 3-term split everywhere */
+  NDSR_PREC_SPLIT3 = 2    /* 3-term split everywhere (default of the Python layer) */
 } ndsr_precision;
 
 /* Mirrors the attributes of NerfModel (hypernerf/models.py:116-229), SE3Field

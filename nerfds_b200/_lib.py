@@ -81,7 +81,7 @@ def _single_skip(skips, what):
   return int(skips[0])
 
 
-def to_c_config(cfg: NerfDSConfig, engine='auto', precision='mixed') -> ndsr_config:
+def to_c_config(cfg: NerfDSConfig, engine='auto', precision='split3') -> ndsr_config:
   cfg.validate()
   c = ndsr_config()
   c.size = C.sizeof(ndsr_config)

@@ -824,6 +824,7 @@ struct KChunkMap {
   uint8_t pat = PAT_SS;    // APattern
   uint8_t wait = 0;        // bit c: needs output chunk c of the previous op
   uint8_t wait_glue = 0;   // needs the per-sample stage (rgb side inputs)
+  uint8_t terms = 0;       // 0: the op's; 1: this K-chunk is 1-term even inside a 3-term op (hi-only operand block)
   uint32_t a_hi = 0, a_lo = 0;   // PAT_SS: shared byte offsets; else tensor-memory columns
   int rows[64];            // W row feeding each of the 64 operand columns (-1 = zero pad)
   int band[64];            // >= 0: the column is a posenc feature of that band; its weights carry the window
@@ -974,13 +975,14 @@ static OpWeights pack_weights(const OpBuild& ob, Packed& out) {
           if (km.band[c] >= 0) windowed = true;
         }
       }
+      const int kterms = km.terms ? km.terms : ob.terms;
       const size_t base = out.stream.size();
-      out.stream.resize(base + img * (ob.terms == 3 ? 2 : 1), 0);
-      write_image(&out.stream[base], w.data(), nullptr, nc_rows, ob.terms);
+      out.stream.resize(base + img * (kterms == 3 ? 2 : 1), 0);
+      write_image(&out.stream[base], w.data(), nullptr, nc_rows, kterms);
       ow.src.push_back((uint32_t)(base / 128));
       if (windowed) {
         WindowedImage wi;
-        wi.stream_off = base; wi.rows = nc_rows; wi.terms = ob.terms; wi.pe = km.pe; wi.w = w;
+        wi.stream_off = base; wi.rows = nc_rows; wi.terms = kterms; wi.pe = km.pe; wi.w = w;
         memcpy(wi.band, km.band, sizeof wi.band);
         out.windowed.push_back(std::move(wi));
       }
@@ -1034,9 +1036,10 @@ static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
     e.d_col = (uint16_t)ob.d_col[nc];
     e.tslot = (uint8_t)ob.tslot;
     e.src = ow.src[(size_t)nc * n_kc + kc];
-    e.rows128 = (uint16_t)(nc_rows * (ob.terms == 3 ? 2 : 1));
+    const int kterms = km.terms ? km.terms : ob.terms;
+    e.rows128 = (uint16_t)(nc_rows * (kterms == 3 ? 2 : 1));
     uint16_t fl = 0;
-    if (ob.terms == 3) fl |= B_TWO;
+    if (kterms == 3) fl |= B_TWO;
     if (!seen[nc]) { fl |= B_FIRST; seen[nc] = 1; }
     if (--left[nc] == 0) fl |= B_LAST;
     if (nc == 1) fl |= B_NC1;
@@ -1276,7 +1279,7 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
   const HostModel& HM = h->host_model;
   const int prec = c.precision;
   const int t_sigma = prec == NDSR_PREC_FP16 ? 1 : 3;
-  if (prec == NDSR_PREC_SPLIT3) { h->err = "tensor-core engine: split3 precision on the rgb branch is not built (use mixed)"; return NDSR_ERR_UNSUPPORTED; }
+  const int t_rgb = prec == NDSR_PREC_SPLIT3 ? 3 : 1;     // mixed: 1-term rgb branch (median rgb error ~2e-4)
   if (h->max_in > 64) { h->err = "tensor-core engine: MLP inputs wider than 64 features"; return NDSR_ERR_UNSUPPORTED; }
   if (h->dim_view + (c.predict_norm ? h->dim_norm : 0) > 64) { h->err = "tensor-core engine: rgb side inputs wider than 64"; return NDSR_ERR_UNSUPPORTED; }
   // ---- shared feature block of the narrow networks
@@ -1352,7 +1355,7 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
       ob.N_logical = ob.N = NR;
       ob.tslot = s;
       ob.n_nc = 1; ob.d_col[0] = ob.d_col[1] = rgbh.d_col[0];
-      ob.terms = 1; ob.relu = 1; ob.epi_kind = EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.prev_produces = 0;
+      ob.terms = t_rgb; ob.relu = 1; ob.epi_kind = t_rgb == 3 ? EPI_INPLACE : EPI_INPLACE_HI; ob.glue = GLUE_NONE; ob.prev_produces = 0;
       const std::vector<float>& WR = R.hidden[0].W;     // [560][NR]
       int row = W;
       const int v0 = row;
@@ -1388,6 +1391,7 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
       if (side > 0) {                                    // side inputs last: the normal features arrive late
         KChunkMap k = kc_input(OFF_IN2, W, side);
         k.wait_glue = 1;
+        k.terms = 1;                                     // the side-input block holds hi halves only
         ob.kcs.push_back(k);
       }
       ops.push_back(ob);
@@ -1396,7 +1400,7 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
       hb.N_logical = R.logit.N;
       hb.tslot = s;
       hb.N = 16; hb.n_nc = 1; hb.d_col[0] = hb.d_col[1] = Tcol;
-      hb.terms = 1; hb.relu = 0; hb.epi_kind = EPI_HEAD; hb.glue = GLUE_RGB; hb.prev_produces = 1; hb.signal_glue = 0;
+      hb.terms = t_rgb; hb.relu = 0; hb.epi_kind = EPI_HEAD; hb.glue = GLUE_RGB; hb.prev_produces = 1; hb.signal_glue = 0;
       hb.W = &R.logit.W; hb.b = &R.logit.b;
       for (int j = 0; j < R.width / 64; ++j) hb.kcs.push_back(kc_hidden(rgbh, j, 0, true));
       ops.push_back(hb);

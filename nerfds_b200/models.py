@@ -32,7 +32,7 @@ def _key_to_seed(key) -> int:
 class NerfModel:
   """B200-native stand-in for ``models.NerfModel`` (models.py:71-1565)."""
 
-  def __init__(self, cfg: NerfDSConfig, device=None, engine: str = 'auto', precision: str = 'mixed'):
+  def __init__(self, cfg: NerfDSConfig, device=None, engine: str = 'auto', precision: str = 'split3'):
     cfg.validate()
     self.cfg = cfg
     self.renderer = Renderer(cfg, device=device, engine=engine, precision=precision)
@@ -131,7 +131,7 @@ class NerfModel:
 
 def construct_nerf(key, batch_size: int, embeddings_dict: Dict[str, Iterable[int]], near: float, far: float,
                    cfg: Optional[NerfDSConfig] = None, device=None, engine: str = 'auto',
-                   precision: str = 'mixed', **overrides):
+                   precision: str = 'split3', **overrides):
   """models.construct_nerf (models.py:2677-2741): returns (model, params).
 
   ``params`` come from the synthetic Flax-like initialiser (params.py); a

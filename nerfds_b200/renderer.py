@@ -58,7 +58,7 @@ def _as_dev(x, device, dtype=torch.float32):
 class Renderer:
   """One ndsr_handle bound to one CUDA device."""
 
-  def __init__(self, cfg: NerfDSConfig, device=None, engine: str = 'auto', precision: str = 'mixed'):
+  def __init__(self, cfg: NerfDSConfig, device=None, engine: str = 'auto', precision: str = 'split3'):
     self.lib = _lib.load_library()          # raises if the .so is missing
     if not torch.cuda.is_available():
       raise NdsrError('nerfds_b200 needs a CUDA device (no CPU fallback)')
