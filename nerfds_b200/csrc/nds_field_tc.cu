@@ -80,7 +80,8 @@ struct TcOp {
   uint8_t n_nc, relu, epi_kind, glue;
   uint16_t d_col[2];     // tensor-memory column of accumulator chunk c
   uint8_t signal_glue;   // the per-sample stage after this head arrives on glue[tile slot]
-  uint8_t pad[3];
+  uint8_t signal_done;   // last tensor-memory read of the tile slot: arrive on done[tile slot] right after it
+  uint8_t pad[2];
 };
 
 // One burst of the MMA issuer = one K-chunk (<= 4 K-steps) of one N-chunk of one op of one tile slot:
@@ -619,6 +620,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           tc_fence_after_sync();
           float hv[16];
           epilogue_head(op, L.bias, tmem_lane, hv);
+          if (op.signal_done) warp_arrive(&ctl->done[s], lane);   // the tile slot's last tensor-memory read
           switch (op.glue) {
             case GLUE_MASK: {            // models.py:967-975
               T.pmask = cfg.mask_output_relu ? fmaxf(hv[0], 0.f) : hv[0];
@@ -696,7 +698,6 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
               for (int c = 0; c < 3; ++c) { PL[(P_ROT + c) * ps + n] = rn[c]; PL[(P_TRANS + c) * ps + n] = T.p[c]; }
             }
           }
-          warp_arrive(&ctl->done[s], lane);
         }
         if (tr) tr[2 * si + 1] = clock64();
       }
@@ -1184,6 +1185,7 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
       OpBuild ob = LB.ops[s][i];
       if (!full && i == n_ops - 1) ob.signal_glue = 0;      // nothing follows the sigma head
       prog.ops[op_index(s, i)] = make_tcop(ob, LB.weights[i]);
+      prog.ops[op_index(s, i)].signal_done = (i == n_ops - 1) ? 1 : 0;
     }
   auto step_of = [&](int s, int i) {
     Step st;
@@ -1210,8 +1212,6 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
   }
   // ---- T phase: tile slot 0, then tile slot 1
   for (int s = 0; s < 2; ++s) {
-    Step v; v.kind = STEP_VIEW; v.tslot = (uint8_t)s; v.op = 0; v.arg = 0;
-    steps.push_back(v);
     int prep_next = 0;
     for (int i = LB.n_narrow; i < n_ops; ++i) {
       std::vector<BurstH> b = make_bursts(LB.ops[s][i], LB.weights[i]);
@@ -1222,6 +1222,11 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
       }
       bursts.insert(bursts.end(), b.begin(), b.end());
       steps.push_back(step_of(s, i));
+      // next pair's sample fetch + viewdir features: off the critical path, in the slack after the second trunk layer
+      if (i == LB.trunk_first + 1) {
+        Step v; v.kind = STEP_VIEW; v.tslot = (uint8_t)s; v.op = 0; v.arg = 0;
+        steps.push_back(v);
+      }
       // the input block of this tile slot is free once the skip layer (or layer 0) has consumed it: write the
       // next pair's features into it, one part per following layer
       if (i >= LB.trunk_skip_op && prep_next < NPREP) {
