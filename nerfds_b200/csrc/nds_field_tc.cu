@@ -55,8 +55,7 @@ constexpr uint32_t OFF_RING = 5 * KBLK;
 constexpr uint32_t UNIT_BYTES = 32768;  // one ring unit: a B_hi image followed by its B_lo image (<= 2 x 16 KB)
 constexpr int NUNIT = 4;
 constexpr uint32_t OFF_CTRL = OFF_RING + NUNIT * UNIT_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 3072 + 1024;  // Ctrl + manual 1024-byte alignment slack
-constexpr int MAX_KC = 10;
+constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 11264 + 1024;  // Ctrl + manual 1024-byte alignment slack
 constexpr int NPREP = 3;                // the shared feature block of the next pair is written in 3 parts
 
 enum EpiKind : uint8_t {
@@ -97,15 +96,19 @@ enum BurstFlags : uint16_t {
   B_RELEASE = 4096           // last use: commit to the unit's empty barrier
 };
 constexpr uint16_t B_WAIT_ANY = B_WAIT_P0 | B_WAIT_P1 | B_WAIT_GLUE | B_PEEK_GLUE_OTHER | B_WAIT_PREP | B_WAIT_DONE_OTHER;
-// Device encoding, everything the issuer needs pre-computed (it is read as two uint4 from the constant bank):
+// Device encoding, everything the issuer needs as FINAL values (it is read as two uint4 from the constant bank):
+// the issuing thread shares its warp scheduler with four epilogue warps, so its instruction count per burst is
+// what separates two bursts on the tensor pipe.  Shared-memory addresses are absolute (TcProgram::smem_base is
+// checked by the kernel), tensor memory is allocated whole (base 0, checked).
 struct alignas(16) Burst {
-  uint32_t a_hi, a_lo;   // PAT_SS: (byte offset from the 1024-aligned smem base) >> 4 | 1 << 16; else tensor-memory column
-  uint32_t d_col;        // accumulator column
+  uint32_t a_hi, a_lo;   // PAT_SS: shared-memory descriptor low word; else tensor-memory address
+  uint32_t d;            // accumulator tensor-memory address
   uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = rows)
-  uint32_t b0, b1;       // B_hi / B_lo image: 16-byte units from the ring base
+  uint32_t b0, b1;       // B_hi / B_lo image: descriptor low words
   uint32_t ctl;          // [0,13) BurstFlags | [13,15) pat | [15,18) steps | [18] tile slot | [19,21) ring unit |
                          // [21,24) 1 + ring unit the NEXT burst acquires (0: none) | [24] that next burst is burst 0
-  uint32_t src;          // [0,22) weight stream offset in 128-byte rows | [22,31) rows to load on B_ACQUIRE
+  uint32_t bars;         // Ctrl barrier indices (0xff: none): [0,8) commit on release | [8,16) commit when the
+                         // accumulators are complete | [16,24) weight barrier of the next burst (probe)
 };
 static_assert(sizeof(Burst) == 32, "Burst is read as two uint4");
 // host-side description of a burst (encode_burst() makes the device form)
@@ -120,15 +123,18 @@ struct Step { uint8_t kind, tslot, op, arg; };
 
 constexpr int MAX_OPS = 80;
 constexpr int MAX_STEPS = 128;
-constexpr int MAX_BURST = 300;
+constexpr int MAX_BURST = 256;
 struct TcProgram {       // passed by value as a __grid_constant__ kernel parameter (constant bank)
   int n_ops, n_burst, n_steps, full;     // full: rgb branch present (else sigma-only)
   // shared feature block: [identity x (3)] [sin/cos of bands f_kmin .. f_kmin + f_nb) (6 each)] [warp embed]
   // [mask embed] [mask]; t_cols = width of the trunk input that later overwrites it
   int f_col_ident, f_col_bands, f_kmin, f_nb, f_col_wembed, f_col_membed, f_col_mask, f_cols, t_cols;
+  uint32_t smem_base;    // shared-window address of the (1024-aligned) dynamic shared memory the bursts were encoded for
   TcOp ops[MAX_OPS];
   Step steps[MAX_STEPS];
   Burst burst[MAX_BURST];
+  uint32_t src[MAX_BURST];   // producer: [0,20) weight stream offset in 128-byte rows | [20,29) rows to load |
+                             // [29,31) ring unit | [31] the burst acquires (loads) its unit
 };
 static_assert(sizeof(TcProgram) < 16384, "kernel parameter budget");
 
@@ -142,7 +148,7 @@ struct TcLevel {
 // ---------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------
-struct Ctrl {
+struct Ctrl {     // the barriers come first, in this order: Burst::bars holds indices into this array
   uint64_t full[NUNIT];
   uint64_t empty[NUNIT];
   uint64_t prep[2];         // compute -> MMA: shared feature block of tile slot s written
@@ -156,6 +162,7 @@ struct Ctrl {
   // few hundred cycles, a shared-memory read ~30
   TcOp ops[MAX_OPS];
   Step steps[MAX_STEPS];
+  alignas(16) Burst burst[MAX_BURST];   // the issuer's copy of the burst program
 };
 
 __device__ __forceinline__ void ctrl_init(Ctrl* ctl) {
@@ -229,55 +236,60 @@ __device__ __forceinline__ uint32_t issue_burst(uint32_t pat, bool two, uint32_t
   return ok;
 }
 
+// Ctrl barrier index -> shared-window address (all barriers are the leading uint64 array of Ctrl)
+__device__ __forceinline__ uint32_t bar_addr(uint32_t ctl_addr, uint32_t idx) { return ctl_addr + 8u * idx; }
+
 // MMA issuer, run by ONE elected thread (the caller guards it with elect_one_sync(), which is what lets ptxas keep
 // the whole loop -- program decode, barrier waits, tcgen05 instructions -- on the uniform datapath).
 // `bits`: one parity bit per barrier the issuer waits on.  bit s: part[s][*]; 2+s: glue[s]; 4+s: prep[s];
 // 6+s: done[s]; 8+u: full[u].
-__device__ __forceinline__ void issue_program(const TcProgram& P, uint32_t smem_base, Ctrl* ctl, uint32_t tmem_base,
-                                              uint32_t& bits_io, bool more, unsigned long long* trace) {
+__device__ __forceinline__ void issue_program(const TcProgram& P, Ctrl* ctl, uint32_t& bits_io, bool more,
+                                              unsigned long long* trace) {
   const int n = P.n_burst;
-  const uint32_t ring_lo32 = smem_desc_lo32(smem_base + OFF_RING), ss_base = smem_base >> 4;
+  const uint32_t ctl_addr = smem_u32(ctl);
   uint32_t bits = bits_io;
-  // program entries are fetched one burst ahead: a constant-bank load with a dynamic index misses the small
-  // immediate-constant cache and costs a few hundred cycles, which must not sit between two bursts
-  uint4 q0 = *reinterpret_cast<const uint4*>(&P.burst[0]);
-  uint4 q1 = *(reinterpret_cast<const uint4*>(&P.burst[0]) + 1);
+  // program entries come from the shared-memory copy (a dynamically indexed constant-bank read misses the small
+  // immediate-constant cache and costs a few hundred cycles), fetched one burst ahead
+  const uint4* bp = reinterpret_cast<const uint4*>(ctl->burst);
+  uint4 q0 = bp[0];
+  uint4 q1 = bp[1];
   for (int i = 0; i < n; ++i) {
     const int ni = (i + 1 < n) ? i + 1 : 0;
-    const uint4 n0 = *reinterpret_cast<const uint4*>(&P.burst[ni]);
-    const uint4 n1 = *(reinterpret_cast<const uint4*>(&P.burst[ni]) + 1);
-    const uint32_t c = q1.z, fl = c & 0x1fffu, pat = (c >> 13) & 3u, steps = (c >> 15) & 7u, s = (c >> 18) & 1u;
-    const uint32_t unit = (c >> 19) & 3u, nu = (c >> 21) & 7u, wrap = (c >> 24) & 1u;
+    const uint4 n0 = bp[2 * ni];
+    const uint4 n1 = bp[2 * ni + 1];
+    const uint32_t c = q1.z, s = (c >> 18) & 1u;
     if (trace) trace[i] = clock64();
-    if (fl & B_WAIT_ANY) {
+    if (c & B_WAIT_ANY) {
       const uint32_t o = s ^ 1u;
-      if (fl & B_WAIT_PREP) { mbar_wait(&ctl->prep[s], (bits >> (4 + s)) & 1u); bits ^= 1u << (4 + s); }
-      if (fl & B_WAIT_DONE_OTHER) { mbar_wait(&ctl->done[o], (bits >> (6 + o)) & 1u); bits ^= 1u << (6 + o); }
-      if (fl & B_WAIT_GLUE) { mbar_wait(&ctl->glue[s], (bits >> (2 + s)) & 1u); bits ^= 1u << (2 + s); }
-      if (fl & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
-      if (fl & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
-      if (fl & B_WAIT_P1) mbar_wait(&ctl->part[s][1], (bits >> s) & 1u);
+      if (c & B_WAIT_PREP) { mbar_wait(&ctl->prep[s], (bits >> (4 + s)) & 1u); bits ^= 1u << (4 + s); }
+      if (c & B_WAIT_DONE_OTHER) { mbar_wait(&ctl->done[o], (bits >> (6 + o)) & 1u); bits ^= 1u << (6 + o); }
+      if (c & B_WAIT_GLUE) { mbar_wait(&ctl->glue[s], (bits >> (2 + s)) & 1u); bits ^= 1u << (2 + s); }
+      if (c & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
+      if (c & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
+      if (c & B_WAIT_P1) mbar_wait(&ctl->part[s][1], (bits >> s) & 1u);
+      tc_fence_after_sync();
     }
-    tc_fence_after_sync();
     if (trace) trace[MAX_BURST + i] = clock64();
-    const bool two = (fl & B_TWO) != 0;
-    const uint32_t abase = pat == PAT_SS ? ss_base : tmem_base;
-    const uint32_t a_hi = abase + q0.x, a_lo = abase + q0.y, d = tmem_base + q0.z, idesc = q0.w;
-    const uint32_t b0 = ring_lo32 + q1.x, b1 = ring_lo32 + q1.y, acc = (fl & B_FIRST) ? 0u : 1u;
     // the next burst's weights (in the ring long ago in steady state) are probed while this burst is issued.
     // Only ring waits may be hoisted: the producer never depends on anything this thread still has to issue.
-    const uint32_t do_probe = (nu && (!wrap || more)) ? 1u : 0u;
-    uint64_t* nbar = &ctl->full[nu ? nu - 1 : 0];
-    const uint32_t ppar = (bits >> (7 + nu)) & 1u;
-    const uint32_t ok = issue_burst(pat, two, steps, d, a_hi, a_lo, b0, b1, idesc, acc, smem_u32(nbar), ppar, do_probe);
-    if (fl & B_RELEASE) umma_commit(&ctl->empty[unit]);
-    if (fl & B_LAST) umma_commit(&ctl->d_full[s][(fl & B_NC1) ? 1 : 0]);
+    const uint32_t nu = (c >> 21) & 7u;
+    const uint32_t do_probe = (nu != 0u && (((c >> 24) & 1u) == 0u || more)) ? 1u : 0u;
+    const uint32_t pbar = bar_addr(ctl_addr, (q1.w >> 16) & 0xffu), ppar = (bits >> (7 + nu)) & 1u;
+    const uint32_t acc = (c & B_FIRST) ? 0u : 1u, pat = (c >> 13) & 3u;
+    const bool two = (c & B_TWO) != 0;
+    uint32_t ok;
+    if (two && pat == PAT_32) ok = burst12_ts32(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
+    else if (two && pat == PAT_16) ok = burst12_ts16(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
+    else ok = issue_burst(pat, two, (c >> 15) & 7u, q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
+    const uint32_t eb = q1.w & 0xffu, db = (q1.w >> 8) & 0xffu;
+    if (eb != 0xffu) umma_commit_a(bar_addr(ctl_addr, eb));
+    if (db != 0xffu) umma_commit_a(bar_addr(ctl_addr, db));
     if (do_probe) {
-      if (!ok) mbar_wait(nbar, ppar);
+      if (!ok) { mbar_wait_a(pbar, ppar); tc_fence_after_sync(); }
       bits ^= 1u << (7 + nu);
     }
     if (trace) trace[2 * MAX_BURST + i] = clock64();
-    if (fl & B_PART_NEXT) bits ^= 1u << s;
+    if (c & B_PART_NEXT) bits ^= 1u << s;
     q0 = n0;
     q1 = n1;
   }
@@ -289,17 +301,16 @@ struct ProducerState { uint32_t ebits, filled; };
 __device__ __forceinline__ void produce_program(const TcProgram& P, const uint8_t* wstream, uint8_t* smem, Ctrl* ctl,
                                                 ProducerState& st) {
   for (int i = 0; i < P.n_burst; ++i) {
-    const uint32_t c = P.burst[i].ctl;
-    if (!(c & B_ACQUIRE)) continue;
-    const uint32_t sw = P.burst[i].src;
-    const uint32_t u = (c >> 19) & 3u, bytes = (sw >> 22) * 128u;
+    const uint32_t sw = P.src[i];
+    if (!(sw >> 31)) continue;
+    const uint32_t u = (sw >> 29) & 3u, bytes = ((sw >> 20) & 0x1ffu) * 128u;
     if ((st.filled >> u) & 1u) {       // the previous fill of this unit has been consumed
       mbar_wait(&ctl->empty[u], (st.ebits >> u) & 1u);
       st.ebits ^= 1u << u;
     }
     st.filled |= 1u << u;
     mbar_arrive_expect_tx(&ctl->full[u], bytes);
-    tma_bulk_g2s(smem + OFF_RING + u * UNIT_BYTES, wstream + (size_t)(sw & 0x3fffffu) * 128u, bytes, &ctl->full[u]);
+    tma_bulk_g2s(smem + OFF_RING + u * UNIT_BYTES, wstream + (size_t)(sw & 0xfffffu) * 128u, bytes, &ctl->full[u]);
   }
 }
 
@@ -488,6 +499,8 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     reinterpret_cast<uint32_t*>(ctl->ops)[i] = reinterpret_cast<const uint32_t*>(P.ops)[i];
   for (int i = threadIdx.x; i < P.n_steps; i += blockDim.x)
     reinterpret_cast<uint32_t*>(ctl->steps)[i] = reinterpret_cast<const uint32_t*>(P.steps)[i];
+  for (int i = threadIdx.x; i < P.n_burst * 8; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ctl->burst)[i] = reinterpret_cast<const uint32_t*>(P.burst)[i];
   if (threadIdx.x == 0) ctrl_init(ctl);
   if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   fence_proxy_async_smem();
@@ -495,6 +508,11 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
+  // the burst program holds absolute shared-memory / tensor-memory addresses
+  if (smem_base != P.smem_base || tmem_base != 0u) {
+    if (threadIdx.x == 0) printf("nerfds_b200: tensor-core program encoded for smem base %u, tmem base 0; got %u, %u\n", P.smem_base, smem_base, tmem_base);
+    __trap();
+  }
 
   const int64_t n_tiles = (a.n_samples_total + TM - 1) / TM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
@@ -512,12 +530,11 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     if (elect_one_sync()) {
       uint32_t bits = 0;
       {   // the very first burst of the kernel: nobody waited for its weights yet
-        const uint32_t c0 = P.burst[0].ctl, u0 = (c0 >> 19) & 3u;
-        if (c0 & B_ACQUIRE) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
+        const uint32_t s0 = P.src[0], u0 = (s0 >> 29) & 3u;
+        if (s0 >> 31) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
       }
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-        issue_program(P, smem_base, ctl, tmem_base, bits, pair + gridDim.x < n_pairs,
-                      (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
+        issue_program(P, ctl, bits, pair + gridDim.x < n_pairs, (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
     }
     __syncwarp();
   } else {
@@ -721,12 +738,19 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + OFF_CTRL);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < P.n_burst * 8; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ctl->burst)[i] = reinterpret_cast<const uint32_t*>(P.burst)[i];
   if (threadIdx.x == 0) ctrl_init(ctl);
   if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = ctl->tmem_base;
+  // the burst program holds absolute shared-memory / tensor-memory addresses
+  if (smem_base != P.smem_base || tmem_base != 0u) {
+    if (threadIdx.x == 0) printf("nerfds_b200: tensor-core program encoded for smem base %u, tmem base 0; got %u, %u\n", P.smem_base, smem_base, tmem_base);
+    __trap();
+  }
   const TcOp& op = P.ops[0];
   if (warp == WARP_TMA) {
     if (lane == 0) {
@@ -737,9 +761,9 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   } else if (warp == WARP_MMA) {
     if (elect_one_sync()) {
       uint32_t bits = 0;
-      const uint32_t c0 = P.burst[0].ctl, u0 = (c0 >> 19) & 3u;
-      if (c0 & B_ACQUIRE) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
-      issue_program(P, smem_base, ctl, tmem_base, bits, false, nullptr);
+      const uint32_t s0 = P.src[0], u0 = (s0 >> 29) & 3u;
+      if (s0 >> 31) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
+      issue_program(P, ctl, bits, false, nullptr);
     }
     __syncwarp();
   } else {
@@ -1058,26 +1082,58 @@ static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
   return out;
 }
 
-// device form of the bursts of a program; `next` links implement the issuer's mid-burst weight wait
-static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, Burst* out) {
+// shared-window address of the 1024-aligned dynamic shared memory of the engine's kernels (none of them has
+// static shared memory, so it is the same for all): measured once with a probe launch
+__global__ void smem_base_probe_kernel(uint32_t* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  if (threadIdx.x == 0) *out = smem_u32(smem);
+}
+static bool query_smem_base(uint32_t& base, std::string& err) {
+  static uint32_t cached = 0;
+  static bool have = false;
+  if (!have) {
+    uint32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 4);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e == cudaSuccess) { smem_base_probe_kernel<<<1, 32, TC_SMEM_BYTES>>>(d); e = cudaDeviceSynchronize(); }
+    if (e == cudaSuccess) e = cudaMemcpy(&cached, d, 4, cudaMemcpyDeviceToHost);
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) { err = std::string("tensor-core engine: shared-memory base probe: ") + cudaGetErrorString(e); return false; }
+    have = true;
+  }
+  base = cached;
+  return true;
+}
+
+// Ctrl barrier indices (Burst::bars)
+#define NDS_BAR_IDX(member) ((uint32_t)(offsetof(Ctrl, member) / 8))
+
+// device form of the bursts of a program; `next` links implement the issuer's weight-barrier probe
+static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, uint32_t smem_base, Burst* out, uint32_t* src) {
   const int n = (int)hb.size();
+  auto desc_lo = [&](uint32_t off) { return (((smem_base + off) & 0x3FFFFu) >> 4) | (1u << 16); };
   for (int i = 0; i < n; ++i) {
     const BurstH& e = hb[i];
     Burst b;
     const bool ss = e.pat == PAT_SS;
-    b.a_hi = ss ? ((e.a_hi >> 4) | (1u << 16)) : e.a_hi;
-    b.a_lo = ss ? ((e.a_lo >> 4) | (1u << 16)) : e.a_lo;
-    b.d_col = e.d_col;
+    b.a_hi = ss ? desc_lo(e.a_hi) : e.a_hi;
+    b.a_lo = ss ? desc_lo(e.a_lo) : e.a_lo;
+    b.d = e.d_col;
     b.idesc = make_idesc_f16(e.rows);
-    b.b0 = (uint32_t)e.unit * (UNIT_BYTES >> 4);
+    b.b0 = desc_lo(OFF_RING + (uint32_t)e.unit * UNIT_BYTES);
     b.b1 = b.b0 + (uint32_t)e.rows * 8u;
     uint32_t nu = 0, wrap = 0;
     if (i + 1 < n) { if (hb[i + 1].flags & B_ACQUIRE) nu = 1u + hb[i + 1].unit; }
     else if (cyclic && (hb[0].flags & B_ACQUIRE)) { nu = 1u + hb[0].unit; wrap = 1; }
     b.ctl = (uint32_t)(e.flags & 0x1fffu) | ((uint32_t)e.pat << 13) | ((uint32_t)e.steps << 15) | ((uint32_t)e.tslot << 18) |
             ((uint32_t)e.unit << 19) | (nu << 21) | (wrap << 24);
-    b.src = (e.src & 0x3fffffu) | ((uint32_t)e.rows128 << 22);
+    const uint32_t eb = (e.flags & B_RELEASE) ? NDS_BAR_IDX(empty) + e.unit : 0xffu;
+    const uint32_t db = (e.flags & B_LAST) ? NDS_BAR_IDX(d_full) + 2u * e.tslot + ((e.flags & B_NC1) ? 1u : 0u) : 0xffu;
+    const uint32_t pb = nu ? NDS_BAR_IDX(full) + (nu - 1u) : 0xffu;
+    b.bars = eb | (db << 8) | (pb << 16);
     out[i] = b;
+    src[i] = (e.src & 0xfffffu) | ((uint32_t)e.rows128 << 20) | ((uint32_t)e.unit << 29) | ((e.flags & B_ACQUIRE) ? (1u << 31) : 0u);
   }
 }
 
@@ -1168,8 +1224,9 @@ struct TcEngine {
 };
 
 // Merges the per-slot op lists into the pair program: bursts (issuer / producer) and steps (compute warps).
-static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::string& err) {
+static bool assemble(const LevelBuild& LB, bool full, uint32_t smem_base, TcProgram& prog, std::string& err) {
   memset(&prog, 0, sizeof prog);
+  prog.smem_base = smem_base;
   const int n_ops = full ? (int)LB.ops[0].size() : LB.n_sigma;
   if (2 * n_ops > MAX_OPS) { err = "tensor-core engine: too many layers"; return false; }
   prog.n_ops = 2 * n_ops;
@@ -1261,7 +1318,7 @@ static bool assemble(const LevelBuild& LB, bool full, TcProgram& prog, std::stri
   }
   prog.n_burst = (int)bursts.size();
   prog.n_steps = (int)steps.size();
-  encode_bursts(bursts, true, prog.burst);
+  encode_bursts(bursts, true, smem_base, prog.burst, prog.src);
   std::copy(steps.begin(), steps.end(), prog.steps);
   return true;
 }
@@ -1420,12 +1477,14 @@ int tc_engine_load(ndsr_handle* h) {
   tc_engine_free(h);
   TcEngine* E = new TcEngine();
   h->tc = E;
+  uint32_t smem_base = 0;
+  if (!query_smem_base(smem_base, h->err)) return NDSR_ERR_CUDA;
   for (int lv = 0; lv < 2; ++lv) {
     int rc = build_level(h, lv, E->lb[lv], E->packed[lv]);
     if (rc) return rc;
     Packed& P = E->packed[lv];
     for (int full = 0; full < 2; ++full)
-      if (!assemble(E->lb[lv], full != 0, E->prog[lv][full], h->err)) return NDSR_ERR_UNSUPPORTED;
+      if (!assemble(E->lb[lv], full != 0, smem_base, E->prog[lv][full], h->err)) return NDSR_ERR_UNSUPPORTED;
     cudaError_t e;
     if ((e = cudaMalloc(&E->d_stream[lv], P.stream.size())) != cudaSuccess ||
         (e = cudaMalloc(&E->d_bias[lv], P.bias.size() * sizeof(float))) != cudaSuccess ||
@@ -1514,7 +1573,7 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
         const Burst& b = prog.burst[i];
         fprintf(f, "burst %d slot %d rows %d steps %d pat %d flags %d unit %d dcol %d top %lld ready %lld issued %lld\n", i,
                 (b.ctl >> 18) & 1, ((b.idesc >> 17) & 63) * 8, (b.ctl >> 15) & 7, (b.ctl >> 13) & 3, b.ctl & 0x1fff,
-                (b.ctl >> 19) & 3, b.d_col, rel(t[i]), rel(t[MAX_BURST + i]), rel(t[2 * MAX_BURST + i]));
+                (b.ctl >> 19) & 3, b.d, rel(t[i]), rel(t[MAX_BURST + i]), rel(t[2 * MAX_BURST + i]));
       }
       for (int i = 0; i < prog.n_steps; ++i) {
         const Step& s = prog.steps[i];
@@ -1574,7 +1633,11 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   int cursor = 0;
   for (auto& e : bursts) { e.unit = (uint8_t)cursor; cursor = (cursor + 1) % NUNIT; e.flags |= B_ACQUIRE | B_RELEASE; }
   prog.n_burst = (int)bursts.size();
-  encode_bursts(bursts, false, prog.burst);
+  {
+    std::string perr;
+    if (!query_smem_base(prog.smem_base, perr)) { fprintf(stderr, "%s\n", perr.c_str()); return NDSR_ERR_CUDA; }
+  }
+  encode_bursts(bursts, false, prog.smem_base, prog.burst, prog.src);
   uint8_t* d_stream; float *d_bias, *d_A, *d_out, *d_rb;
   const int N = prog.ops[0].N;
   const int K = k_hid + k_in;

@@ -219,6 +219,18 @@ __device__ __forceinline__ void umma_commit_p(uint64_t* bar, uint32_t issue) {
       "r"(issue)
       : "memory");
 }
+// address forms (shared-window address of the barrier)
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "NDS_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra NDS_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -276,6 +288,47 @@ __device__ __forceinline__ uint32_t mma4_ss(uint32_t d, uint32_t a_lo32, uint32_
                : "memory");
   return ok;
 }
+// A whole 3-term K-chunk (12 tcgen05.mma, tensor-memory A operand) as ONE asm block with the barrier probe of
+// mma4_ts: the issuing thread shares its scheduler with four busy epilogue warps, so every instruction it does
+// NOT execute between two bursts is worth several cycles of tensor-pipe time.  All operands are final
+// (absolute) values; S1..S3 are the K-step column offsets of the operand pattern.
+#define NDS_DEFINE_BURST12_TS(NAME, S1, S2, S3)                                                                          \
+  __device__ __forceinline__ uint32_t NAME(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b0_lo32, uint32_t b1_lo32, \
+                                           uint32_t idesc, uint32_t accumulate, uint32_t probe_bar, uint32_t probe_parity, \
+                                           uint32_t do_probe) {                                                          \
+    uint32_t ok;                                                                                                         \
+    asm volatile(                                                                                                        \
+        "{\n\t.reg .pred p, t, pq, ok;\n\t.reg .b64 H0, H1, H2, H3, G0, G1, G2, G3;\n\t"                                 \
+        ".reg .b32 w, A1, A2, A3, L1, L2, L3;\n\t"                                                                       \
+        "setp.ne.b32 p, %7, 0;\n\tsetp.eq.u32 t, 0, 0;\n\tsetp.eq.u32 ok, 0, 0;\n\tsetp.ne.b32 pq, %10, 0;\n\t"          \
+        "mov.b64 H0, {%4, %11};\n\tadd.u32 w, %4, 2;\n\tmov.b64 H1, {w, %11};\n\tadd.u32 w, %4, 4;\n\tmov.b64 H2, {w, %11};\n\t" \
+        "add.u32 w, %4, 6;\n\tmov.b64 H3, {w, %11};\n\t"                                                                 \
+        "mov.b64 G0, {%5, %11};\n\tadd.u32 w, %5, 2;\n\tmov.b64 G1, {w, %11};\n\tadd.u32 w, %5, 4;\n\tmov.b64 G2, {w, %11};\n\t" \
+        "add.u32 w, %5, 6;\n\tmov.b64 G3, {w, %11};\n\t"                                                                 \
+        "add.u32 A1, %2, " S1 ";\n\tadd.u32 A2, %2, " S2 ";\n\tadd.u32 A3, %2, " S3 ";\n\t"                               \
+        "add.u32 L1, %3, " S1 ";\n\tadd.u32 L2, %3, " S2 ";\n\tadd.u32 L3, %3, " S3 ";\n\t"                               \
+        "@pq mbarrier.try_wait.parity.shared::cta.b64 ok, [%8], %9;\n\t"                                                 \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], H0, %6, p;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [A1], H1, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [A2], H2, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [A3], H3, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%3], H0, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [L1], H1, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [L2], H2, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [L3], H3, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], G0, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [A1], G1, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [A2], G2, %6, t;\n\t"                                                  \
+        "tcgen05.mma.cta_group::1.kind::f16 [%1], [A3], G3, %6, t;\n\t"                                                  \
+        "selp.u32 %0, 1, 0, ok;\n\t}"                                                                                    \
+        : "=r"(ok)                                                                                                       \
+        : "r"(d), "r"(a_hi), "r"(a_lo), "r"(b0_lo32), "r"(b1_lo32), "r"(idesc), "r"(accumulate), "r"(probe_bar),         \
+          "r"(probe_parity), "r"(do_probe), "r"(NDS_DESC_HI)                                                             \
+        : "memory");                                                                                                     \
+    return ok;                                                                                                           \
+  }
+NDS_DEFINE_BURST12_TS(burst12_ts32, "8", "32", "40")
+NDS_DEFINE_BURST12_TS(burst12_ts16, "16", "32", "48")
 __device__ __forceinline__ uint32_t smem_desc_lo32(uint32_t smem_addr) {
   return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
 }
