@@ -11,16 +11,17 @@
 //   * B = the layer's weights, pre-packed on the host into the exact shared-memory image (scaled by a power of
 //     two, split hi + lo, swizzled) and streamed through a ring of 4 x 32 KB units by bulk TMA (cp.async.bulk);
 //   * "3-term" layers issue A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (~fp32 accuracy, needed on the sigma path for the
-//     1e-3 RGB bound -- tools/precision_study.py), "1-term" layers A_hi*B_hi only (bottleneck, rgb branch).
+//     1e-3 RGB bound -- tools/precision_study.py), "1-term" layers A_hi*B_hi only (rgb branch in `mixed` precision).
 //
 // Schedule of one pair (static, built on the host: TcProgram):
 //   N phase  the narrow networks (mask MLP -> hyper sheet -> SE(3) warp field; width <= 128) of BOTH tiles,
 //            interleaved op by op: each tile owns 256 TMEM columns (two regions of 128), the tensor core works on
 //            one tile while the compute warps run the other tile's epilogue / per-sample stage, and every weight
 //            image loaded into the ring is used by both tiles before it is released;
-//   T phase  the template NeRF (trunk 8 x 256, sigma/normal head, bottleneck, rgb branch) needs all 512 columns
-//            (two regions of 256), so tile A then tile B run it alone, each layer split into two N-chunks whose
-//            K-ranges are ordered so that the tensor core never waits for the second chunk's epilogue.
+//   T phase  the template NeRF (trunk 8 x 256, sigma/normal head, rgb branch with the activation-free bottleneck
+//            folded into its first layer) needs all 512 columns (two regions of 256), so tile A then tile B run it
+//            alone, each layer split into two N-chunks whose K-ranges are ordered so that the tensor core never
+//            waits for the second chunk's epilogue.
 //   The three narrow networks read ONE shared feature block per tile ([sin/cos bands of x | embeddings | mask],
 //   posenc windows folded into the first-layer weights on the host), written one pair ahead during the T phase.
 // Warp roles: warps 0-15 = compute (TMEM lane quarter = warp % 4 -> 32 samples, column slice = warp / 4):
