@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from nerfds_b200 import synthetic as syn
+from oracle.nerfds_oracle import OracleNerfModel, to_numpy
 from tests.common import RGB_TOL, linf, make_case, run_oracle
 
 pytestmark = pytest.mark.gpu
@@ -242,3 +243,52 @@ def test_tc_end_to_end_matches_simt(cuda_device):
   # (the fp32 and fp64 ORACLES disagree on a comparable fraction of rays after resampling)
   assert np.mean(err <= RGB_TOL) >= 0.97, np.sort(err)[-5:]
   assert np.median(err) <= 3e-4
+
+
+def test_tc_mid_schedule_windows_and_mask_ratio(cuda_device):
+  """Mid-training extra_params: fractional posenc windows (folded into the first-layer weight images of the
+  shared feature block and re-packed when they change between calls) and a mask_ratio that mixes in the gt mask."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=10, seed=2)
+  m = _model(cfg, cuda_device, engine='tc')
+  m.renderer.ensure_params(params)
+  schedules = [dict(nerf_alpha=5.3, warp_alpha=2.4, hyper_alpha=0.6, hyper_sheet_alpha=3.7, norm_input_alpha=1.5),
+               dict(nerf_alpha=8.0, warp_alpha=4.0, hyper_alpha=1.0, hyper_sheet_alpha=6.0, norm_input_alpha=4.0),
+               dict(nerf_alpha=2.1, warp_alpha=0.9, hyper_alpha=0.2, hyper_sheet_alpha=5.1, norm_input_alpha=3.3)]
+  for i, sch in enumerate(schedules):
+    ep = dict(syn.final_extra_params(), **sch)
+    mask_ratio = (0.35, 1.0, 0.8)[i]
+    om = OracleNerfModel(cfg, params)
+    ref = to_numpy(om.apply(rays, ep, t_rand, u, return_points=True, return_weights=True, keep_internal=True,
+                            use_predicted_norm=True, compute_sigma_gradient=False, mask_ratio=mask_ratio))
+    extra = m.renderer.make_extra(ep, use_predicted_norm=True, mask_ratio=mask_ratio)
+    keys = [k for k in m.renderer.level_keys(return_points=True, return_weights=True, want_target_norm=False)]
+    for lvl, name in ((0, 'coarse'), (1, 'fine')):
+      r = ref[name]
+      out = _np(m.renderer.render_samples(lvl, r['z_vals'], rays['directions'], origins=rays['origins'],
+                                           warp_id=rays['metadata']['warp'], gt_mask=rays['mask'], extra=extra,
+                                           use_sample_at_infinity=cfg.use_sample_at_infinity, keys=keys))
+      for k in PER_RAY_KEYS:
+        if k in out and r[k].size:
+          assert linf(out[k].reshape(r[k].shape), r[k]) <= RGB_TOL, (i, name, k, linf(out[k].reshape(r[k].shape), r[k]))
+      for k in ('warped_points', 'predicted_mask'):
+        assert linf(out[k].reshape(r[k].shape), r[k]) <= 5e-4, (i, name, k)
+
+
+@pytest.mark.parametrize('n_rays', [1, 7, 130])
+def test_tc_ragged_batches_match_simt(cuda_device, n_rays):
+  """Batches that do not fill a pair of 128-sample tiles (the last tile / the second tile slot run on padding)."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=12, seed=3)
+  sub = {'origins': rays['origins'][:n_rays], 'directions': rays['directions'][:n_rays],
+         'metadata': {k: v[:n_rays] for k, v in rays['metadata'].items()}, 'mask': rays['mask'][:n_rays]}
+  if 'viewdirs' in rays:
+    sub['viewdirs'] = rays['viewdirs'][:n_rays]
+  outs = {}
+  for eng in ('simt', 'tc'):
+    m = _model(cfg, cuda_device, engine=eng)
+    o = m.apply({'params': params}, sub, syn.final_extra_params(), t_rand=t_rand[:n_rays], u=u[:n_rays],
+                use_predicted_norm=True, keys=('rgb', 'depth', 'acc'), coarse_keys=('rgb', 'weights'))
+    outs[eng] = {k: _np(v) for k, v in o.items()}
+  assert outs['tc']['coarse']['rgb'].shape == (n_rays, 3)
+  assert linf(outs['tc']['coarse']['rgb'], outs['simt']['coarse']['rgb']) <= RGB_TOL
+  assert np.isfinite(outs['tc']['fine']['rgb']).all()
+  assert np.median(np.abs(outs['tc']['fine']['rgb'] - outs['simt']['fine']['rgb'])) <= RGB_TOL
