@@ -5,15 +5,23 @@ This file is the checker, never the product: only ``tests/``,
 ``--impl reference`` legs may import it.  Nothing under ``nerfds_b200/``
 imports it, and the product fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED.  The reference (JokerYan/NeRF-DS @ f0bd3844, JAX/Flax) ships
-no tests, golden vectors or fixtures for this path, and jax/flax/gin are not
-installable in this environment (no wheels, no network), so this restatement
-could not be checked against outputs of the reference itself.  It is a
-line-by-line restatement of the reference source in PyTorch-CPU (every torch
-op used here is the direct counterpart of the ``jnp`` op in the cited line;
-``torch.autograd.grad`` stands in for ``jax.value_and_grad``), pinned only by
-closed-form known-answer tests (tests/test_oracle_kat.py) and by the frozen
-vectors under tests/golden/ that it generated itself.
+PARITY: PARTLY PINNED.  The reference (JokerYan/NeRF-DS @ f0bd3844, JAX/Flax)
+ships no tests, golden vectors or fixtures for this path, and jax/flax/gin are
+not installable in this environment (no wheels, no network).  What could be
+done instead:
+  * the array-level functions (model_utils.py: posenc, posenc_window,
+    normalize_vector, sample_along_rays, volumetric_rendering, cal_weights,
+    sharpen_weights, compute_depth_*, piecewise_constant_pdf, sample_pdf;
+    rigid_body.py: skew, exp_so3, exp_se3, to/from_homogenous) ARE pinned
+    against the reference's own source: tools/make_golden.py imports the
+    unmodified reference files under a numpy stand-in for jax.numpy (with
+    jax's float32 / int32 promotion) and freezes their outputs in
+    tests/golden/reference_shim.npz; tests/test_oracle_golden.py compares;
+  * the Flax-module part (Dense / MLP / GLOEmbed wiring, NerfModel
+    orchestration, the value_and_grad closures) remains PARITY UNPINNED: it
+    is a line-by-line restatement in PyTorch-CPU (``torch.autograd.grad``
+    stands in for ``jax.value_and_grad``), checked only by closed-form
+    known-answer tests (tests/test_oracle_kat.py) and an fp64 run of itself.
 
 Deliberate, documented choices where the reference leaves the result to XLA:
   * reductions that feed *discrete* results (pdf normalisation and cdf in
