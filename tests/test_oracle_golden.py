@@ -110,3 +110,69 @@ def test_se3_exponential(G):
   x = T(G['hom_in'])
   np.testing.assert_array_equal(torch.cat([x, torch.ones_like(x[..., :1])], -1).numpy(), G['to_homogenous'])
   close(x, G['from_homogenous'], rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Flax-module level: the reference's modules.py / warping.py classes were run (tools/make_golden.py, flax.linen
+# stand-in) on a reduced nerf_ds.gin configuration with a parameter pytree from nerfds_b200.params.init_params.
+# ---------------------------------------------------------------------------------------------------------------
+def _module_case(G):
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import unflatten_params
+  small = {str(k): int(v) for k, v in zip(G['mod_cfg_keys'], G['mod_cfg_vals'])}
+  cfg = nerf_ds_config(**small)
+  P = unflatten_params({k[2:]: v for k, v in G.items() if k.startswith('P/')})
+  ep = dict(zip(('warp_alpha', 'hyper_sheet_alpha', 'nerf_alpha', 'hyper_alpha', 'norm_input_alpha'),
+                (float(v) for v in G['mod_extra'])))
+  return cfg, P, ep, O.OracleNerfModel(cfg, P)
+
+
+def test_modules_embeddings_mask_and_hyper_sheet(G):
+  cfg, P, ep, om = _module_case(G)
+  ids = T(G['mod_ids'].astype(np.int64)).reshape(-1)
+  wemb = om.P['warp_embed']['embed']['embedding'][ids]
+  memb = om.P['mask_embed']['embed']['embedding'][ids]
+  np.testing.assert_array_equal(wemb.numpy(), G['mod_warp_embed'])
+  np.testing.assert_array_equal(memb.numpy(), G['mod_mask_embed'])
+  x = T(G['mod_points'])
+  # the oracle's mask branch (render_samples, models.py:955-975)
+  pe = O.posenc(x, cfg.mask_min_deg, cfg.mask_max_deg, alpha=ep['warp_alpha'])
+  pm = O.mlp_apply(om.P['mask_mlp']['MLP_0'], torch.cat([pe, memb], -1), cfg.mask_depth, cfg.mask_skips,
+                   out_relu=cfg.mask_output_relu)
+  close(pm, G['mod_mask_mlp'], rtol=2e-5, atol=2e-6)
+
+
+def test_modules_sigma_field_pieces(G):
+  """_sigma_field (the oracle's cal_single_pt_sigma) against the reference classes it restates: SE3Field.warp,
+  HyperSheetMLP, NerfMLP.query_bottleneck / query_sigma."""
+  cfg, P, ep, om = _module_case(G)
+  x, mask = T(G['mod_points']), T(G['mod_mask'])
+  wemb = T(G['mod_warp_embed'])
+  with torch.no_grad():
+    _, aux = om._sigma_field('fine', x, wemb, mask, ep)
+  close(aux['screw_axis'], G['mod_se3_screw'], rtol=5e-5, atol=5e-6)
+  close(aux['warped_points'][:, :3], G['mod_se3_points'], rtol=2e-5, atol=5e-6)
+  close(aux['warped_points'][:, 3:], G['mod_hyper_sheet'], rtol=2e-5, atol=2e-6)
+  # map_vectors (models.py:581-607): rotate a vector forward / inverse, and the translation field
+  v = T(G['mod_vec'])
+  close(O.se3_apply(aux['R'], aux['p'], v, rotation_only=True), G['mod_se3_vec_fwd'], rtol=2e-5, atol=5e-6)
+  close(O.se3_apply(aux['R'], aux['p'], v, rotation_only=True, inverse=True), G['mod_se3_vec_inv'], rtol=2e-5, atol=5e-6)
+  close(O.se3_apply(aux['R'], aux['p'], v * 0), G['mod_se3_vec_trans'], rtol=2e-5, atol=5e-6)
+
+
+def test_modules_nerf_mlp(G):
+  """The template MLP as the oracle evaluates it (trunk, bottleneck, sigma/normal head, rgb-branch input order
+  [bottleneck | viewdir feats | trunk_out | norm feats]) against NerfMLP.query_bottleneck / query_sigma / query_rgb."""
+  cfg, P, ep, om = _module_case(G)
+  pn = om.P['nerf_mlps_fine']
+  feat, vfeat, nfeat = T(G['mod_trunk_in']), T(G['mod_view_feat']), T(G['mod_norm_feat'])
+  trunk_out = O.mlp_apply(pn['trunk_mlp'], feat, cfg.nerf_trunk_depth, cfg.nerf_skips)
+  bott = trunk_out @ pn['bottleneck']['kernel'] + pn['bottleneck']['bias']
+  alpha_out = trunk_out @ pn['alpha_mlp']['logit']['kernel'] + pn['alpha_mlp']['logit']['bias']
+  close(trunk_out, G['mod_trunk_out'], rtol=2e-5, atol=2e-6)
+  close(bott, G['mod_bottleneck'], rtol=2e-5, atol=2e-6)
+  close(alpha_out[:, :1], G['mod_alpha'], rtol=2e-5, atol=1e-5)
+  close(alpha_out[:, 1:4], G['mod_norm'], rtol=2e-5, atol=2e-6)
+  rgb_in = torch.cat([bott, vfeat, trunk_out, nfeat], -1)
+  rgb_raw = O.mlp_apply(pn['rgb_mlp'], rgb_in, cfg.nerf_rgb_branch_depth, ())
+  close(rgb_raw, G['mod_rgb_raw'], rtol=2e-5, atol=5e-6)

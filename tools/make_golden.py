@@ -12,6 +12,8 @@ Run here (the reference must be mounted):  python tools/make_golden.py
 """
 from __future__ import annotations
 
+from typing import Any, Optional
+
 import dataclasses
 import importlib.util
 import os
@@ -104,6 +106,133 @@ def _vmap(fn, in_axes=0, out_axes=0):
   return mapped
 
 
+# ------------------------------------------------------------------ flax.linen stand-in
+# Just enough of flax.linen's module system to run the reference's modules.py / warping.py on a given parameter
+# pytree: dataclass-style attributes, `setup()` sub-modules named after their attribute (dict attributes ->
+# `attr_key`), `@nn.compact` sub-modules named explicitly or `ClassName_i`, parameters looked up by that path.
+class _Ctx:
+  stack = []
+
+
+def _compact(fn):
+  fn._compact = True
+  return fn
+
+
+class Module:
+  name = None
+  parent = None
+  _manual = False
+
+  def __init_subclass__(cls, **kw):
+    super().__init_subclass__(**kw)
+    fields = cls.__dict__.get('__annotations__', {})
+    for attr, fn in list(cls.__dict__.items()):
+      if attr not in fields and callable(fn) and not isinstance(fn, (staticmethod, classmethod, type)) and attr != 'setup' and \
+         (attr == '__call__' or not attr.startswith('_')) and hasattr(fn, '__code__'):
+        setattr(cls, attr, Module._wrap(fn))
+    if not cls.__dict__.get('_manual', False):
+      ann = dict(cls.__dict__.get('__annotations__', {}))
+      ann['name'] = Optional[str]
+      ann['parent'] = Any
+      cls.__annotations__ = ann
+      cls.name = None
+      cls.parent = None
+      dataclasses.dataclass(cls, kw_only=True, eq=False, repr=False)
+
+  @staticmethod
+  def _wrap(fn):
+    def wrapped(self, *a, **k):
+      self._ensure_setup()
+      mode = 'compact' if getattr(fn, '_compact', False) else 'method'
+      if mode == 'compact':
+        object.__setattr__(self, '_auto', {})
+      _Ctx.stack.append((self, mode))
+      try:
+        return fn(self, *a, **k)
+      finally:
+        _Ctx.stack.pop()
+    wrapped.__name__ = fn.__name__
+    return wrapped
+
+  def __post_init__(self):
+    object.__setattr__(self, '_scope', None)
+    object.__setattr__(self, '_setup_done', False)
+    object.__setattr__(self, '_auto', {})
+    if _Ctx.stack and _Ctx.stack[-1][1] == 'compact':
+      par = _Ctx.stack[-1][0]
+      if self.name is None:
+        i = par._auto.get(type(self).__name__, 0)
+        par._auto[type(self).__name__] = i + 1
+        object.__setattr__(self, 'name', f'{type(self).__name__}_{i}')
+      object.__setattr__(self, 'parent', par)
+
+  def __setattr__(self, k, v):
+    if _Ctx.stack and _Ctx.stack[-1] == (self, 'setup'):
+      if isinstance(v, Module):
+        if v.name is None:
+          object.__setattr__(v, 'name', k)
+        object.__setattr__(v, 'parent', self)
+      elif isinstance(v, dict) and v and all(isinstance(m, Module) for m in v.values()):
+        for kk, m in v.items():
+          object.__setattr__(m, 'name', f'{k}_{kk}')
+          object.__setattr__(m, 'parent', self)
+    object.__setattr__(self, k, v)
+
+  def _ensure_setup(self):
+    if not self._setup_done:
+      object.__setattr__(self, '_setup_done', True)
+      if hasattr(self, 'setup'):
+        _Ctx.stack.append((self, 'setup'))
+        try:
+          self.setup()
+        finally:
+          _Ctx.stack.pop()
+
+  def _params(self):
+    if self._scope is not None:
+      return self._scope
+    return self.parent._params()[self.name]
+
+  def apply(self, variables, *a, method=None, **k):
+    object.__setattr__(self, '_scope', variables['params'])
+    fn = method if method is not None else type(self).__call__
+    return fn(self, *a, **k)
+
+
+class Dense(Module):
+  _manual = True
+
+  def __init__(self, features, use_bias=True, kernel_init=None, bias_init=None, name=None, **_):
+    self.features, self.use_bias = features, use_bias
+    object.__setattr__(self, 'name', name)
+    object.__setattr__(self, 'parent', None)
+    self.__post_init__()
+    if self.parent is None and _Ctx.stack and _Ctx.stack[-1][1] == 'setup':
+      object.__setattr__(self, 'parent', _Ctx.stack[-1][0])      # functools.partial(nn.Dense)(..., name=...) in setup()
+
+  def __call__(self, x):
+    p = self._params()
+    assert p['kernel'].shape == (x.shape[-1], self.features), (p['kernel'].shape, x.shape, self.features)
+    y = np.matmul(x, p['kernel'])
+    return y + p['bias'] if self.use_bias else y
+
+
+class Embed(Module):
+  _manual = True
+
+  def __init__(self, num_embeddings, features, embedding_init=None, name=None, **_):
+    self.num_embeddings, self.features = num_embeddings, features
+    object.__setattr__(self, 'name', name)
+    object.__setattr__(self, 'parent', None)
+    self.__post_init__()
+
+  def __call__(self, ids):
+    e = self._params()['embedding']
+    assert e.shape == (self.num_embeddings, self.features)
+    return e[np.asarray(ids)]
+
+
 def install_shim():
   jax = types.ModuleType('jax')
   lax = types.ModuleType('jax.lax')
@@ -120,12 +249,41 @@ def install_shim():
   jax.numpy, jax.lax, jax.random, jax.scipy = jnp, lax, random, jscipy
   jax.vmap = _vmap
   jax.jit = lambda f=None, **k: f if f is not None else (lambda g: g)
+
+  def _custom_jvp(f, **k):
+    f.defjvp = lambda g: g
+    return f
+  jax.custom_jvp = _custom_jvp
+  jax.custom_vjp = _custom_jvp
   _matmul = np.matmul
   jnp.matmul = lambda a, b, precision=None: _matmul(a, b)
   flax = types.ModuleType('flax')
   linen = types.ModuleType('flax.linen')
   linen.vmap = lambda fn, **k: fn
-  linen.Module = object
+  linen.Module, linen.Dense, linen.Embed, linen.compact = Module, Dense, Embed, _compact
+  linen.relu = lambda x: np.maximum(x, 0)
+  linen.sigmoid = lambda x: (1 / (1 + np.exp(-x))).astype(np.float32)
+  linen.softplus = lambda x: np.logaddexp(x, 0).astype(np.float32)
+  _init = lambda *a, **k: (lambda *aa, **kk: None)
+  linen.initializers = types.SimpleNamespace(uniform=_init, normal=_init, zeros=None, ones=None)
+  for _n in ('LayerNorm', 'GroupNorm', 'BatchNorm'):
+    setattr(linen, _n, None)
+  jnn = types.ModuleType('jax.nn')
+  jnn.initializers = types.SimpleNamespace(glorot_uniform=_init, xavier_uniform=_init, uniform=_init, normal=_init,
+                                           zeros=None, ones=None)
+  jnn.relu, jnn.sigmoid, jnn.softplus = linen.relu, linen.sigmoid, linen.softplus
+  jax.nn = jnn
+  tree_util = types.ModuleType('jax.tree_util')
+  tree_util.tree_map = lambda f, t: {k: tree_util.tree_map(f, v) for k, v in t.items()} if isinstance(t, dict) else f(t)
+  jax.tree_util = tree_util
+  jax.tree_map = tree_util.tree_map
+  gin = types.ModuleType('gin')
+  gin.REQUIRED = None
+  gin.configurable = lambda *a, **k: (a[0] if a and isinstance(a[0], type) else (lambda c: c))
+  gin.constant = lambda *a, **k: None
+  sys.modules['gin'] = gin
+  sys.modules['jax.nn'] = jnn
+  sys.modules['jax.tree_util'] = tree_util
   struct = types.ModuleType('flax.struct')
   struct.dataclass = dataclasses.dataclass
   struct.field = dataclasses.field
@@ -224,6 +382,77 @@ def main():
   G['hom_in'] = p
   G['to_homogenous'] = f32(rb.to_homogenous(p))
   G['from_homogenous'] = f32(rb.from_homogenous(np.concatenate([p * 2.0, np.full((8, 1), 2.0, np.float32)], -1)))
+
+  # ------------------------------------------------------------------ Flax-module level (modules.py, warping.py)
+  # The reference's own module classes, run through the flax.linen stand-in above on a reduced nerf_ds.gin
+  # configuration (same depths / skips / posenc degrees / embedding sizes, narrow widths) whose parameter pytree
+  # comes from nerfds_b200.params.init_params -- so the Flax parameter paths the product expects are exercised too.
+  sys.path.insert(0, REF)
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  import importlib
+  modules = importlib.import_module('hypernerf.modules')
+  warping = importlib.import_module('hypernerf.warping')
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import flatten_params, init_params
+  small = dict(nerf_trunk_width=32, nerf_rgb_branch_width=16, warp_trunk_width=16, hyper_sheet_width=16, mask_width=16,
+               num_warp_embeds=5)
+  cfg = nerf_ds_config(**small)
+  P = init_params(cfg, 7)
+  for name, arr in flatten_params(P):
+    G['P/' + name] = f32(arr)
+  G['mod_cfg_keys'] = np.array(sorted(small.keys()))
+  G['mod_cfg_vals'] = np.array([small[k] for k in sorted(small.keys())], np.int32)
+  ep = {'warp_alpha': 2.6, 'hyper_sheet_alpha': 4.4, 'nerf_alpha': 5.5, 'hyper_alpha': 0.7, 'norm_input_alpha': 3.2}
+  G['mod_extra'] = f32([ep['warp_alpha'], ep['hyper_sheet_alpha'], ep['nerf_alpha'], ep['hyper_alpha'], ep['norm_input_alpha']])
+  N = 23
+  pts = f32(rng.uniform(-1.2, 1.2, size=(N, 3)))
+  ids = rng.integers(0, cfg.num_warp_embeds, size=(N, 1)).astype(np.uint32)
+  maskv = f32(rng.uniform(0, 1.2, size=(N, 1)))
+  G['mod_points'], G['mod_ids'], G['mod_mask'] = pts, ids, maskv
+  # GLOEmbed (modules.py:316-348)
+  wemb = f32(modules.GLOEmbed(num_embeddings=cfg.num_warp_embeds, num_dims=cfg.warp_embed_dims).apply({'params': P['warp_embed']}, ids))
+  memb = f32(modules.GLOEmbed(num_embeddings=cfg.num_warp_embeds, num_dims=cfg.mask_embed_dims).apply({'params': P['mask_embed']}, ids))
+  G['mod_warp_embed'], G['mod_mask_embed'] = wemb, memb
+  # MaskMLP (modules.py:394-434; nerf_ds.gin:116-118: depth 8, relu output), called as models.py:967
+  mm = modules.MaskMLP(depth=cfg.mask_depth, width=cfg.mask_width, skips=tuple(cfg.mask_skips), min_deg=cfg.mask_min_deg,
+                       max_deg=cfg.mask_max_deg, output_activation=sys.modules['jax'].nn.relu)
+  G['mod_mask_mlp'] = f32(mm.apply({'params': P['mask_mlp']}, pts, memb, alpha=ep['warp_alpha']))
+  # HyperSheetMLP (modules.py:351-392), called as models.py:663-666 with [warp embed | mask]
+  hs = modules.HyperSheetMLP(output_channels=cfg.hyper_num_dims, min_deg=cfg.hyper_sheet_min_deg, max_deg=cfg.hyper_sheet_max_deg,
+                             depth=cfg.hyper_sheet_depth, width=cfg.hyper_sheet_width, skips=tuple(cfg.hyper_sheet_skips))
+  hin = np.concatenate([wemb, maskv], -1)
+  G['mod_hyper_sheet'] = f32(hs.apply({'params': P['hyper_sheet_mlp']}, pts, hin, alpha=ep['hyper_sheet_alpha']))
+  # SE3Field (warping.py:123-281): warp of points; rotation of a vector (map_vectors), forward and inverse
+  se3 = warping.SE3Field(min_deg=cfg.warp_min_deg, max_deg=cfg.warp_max_deg, use_posenc_identity=bool(cfg.warp_use_posenc_identity),
+                         skips=tuple(cfg.warp_skips), trunk_depth=cfg.warp_trunk_depth, trunk_width=cfg.warp_trunk_width)
+  # init_params draws the w / v logits small enough that theta stays away from 0
+  # (SE3Field.warp works on ONE point; the reference vmaps it over batch and samples, models.py:609-630)
+  def warp_all(**kw):
+    outs = [se3.apply({'params': P['warp_field']}, pts[i], hin[i], ep, method=warping.SE3Field.warp,
+                      **{k: (v[i] if isinstance(v, np.ndarray) else v) for k, v in kw.items()}) for i in range(N)]
+    return [np.stack([o[j] for o in outs]) if outs[0][j] is not None else None for j in range(2)]
+  wp, screw = warp_all(return_screw=True)
+  G['mod_se3_points'], G['mod_se3_screw'] = f32(wp), f32(screw)
+  vec = f32(rng.normal(size=(N, 3)))
+  G['mod_vec'] = vec
+  G['mod_se3_vec_fwd'] = f32(warp_all(vector=vec)[0])
+  G['mod_se3_vec_inv'] = f32(warp_all(vector=vec, inverse=True)[0])
+  G['mod_se3_vec_trans'] = f32(warp_all(vector=vec * 0, with_translation=True)[0])
+  # NerfMLP (modules.py:86-313): trunk -> bottleneck -> sigma/normal head -> rgb branch, as models.py:525-565 calls it
+  nm = modules.NerfMLP(trunk_depth=cfg.nerf_trunk_depth, trunk_width=cfg.nerf_trunk_width,
+                       rgb_branch_depth=cfg.nerf_rgb_branch_depth, rgb_branch_width=cfg.nerf_rgb_branch_width,
+                       skips=tuple(cfg.nerf_skips), alpha_channels=cfg.alpha_channels, rgb_channels=cfg.rgb_channels,
+                       predict_norm=bool(cfg.predict_norm))
+  feat = f32(rng.normal(size=(N, cfg.trunk_in_dim)))
+  vfeat = f32(rng.normal(size=(N, 24)))
+  nfeat = f32(rng.normal(size=(N, 24)))
+  G['mod_trunk_in'], G['mod_view_feat'], G['mod_norm_feat'] = feat, vfeat, nfeat
+  PN = {'params': P['nerf_mlps_fine']}
+  trunk_out, bott = nm.apply(PN, feat, None, vfeat, method=modules.NerfMLP.query_bottleneck)
+  alpha, nrm, _, _ = nm.apply(PN, trunk_out, bott, None, method=modules.NerfMLP.query_sigma)
+  rgb_raw = nm.apply(PN, trunk_out, bott, vfeat, norm=nfeat, extra_rgb_condition=trunk_out, method=modules.NerfMLP.query_rgb)
+  G['mod_trunk_out'], G['mod_bottleneck'], G['mod_alpha'], G['mod_norm'], G['mod_rgb_raw'] = (
+      f32(trunk_out), f32(bott), f32(alpha), f32(nrm), f32(rgb_raw))
 
   assert not _DRAWS
   os.makedirs(os.path.dirname(OUT), exist_ok=True)
