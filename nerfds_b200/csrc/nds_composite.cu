@@ -195,9 +195,11 @@ sharpen_weights_kernel(int64_t n_rays, int S, const float* __restrict__ weights_
     int64_t src = (int64_t)argmax_idx[ray];
     if (src > n_rays - 1) src = n_rays - 1;
     float tot = 0.f;
+    const float scale_sq = stdv * stdv, log_norm = logf(6.28318530717958647692f * scale_sq);
     for (int s = lane; s < S; s += 32) {
-      const float d = (z[ray * S + s] - z[src * S + s]) / stdv;
-      const float g = expf(-0.5f * (d * d)) / (2.50662827463100050242f * stdv);   // jscipy.stats.norm.pdf
+      // jax.scipy.stats.norm.pdf = exp((log(2 pi scale^2) + (x - loc)^2 / scale^2) / -2)
+      const float d = z[ray * S + s] - z[src * S + s];
+      const float g = expf((log_norm + (d * d) / scale_sq) / -2.0f);
       const float v = weights_sg[ray * S + s] * g;
       out[ray * S + s] = v;
       tot += v;

@@ -5,23 +5,28 @@ This file is the checker, never the product: only ``tests/``,
 ``--impl reference`` legs may import it.  Nothing under ``nerfds_b200/``
 imports it, and the product fails loudly when its CUDA library is missing.
 
-PARITY: PARTLY PINNED.  The reference (JokerYan/NeRF-DS @ f0bd3844, JAX/Flax)
-ships no tests, golden vectors or fixtures for this path, and jax/flax/gin are
-not installable in this environment (no wheels, no network).  What could be
-done instead:
-  * the array-level functions (model_utils.py: posenc, posenc_window,
-    normalize_vector, sample_along_rays, volumetric_rendering, cal_weights,
-    sharpen_weights, compute_depth_*, piecewise_constant_pdf, sample_pdf;
-    rigid_body.py: skew, exp_so3, exp_se3, to/from_homogenous) ARE pinned
-    against the reference's own source: tools/make_golden.py imports the
-    unmodified reference files under a numpy stand-in for jax.numpy (with
-    jax's float32 / int32 promotion) and freezes their outputs in
-    tests/golden/reference_shim.npz; tests/test_oracle_golden.py compares;
-  * the Flax-module part (Dense / MLP / GLOEmbed wiring, NerfModel
-    orchestration, the value_and_grad closures) remains PARITY UNPINNED: it
-    is a line-by-line restatement in PyTorch-CPU (``torch.autograd.grad``
-    stands in for ``jax.value_and_grad``), checked only by closed-form
-    known-answer tests (tests/test_oracle_kat.py) and an fp64 run of itself.
+PARITY: PINNED AGAINST THE REFERENCE'S OWN SOURCE for the forward pass, with one
+exception.  The reference (JokerYan/NeRF-DS @ f0bd3844, JAX/Flax) ships no
+tests, golden vectors or fixtures for this path, and jax/flax/gin are not
+installable in this environment (no wheels, no network).  Instead,
+tools/make_golden.py imports the UNMODIFIED reference files (model_utils.py,
+rigid_body.py, modules.py, warping.py, models.py) under thin stand-ins for
+``jax`` (jax.numpy -> numpy with jax's float32 / int32 promotion and array
+immutability, vmap -> a Python loop over pytrees, random.uniform -> injected
+draws) and ``flax.linen`` (module tree, setup / compact naming, Dense, Embed)
+and freezes, in tests/golden/reference_shim.npz:
+  * the array-level functions (posenc, windows, sample_along_rays,
+    volumetric_rendering, cal_weights, sharpen_weights, compute_depth_*,
+    piecewise_constant_pdf, sample_pdf, skew, exp_so3, exp_se3, ...);
+  * the Flax modules (MLP, NerfMLP, HyperSheetMLP, MaskMLP, GLOEmbed,
+    SE3Field) applied to the product's parameter pytree;
+  * the whole ``NerfModel.__call__`` under nerf_ds.gin's bindings (reduced
+    widths / sample counts): every key of both level dicts.
+tests/test_oracle_golden.py compares this oracle with all of them.
+STILL UNPINNED: ``target_norm`` (and ``ray_norm`` without predicted normals),
+which need ``jax.value_and_grad`` -- no autodiff under the stand-in;
+``torch.autograd.grad`` stands in for it here, checked by finite differences
+(tests/test_oracle_kat.py).
 
 Deliberate, documented choices where the reference leaves the result to XLA:
   * reductions that feed *discrete* results (pdf normalisation and cdf in
@@ -152,8 +157,11 @@ def sharpen_weights(weights, z_vals, std=0.01):
   max_idx = torch.clamp(max_idx, max=z_vals.shape[0] - 1)
   max_z = z_vals[max_idx]                                       # (B, S) rows!
   std_t = torch.as_tensor(std, dtype=weights.dtype)
-  g = torch.exp(-0.5 * ((z_vals - max_z) / std_t) ** 2) / (
-      math.sqrt(2 * math.pi) * std_t)                           # jscipy norm.pdf
+  # jax.scipy.stats.norm.pdf = exp(logpdf) with logpdf = (log(2 pi scale^2) + (x - loc)^2 / scale^2) / -2, all in
+  # the working dtype: the deep tail underflows where THIS form does (pinned by tests/test_oracle_golden.py)
+  scale_sq = std_t * std_t
+  log_norm = torch.log(torch.as_tensor(2 * math.pi, dtype=weights.dtype) * scale_sq)
+  g = torch.exp((log_norm + (z_vals - max_z) ** 2 / scale_sq) / -2.0)
   sharp = weights * g
   return sharp / torch.sum(sharp, dim=1)[..., None]
 

@@ -176,3 +176,72 @@ def test_modules_nerf_mlp(G):
   rgb_in = torch.cat([bott, vfeat, trunk_out, nfeat], -1)
   rgb_raw = O.mlp_apply(pn['rgb_mlp'], rgb_in, cfg.nerf_rgb_branch_depth, ())
   close(rgb_raw, G['mod_rgb_raw'], rtol=2e-5, atol=5e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Whole forward: the reference's NerfModel.__call__ (models.py:1419-1565) was run under the stand-in with nerf_ds.gin's
+# bindings, the product's parameter pytree and injected draws.  Every key of both level dicts except the
+# gradient-derived `target_norm` (no autodiff under the stand-in) is compared with OracleNerfModel.apply.
+# ---------------------------------------------------------------------------------------------------------------
+def test_whole_forward_matches_reference_nerf_model(G):
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import unflatten_params
+  small = {str(k): int(v) for k, v in zip(G['model_cfg_keys'], G['model_cfg_vals'])}
+  cfg = nerf_ds_config(**small)
+  P = unflatten_params({k[3:]: v for k, v in G.items() if k.startswith('MP/')})
+  ep = {str(k): float(v) for k, v in zip(G['model_extra_keys'], G['model_extra_vals'])}
+  rays = {'origins': G['model_origins'], 'directions': G['model_dirs'], 'metadata': {'warp': G['model_warp']},
+          'mask': G['model_gt_mask']}
+  om = O.OracleNerfModel(cfg, P)
+  out = O.to_numpy(om.apply(rays, ep, G['model_t_rand'], G['model_u'], return_points=True, return_weights=True,
+                            use_predicted_norm=True, compute_sigma_gradient=False, keep_internal=True,
+                            mask_ratio=float(G['model_mask_ratio']), sharp_weights_std=float(G['model_sharp_std'])))
+  o3, d3 = G['model_origins'], G['model_dirs']
+  depth_of = lambda pts: (((pts - o3[:, None]) * d3[:, None]).sum(-1) / (d3 ** 2).sum(-1)[:, None]).astype(np.float32)
+  # (1) the resampling step on the REFERENCE's coarse weights reproduces the reference's fine depths
+  zc, zf = depth_of(G['model_coarse_points']), depth_of(G['model_fine_points'])
+  wc = G['model_coarse_weights']
+  z_re, _ = O.sample_pdf(T(G['model_u']), T(.5 * (zc[..., 1:] + zc[..., :-1])), T(wc[..., 1:-1]), T(o3), T(d3), T(zc))
+  np.testing.assert_allclose(z_re.numpy(), zf, rtol=2e-5, atol=2e-5)
+  # (2) the fine level is evaluated on the reference's own fine samples: end to end, 1e-7 differences in the coarse
+  # weights move resampled depths inside near-empty bins by 1e-3 (the inverse CDF is ill-conditioned there)
+  fine_on_ref = O.to_numpy(om.render_samples(
+      'fine', T(G['model_fine_points']), T(zf), T(d3), T(d3), rays['metadata'], ep, G['model_gt_mask'],
+      use_sample_at_infinity=cfg.use_sample_at_infinity, use_predicted_norm=True, compute_sigma_gradient=False,
+      mask_ratio=float(G['model_mask_ratio']), sharp_weights_std=float(G['model_sharp_std'])))
+  assert np.abs(out['fine']['rgb'] - G['model_fine_rgb']).max() <= 2e-2       # end to end: loose, see (2)
+  out = {'coarse': out['coarse'], 'fine': fine_on_ref}
+  checked = 0
+  for lvl in ('coarse', 'fine'):
+    gold = {k[len(f'model_{lvl}_'):]: v for k, v in G.items() if k.startswith(f'model_{lvl}_')}
+    assert {'rgb', 'depth', 'med_depth', 'acc', 'weights', 'sigma', 'warped_points', 'predicted_mask', 'predicted_norm',
+            'ray_norm', 'ray_rotation_field', 'ray_translation_field', 'ray_delta_x', 'ray_hyper_points',
+            'ray_predicted_mask', 'med_points', 'sharp_weights', 'back_facing', 'points'} <= set(gold)
+    for k, g in gold.items():
+      assert k in out[lvl], (lvl, k, sorted(out[lvl]))
+      o = np.asarray(out[lvl][k]).reshape(g.shape)
+      if k == 'sharp_weights':
+        # Each row is weights x Gaussian(z - z[row of its argmax sample index]) normalised by its sum.  Rows whose
+        # sum lands in (or near) float32's denormal range are 0/0 or ratios of few-bit numbers, decided by the exp
+        # implementation's denormal handling: only rows with a healthy normaliser are compared (NaN-ness included).
+        z = (((gold['points'] - G['model_origins'][:, None]) * G['model_dirs'][:, None]).sum(-1) /
+             (G['model_dirs'] ** 2).sum(-1)[:, None]).astype(np.float64)
+        w = gold['weights'].astype(np.float64)
+        rows = np.minimum(w.argmax(1), z.shape[0] - 1)
+        std = float(G['model_sharp_std'])
+        tot = (w * np.exp(-0.5 * ((z - z[rows]) / std) ** 2)).sum(1)
+        healthy = tot > 1e-25
+        assert healthy.sum() >= 3
+        # (atol: alpha = 1 - exp(-sigma delta) is quantised to ulps of 1.0 = 6e-8, a row of such weights has maxima
+        # of ~1e-3, so one ulp of a weight is ~1e-4 of the normalised row)
+        # (a Gaussian of width 0.1 over depth differences of ~1 turns the 1e-6 of the recovered depths into 1e-3)
+        np.testing.assert_allclose(o[healthy], g[healthy], rtol=1e-3, atol=5e-3 if lvl == 'fine' else 2e-4, err_msg=f'{lvl}/{k}')
+      elif k == 'sigma':                    # softplus of +-30-sized logits: relative
+        np.testing.assert_allclose(o, g, rtol=2e-4, atol=2e-5, err_msg=f'{lvl}/{k}')
+      elif k in ('med_depth', 'med_points'):
+        # a selection (first sample past half the accumulated weight); the sampled depths feeding it agree to ~1e-6
+        np.testing.assert_allclose(o, g, rtol=1e-5, atol=1e-5, err_msg=f'{lvl}/{k}')
+      else:
+        np.testing.assert_allclose(o, g, rtol=1e-4, atol=2e-5, equal_nan=True, err_msg=f'{lvl}/{k}')
+      checked += 1
+  assert checked >= 40

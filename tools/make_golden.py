@@ -21,7 +21,6 @@ import sys
 import types
 
 import numpy as np
-import scipy.stats
 
 REF = os.environ.get('NERFDS_REFERENCE', '/root/reference')
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'reference_shim.npz')
@@ -95,15 +94,54 @@ def _draw(key, shape, dtype=np.float32, **_):
   return a.astype(dtype)
 
 
+def _tree_stack(outs):
+  o0 = outs[0]
+  if isinstance(o0, tuple):
+    return tuple(_tree_stack([o[i] for o in outs]) for i in range(len(o0)))
+  if isinstance(o0, list):
+    return [_tree_stack([o[i] for o in outs]) for i in range(len(o0))]
+  if isinstance(o0, dict):
+    return {k: _tree_stack([o[k] for o in outs]) for k in o0}
+  if o0 is None:
+    return None
+  return np.stack([np.asarray(o) for o in outs], 0)
+
+
+def _tree_take(a, i, ax):
+  if ax is None or a is None:
+    return a
+  if isinstance(a, dict):
+    return {k: _tree_take(v, i, ax) for k, v in a.items()}
+  if isinstance(a, (tuple, list)):
+    return type(a)(_tree_take(v, i, ax) for v in a)
+  return np.take(a, i, axis=ax)
+
+
+def _tree_len(a, ax):
+  if isinstance(a, dict):
+    return _tree_len(next(iter(a.values())), ax)
+  if isinstance(a, (tuple, list)):
+    return _tree_len(a[0], ax)
+  return np.asarray(a).shape[ax]
+
+
 def _vmap(fn, in_axes=0, out_axes=0):
+  """jax.vmap as a Python loop over pytrees (the reference vmaps per-point closures over batch and samples)."""
   def mapped(*args):
     axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
-    n = next(np.asarray(a).shape[ax] for a, ax in zip(args, axes) if ax is not None)
-    outs = [fn(*[a if ax is None else np.take(a, i, axis=ax) for a, ax in zip(args, axes)]) for i in range(n)]
-    if isinstance(outs[0], tuple):
-      return tuple(np.stack([o[j] for o in outs], 0) for j in range(len(outs[0])))
-    return np.stack(outs, 0)
+    n = next(_tree_len(a, ax) for a, ax in zip(args, axes) if ax is not None and a is not None)
+    return _tree_stack([fn(*[_tree_take(a, i, ax) for a, ax in zip(args, axes)]) for i in range(n)])
   return mapped
+
+
+def _value_and_grad(f, argnums=0, has_aux=False):
+  """No autodiff here: the VALUE is the reference's, the gradient is zeros.  Only `target_norm` (and `ray_norm`
+  without predicted normals) depend on it; the golden vectors omit those keys."""
+  return lambda *a: (f(*a), np.zeros_like(np.asarray(a[argnums])))
+
+
+def _grad(f, argnums=0, has_aux=False):
+  return lambda *a: np.zeros_like(np.asarray(a[argnums]))
 
 
 # ------------------------------------------------------------------ flax.linen stand-in
@@ -189,6 +227,9 @@ class Module:
         finally:
           _Ctx.stack.pop()
 
+  def make_rng(self, name):
+    return None
+
   def _params(self):
     if self._scope is not None:
       return self._scope
@@ -244,10 +285,17 @@ def install_shim():
   random.split = lambda key, num=2: [key] * num
   random.PRNGKey = lambda seed: np.zeros(2, np.uint32)
   jscipy = types.ModuleType('jax.scipy')
-  jscipy.stats = types.SimpleNamespace(norm=types.SimpleNamespace(
-      pdf=lambda x, loc=0, scale=1: scipy.stats.norm.pdf(x, loc, scale).astype(np.float32)))
+
+  def _norm_pdf(x, loc=0, scale=1):
+    # jax.scipy.stats.norm.pdf (jax 0.3.15) = exp(logpdf), evaluated in float32
+    x, loc, scale = (np.asarray(v, np.float32) for v in (x, loc, scale))
+    scale_sqrd = np.square(scale)
+    log_normalizer = np.log(np.float32(2 * np.pi) * scale_sqrd)
+    quadratic = np.square(x - loc) / scale_sqrd
+    return np.exp((log_normalizer + quadratic) / np.float32(-2)).astype(np.float32)
+  jscipy.stats = types.SimpleNamespace(norm=types.SimpleNamespace(pdf=_norm_pdf))
   jax.numpy, jax.lax, jax.random, jax.scipy = jnp, lax, random, jscipy
-  jax.vmap = _vmap
+  jax.vmap, jax.value_and_grad, jax.grad = _vmap, _value_and_grad, _grad
   jax.jit = lambda f=None, **k: f if f is not None else (lambda g: g)
 
   def _custom_jvp(f, **k):
@@ -290,6 +338,11 @@ def install_shim():
   optim = types.ModuleType('flax.optim')
   optim.Optimizer = object
   flax.linen, flax.struct, flax.optim = linen, struct, optim
+  flax.jax_utils = types.ModuleType('flax.jax_utils')
+  sys.modules['flax.jax_utils'] = flax.jax_utils
+  imm = types.ModuleType('immutabledict')
+  imm.immutabledict = dict
+  sys.modules['immutabledict'] = imm
   for name, mod in (('jax', jax), ('jax.numpy', jnp), ('jax.lax', lax), ('jax.random', random), ('jax.scipy', jscipy),
                     ('flax', flax), ('flax.linen', linen), ('flax.struct', struct), ('flax.optim', optim)):
     sys.modules[name] = mod
@@ -303,10 +356,22 @@ def load_reference(name):
   return mod
 
 
+def _immutable_args(fn):
+  """jax arrays are immutable: `weights += eps` inside piecewise_constant_pdf rebinds a local.  Under numpy it
+  would add eps in place to the caller's array (a view of the coarse level's `weights`), so the function gets copies."""
+  def wrapped(*a, **k):
+    return fn(*[np.array(x) if isinstance(x, np.ndarray) else x for x in a],
+              **{kk: (np.array(v) if isinstance(v, np.ndarray) else v) for kk, v in k.items()})
+  return wrapped
+
+
 def main():
   install_shim()
-  mu = load_reference('model_utils')
-  rb = load_reference('rigid_body')
+  sys.path.insert(0, REF)
+  import importlib
+  mu = importlib.import_module('hypernerf.model_utils')
+  mu.piecewise_constant_pdf = _immutable_args(mu.piecewise_constant_pdf)
+  rb = importlib.import_module('hypernerf.rigid_body')
   rng = np.random.default_rng(20261017)
   f32 = lambda a: np.asarray(a, np.float32)
   G = {}
@@ -387,9 +452,7 @@ def main():
   # The reference's own module classes, run through the flax.linen stand-in above on a reduced nerf_ds.gin
   # configuration (same depths / skips / posenc degrees / embedding sizes, narrow widths) whose parameter pytree
   # comes from nerfds_b200.params.init_params -- so the Flax parameter paths the product expects are exercised too.
-  sys.path.insert(0, REF)
   sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-  import importlib
   modules = importlib.import_module('hypernerf.modules')
   warping = importlib.import_module('hypernerf.warping')
   from nerfds_b200.config import nerf_ds_config
@@ -453,6 +516,64 @@ def main():
   rgb_raw = nm.apply(PN, trunk_out, bott, vfeat, norm=nfeat, extra_rgb_condition=trunk_out, method=modules.NerfMLP.query_rgb)
   G['mod_trunk_out'], G['mod_bottleneck'], G['mod_alpha'], G['mod_norm'], G['mod_rgb_raw'] = (
       f32(trunk_out), f32(bott), f32(alpha), f32(nrm), f32(rgb_raw))
+
+  # ------------------------------------------------------------------ NerfModel.__call__ (models.py:1419-1565)
+  # The reference's whole forward -- sample_along_rays, render_samples('coarse'), sample_pdf, render_samples('fine')
+  # -- with the gin bindings of nerf_ds.gin / defaults.gin passed as constructor arguments (reduced widths and
+  # sample counts), the product's parameter pytree and injected uniform draws.  B >= S_c + S_f because the
+  # row-gather of sharpen_weights (model_utils.py:182) indexes ROWS with a sample index: jax clamps
+  # an out-of-range gather, numpy raises.
+  import functools
+  models = importlib.import_module('hypernerf.models')
+  jx = sys.modules['jax']
+  msmall = dict(small, num_coarse_samples=8, num_fine_samples=8)
+  mcfg = nerf_ds_config(**msmall)
+  MP = init_params(mcfg, 11)
+  for name, arr in flatten_params(MP):
+    G['MP/' + name] = f32(arr)
+  G['model_cfg_keys'] = np.array(sorted(msmall.keys()))
+  G['model_cfg_vals'] = np.array([msmall[k] for k in sorted(msmall.keys())], np.int32)
+  modules.MaskMLP = functools.partial(modules.MaskMLP, depth=mcfg.mask_depth, width=mcfg.mask_width,
+                                      output_activation=jx.nn.relu)                       # nerf_ds.gin:116-118
+  model = models.NerfModel(
+      embeddings_dict={'warp': list(range(mcfg.num_warp_embeds)), 'appearance': [0], 'camera': [0]},
+      near=mcfg.near, far=mcfg.far, num_coarse_samples=mcfg.num_coarse_samples, num_fine_samples=mcfg.num_fine_samples,
+      use_viewdirs=True, use_stratified_sampling=True, norm_type='none', activation=jx.nn.relu, use_posenc_identity=False,
+      spatial_point_min_deg=0, spatial_point_max_deg=8, hyper_point_min_deg=0, hyper_point_max_deg=1,
+      hyper_slice_method='bendy_sheet', hyper_use_warp_embed=True,
+      hyper_sheet_mlp_cls=functools.partial(modules.HyperSheetMLP, min_deg=0, max_deg=6, output_channels=2,
+                                            width=mcfg.hyper_sheet_width),
+      use_warp=True,
+      warp_field_cls=functools.partial(warping.SE3Field, min_deg=0, max_deg=4, use_posenc_identity=False,
+                                       trunk_width=mcfg.warp_trunk_width),
+      warp_embed_cls=functools.partial(modules.GLOEmbed, num_dims=8),
+      hyper_embed_cls=functools.partial(modules.GLOEmbed, num_dims=2),
+      use_rgb_condition=False, predict_norm=True, norm_supervision_type='warped', use_viewdirs_in_hyper=False,
+      use_x_in_rgb_condition=True, use_hyper_c=False, hyper_c_hyper_input=True, use_hyper_c_embed=False,
+      use_mask_in_warp=True, use_mask_in_hyper=True, use_mask_in_rgb=False, use_predicted_mask=True, use_3d_mask=True,
+      use_mask_sharp_weights=True, nerf_trunk_width=mcfg.nerf_trunk_width, nerf_rgb_branch_width=mcfg.nerf_rgb_branch_width)
+  MB = 19
+  mo = f32(rng.normal(size=(MB, 3)) * 0.3)
+  md = f32(rng.normal(size=(MB, 3)))
+  md /= np.linalg.norm(md, axis=-1, keepdims=True)
+  mmeta = rng.integers(0, mcfg.num_warp_embeds, size=(MB, 1)).astype(np.uint32)
+  mgt = f32(rng.integers(0, 2, size=(MB, 1)))
+  mt = f32(rng.uniform(size=(MB, mcfg.num_coarse_samples)))
+  mu_ = f32(rng.uniform(size=(MB, mcfg.num_fine_samples)))
+  mep = {'nerf_alpha': 5.5, 'warp_alpha': 2.6, 'hyper_alpha': 0.7, 'hyper_sheet_alpha': 4.4, 'norm_loss_weight': 1.0,
+         'norm_input_alpha': 3.2, 'norm_voxel_lr': 0.0, 'norm_voxel_ratio': 0.0}
+  G['model_origins'], G['model_dirs'], G['model_warp'], G['model_gt_mask'] = mo, md, mmeta, mgt
+  G['model_t_rand'], G['model_u'] = mt, mu_
+  G['model_extra_keys'] = np.array(sorted(mep.keys()))
+  G['model_extra_vals'] = f32([mep[k] for k in sorted(mep.keys())])
+  G['model_mask_ratio'], G['model_sharp_std'] = f32(0.7), f32(0.1)
+  _DRAWS.extend([mt, mu_])
+  res = model.apply({'params': MP}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mep,
+                    use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.1)
+  for lvl in ('coarse', 'fine'):
+    for k, v in res[lvl].items():
+      if k != 'target_norm' and v is not None:          # gradient-derived: no autodiff under the stand-in
+        G[f'model_{lvl}_{k}'] = f32(v)
 
   assert not _DRAWS
   os.makedirs(os.path.dirname(OUT), exist_ok=True)
