@@ -58,6 +58,9 @@ constexpr int NUNIT = 4;
 constexpr uint32_t OFF_CTRL = OFF_RING + NUNIT * UNIT_BYTES;
 constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 11264 + 1024;  // Ctrl + manual 1024-byte alignment slack
 constexpr int NPREP = 3;                // the shared feature block of the next pair is written in 3 parts
+#ifndef NDS_EPI_RZ
+#define NDS_EPI_RZ 0    // 1: ReLU folded into cvt.rz.relu (2 instructions fewer per pair, hi truncated -> lo twice as large)
+#endif
 
 enum EpiKind : uint8_t {
   EPI_INPLACE = 0,      // slice of CW accumulator columns -> hi (CW/2 columns) | lo (CW/2 columns) over the same slice
@@ -351,7 +354,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
   uint32_t hi[CW / 2], lo[CW / 2];
-  if (relu && !dbg_out) {
+  if (NDS_EPI_RZ && relu && !dbg_out) {
     // ReLU folded into the conversions: hi = relu(x) truncated to fp16 (round toward zero, so the residual of a
     // positive x is never negative), lo = relu(x - hi) -- for x < 0 both come out 0.  hi + lo still carries 21+ bits.
 #pragma unroll
