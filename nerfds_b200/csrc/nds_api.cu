@@ -5,6 +5,7 @@
 //   field(fine) -> composite.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -442,6 +443,12 @@ static int ensure_scratch(ndsr_handle* h, int64_t rays, cudaStream_t st) {
   NDS_CUDA(h, alloc(&h->w_coarse, rays * c.num_coarse_samples));
   NDS_CUDA(h, alloc(&h->w_sg, rays * smax));
   NDS_CUDA(h, alloc(&h->argmax, rays));
+  NDS_CUDA(h, alloc(&h->carry, (int64_t)C_COUNT * rays * c.num_coarse_samples));
+  {
+    float* pf = nullptr;
+    NDS_CUDA(h, alloc(&pf, rays * smax));
+    h->perm = reinterpret_cast<int32_t*>(pf);
+  }
   h->cap_rays = rays;
   h->cap_samples = smax;
   return NDSR_OK;
@@ -472,7 +479,7 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
                      const float* z, const float* origins, const float* dirs, const float* viewdirs,
                      const uint32_t* warp_id, const float* gt_mask, const ndsr_extra_params& ep,
                      const CallParams& cp, int sample_at_infinity, const ndsr_outputs* out, float* weights_keep,
-                     bool need_rgb) {
+                     bool need_rgb, float* carry_out = nullptr, const int32_t* perm = nullptr, int n_carried = 0) {
   const ndsr_config& c = h->cfg;
   ndsr_outputs o;
   memset(&o, 0, sizeof o);
@@ -488,7 +495,19 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   fa.sigma_only = need_rgb ? 0 : 1; fa.need_grad = need_grad ? 1 : 0;
   {
     ProfScope ps(h, st, level == 0 ? NDSR_STAGE_FIELD_COARSE : NDSR_STAGE_FIELD_FINE);
-    if (h->engine == NDSR_ENGINE_TC && !need_grad) {
+    if (h->engine == NDSR_ENGINE_TC && !need_grad && perm) {
+      // split fine pass: the n_carried coarse depths of every ray re-use the coarse pass's warp / hyper / mask
+      // results (same points, same shared networks) and only run the template NeRF; the new depths run everything
+      FieldArgs fb = fa;
+      fb.perm = perm; fb.list_S = S - n_carried; fb.list_off = n_carried; fb.n_samples_total = B * (S - n_carried);
+      int rc = tc_engine_field(h, cp, fb, st);
+      if (rc) return rc;
+      fb.list_S = n_carried; fb.list_off = 0; fb.n_samples_total = B * n_carried;
+      fb.carry = h->carry; fb.carry_stride = B * n_carried;
+      rc = tc_engine_field(h, cp, fb, st);
+      if (rc) return rc;
+    } else if (h->engine == NDSR_ENGINE_TC && !need_grad) {
+      fa.carry_out = carry_out; fa.carry_stride = B * S;
       int rc = tc_engine_field(h, cp, fa, st);
       if (rc) return rc;
     } else {
@@ -573,8 +592,15 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   }
   // coarse level always uses the configured sample_at_infinity (models.py:1509)
   const bool coarse_rgb = coarse && (coarse->rgb || wants_per_sample(coarse) || coarse->ray_norm);
+  // tensor-core engine, no gradient keys on either level: the fine pass re-uses the coarse pass's narrow-network
+  // results at the coarse depths (run_level)
+  const bool fine_grad = fine && ((c.predict_norm && fine->target_norm) || (!c.predict_norm && fine->ray_norm));
+  const bool coarse_grad = coarse && ((c.predict_norm && coarse->target_norm) || (!c.predict_norm && coarse->ray_norm));
+  const bool split = h->engine == NDSR_ENGINE_TC && !ep.use_sigma_gradient && !fine_grad && !coarse_grad &&
+                     getenv("NDS_TC_NO_SPLIT") == nullptr;
   int rc = run_level(h, st, 0, B, Sc, nullptr, h->z_coarse, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
-                     c.use_sample_at_infinity, coarse, h->w_coarse, coarse_rgb || coarse != nullptr);
+                     c.use_sample_at_infinity, coarse, h->w_coarse, coarse_rgb || coarse != nullptr,
+                     split ? h->carry : nullptr);
   if (rc) return rc;
   SamplePdfArgs sa;
   memset(&sa, 0, sizeof sa);
@@ -584,6 +610,7 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   sa.w_stride = Sc;
   sa.u = c.use_stratified_sampling ? u : nullptr;
   sa.z_coarse = h->z_coarse; sa.z_out = h->z_fine;
+  sa.perm_out = split ? h->perm : nullptr;
   {
     ProfScope ps(h, st, NDSR_STAGE_RESAMPLE);
     NDS_CUDA(h, launch_sample_pdf(sa, h->num_sms, st));
@@ -591,7 +618,7 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   }
   const int inf_fine = ep.sample_at_infinity_override < 0 ? c.use_sample_at_infinity : ep.sample_at_infinity_override;
   return run_level(h, st, 1, B, Sc + Sf, nullptr, h->z_fine, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
-                   inf_fine, fine, nullptr, true);
+                   inf_fine, fine, nullptr, true, nullptr, split ? h->perm : nullptr, Sc);
 }
 
 extern "C" int ndsr_render_rays(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,

@@ -84,7 +84,23 @@ struct FieldArgs {
   int64_t plane_stride;
   int sigma_only;            // skip bottleneck/rgb/normal-input work
   int need_grad;             // compute P_GRAD / P_TNORM
+  // ---- tensor-core engine only: fine pass split into "new" and "carried" samples --------------------------
+  // The warp field, hyper-sheet and mask networks are shared by the two levels and the fine level re-visits every
+  // coarse depth (model_utils.py:266: sort(concat(z_coarse, z_samples))), so for those samples the coarse pass
+  // already computed the warped point, the hyper coordinates, the mask and the SE(3) transform.  The coarse pass
+  // stores them (`carry_out`), and the fine pass runs as two launches over sample LISTS: the new samples through
+  // the whole network chain, the carried ones through the template NeRF only.  List element i = ray * list_S + j
+  // lands at sample ray * S + perm[ray * S + list_off + j] of the level (perm = sorted position of element
+  // list_off + j of concat(z_coarse, z_samples), written by sample_pdf_kernel).
+  const int32_t* perm;       // null: element i of the launch is sample i of the level
+  int list_S, list_off;
+  const float* carry;        // non-null: "carried" launch, reads C_* planes [c * carry_stride + i]
+  float* carry_out;          // non-null: also store the C_* planes of every sample
+  int64_t carry_stride;
 };
+
+// carried per-sample planes (coarse pass -> fine pass)
+enum CarryPlane { C_WARPED = 0 /* 3 + 2 */, C_MASK = 5, C_R = 6 /* 9 */, C_P = 15 /* 3 */, C_COUNT = 18 };
 
 // ---- small exact-math helpers ----------------------------------------------
 #define NDS_HALF_PI_F 1.57079637050628662109375f   // fp32(0.5 * pi), model_utils.py:405

@@ -279,6 +279,7 @@ sample_pdf_kernel(const __grid_constant__ SamplePdfArgs a) {
         rank += (o < v || (o == v && j < i)) ? 1 : 0;
       }
       a.z_out[ray * nt + rank] = v;
+      if (a.perm_out) a.perm_out[ray * nt + i] = rank;
     }
     __syncwarp();
   }

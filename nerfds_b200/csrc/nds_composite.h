@@ -35,6 +35,7 @@ struct SamplePdfArgs {
   int32_t* idx_lo;        // optional
   int32_t* idx_hi;        // optional
   float* cdf_out;         // optional [B, n]
+  int32_t* perm_out;      // optional [B, n_coarse + n_fine]: sorted position of element i of concat(z_coarse, z_samples)
 };
 
 cudaError_t launch_sample_along_rays(int64_t n_rays, int S, float near_, float far_, int lindisp,

@@ -130,6 +130,7 @@ constexpr int MAX_STEPS = 128;
 constexpr int MAX_BURST = 256;
 struct TcProgram {       // passed by value as a __grid_constant__ kernel parameter (constant bank)
   int n_ops, n_burst, n_steps, full;     // full: rgb branch present (else sigma-only)
+  int carried;           // the program has no N phase: the narrow networks' results are read from the carry planes
   // shared feature block: [identity x (3)] [sin/cos of bands f_kmin .. f_kmin + f_nb) (6 each)] [warp embed]
   // [mask embed] [mask]; t_cols = width of the trunk input that later overwrites it
   int f_col_ident, f_col_bands, f_kmin, f_nb, f_col_wembed, f_col_membed, f_col_mask, f_cols, t_cols;
@@ -476,6 +477,7 @@ struct TileState {
   float x[3], vd[3], gt;
   uint32_t wid;
   int valid;
+  int64_t n_out;          // sample index inside the level (planes / carry_out position)
   float xw[3], om[2], maskv, pmask, sigma_raw, nrm[3], rgb[3];
   float R[9], p[3];
 };
@@ -483,6 +485,8 @@ struct NextSample {
   float x[3], vd[3], gt;
   uint32_t wid;
   int valid;
+  int64_t n_out;
+  float xw[3], om[2], pmask, R[9], p[3];   // carried launches only
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -552,11 +556,32 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     // per-sample inputs are fetched one pair ahead, so their global-memory latency hides behind the T phase
     auto load_next = [&](int64_t pair_, int s_) {
       NextSample& ns = nxt[s_];
-      const int64_t n_ = (2 * pair_ + s_) * TM + row;
-      ns.valid = (pair_ < n_pairs && n_ < a.n_samples_total) ? 1 : 0;
-      ns.x[0] = ns.x[1] = ns.x[2] = 0.f; ns.vd[0] = ns.vd[1] = ns.vd[2] = 0.f; ns.gt = 0.f; ns.wid = 0;
+      const int64_t li = (2 * pair_ + s_) * TM + row;      // element of the launch's sample list
+      ns.valid = (pair_ < n_pairs && li < a.n_samples_total) ? 1 : 0;
+      ns.x[0] = ns.x[1] = ns.x[2] = 0.f; ns.vd[0] = ns.vd[1] = ns.vd[2] = 0.f; ns.gt = 0.f; ns.wid = 0; ns.n_out = 0;
+      ns.xw[0] = ns.xw[1] = ns.xw[2] = 0.f; ns.om[0] = ns.om[1] = 0.f; ns.pmask = 0.f;
+      for (int i = 0; i < 9; ++i) ns.R[i] = (i % 4 == 0) ? 1.f : 0.f;
+      ns.p[0] = ns.p[1] = ns.p[2] = 0.f;
       if (!ns.valid) return;
-      const int64_t ray = n_ / a.S;
+      int64_t ray, n_;
+      if (a.perm) {
+        ray = li / a.list_S;
+        n_ = ray * a.S + a.perm[ray * a.S + a.list_off + (li - ray * a.list_S)];
+      } else {
+        n_ = li;
+        ray = n_ / a.S;
+      }
+      ns.n_out = n_;
+      ns.vd[0] = a.viewdirs[ray * 3]; ns.vd[1] = a.viewdirs[ray * 3 + 1]; ns.vd[2] = a.viewdirs[ray * 3 + 2];
+      if (a.carry) {
+        const float* C = a.carry + li;
+        const int64_t cs = a.carry_stride;
+        for (int c = 0; c < 3; ++c) { ns.xw[c] = C[(C_WARPED + c) * cs]; ns.p[c] = C[(C_P + c) * cs]; }
+        for (int c = 0; c < H; ++c) ns.om[c] = C[(C_WARPED + 3 + c) * cs];
+        ns.pmask = C[C_MASK * cs];
+        for (int i = 0; i < 9; ++i) ns.R[i] = C[(C_R + i) * cs];
+        return;
+      }
       if (a.points) { ns.x[0] = a.points[n_ * 3]; ns.x[1] = a.points[n_ * 3 + 1]; ns.x[2] = a.points[n_ * 3 + 2]; }
       else {
         const float z = a.z[n_];
@@ -564,9 +589,36 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         ns.x[1] = a.origins[ray * 3 + 1] + z * a.dirs[ray * 3 + 1];
         ns.x[2] = a.origins[ray * 3 + 2] + z * a.dirs[ray * 3 + 2];
       }
-      ns.vd[0] = a.viewdirs[ray * 3]; ns.vd[1] = a.viewdirs[ray * 3 + 1]; ns.vd[2] = a.viewdirs[ray * 3 + 2];
       if (a.warp_id) ns.wid = a.warp_id[ray];
       if (a.gt_mask) ns.gt = a.gt_mask[ray];
+    };
+    // trunk input (models.py:493-523) of one tile: posenc of the warped point and the hyper coordinates, the
+    // (sin, cos) pairs dealt to the 4 warps sharing a sample; `part` < 0: all of it, else one of NPREP parts
+    auto trunk_input = [&](uint8_t* blk, const float* xw, const float* om, int part) {
+      auto st = [&](int c, float v) { store_in(blk, row, (uint32_t)c, v); };
+      const PosencSpec* specs[2] = {&cp.pe_spatial, &cp.pe_hyperpt};
+      int o = 0, gp = 0;       // running feature offset / global pair counter (deals pairs to warps and parts)
+      for (int e = 0; e < (H > 0 ? 2 : 1); ++e) {
+        const PosencSpec& pe = *specs[e];
+        const int C = e == 0 ? 3 : H;
+        const float* xv = e == 0 ? xw : om;
+        if (pe.identity) {
+          if (sub == 0 && part <= 0) for (int c = 0; c < C; ++c) st(o + c, xv[c]);
+          o += C;
+        }
+        const int npair = pe.num_bands * C;
+        for (int p = 0; p < npair; ++p, ++gp) {
+          if ((gp & (NSUB - 1)) != sub) continue;
+          if (part >= 0 && ((gp >> 2) % NPREP) != part) continue;
+          const int k = p / C, c = p - k * C;
+          const float xb = xv[c] * __int_as_float((127 + pe.min_deg + k) << 23);    // x * 2^(min_deg + k), exact
+          const float w = pe.window[k];
+          st(o + 2 * C * k + c, w * pe_sin(xb));
+          st(o + 2 * C * k + C + c, w * pe_sin(xb + NDS_HALF_PI_F));
+        }
+        o += 2 * npair;
+      }
+      if (part <= 0) for (int c = o + sub; c < P.f_cols; c += NSUB) st(c, 0.f);     // the feature block was wider
     };
     // Part `part` of the shared feature block of the NEXT tile of slot s_ (model_utils.py:398-417 without the
     // window, which is folded into the weights): the (sin, cos) pairs are dealt to the 4 warps sharing a sample
@@ -574,6 +626,11 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     auto prep_part = [&](int s_, int part) {
       const NextSample& ns = nxt[s_];
       uint8_t* blk = smem + OFF_IN + (uint32_t)s_ * 2u * KBLK;
+      if (P.carried) {          // no N phase: the next tile's trunk input straight from the carried results
+        trunk_input(blk, ns.xw, ns.om, part);
+        if (part == NPREP - 1) warp_arrive(&ctl->prep[s_], lane);
+        return;
+      }
       const int npair = P.f_nb * 3;
       for (int pi = sub; pi < npair; pi += NSUB) {
         if (((pi >> 2) % NPREP) != part) continue;
@@ -612,8 +669,13 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         const NextSample& ns = nxt[s];
         for (int c = 0; c < 3; ++c) { T.x[c] = ns.x[c]; T.vd[c] = ns.vd[c]; T.xw[c] = 0.f; T.nrm[c] = 0.f; T.rgb[c] = 0.f; T.p[c] = 0.f; }
         for (int i = 0; i < 9; ++i) T.R[i] = (i % 4 == 0) ? 1.f : 0.f;
-        T.gt = ns.gt; T.wid = ns.wid; T.valid = ns.valid;
+        T.gt = ns.gt; T.wid = ns.wid; T.valid = ns.valid; T.n_out = ns.n_out;
         T.om[0] = T.om[1] = 0.f; T.maskv = ns.gt; T.pmask = 0.f; T.sigma_raw = 0.f;
+        if (P.carried) {
+          for (int c = 0; c < 3; ++c) { T.xw[c] = ns.xw[c]; T.p[c] = ns.p[c]; }
+          for (int i = 0; i < 9; ++i) T.R[i] = ns.R[i];
+          T.om[0] = ns.om[0]; T.om[1] = ns.om[1]; T.pmask = ns.pmask;
+        }
       }
       unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 3 * MAX_BURST : nullptr;
       if (tr) tr[2 * MAX_STEPS] = clock64();
@@ -658,11 +720,8 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
               for (int c = 0; c < 3; ++c) xw[c] = se.R[c * 3 + 0] * T.x[0] + se.R[c * 3 + 1] * T.x[1] + se.R[c * 3 + 2] * T.x[2] + se.p[c];
               for (int i = 0; i < 9; ++i) T.R[i] = se.R[i];
               for (int c = 0; c < 3; ++c) { T.p[c] = se.p[c]; T.xw[c] = xw[c]; }
-              // trunk input (models.py:493-523) over the feature block, which the narrow networks are done with
-              int pr = 0;
-              int o = posenc_emit_sub(xw[0], xw[1], xw[2], 3, cp.pe_spatial, st_in, 0, sub, pr);
-              if (H > 0) o = posenc_emit_sub(T.om[0], T.om[1], 0.f, H, cp.pe_hyperpt, st_in, o, sub, pr);
-              for (int c = o + sub; c < P.f_cols; c += NSUB) st_in(c, 0.f);
+              // trunk input over the feature block, which the narrow networks are done with
+              trunk_input(blk, xw, T.om, -1);
             } break;
             case GLUE_ALPHA: {
               T.sigma_raw = hv[0];
@@ -698,7 +757,15 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           prep_part(s, sp.arg);
         } else {
           // ---- STEP_OUT: write planes (the warps sharing a sample take different planes) ----
-          const int64_t n = (2 * pair + s) * TM + row;
+          const int64_t n = T.n_out;
+          if (T.valid && a.carry_out) {          // what a later "carried" launch needs of this sample
+            float* C = a.carry_out + n;
+            const int64_t cs = a.carry_stride;
+            if (sub == 0) { for (int c = 0; c < 3; ++c) C[(C_WARPED + c) * cs] = T.xw[c]; for (int c = 0; c < H; ++c) C[(C_WARPED + 3 + c) * cs] = T.om[c]; }
+            else if (sub == 1) { C[C_MASK * cs] = T.pmask; for (int c = 0; c < 3; ++c) C[(C_P + c) * cs] = T.p[c]; }
+            else if (sub == 2) { for (int i = 0; i < 5; ++i) C[(C_R + i) * cs] = T.R[i]; }
+            else { for (int i = 5; i < 9; ++i) C[(C_R + i) * cs] = T.R[i]; }
+          }
           if (T.valid) {
             float* PL = a.planes;
             const int64_t ps = a.plane_stride;
@@ -1220,7 +1287,7 @@ struct LevelBuild {
 struct TcEngine {
   Packed packed[2];
   LevelBuild lb[2];
-  TcProgram prog[2][2];               // [level][full]
+  TcProgram prog[2][3];               // [level][0 sigma-only | 1 full | 2 full, carried (no N phase)]
   uint8_t* d_stream[2] = {nullptr, nullptr};
   float* d_bias[2] = {nullptr, nullptr};
   float win[2][3][NDSR_MAX_BANDS];    // windows currently folded into the streams, per level
@@ -1228,9 +1295,12 @@ struct TcEngine {
 };
 
 // Merges the per-slot op lists into the pair program: bursts (issuer / producer) and steps (compute warps).
-static bool assemble(const LevelBuild& LB, bool full, uint32_t smem_base, TcProgram& prog, std::string& err) {
+// `carried`: no N phase -- the narrow networks' results come from the carry planes, the trunk input is written by
+// the PREP steps and the first trunk layer waits for them.
+static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t smem_base, TcProgram& prog, std::string& err) {
   memset(&prog, 0, sizeof prog);
   prog.smem_base = smem_base;
+  prog.carried = carried ? 1 : 0;
   const int n_ops = full ? (int)LB.ops[0].size() : LB.n_sigma;
   if (2 * n_ops > MAX_OPS) { err = "tensor-core engine: too many layers"; return false; }
   prog.n_ops = 2 * n_ops;
@@ -1256,7 +1326,7 @@ static bool assemble(const LevelBuild& LB, bool full, uint32_t smem_base, TcProg
   };
   // ---- N phase: both tile slots op by op; slot 0 acquires the weights, slot 1 releases them
   int cursor = 0;
-  for (int i = 0; i < LB.n_narrow; ++i) {
+  for (int i = 0; i < (carried ? 0 : LB.n_narrow); ++i) {
     std::vector<BurstH> b0 = make_bursts(LB.ops[0][i], LB.weights[i]);
     std::vector<BurstH> b1 = make_bursts(LB.ops[1][i], LB.weights[i]);
     if ((int)b0.size() > NUNIT - 1) { err = "tensor-core engine: narrow layer with too many K-chunks for the weight ring"; return false; }
@@ -1276,6 +1346,9 @@ static bool assemble(const LevelBuild& LB, bool full, uint32_t smem_base, TcProg
     int prep_next = 0;
     for (int i = LB.n_narrow; i < n_ops; ++i) {
       std::vector<BurstH> b = make_bursts(LB.ops[s][i], LB.weights[i]);
+      if (carried && i == LB.trunk_first)       // inputs come from the PREP steps; the other slot must have left the T phase
+        b[0].flags = (uint16_t)((b[0].flags & ~B_WAIT_GLUE) | B_WAIT_PREP | B_WAIT_DONE_OTHER);
+      if (carried && i == LB.trunk_first + 1) b[0].flags &= (uint16_t)~B_PEEK_GLUE_OTHER;
       for (auto& e : b) {
         e.unit = (uint8_t)cursor;
         cursor = (cursor + 1) % NUNIT;
@@ -1487,8 +1560,8 @@ int tc_engine_load(ndsr_handle* h) {
     int rc = build_level(h, lv, E->lb[lv], E->packed[lv]);
     if (rc) return rc;
     Packed& P = E->packed[lv];
-    for (int full = 0; full < 2; ++full)
-      if (!assemble(E->lb[lv], full != 0, smem_base, E->prog[lv][full], h->err)) return NDSR_ERR_UNSUPPORTED;
+    for (int mode = 0; mode < 3; ++mode)
+      if (!assemble(E->lb[lv], mode != 0, mode == 2, smem_base, E->prog[lv][mode], h->err)) return NDSR_ERR_UNSUPPORTED;
     cudaError_t e;
     if ((e = cudaMalloc(&E->d_stream[lv], P.stream.size())) != cudaSuccess ||
         (e = cudaMalloc(&E->d_bias[lv], P.bias.size() * sizeof(float))) != cudaSuccess ||
@@ -1548,7 +1621,8 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
   int rc = fold_windows(h, fa.level, cp, st);
   if (rc) return rc;
   TcKernelArgs K;
-  const TcProgram& prog = E->prog[fa.level][fa.sigma_only ? 0 : 1];
+  if (fa.carry && fa.sigma_only) { h->err = "tensor-core engine: carried launches are built for the full program"; return NDSR_ERR_INVALID; }
+  const TcProgram& prog = E->prog[fa.level][fa.carry ? 2 : (fa.sigma_only ? 0 : 1)];
   K.lvl.weights = E->d_stream[fa.level];
   K.lvl.bias = E->d_bias[fa.level];
   K.warp_embed = h->M.warp_embed;

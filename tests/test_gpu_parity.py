@@ -292,3 +292,28 @@ def test_tc_ragged_batches_match_simt(cuda_device, n_rays):
   assert linf(outs['tc']['coarse']['rgb'], outs['simt']['coarse']['rgb']) <= RGB_TOL
   assert np.isfinite(outs['tc']['fine']['rgb']).all()
   assert np.median(np.abs(outs['tc']['fine']['rgb'] - outs['simt']['fine']['rgb'])) <= RGB_TOL
+
+
+def test_tc_split_fine_pass_is_exact(cuda_device, monkeypatch):
+  """The fine pass as two launches (new samples: whole chain; coarse depths: template NeRF on the coarse pass's
+  carried warp / hyper / mask results) gives the results of the single launch, sample for sample."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=14, seed=5)
+  m = _model(cfg, cuda_device, engine='tc')
+  keys = ('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'ray_hyper_points', 'ray_predicted_mask',
+          'ray_rotation_field', 'ray_translation_field', 'med_points', 'weights', 'sigma', 'warped_points',
+          'predicted_mask', 'predicted_norm')
+  outs = []
+  for no_split in ('', '1'):
+    if no_split:
+      monkeypatch.setenv('NDS_TC_NO_SPLIT', '1')
+    else:
+      monkeypatch.delenv('NDS_TC_NO_SPLIT', raising=False)
+    l0 = m.renderer.kernel_launches
+    o = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True,
+                keys=keys, coarse_keys=('rgb', 'weights'))
+    outs.append(({k: _np(v) for k, v in o.items()}, m.renderer.kernel_launches - l0))
+  (a, la), (b, lb) = outs
+  assert la == lb + 1          # one more field launch on the split path: it really ran
+  for k in keys:
+    np.testing.assert_allclose(a['fine'][k], b['fine'][k], rtol=0, atol=1e-6, err_msg=k)
+  np.testing.assert_array_equal(a['coarse']['rgb'], b['coarse']['rgb'])
