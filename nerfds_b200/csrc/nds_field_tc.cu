@@ -574,12 +574,18 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
       ns.n_out = n_;
       ns.vd[0] = a.viewdirs[ray * 3]; ns.vd[1] = a.viewdirs[ray * 3 + 1]; ns.vd[2] = a.viewdirs[ray * 3 + 2];
       if (a.carry) {
+        // all C_COUNT loads in flight before the first one is consumed
         const float* C = a.carry + li;
         const int64_t cs = a.carry_stride;
-        for (int c = 0; c < 3; ++c) { ns.xw[c] = C[(C_WARPED + c) * cs]; ns.p[c] = C[(C_P + c) * cs]; }
-        for (int c = 0; c < H; ++c) ns.om[c] = C[(C_WARPED + 3 + c) * cs];
-        ns.pmask = C[C_MASK * cs];
-        for (int i = 0; i < 9; ++i) ns.R[i] = C[(C_R + i) * cs];
+        float t[C_COUNT];
+#pragma unroll
+        for (int i = 0; i < C_COUNT; ++i) t[i] = __ldg(C + i * cs);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { ns.xw[c] = t[C_WARPED + c]; ns.p[c] = t[C_P + c]; }
+        ns.om[0] = t[C_WARPED + 3]; ns.om[1] = t[C_WARPED + 4];
+        ns.pmask = t[C_MASK];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ns.R[i] = t[C_R + i];
         return;
       }
       if (a.points) { ns.x[0] = a.points[n_ * 3]; ns.x[1] = a.points[n_ * 3 + 1]; ns.x[2] = a.points[n_ * 3 + 2]; }
@@ -596,29 +602,35 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     // (sin, cos) pairs dealt to the 4 warps sharing a sample; `part` < 0: all of it, else one of NPREP parts
     auto trunk_input = [&](uint8_t* blk, const float* xw, const float* om, int part) {
       auto st = [&](int c, float v) { store_in(blk, row, (uint32_t)c, v); };
-      const PosencSpec* specs[2] = {&cp.pe_spatial, &cp.pe_hyperpt};
-      int o = 0, gp = 0;       // running feature offset / global pair counter (deals pairs to warps and parts)
-      for (int e = 0; e < (H > 0 ? 2 : 1); ++e) {
-        const PosencSpec& pe = *specs[e];
-        const int C = e == 0 ? 3 : H;
-        const float* xv = e == 0 ? xw : om;
-        if (pe.identity) {
-          if (sub == 0 && part <= 0) for (int c = 0; c < C; ++c) st(o + c, xv[c]);
-          o += C;
-        }
-        const int npair = pe.num_bands * C;
-        for (int p = 0; p < npair; ++p, ++gp) {
-          if ((gp & (NSUB - 1)) != sub) continue;
-          if (part >= 0 && ((gp >> 2) % NPREP) != part) continue;
-          const int k = p / C, c = p - k * C;
-          const float xb = xv[c] * __int_as_float((127 + pe.min_deg + k) << 23);    // x * 2^(min_deg + k), exact
-          const float w = pe.window[k];
-          st(o + 2 * C * k + c, w * pe_sin(xb));
-          st(o + 2 * C * k + C + c, w * pe_sin(xb + NDS_HALF_PI_F));
-        }
-        o += 2 * npair;
+      const float v0 = xw[0], v1 = xw[1], v2 = xw[2], h0 = om[0], h1 = om[1];
+      const PosencSpec& ps = cp.pe_spatial;
+      const PosencSpec& ph = cp.pe_hyperpt;
+      const int o_sp = ps.identity ? 3 : 0, n_sp = ps.num_bands * 3;
+      const int o_h0 = o_sp + 2 * n_sp, o_hy = o_h0 + ((H > 0 && ph.identity) ? H : 0), n_hy = H > 0 ? ph.num_bands * H : 0;
+      if (part <= 0 && sub == 0) {
+        if (ps.identity) { st(0, v0); st(1, v1); st(2, v2); }
+        if (H > 0 && ph.identity) { st(o_h0, h0); if (H > 1) st(o_h0 + 1, h1); }
       }
-      if (part <= 0) for (int c = o + sub; c < P.f_cols; c += NSUB) st(c, 0.f);     // the feature block was wider
+      // global pair index gp = sub + 4 m: this warp's pairs; part p takes the m with m % NPREP == p
+      const int m0 = part < 0 ? 0 : part, dm = part < 0 ? 1 : NPREP;
+      for (int m = m0; sub + NSUB * m < n_sp + n_hy; m += dm) {
+        const int gp = sub + NSUB * m;
+        float xv, w;
+        int deg, col, stride;
+        if (gp < n_sp) {
+          const int k = gp / 3, c = gp - 3 * k;
+          xv = c == 0 ? v0 : (c == 1 ? v1 : v2);
+          deg = ps.min_deg + k; w = ps.window[k]; col = o_sp + 6 * k + c; stride = 3;
+        } else {
+          const int q = gp - n_sp, k = H == 2 ? (q >> 1) : q, c = q - H * k;
+          xv = c == 0 ? h0 : h1;
+          deg = ph.min_deg + k; w = ph.window[k]; col = o_hy + 2 * H * k + c; stride = H;
+        }
+        const float xb = xv * __int_as_float((127 + deg) << 23);    // x * 2^deg, exact
+        st(col, w * pe_sin(xb));
+        st(col + stride, w * pe_sin(xb + NDS_HALF_PI_F));
+      }
+      if (part <= 0) for (int c = o_hy + 2 * n_hy + sub; c < P.f_cols; c += NSUB) st(c, 0.f);     // the feature block was wider
     };
     // Part `part` of the shared feature block of the NEXT tile of slot s_ (model_utils.py:398-417 without the
     // window, which is folded into the weights): the (sin, cos) pairs are dealt to the 4 warps sharing a sample
@@ -675,6 +687,16 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           for (int c = 0; c < 3; ++c) { T.xw[c] = ns.xw[c]; T.p[c] = ns.p[c]; }
           for (int i = 0; i < 9; ++i) T.R[i] = ns.R[i];
           T.om[0] = ns.om[0]; T.om[1] = ns.om[1]; T.pmask = ns.pmask;
+        }
+      }
+      if (a.carry) {
+        // the carry planes of the next pair's tiles (written by the coarse pass long ago: DRAM) -> L2, so that the
+        // loads in the VIEW steps do not sit on the critical path of the trunk
+        for (int s = 0; s < 2; ++s) {
+          const int64_t li = (2 * (pair + gridDim.x) + s) * TM + row;
+          if (li < a.n_samples_total && (sub == s || sub == s + 2))
+            for (int i = (sub >> 1); i < C_COUNT; i += 2)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.carry + li + (int64_t)i * a.carry_stride));
         }
       }
       unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 3 * MAX_BURST : nullptr;
@@ -747,9 +769,9 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           }
           // the MMA issuer may overwrite the head accumulators / read the new inputs from here on
           if (op.signal_glue) warp_arrive(&ctl->glue[s], lane);
-        } else if (sp.kind == STEP_VIEW) {
-          load_next(pair + gridDim.x, s);
-          if (P.full && cfg.use_viewdirs) {
+        } else if (sp.kind == STEP_VIEW) {      // arg: 0 = both halves, 1 = sample fetch only, 2 = viewdir features only
+          if (sp.arg != 2) load_next(pair + gridDim.x, s);
+          if (sp.arg != 1 && P.full && cfg.use_viewdirs) {
             int pr = 0;
             posenc_emit_sub(T.vd[0], T.vd[1], T.vd[2], 3, cp.pe_view, st_in2, 0, sub, pr);
           }
@@ -761,7 +783,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           if (T.valid && a.carry_out) {          // what a later "carried" launch needs of this sample
             float* C = a.carry_out + n;
             const int64_t cs = a.carry_stride;
-            if (sub == 0) { for (int c = 0; c < 3; ++c) C[(C_WARPED + c) * cs] = T.xw[c]; for (int c = 0; c < H; ++c) C[(C_WARPED + 3 + c) * cs] = T.om[c]; }
+            if (sub == 0) { for (int c = 0; c < 3; ++c) C[(C_WARPED + c) * cs] = T.xw[c]; for (int c = 0; c < 2; ++c) C[(C_WARPED + 3 + c) * cs] = c < H ? T.om[c] : 0.f; }
             else if (sub == 1) { C[C_MASK * cs] = T.pmask; for (int c = 0; c < 3; ++c) C[(C_P + c) * cs] = T.p[c]; }
             else if (sub == 2) { for (int i = 0; i < 5; ++i) C[(C_R + i) * cs] = T.R[i]; }
             else { for (int i = 5; i < 9; ++i) C[(C_R + i) * cs] = T.R[i]; }
@@ -1357,8 +1379,10 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
       bursts.insert(bursts.end(), b.begin(), b.end());
       steps.push_back(step_of(s, i));
       // next pair's sample fetch + viewdir features: off the critical path, in the slack after the second trunk layer
-      if (i == LB.trunk_first + 1) {
-        Step v; v.kind = STEP_VIEW; v.tslot = (uint8_t)s; v.op = 0; v.arg = 0;
+      // (carried programs fetch 18 carry planes per sample: the two halves go into the slack of different layers)
+      if (i == LB.trunk_first + 1 || (carried && i == LB.trunk_first + 2)) {
+        Step v; v.kind = STEP_VIEW; v.tslot = (uint8_t)s; v.op = 0;
+        v.arg = (uint8_t)(carried ? (i == LB.trunk_first + 1 ? 1 : 2) : 0);
         steps.push_back(v);
       }
       // the input block of this tile slot is free once the skip layer (or layer 0) has consumed it: write the
@@ -1645,7 +1669,8 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
     cudaMemcpy(t.data(), K.trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(K.trace);
     const unsigned long long t0 = t[3 * MAX_BURST + 2 * MAX_STEPS];
-    if (FILE* f = fopen(trace_path, "w")) {
+    const std::string tp = std::string(trace_path) + (fa.carry ? ".carried" : "");
+    if (FILE* f = fopen(tp.c_str(), "w")) {
       auto rel = [&](unsigned long long v) { return v ? (long long)(v - t0) : -1LL; };
       for (int i = 0; i < prog.n_burst; ++i) {
         const Burst& b = prog.burst[i];
