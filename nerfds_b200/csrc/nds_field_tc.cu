@@ -24,8 +24,8 @@
 //            waits for the second chunk's epilogue.
 //   The three narrow networks read ONE shared feature block per tile ([sin/cos bands of x | embeddings | mask],
 //   posenc windows folded into the first-layer weights on the host), written one pair ahead during the T phase.
-// Warp roles: warps 0-15 = compute (TMEM lane quarter = warp % 4 -> 32 samples, column slice = warp / 4):
-// positional encodings, SE(3) exponential, epilogues; warp 16 = MMA issuer; warp 17 = TMA producer.
+// Warp roles: warp 0 = MMA issuer, warp 1 = TMA producer, warps 4-19 = compute (TMEM lane quarter = warp % 4 ->
+// 32 samples, column slice = (warp - 4) / 4): positional encodings, SE(3) exponential, epilogues.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -46,8 +46,10 @@ using namespace tc;
 constexpr int TM = 128;                 // samples per tile (UMMA M)
 constexpr int NSUB = 4;                 // compute warps per TMEM lane quarter
 constexpr int N_CWARPS = 4 * NSUB;
-constexpr int WARP_MMA = N_CWARPS, WARP_TMA = N_CWARPS + 1;
-constexpr int TC_THREADS = (N_CWARPS + 2) * 32;
+// The MMA issuer is warp 0: it shares its scheduler with four compute warps, and the oldest warp of a scheduler
+// wins the issue slot.  Warps 2 and 3 only keep the compute warps' TMEM lane quarter = warp % 4.
+constexpr int WARP_MMA = 0, WARP_TMA = 1, CWARP0 = 4;
+constexpr int TC_THREADS = (CWARP0 + N_CWARPS) * 32;
 constexpr uint32_t KBLK = 16384;        // one 128-row K-block (64 fp16 columns)
 // shared memory map
 constexpr uint32_t OFF_IN = 0;          // IN[tile slot]: hi block at slot * 2 KBLK, lo block right after
@@ -545,9 +547,9 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         issue_program(P, ctl, bits, pair + gridDim.x < n_pairs, (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
     }
     __syncwarp();
-  } else {
+  } else if (warp >= CWARP0) {
     // ===================== compute warps =====================
-    const int q = warp & 3, sub = warp >> 2;
+    const int q = warp & 3, sub = (warp - CWARP0) >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     uint32_t dc = 0;      // parity of d_full[s][c]: bit 2 s + c
@@ -699,7 +701,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
               asm volatile("prefetch.global.L2 [%0];" ::"l"(a.carry + li + (int64_t)i * a.carry_stride));
         }
       }
-      unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == 0) ? K.trace + 3 * MAX_BURST : nullptr;
+      unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == CWARP0 * 32) ? K.trace + 3 * MAX_BURST : nullptr;
       if (tr) tr[2 * MAX_STEPS] = clock64();
       for (int si = 0; si < P.n_steps; ++si) {
         const Step sp = ctl->steps[si];
@@ -859,8 +861,8 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
       issue_program(P, ctl, bits, false, nullptr);
     }
     __syncwarp();
-  } else {
-    const int q = warp & 3, sub = warp >> 2;
+  } else if (warp >= CWARP0) {
+    const int q = warp & 3, sub = (warp - CWARP0) >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     const int ld = k_hid + k_in;
@@ -905,8 +907,8 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   __syncthreads();
   tc_fence_after_sync();
   // read back the operand image the epilogue left in tensor memory -- what the next layer's MMA would see
-  if (warp < N_CWARPS && op.epi_kind != EPI_HEAD && out_readback) {
-    const int q = warp & 3, sub = warp >> 2;
+  if (warp >= CWARP0 && op.epi_kind != EPI_HEAD && out_readback) {
+    const int q = warp & 3, sub = (warp - CWARP0) >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
     const int cw = op.nc_rows / NSUB;
