@@ -447,8 +447,9 @@ static int ensure_scratch(ndsr_handle* h, int64_t rays, cudaStream_t st) {
   {
     float* pf = nullptr;
     NDS_CUDA(h, alloc(&pf, rays * smax));
-    h->perm = reinterpret_cast<int32_t*>(pf);
+    h->src_elem = reinterpret_cast<int32_t*>(pf);
   }
+  NDS_CUDA(h, alloc(&h->z_new, rays * (smax > c.num_coarse_samples ? smax - c.num_coarse_samples : 1)));
   h->cap_rays = rays;
   h->cap_samples = smax;
   return NDSR_OK;
@@ -479,7 +480,7 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
                      const float* z, const float* origins, const float* dirs, const float* viewdirs,
                      const uint32_t* warp_id, const float* gt_mask, const ndsr_extra_params& ep,
                      const CallParams& cp, int sample_at_infinity, const ndsr_outputs* out, float* weights_keep,
-                     bool need_rgb, float* carry_out = nullptr, const int32_t* perm = nullptr, int n_carried = 0) {
+                     bool need_rgb, float* carry_out = nullptr, const int32_t* src_elem = nullptr, int n_carried = 0) {
   const ndsr_config& c = h->cfg;
   ndsr_outputs o;
   memset(&o, 0, sizeof o);
@@ -495,14 +496,16 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   fa.sigma_only = need_rgb ? 0 : 1; fa.need_grad = need_grad ? 1 : 0;
   {
     ProfScope ps(h, st, level == 0 ? NDSR_STAGE_FIELD_COARSE : NDSR_STAGE_FIELD_FINE);
-    if (h->engine == NDSR_ENGINE_TC && !need_grad && perm) {
+    if (h->engine == NDSR_ENGINE_TC && !need_grad && src_elem) {
       // split fine pass: the n_carried coarse depths of every ray re-use the coarse pass's warp / hyper / mask
-      // results (same points, same shared networks) and only run the template NeRF; the new depths run everything
+      // results (same points, same shared networks) and only run the template NeRF; the new depths run everything.
+      // Dense blocks of the planes: carried samples [0, B n_carried), new samples after them.
       FieldArgs fb = fa;
-      fb.perm = perm; fb.list_S = S - n_carried; fb.list_off = n_carried; fb.n_samples_total = B * (S - n_carried);
+      fb.S = S - n_carried; fb.z = h->z_new; fb.n_samples_total = B * (S - n_carried);
+      fb.planes = h->planes + B * n_carried;
       int rc = tc_engine_field(h, cp, fb, st);
       if (rc) return rc;
-      fb.list_S = n_carried; fb.list_off = 0; fb.n_samples_total = B * n_carried;
+      fb.S = n_carried; fb.z = nullptr; fb.n_samples_total = B * n_carried; fb.planes = h->planes;
       fb.carry = h->carry; fb.carry_stride = B * n_carried;
       rc = tc_engine_field(h, cp, fb, st);
       if (rc) return rc;
@@ -522,6 +525,7 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   ca.sigma_is_activated = 0; ca.white_bkgd = c.use_white_background; ca.sample_at_infinity = sample_at_infinity;
   ca.has_norm = c.predict_norm; ca.has_warp = c.use_warp; ca.has_mask = c.use_predicted_mask; ca.has_grad = need_grad;
   ca.out = o;
+  ca.src_elem = (h->engine == NDSR_ENGINE_TC && !need_grad) ? src_elem : nullptr; ca.n_carried = n_carried;
   if (weights_keep) ca.out.weights = weights_keep;   // coarse weights feed sample_pdf
   const bool sharp = c.use_mask_sharp_weights && o.sharp_weights;
   ca.argmax_idx = sharp ? h->argmax : nullptr;
@@ -610,7 +614,8 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   sa.w_stride = Sc;
   sa.u = c.use_stratified_sampling ? u : nullptr;
   sa.z_coarse = h->z_coarse; sa.z_out = h->z_fine;
-  sa.perm_out = split ? h->perm : nullptr;
+  sa.src_elem_out = split ? h->src_elem : nullptr;
+  sa.z_samples = split ? h->z_new : nullptr;
   {
     ProfScope ps(h, st, NDSR_STAGE_RESAMPLE);
     NDS_CUDA(h, launch_sample_pdf(sa, h->num_sms, st));
@@ -618,7 +623,7 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   }
   const int inf_fine = ep.sample_at_infinity_override < 0 ? c.use_sample_at_infinity : ep.sample_at_infinity_override;
   return run_level(h, st, 1, B, Sc + Sf, nullptr, h->z_fine, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
-                   inf_fine, fine, nullptr, true, nullptr, split ? h->perm : nullptr, Sc);
+                   inf_fine, fine, nullptr, true, nullptr, split ? h->src_elem : nullptr, Sc);
 }
 
 extern "C" int ndsr_render_rays(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,

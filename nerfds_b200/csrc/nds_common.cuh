@@ -88,12 +88,10 @@ struct FieldArgs {
   // The warp field, hyper-sheet and mask networks are shared by the two levels and the fine level re-visits every
   // coarse depth (model_utils.py:266: sort(concat(z_coarse, z_samples))), so for those samples the coarse pass
   // already computed the warped point, the hyper coordinates, the mask and the SE(3) transform.  The coarse pass
-  // stores them (`carry_out`), and the fine pass runs as two launches over sample LISTS: the new samples through
-  // the whole network chain, the carried ones through the template NeRF only.  List element i = ray * list_S + j
-  // lands at sample ray * S + perm[ray * S + list_off + j] of the level (perm = sorted position of element
-  // list_off + j of concat(z_coarse, z_samples), written by sample_pdf_kernel).
-  const int32_t* perm;       // null: element i of the launch is sample i of the level
-  int list_S, list_off;
+  // stores them (`carry_out`), and the fine pass runs as two launches over DENSE sample lists -- the S_f new
+  // depths of every ray through the whole network chain, the S_c carried ones through the template NeRF only --
+  // each writing its own dense block of the planes; composite_kernel gathers the sorted order back
+  // (CompositeArgs::src_elem, written by sample_pdf_kernel).
   const float* carry;        // non-null: "carried" launch, reads C_* planes [c * carry_stride + i]
   float* carry_out;          // non-null: also store the C_* planes of every sample
   int64_t carry_stride;

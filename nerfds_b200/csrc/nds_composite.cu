@@ -60,12 +60,19 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
   const int64_t ps = a.plane_stride;
   for (int64_t ray = (int64_t)blockIdx.x * CW + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * CW) {
     const int64_t base = ray * S;
+    // where the planes of sample s live (split fine pass: two dense blocks, see CompositeArgs::src_elem)
+    auto pidx = [&](int s) -> int64_t {
+      if (!a.src_elem) return base + s;
+      const int e = a.src_elem[base + s];
+      return e < a.n_carried ? ray * a.n_carried + e
+                             : a.n_rays * a.n_carried + ray * (S - a.n_carried) + (e - a.n_carried);
+    };
     const float dx = a.dirs[ray * 3], dy = a.dirs[ray * 3 + 1], dz = a.dirs[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);   // jnp.linalg.norm(dirs)
     const float last = a.sample_at_infinity ? 1e10f : 1e-19f;
     float alpha_inf_last = 0.f;
     for (int s = lane; s < S; s += 32) {
-      const float raw = a.planes[P_SIGMA_RAW * ps + base + s];
+      const float raw = a.planes[P_SIGMA_RAW * ps + pidx(s)];
       const float sigma = a.sigma_is_activated ? raw : softplus_f(raw);
       const float zs = a.z[base + s];
       const float dist = ((s == S - 1) ? last : (a.z[base + s + 1] - zs)) * dnorm;
@@ -105,9 +112,10 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       const int64_t n = base + s;
       const float w = s_w[s];
       const float zs = a.z[n];
+      const int64_t pn = pidx(s);
       float c[3], nv[3] = {0, 0, 0}, wp[5], px[3];
-      for (int i = 0; i < 3; ++i) c[i] = a.planes[(P_RGB + i) * ps + n];
-      for (int i = 0; i < 3 + a.H; ++i) wp[i] = a.planes[(P_WARPED + i) * ps + n];
+      for (int i = 0; i < 3; ++i) c[i] = a.planes[(P_RGB + i) * ps + pn];
+      for (int i = 0; i < 3 + a.H; ++i) wp[i] = a.planes[(P_WARPED + i) * ps + pn];
       if (a.points) { px[0] = a.points[n * 3]; px[1] = a.points[n * 3 + 1]; px[2] = a.points[n * 3 + 2]; }
       else { px[0] = ox + zs * dx; px[1] = oy + zs * dy; px[2] = oz + zs * dz; }
       for (int i = 0; i < 3; ++i) r[i] += w * c[i];
@@ -115,20 +123,20 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       acc += w;
       if (s < S - 1) acc_m1 += w;
       if (a.has_norm) {
-        for (int i = 0; i < 3; ++i) { nv[i] = a.planes[(P_NORM + i) * ps + n]; rn[i] += w * nv[i]; }
+        for (int i = 0; i < 3; ++i) { nv[i] = a.planes[(P_NORM + i) * ps + pn]; rn[i] += w * nv[i]; }
         if (a.out.back_facing) {
           const float bf = fmaxf(nv[0] * vx + nv[1] * vy + nv[2] * vz, 0.f);
           a.out.back_facing[n] = bf * bf;
         }
         if (a.out.predicted_norm) for (int i = 0; i < 3; ++i) a.out.predicted_norm[n * 3 + i] = nv[i];
       } else if (a.has_grad) {
-        for (int i = 0; i < 3; ++i) rn[i] += w * a.planes[(P_GRAD + i) * ps + n];   // models.py:1353
+        for (int i = 0; i < 3; ++i) rn[i] += w * a.planes[(P_GRAD + i) * ps + pn];   // models.py:1353
       }
       if (a.has_grad && a.has_norm && a.out.target_norm)
-        for (int i = 0; i < 3; ++i) a.out.target_norm[n * 3 + i] = a.planes[(P_TNORM + i) * ps + n];
+        for (int i = 0; i < 3; ++i) a.out.target_norm[n * 3 + i] = a.planes[(P_TNORM + i) * ps + pn];
       if (a.has_warp) for (int i = 0; i < 3; ++i) {
-        rr[i] += w * a.planes[(P_ROT + i) * ps + n];
-        rt[i] += w * a.planes[(P_TRANS + i) * ps + n];
+        rr[i] += w * a.planes[(P_ROT + i) * ps + pn];
+        rt[i] += w * a.planes[(P_TRANS + i) * ps + pn];
       }
       for (int i = 0; i < 3; ++i) {
         const float d = wp[i] - px[i];
@@ -139,7 +147,7 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       for (int i = 0; i < a.H; ++i) rh[i] += w * wp[3 + i];
       if (a.out.warped_points) for (int i = 0; i < 3 + a.H; ++i) a.out.warped_points[n * (3 + a.H) + i] = wp[i];
       if (a.has_mask) {
-        const float m = a.planes[P_MASK * ps + n];
+        const float m = a.planes[P_MASK * ps + pn];
         rm += w * m;
         if (a.out.predicted_mask) a.out.predicted_mask[n] = m;
       }
@@ -177,7 +185,7 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       if (o.ray_hyper_points) for (int i = 0; i < a.H; ++i) o.ray_hyper_points[ray * a.H + i] = rh[i];
       if (o.ray_predicted_mask && a.has_mask) o.ray_predicted_mask[ray] = rm;
       if (o.med_points) for (int i = 0; i < 3 + a.H; ++i)
-        o.med_points[ray * (3 + a.H) + i] = a.planes[(P_WARPED + i) * ps + base + med_idx];
+        o.med_points[ray * (3 + a.H) + i] = a.planes[(P_WARPED + i) * ps + pidx(med_idx)];
       if (a.argmax_idx) a.argmax_idx[ray] = (float)best_i;
     }
     __syncwarp();
@@ -279,7 +287,7 @@ sample_pdf_kernel(const __grid_constant__ SamplePdfArgs a) {
         rank += (o < v || (o == v && j < i)) ? 1 : 0;
       }
       a.z_out[ray * nt + rank] = v;
-      if (a.perm_out) a.perm_out[ray * nt + i] = rank;
+      if (a.src_elem_out) a.src_elem_out[ray * nt + rank] = i;
     }
     __syncwarp();
   }

@@ -20,6 +20,11 @@ struct CompositeArgs {
   ndsr_outputs out;
   float* argmax_idx;     // scratch [B] (as float) for sharpen_weights
   float* weights_sg;     // scratch [B,S] or null: cal_weights() weights for sharpen_weights
+  // split fine pass (tensor-core engine): sample s of ray r is element e = src_elem[r S + s] of
+  // concat(coarse depths, new depths); its planes sit at r n_carried + e (e < n_carried) or at
+  // B n_carried + r (S - n_carried) + (e - n_carried).  null: planes are in sample order.
+  const int32_t* src_elem;
+  int n_carried;
 };
 
 struct SamplePdfArgs {
@@ -35,7 +40,7 @@ struct SamplePdfArgs {
   int32_t* idx_lo;        // optional
   int32_t* idx_hi;        // optional
   float* cdf_out;         // optional [B, n]
-  int32_t* perm_out;      // optional [B, n_coarse + n_fine]: sorted position of element i of concat(z_coarse, z_samples)
+  int32_t* src_elem_out;  // optional [B, n_coarse + n_fine]: which element of concat(z_coarse, z_samples) sits at sorted position s
 };
 
 cudaError_t launch_sample_along_rays(int64_t n_rays, int S, float near_, float far_, int lindisp,

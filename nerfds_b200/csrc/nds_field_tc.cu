@@ -558,21 +558,14 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     // per-sample inputs are fetched one pair ahead, so their global-memory latency hides behind the T phase
     auto load_next = [&](int64_t pair_, int s_) {
       NextSample& ns = nxt[s_];
-      const int64_t li = (2 * pair_ + s_) * TM + row;      // element of the launch's sample list
+      const int64_t li = (2 * pair_ + s_) * TM + row;      // sample of the launch
       ns.valid = (pair_ < n_pairs && li < a.n_samples_total) ? 1 : 0;
       ns.x[0] = ns.x[1] = ns.x[2] = 0.f; ns.vd[0] = ns.vd[1] = ns.vd[2] = 0.f; ns.gt = 0.f; ns.wid = 0; ns.n_out = 0;
       ns.xw[0] = ns.xw[1] = ns.xw[2] = 0.f; ns.om[0] = ns.om[1] = 0.f; ns.pmask = 0.f;
       for (int i = 0; i < 9; ++i) ns.R[i] = (i % 4 == 0) ? 1.f : 0.f;
       ns.p[0] = ns.p[1] = ns.p[2] = 0.f;
       if (!ns.valid) return;
-      int64_t ray, n_;
-      if (a.perm) {
-        ray = li / a.list_S;
-        n_ = ray * a.S + a.perm[ray * a.S + a.list_off + (li - ray * a.list_S)];
-      } else {
-        n_ = li;
-        ray = n_ / a.S;
-      }
+      const int64_t n_ = li, ray = li / a.S;
       ns.n_out = n_;
       ns.vd[0] = a.viewdirs[ray * 3]; ns.vd[1] = a.viewdirs[ray * 3 + 1]; ns.vd[2] = a.viewdirs[ray * 3 + 2];
       if (a.carry) {

@@ -50,7 +50,8 @@ struct ndsr_handle {
   int64_t cap_rays = 0, cap_samples = 0, max_samples_seen = 0;
   int64_t max_chunk = 65536;
   float* carry = nullptr;      // C_COUNT planes of the coarse samples (tensor-core engine: split fine pass)
-  int32_t* perm = nullptr;     // [rays, S_c + S_f] sorted positions from sample_pdf
+  int32_t* src_elem = nullptr; // [rays, S_c + S_f] from sample_pdf: element of concat(coarse, new) at each sorted position
+  float* z_new = nullptr;      // [rays, S_f] the new depths in draw order
   float *planes = nullptr, *z_coarse = nullptr, *z_fine = nullptr, *w_coarse = nullptr, *w_sg = nullptr,
         *argmax = nullptr;
   void* in_stage = nullptr;
