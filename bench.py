@@ -316,8 +316,15 @@ def run_ours(args):
     ach = fine_flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
     peak = float(pk.get('bf16_tflops_sustained', pk['bf16_tflops']))
     roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                'traffic': args.traffic,
-                'kernel': f'field_{R.engine}_kernel (fine level)', 'peak_kind': f'{pk_kind} sustained bf16 (burst {pk["bf16_tflops"]})',
+                # DRAM bytes per fine-level pass, from the ncu capture of the same command (profiles/): 397 B per
+                # sample evaluation (planes written once, carry planes read once, plus write-backs of the previous
+                # kernel's dirty L2 lines that ncu attributes to this one); --traffic overrides
+                'traffic': args.traffic if args.traffic is not None else (
+                    NCU_DRAM_BYTES_PER_EVAL * (Sc + Sf) * rays_local_total / max(f_n, 1) if R.engine == 'tc' else None),
+                'kernel': (f'field_tc_kernel x2 (fine level: {Sf} new depths per ray through every network + {Sc} coarse depths '
+                           'through the template NeRF on carried warp/hyper/mask results)') if R.engine == 'tc'
+                else f'field_{R.engine}_kernel (fine level)',
+                'peak_kind': f'{pk_kind} sustained bf16 (burst {pk["bf16_tflops"]})',
                 'launches': f_n, 'avg_launch_ms': f_ms / max(f_n, 1),
                 'flops_per_launch': fine_flops / max(f_n, 1),
                 'whole_step_tflops': (fine_flops + coarse_flops) / (ms * 1e-3) / 1e12,
@@ -347,6 +354,9 @@ def run_ours(args):
 def ALL_SHAPES_local(k, S, H):
   from nerfds_b200.renderer import ALL_SHAPES
   return ALL_SHAPES[k](S, H) or (1,)
+
+
+NCU_DRAM_BYTES_PER_EVAL = 397.0   # profiles/r1_field_tc_fine_ncu_full.txt
 
 
 def main():
