@@ -203,6 +203,9 @@ extern "C" void ndsr_destroy(ndsr_handle* h) {
   free_scratch(h);
   if (h->arena) cudaFree(h->arena);
   if (h->in_stage) cudaFree(h->in_stage);
+  if (h->out_stage) cudaFree(h->out_stage);
+  for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   prof_drain(h, false);
   for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   tc_engine_free(h);
@@ -665,17 +668,16 @@ struct Stage {
 };
 }
 
-static int stage_outputs(ndsr_handle* h, const ndsr_outputs* host, int64_t B, int S, int H, ndsr_outputs& dev,
-                         std::vector<void*>& tmp, Stage& stg) {
+// device copies of the requested outputs, carved out of one persistent buffer (`base` null: only count bytes)
+static size_t stage_outputs(const ndsr_outputs* host, int64_t B, int S, int H, ndsr_outputs& dev, char* base, size_t off,
+                            Stage& stg) {
   memset(&dev, 0, sizeof dev);
-  if (!host) return NDSR_OK;
+  if (!host) return off;
 #define ST(field, per)                                                                        \
   if (host->field) {                                                                          \
-    float* d = nullptr;                                                                       \
     const size_t bytes = (size_t)B * (per) * sizeof(float);                                   \
-    if (bytes) { NDS_CUDA(h, cudaMalloc((void**)&d, bytes)); tmp.push_back(d); }              \
-    dev.field = d;                                                                            \
-    stg.d2h.push_back({host->field, {d, bytes}});                                             \
+    if (base) { dev.field = reinterpret_cast<float*>(base + off); stg.d2h.push_back({host->field, {dev.field, bytes}}); } \
+    off += (bytes + 255) & ~(size_t)255;                                                      \
   }
   ST(rgb, 3) ST(depth, 1) ST(med_depth, 1) ST(acc, 1) ST(ray_norm, 3) ST(ray_rotation_field, 3)
   ST(ray_translation_field, 3) ST(ray_delta_x, 3) ST(ray_hyper_points, H) ST(ray_predicted_mask, 1)
@@ -683,9 +685,12 @@ static int stage_outputs(ndsr_handle* h, const ndsr_outputs* host, int64_t B, in
   ST(sharp_weights, S) ST(back_facing, S) ST(predicted_mask, S) ST(points, 3 * S) ST(warped_points, (3 + H) * S)
   ST(delta_x, 3 * S) ST(predicted_norm, 3 * S) ST(target_norm, 3 * S)
 #undef ST
-  return NDSR_OK;
+  return off;
 }
 
+// Host buffers in, host buffers out (what a ctypes caller of the reference's render_image chunk loop has).  The
+// rays are processed in chunks of max_chunk; the inputs of chunk k + 1 are copied on a second stream while chunk k
+// computes (pinned host memory makes the copies asynchronous), the outputs come back in one copy per key at the end.
 extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,
                                      const float* directions, const float* viewdirs, const uint32_t* warp_id,
                                      const float* gt_mask, const float* t_rand, const float* u,
@@ -698,38 +703,72 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
   NDS_CUDA(h, cudaSetDevice(h->device));
   const ndsr_config& c = h->cfg;
   const int Sc = c.num_coarse_samples, Sf = c.num_fine_samples;
-  // persistent input staging (grown on demand, reused across calls)
-  const size_t need = (size_t)n_rays * (3 + 3 + 3 + 1 + 1 + Sc + Sf) * sizeof(float);
-  if (need > h->in_stage_bytes) {
-    NDS_CUDA(h, cudaStreamSynchronize(st));
+  // sharpen_weights couples the rays of one call (App. C-2): no chunking when it is requested
+  const bool coupled = c.use_mask_sharp_weights && ((coarse && coarse->sharp_weights) || (fine && fine->sharp_weights));
+  const int64_t chunk = coupled ? n_rays : (n_rays < h->max_chunk ? n_rays : h->max_chunk);
+  if (!h->copy_stream) {
+    NDS_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      NDS_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      NDS_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  // persistent staging (grown on demand, reused across calls)
+  const size_t per_ray = (size_t)(3 + 3 + 3 + 1 + 1 + Sc + Sf) * sizeof(float);
+  const size_t half = ((size_t)chunk * per_ray + 255) & ~(size_t)255;
+  if (2 * half > h->in_stage_bytes) {
+    NDS_CUDA(h, cudaDeviceSynchronize());
     if (h->in_stage) cudaFree(h->in_stage);
     h->in_stage = nullptr; h->in_stage_bytes = 0;
-    NDS_CUDA(h, cudaMalloc(&h->in_stage, need));
-    h->in_stage_bytes = need;
+    NDS_CUDA(h, cudaMalloc(&h->in_stage, 2 * half));
+    h->in_stage_bytes = 2 * half;
   }
-  float* p = (float*)h->in_stage;
-  auto up = [&](const void* src, size_t nfloats, float** dst) -> cudaError_t {
-    if (!src) { *dst = nullptr; return cudaSuccess; }
-    *dst = p;
-    p += nfloats;
-    return cudaMemcpyAsync(*dst, src, nfloats * sizeof(float), cudaMemcpyHostToDevice, st);
-  };
-  float *d_o, *d_d, *d_v, *d_w, *d_m, *d_t, *d_u;
-  NDS_CUDA(h, up(origins, (size_t)n_rays * 3, &d_o));
-  NDS_CUDA(h, up(directions, (size_t)n_rays * 3, &d_d));
-  NDS_CUDA(h, up(viewdirs, (size_t)n_rays * 3, &d_v));
-  NDS_CUDA(h, up(warp_id, (size_t)n_rays, &d_w));
-  NDS_CUDA(h, up(gt_mask, (size_t)n_rays, &d_m));
-  NDS_CUDA(h, up(t_rand, (size_t)n_rays * Sc, &d_t));
-  NDS_CUDA(h, up(u, (size_t)n_rays * Sf, &d_u));
-  std::vector<void*> tmp;
   Stage stg;
   ndsr_outputs dc, df;
-  int rc = stage_outputs(h, coarse, n_rays, Sc, h->H, dc, tmp, stg);
-  if (!rc) rc = stage_outputs(h, fine, n_rays, Sc + Sf, h->H, df, tmp, stg);
-  if (!rc)
-    rc = ndsr_render_rays(h, stream, n_rays, d_o, d_d, d_v, (const uint32_t*)d_w, d_m, d_t, d_u, ep,
-                          coarse ? &dc : nullptr, fine ? &df : nullptr);
+  size_t out_need = stage_outputs(coarse, n_rays, Sc, h->H, dc, nullptr, 0, stg);
+  out_need = stage_outputs(fine, n_rays, Sc + Sf, h->H, df, nullptr, out_need, stg);
+  if (out_need > h->out_stage_bytes) {
+    NDS_CUDA(h, cudaDeviceSynchronize());
+    if (h->out_stage) cudaFree(h->out_stage);
+    h->out_stage = nullptr; h->out_stage_bytes = 0;
+    NDS_CUDA(h, cudaMalloc(&h->out_stage, out_need));
+    h->out_stage_bytes = out_need;
+  }
+  size_t off = stage_outputs(coarse, n_rays, Sc, h->H, dc, (char*)h->out_stage, 0, stg);
+  stage_outputs(fine, n_rays, Sc + Sf, h->H, df, (char*)h->out_stage, off, stg);
+  // the copy stream must not overwrite a staging half that work already queued on `st` still reads
+  NDS_CUDA(h, cudaEventRecord(h->ev_free[0], st));
+  NDS_CUDA(h, cudaEventRecord(h->ev_free[1], st));
+  int rc = NDSR_OK;
+  int64_t k = 0;
+  for (int64_t r0 = 0; r0 < n_rays && !rc; r0 += chunk, ++k) {
+    const int64_t B = (n_rays - r0) < chunk ? (n_rays - r0) : chunk;
+    const int b = (int)(k & 1);
+    float* p = reinterpret_cast<float*>((char*)h->in_stage + (size_t)b * half);
+    cudaStream_t cs = h->copy_stream;
+    NDS_CUDA(h, cudaStreamWaitEvent(cs, h->ev_free[b], 0));
+    auto up = [&](const void* src, size_t per, float** dst) -> cudaError_t {
+      if (!src) { *dst = nullptr; return cudaSuccess; }
+      *dst = p;
+      p += (size_t)B * per;
+      return cudaMemcpyAsync(*dst, (const char*)src + (size_t)r0 * per * sizeof(float), (size_t)B * per * sizeof(float),
+                             cudaMemcpyHostToDevice, cs);
+    };
+    float *d_o, *d_d, *d_v, *d_w, *d_m, *d_t, *d_u;
+    NDS_CUDA(h, up(origins, 3, &d_o));
+    NDS_CUDA(h, up(directions, 3, &d_d));
+    NDS_CUDA(h, up(viewdirs, 3, &d_v));
+    NDS_CUDA(h, up(warp_id, 1, &d_w));
+    NDS_CUDA(h, up(gt_mask, 1, &d_m));
+    NDS_CUDA(h, up(t_rand, (size_t)Sc, &d_t));
+    NDS_CUDA(h, up(u, (size_t)Sf, &d_u));
+    NDS_CUDA(h, cudaEventRecord(h->ev_in[b], cs));
+    NDS_CUDA(h, cudaStreamWaitEvent(st, h->ev_in[b], 0));
+    ndsr_outputs oc = offset_outputs(coarse ? &dc : nullptr, r0, Sc, h->H), of = offset_outputs(fine ? &df : nullptr, r0, Sc + Sf, h->H);
+    rc = ndsr_render_rays(h, stream, B, d_o, d_d, d_v, (const uint32_t*)d_w, d_m, d_t, d_u, ep, coarse ? &oc : nullptr,
+                          fine ? &of : nullptr);
+    NDS_CUDA(h, cudaEventRecord(h->ev_free[b], st));
+  }
   if (!rc) {
     for (auto& e : stg.d2h)
       if (e.second.second) {
@@ -739,7 +778,6 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
   }
   cudaError_t se = cudaStreamSynchronize(st);
   if (!rc && se != cudaSuccess) { h->err = cudaGetErrorString(se); rc = NDSR_ERR_CUDA; }
-  for (void* q : tmp) cudaFree(q);
   return rc;
 }
 

@@ -54,8 +54,12 @@ struct ndsr_handle {
   float* z_new = nullptr;      // [rays, S_f] the new depths in draw order
   float *planes = nullptr, *z_coarse = nullptr, *z_fine = nullptr, *w_coarse = nullptr, *w_sg = nullptr,
         *argmax = nullptr;
-  void* in_stage = nullptr;
+  void* in_stage = nullptr;       // host-buffer calls: two input staging halves (double-buffered per ray chunk)
   size_t in_stage_bytes = 0;
+  void* out_stage = nullptr;      // ... and the device copies of the requested outputs
+  size_t out_stage_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   // per-stage device timing (ndsr_profile_enable / ndsr_profile_read)
   bool prof = false;
   struct ProfSpan { int stage; cudaEvent_t a, b; };

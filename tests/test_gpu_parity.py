@@ -317,3 +317,21 @@ def test_tc_split_fine_pass_is_exact(cuda_device, monkeypatch):
   for k in keys:
     np.testing.assert_allclose(a['fine'][k], b['fine'][k], rtol=0, atol=1e-6, err_msg=k)
   np.testing.assert_array_equal(a['coarse']['rgb'], b['coarse']['rgb'])
+
+
+def test_host_buffer_path_matches_device_path(cuda_device):
+  """ndsr_render_rays_host (numpy in / numpy out, input copies of chunk k + 1 overlapped with the compute of chunk k
+  on a second stream) returns what the device-pointer path returns, for several chunks incl. a ragged last one."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=18, seed=6)       # 324 rays
+  m = _model(cfg, cuda_device, engine='tc')
+  m.renderer.ensure_params(params)
+  m.renderer.set_max_chunk(100)                                               # 4 chunks: 100, 100, 100, 24
+  keys = ('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'med_points')
+  dev = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True,
+                keys=keys, coarse_keys=('rgb',))
+  extra = m.renderer.make_extra(syn.final_extra_params(), use_predicted_norm=True)
+  for _ in range(2):                                                          # second call re-uses the staging
+    host = m.renderer.render_rays_host(rays['origins'], rays['directions'], warp_id=rays['metadata']['warp'],
+                                       gt_mask=rays['mask'], t_rand=t_rand, u=u, extra=extra, fine_keys=keys)
+    for k in keys:
+      np.testing.assert_array_equal(host[k].reshape(_np(dev['fine'])[k].shape), _np(dev['fine'])[k], err_msg=k)
