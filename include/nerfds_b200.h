@@ -221,6 +221,26 @@ int ndsr_sample_pdf(ndsr_handle* h, void* stream, int64_t n_rays,
                     const float* z_vals, float* z_out, float* z_samples,
                     int32_t* idx_lo, int32_t* idx_hi, float* cdf);
 
+/* A pinhole camera with radial / tangential distortion, as hypernerf/camera.py:112-138 stores it (float32). */
+typedef struct ndsr_camera {
+  float orientation[9];          /* world-to-camera rotation, row-major (camera.py:127) */
+  float position[3];
+  float focal_length;
+  float principal_point[2];
+  float skew;
+  float pixel_aspect_ratio;
+  float radial_distortion[3];    /* k1, k2, k3 */
+  float tangential_distortion[2];/* p1, p2 */
+  int32_t image_size[2];         /* (width, height), camera.py:136 */
+} ndsr_camera;
+
+/* Replaces datasets/core.py:51-76 camera_to_rays = Camera.pixels_to_rays(Camera.get_pixel_centers())
+ * (camera.py:226-270, 364-368; the 10 Newton iterations of _radial_and_tangential_undistort, camera.py:27-106) on the
+ * device: origins [H*W,3] (the camera position), directions [H*W,3] (unit, world frame), pixels [H*W,2] (pixel
+ * centres; nullable), row-major over (y, x).  Stateless: `device` is the CUDA device index. */
+int ndsr_camera_rays(int device, void* stream, const ndsr_camera* camera, float* origins, float* directions,
+                     float* pixels);
+
 /* Replaces model_utils.volumetric_rendering (model_utils.py:95-159) +
  * compute_depth_map.  rgb [n,S,3], sigma [n,S], z_vals [n,S], dirs [n,3]. */
 int ndsr_volumetric_rendering(ndsr_handle* h, void* stream, int64_t n_rays,

@@ -127,13 +127,21 @@ def to_c_config(cfg: NerfDSConfig, engine='auto', precision='split3') -> ndsr_co
   return c
 
 
+class ndsr_camera(C.Structure):
+  """include/nerfds_b200.h: ndsr_camera (hypernerf/camera.py:112-138)."""
+  _fields_ = [('orientation', C.c_float * 9), ('position', C.c_float * 3), ('focal_length', C.c_float),
+              ('principal_point', C.c_float * 2), ('skew', C.c_float), ('pixel_aspect_ratio', C.c_float),
+              ('radial_distortion', C.c_float * 3), ('tangential_distortion', C.c_float * 2),
+              ('image_size', C.c_int32 * 2)]
+
+
 _lib = None
 
 EXPORTS = ['ndsr_create', 'ndsr_destroy', 'ndsr_last_error', 'ndsr_load_params', 'ndsr_render_rays',
            'ndsr_render_rays_host', 'ndsr_render_samples', 'ndsr_sample_along_rays', 'ndsr_sample_pdf',
            'ndsr_volumetric_rendering', 'ndsr_engine_in_use', 'ndsr_kernel_launches', 'ndsr_abi_version',
            'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense', 'ndsr_profile_enable',
-           'ndsr_profile_read']
+           'ndsr_profile_read', 'ndsr_camera_rays']
 
 
 def load_library() -> C.CDLL:
@@ -171,6 +179,7 @@ def load_library() -> C.CDLL:
   lib.ndsr_profile_enable.argtypes = [vp, C.c_int]
   lib.ndsr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   lib.ndsr_selftest_tc_dense.argtypes = [C.c_int] * 7 + [vp] * 5
+  lib.ndsr_camera_rays.argtypes = [C.c_int, vp, C.POINTER(ndsr_camera), vp, vp, vp]
   if lib.ndsr_abi_version() != NDSR_ABI_VERSION:
     raise ImportError('libnerfds_b200.so ABI version mismatch; rebuild')
   a, b, c = i32(), i32(), i32()

@@ -781,6 +781,14 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
   return rc;
 }
 
+// ------------------------------------------------- ray generation
+extern "C" int ndsr_camera_rays(int device, void* stream, const ndsr_camera* camera, float* origins, float* directions,
+                                float* pixels) {
+  if (!camera || !origins || !directions || camera->image_size[0] < 0 || camera->image_size[1] < 0) return NDSR_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  return launch_camera_rays(*camera, origins, directions, pixels, (cudaStream_t)stream) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
+}
+
 // ------------------------------------------------- stand-alone stage calls
 extern "C" int ndsr_sample_along_rays(ndsr_handle* h, void* stream, int64_t n_rays, int32_t n_samples, float near_,
                                       float far_, int32_t use_linear_disparity, const float* t_rand,

@@ -294,6 +294,56 @@ sample_pdf_kernel(const __grid_constant__ SamplePdfArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// datasets/core.py:51-76 camera_to_rays: Camera.pixels_to_rays over the pixel centres
+// (camera.py:226-270), float32 like the reference's default camera dtype, no FMA
+// contraction (this file is compiled with -fmad=false).
+// ---------------------------------------------------------------------------
+__global__ void camera_rays_kernel(const __grid_constant__ ndsr_camera cam, float* __restrict__ origins,
+                                   float* __restrict__ dirs, float* __restrict__ pixels) {
+  const int W = cam.image_size[0], Hh = cam.image_size[1];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)W * Hh) return;
+  const float px = (float)(i % W) + 0.5f, py = (float)(i / W) + 0.5f;     // get_pixel_centers (camera.py:364-368)
+  const float sx = cam.focal_length, sy = cam.focal_length * cam.pixel_aspect_ratio;
+  float y = (py - cam.principal_point[1]) / sy;                            // pixel_to_local_rays (camera.py:228-230)
+  float x = (px - cam.principal_point[0] - y * cam.skew) / sx;
+  const float k1 = cam.radial_distortion[0], k2 = cam.radial_distortion[1], k3 = cam.radial_distortion[2];
+  const float p1 = cam.tangential_distortion[0], p2 = cam.tangential_distortion[1];
+  if (k1 != 0.f || k2 != 0.f || k3 != 0.f || p1 != 0.f || p2 != 0.f) {
+    // _radial_and_tangential_undistort (camera.py:75-106): 10 Newton steps from the distorted point
+    const float xd = x, yd = y;
+    for (int it = 0; it < 10; ++it) {
+      // _compute_residual_and_jacobian (camera.py:27-72), same association as the numpy expressions
+      const float r = x * x + y * y;
+      const float d = 1.0f + r * (k1 + r * (k2 + k3 * r));
+      const float fx = d * x + 2.f * p1 * x * y + p2 * (r + 2.f * x * x) - xd;
+      const float fy = d * y + 2.f * p2 * x * y + p1 * (r + 2.f * y * y) - yd;
+      const float d_r = k1 + r * (2.0f * k2 + 3.0f * k3 * r);
+      const float d_x = 2.0f * x * d_r, d_y = 2.0f * y * d_r;
+      const float fx_x = d + d_x * x + 2.0f * p1 * y + 6.0f * p2 * x;
+      const float fx_y = d_y * x + 2.0f * p1 * x + 2.0f * p2 * y;
+      const float fy_x = d_x * y + 2.0f * p2 * y + 2.0f * p1 * x;
+      const float fy_y = d + d_y * y + 2.0f * p2 * x + 6.0f * p1 * y;
+      const float den = fy_x * fx_y - fx_x * fy_y;
+      const float xn = fx * fy_y - fy * fx_y, yn = fy * fx_x - fx * fy_x;
+      const bool ok = fabsf(den) > 1e-9f;
+      x = x + (ok ? xn / den : 0.f);
+      y = y + (ok ? yn / den : 0.f);
+    }
+  }
+  float n = sqrtf(x * x + y * y + 1.f);                                     // camera.py:242-243
+  const float lx = x / n, ly = y / n, lz = 1.f / n;
+  const float* R = cam.orientation;                                         // orientation.T @ local (camera.py:263)
+  float wx = R[0] * lx + R[3] * ly + R[6] * lz;
+  float wy = R[1] * lx + R[4] * ly + R[7] * lz;
+  float wz = R[2] * lx + R[5] * ly + R[8] * lz;
+  n = sqrtf(wx * wx + wy * wy + wz * wz);                                   // camera.py:267
+  dirs[i * 3] = wx / n; dirs[i * 3 + 1] = wy / n; dirs[i * 3 + 2] = wz / n;
+  origins[i * 3] = cam.position[0]; origins[i * 3 + 1] = cam.position[1]; origins[i * 3 + 2] = cam.position[2];
+  if (pixels) { pixels[i * 2] = px; pixels[i * 2 + 1] = py; }
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
 static int grid_for(int64_t rays, int num_sms) {
@@ -328,6 +378,13 @@ cudaError_t launch_pack_rgb_sigma(int64_t total, const float* rgb, const float* 
                                   cudaStream_t st) {
   if (total == 0) return cudaSuccess;
   pack_rgb_sigma_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, rgb, sigma, planes, ps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_camera_rays(const ndsr_camera& cam, float* origins, float* dirs, float* pixels, cudaStream_t st) {
+  const int64_t n = (int64_t)cam.image_size[0] * cam.image_size[1];
+  if (n <= 0) return cudaSuccess;
+  camera_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cam, origins, dirs, pixels);
   return cudaGetLastError();
 }
 

@@ -335,3 +335,25 @@ def test_host_buffer_path_matches_device_path(cuda_device):
                                        gt_mask=rays['mask'], t_rand=t_rand, u=u, extra=extra, fine_keys=keys)
     for k in keys:
       np.testing.assert_array_equal(host[k].reshape(_np(dev['fine'])[k].shape), _np(dev['fine'])[k], err_msg=k)
+
+
+def test_camera_rays_match_reference_camera(cuda_device):
+  """ndsr_camera_rays (datasets/core.py:51-76 on the device) against golden vectors from the reference's own
+  camera.py and against the numpy oracle at a full 800x800 frame with distortion."""
+  import os
+  from nerfds_b200.camera import Camera, camera_to_rays
+  from oracle import camera_oracle
+  from tests.test_oracle_golden import GOLDEN, golden_cameras
+  G = dict(np.load(GOLDEN))
+  for name, kw, gold in golden_cameras(G):
+    out = {k: v.cpu().numpy() for k, v in camera_to_rays(Camera(**kw), cuda_device).items()}
+    np.testing.assert_array_equal(out['origins'], gold['origins'], err_msg=name)
+    np.testing.assert_array_equal(out['pixels'], gold['pixels'], err_msg=name)
+    np.testing.assert_allclose(out['directions'], gold['directions'], rtol=0, atol=5e-7, err_msg=name)
+  kw = dict(orientation=np.eye(3), position=[0.0, 0.1, -1.0], focal_length=800.0, principal_point=[400.0, 400.0],
+            image_size=[800, 800], skew=0.01, pixel_aspect_ratio=1.0, radial_distortion=[0.05, -0.01, 0.002],
+            tangential_distortion=[0.001, -0.002])
+  ref = camera_oracle.camera_to_rays(**kw)
+  out = camera_to_rays(Camera(**kw), cuda_device)
+  assert out['directions'].shape == (800, 800, 3)
+  assert np.abs(out['directions'].cpu().numpy() - ref['directions']).max() <= 5e-7

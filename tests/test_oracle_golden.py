@@ -245,3 +245,34 @@ def test_whole_forward_matches_reference_nerf_model(G):
         np.testing.assert_allclose(o, g, rtol=1e-4, atol=2e-5, equal_nan=True, err_msg=f'{lvl}/{k}')
       checked += 1
   assert checked >= 40
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Ray generation: the reference's own hypernerf/camera.py (plain numpy) on three cameras
+# ---------------------------------------------------------------------------------------------------------------
+CAMERA_KEYS = ('orientation', 'position', 'focal_length', 'principal_point', 'image_size', 'skew', 'pixel_aspect_ratio',
+               'radial_distortion', 'tangential_distortion')
+
+
+def golden_cameras(G):
+  for name in G['camera_names']:
+    name = str(name)
+    kw = {k: G[f'camera_{name}_{k}'] for k in CAMERA_KEYS if f'camera_{name}_{k}' in G}
+    kw['image_size'] = [int(v) for v in kw['image_size']]
+    for k in ('focal_length', 'skew', 'pixel_aspect_ratio'):
+      if k in kw:
+        kw[k] = float(kw[k])
+    yield name, kw, {k: G[f'camera_{name}_{k}'] for k in ('origins', 'directions', 'pixels')}
+
+
+def test_camera_rays_oracle(G):
+  from oracle import camera_oracle
+  n = 0
+  for name, kw, gold in golden_cameras(G):
+    out = camera_oracle.camera_to_rays(**kw)
+    np.testing.assert_array_equal(out['origins'], gold['origins'], err_msg=name)
+    np.testing.assert_array_equal(out['pixels'], gold['pixels'], err_msg=name)
+    np.testing.assert_allclose(out['directions'], gold['directions'], rtol=0, atol=3e-7, err_msg=name)
+    assert np.allclose(np.linalg.norm(out['directions'], axis=-1), 1.0, atol=1e-6)
+    n += 1
+  assert n == 3

@@ -575,6 +575,34 @@ def main():
       if k != 'target_norm' and v is not None:          # gradient-derived: no autodiff under the stand-in
         G[f'model_{lvl}_{k}'] = f32(v)
 
+  # ------------------------------------------------------------------ ray generation
+  # hypernerf/camera.py is plain numpy; its module imports gpath -> tensorflow, stubbed out
+  tf = types.ModuleType('tensorflow')
+  tf.io = types.SimpleNamespace(gfile=types.SimpleNamespace())
+  sys.modules['tensorflow'] = tf
+  camera_mod = importlib.import_module('hypernerf.camera')
+  th = 0.3
+  Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+  Rx = np.array([[1, 0, 0], [0, np.cos(0.5), -np.sin(0.5)], [0, np.sin(0.5), np.cos(0.5)]])
+  cams = {
+      'plain': dict(orientation=np.eye(3), position=[0.1, -0.2, -1.2], focal_length=20.0, principal_point=[6.5, 4.5],
+                    image_size=[13, 9]),
+      'radial': dict(orientation=Rz @ Rx, position=[0.4, 0.3, -0.9], focal_length=17.5, principal_point=[6.2, 4.9],
+                     image_size=[13, 9], radial_distortion=[0.08, -0.02, 0.004]),
+      'full': dict(orientation=Rx @ Rz, position=[-0.3, 0.2, 1.1], focal_length=15.0, principal_point=[5.7, 5.3],
+                   image_size=[12, 10], skew=0.03, pixel_aspect_ratio=1.02, radial_distortion=[0.11, 0.03, -0.006],
+                   tangential_distortion=[0.004, -0.003]),
+  }
+  G['camera_names'] = np.array(sorted(cams))
+  for name, kw in cams.items():
+    cam_ref = camera_mod.Camera(**{k: np.asarray(v) for k, v in kw.items()})
+    for k, v in kw.items():
+      G[f'camera_{name}_{k}'] = np.asarray(v, np.float64)
+    rays_dir = cam_ref.pixels_to_rays(cam_ref.get_pixel_centers())          # datasets/core.py:66-71
+    G[f'camera_{name}_directions'] = rays_dir.astype(np.float32)
+    G[f'camera_{name}_origins'] = np.tile(cam_ref.position[None, None, :], cam_ref.image_shape + (1,)).astype(np.float32)
+    G[f'camera_{name}_pixels'] = cam_ref.get_pixel_centers().astype(np.float32)
+
   assert not _DRAWS
   os.makedirs(os.path.dirname(OUT), exist_ok=True)
   np.savez_compressed(OUT, **G)
