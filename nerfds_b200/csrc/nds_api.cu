@@ -568,6 +568,7 @@ extern "C" int ndsr_render_samples(ndsr_handle* h, void* stream, int level, int6
                                    const float* gt_mask, const ndsr_extra_params* ep,
                                    int32_t use_sample_at_infinity, const ndsr_outputs* out) {
   if (!h) return NDSR_ERR_INVALID;
+  if (n_rays == 0) return NDSR_OK;
   int rc = check_call(h, ep, warp_id, gt_mask);
   if (rc) return rc;
   if (level < 0 || level > 1 || n_rays < 0 || n_samples < 2 || !z_vals || !directions || (!points && !origins))
@@ -634,12 +635,12 @@ extern "C" int ndsr_render_rays(ndsr_handle* h, void* stream, int64_t n_rays, co
                                 const float* gt_mask, const float* t_rand, const float* u,
                                 const ndsr_extra_params* ep, const ndsr_outputs* coarse, const ndsr_outputs* fine) {
   if (!h) return NDSR_ERR_INVALID;
+  if (n_rays == 0) return NDSR_OK;                  // empty batch: nothing to read, nothing to write
   int rc = check_call(h, ep, warp_id, gt_mask);
   if (rc) return rc;
   if (n_rays < 0 || !origins || !directions) return fail(h, NDSR_ERR_INVALID, "origins/directions required");
   const ndsr_config& c = h->cfg;
   if (c.use_stratified_sampling && (!t_rand || !u)) return fail(h, NDSR_ERR_INVALID, "t_rand and u required with use_stratified_sampling");
-  if (n_rays == 0) return NDSR_OK;
   cudaStream_t st = (cudaStream_t)stream;
   NDS_CUDA(h, cudaSetDevice(h->device));
   CallParams cp;
@@ -697,8 +698,8 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
                                      const ndsr_extra_params* ep, const ndsr_outputs* coarse,
                                      const ndsr_outputs* fine) {
   if (!h) return NDSR_ERR_INVALID;
-  if (n_rays < 0 || !origins || !directions) return fail(h, NDSR_ERR_INVALID, "origins/directions required");
   if (n_rays == 0) return NDSR_OK;
+  if (n_rays < 0 || !origins || !directions) return fail(h, NDSR_ERR_INVALID, "origins/directions required");
   cudaStream_t st = (cudaStream_t)stream;
   NDS_CUDA(h, cudaSetDevice(h->device));
   const ndsr_config& c = h->cfg;

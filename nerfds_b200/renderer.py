@@ -210,9 +210,9 @@ class Renderer:
     v = None if viewdirs is None else _as_dev(viewdirs, dev).reshape(-1, 3)
     w = None if warp_id is None else _as_dev(warp_id, dev, torch.int32).reshape(-1)
     m = None if gt_mask is None else _as_dev(gt_mask, dev).reshape(-1)
-    tr = None if t_rand is None else _as_dev(t_rand, dev).reshape(B, -1)
-    uu = None if u is None else _as_dev(u, dev).reshape(B, -1)
     c = self.cfg
+    tr = None if t_rand is None else _as_dev(t_rand, dev).reshape(B, -1 if B else c.num_coarse_samples)
+    uu = None if u is None else _as_dev(u, dev).reshape(B, -1 if B else c.num_fine_samples)
     if tr is not None and tr.shape[1] != c.num_coarse_samples:
       raise ValueError('t_rand must be [B, num_coarse_samples]')
     if uu is not None and uu.shape[1] != c.num_fine_samples:

@@ -357,3 +357,19 @@ def test_camera_rays_match_reference_camera(cuda_device):
   out = camera_to_rays(Camera(**kw), cuda_device)
   assert out['directions'].shape == (800, 800, 3)
   assert np.abs(out['directions'].cpu().numpy() - ref['directions']).max() <= 5e-7
+
+
+def test_empty_and_minimal_inputs(cuda_device):
+  """Zero rays is a no-op returning empty arrays; the smallest legal sample counts (3 coarse + 1 fine) render."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=4, seed=7, num_coarse_samples=3, num_fine_samples=1)
+  m = _model(cfg, cuda_device, engine='tc')
+  out = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True,
+                keys=('rgb', 'depth', 'acc'), coarse_keys=('rgb',))
+  ref = run_oracle(cfg, params, rays, t_rand, u, compute_sigma_gradient=False)
+  assert linf(_np(out['coarse'])['rgb'], ref['coarse']['rgb']) <= RGB_TOL
+  assert np.isfinite(_np(out['fine'])['rgb']).all()
+  empty = {'origins': rays['origins'][:0], 'directions': rays['directions'][:0],
+           'metadata': {k: v[:0] for k, v in rays['metadata'].items()}, 'mask': rays['mask'][:0]}
+  out0 = m.apply({'params': params}, empty, syn.final_extra_params(), t_rand=t_rand[:0], u=u[:0], use_predicted_norm=True,
+                 keys=('rgb',), coarse_keys=('rgb',))
+  assert tuple(out0['fine']['rgb'].shape) == (0, 3)
