@@ -45,6 +45,15 @@ class Camera:
   def image_shape(self):
     return int(self.image_size[1]), int(self.image_size[0])
 
+  def scale(self, scale: float) -> 'Camera':
+    """camera.py:370-387: intrinsics and image size scaled, extrinsics and distortion kept."""
+    if scale <= 0:
+      raise ValueError('scale needs to be positive.')
+    return dataclasses.replace(
+        self, focal_length=self.focal_length * scale,
+        principal_point=[float(v) * scale for v in self.principal_point],
+        image_size=[int(round(self.image_size[0] * scale)), int(round(self.image_size[1] * scale))])
+
   def to_c(self) -> _lib.ndsr_camera:
     c = _lib.ndsr_camera()
     f32 = lambda a, n: np.asarray(a if a is not None else np.zeros(n), np.float32).reshape(n)
@@ -58,6 +67,22 @@ class Camera:
     c.tangential_distortion[:] = f32(self.tangential_distortion, 2).tolist()
     c.image_size[:] = [int(self.image_size[0]), int(self.image_size[1])]
     return c
+
+
+def load_camera(camera_path, scale_factor: float = 1.0, scene_center=None, scene_scale=None) -> Camera:
+  """datasets/core.py:79-111: JSON camera, rescaled, moved into the normalised scene frame."""
+  if not str(camera_path).endswith('.json'):
+    raise ValueError('File must have extension .pb or .json.' if not str(camera_path).endswith('.pb')
+                     else 'camera protos are not supported; export the camera as JSON')
+  camera = Camera.from_json(camera_path)
+  if scale_factor != 1.0:
+    camera = camera.scale(scale_factor)
+  pos = np.asarray(camera.position, np.float64)
+  if scene_center is not None:
+    pos = pos - np.asarray(scene_center, np.float64)
+  if scene_scale is not None:
+    pos = pos * scene_scale
+  return dataclasses.replace(camera, position=pos.tolist())
 
 
 def camera_to_rays(camera: Camera, device='cuda:0') -> Dict[str, torch.Tensor]:
