@@ -373,3 +373,68 @@ def test_empty_and_minimal_inputs(cuda_device):
   out0 = m.apply({'params': params}, empty, syn.final_extra_params(), t_rand=t_rand[:0], u=u[:0], use_predicted_norm=True,
                  keys=('rgb',), coarse_keys=('rgb',))
   assert tuple(out0['fine']['rgb'].shape) == (0, 3)
+
+
+def test_full_frame_properties_at_baseline_size(cuda_device):
+  """BASELINE configs[1] at its full size (800x800 rays, 128 + 128 samples): size-independent properties of the
+  path -- sorted resampled depths that contain the coarse depths' range, weights that sum to acc, bounded colours,
+  bit-identical repeat, rays independent of their position in the batch / tile / chunk -- and the oracle on a
+  scattered subset of the same frame."""
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import init_params
+  cfg = nerf_ds_config(num_coarse_samples=128, num_fine_samples=128, near=0.1, far=2.5, num_warp_embeds=100)
+  params = init_params(cfg, 0)
+  rays = syn.frame_rays(800, 800, frame=4, num_frames=30, focal=800.0)
+  n = rays['origins'].shape[0]
+  assert n == 640_000
+  gen = torch.Generator(device=cuda_device)
+  gen.manual_seed(9)
+  t_rand = torch.rand((n, 128), generator=gen, device=cuda_device)
+  u = torch.rand((n, 128), generator=gen, device=cuda_device)
+  rays['mask'] = np.zeros((n, 1), np.float32)
+  m = _model(cfg, cuda_device, engine='tc')
+  keys = ('rgb', 'acc', 'depth', 'med_depth', 'weights', 'z_vals')
+  run = lambda r, t, uu: m.apply({'params': params}, r, syn.final_extra_params(), t_rand=t, u=uu,
+                                 use_predicted_norm=True, mask_ratio=1, sharp_weights_std=0.1, keys=keys,
+                                 coarse_keys=('rgb', 'z_vals'))
+  out = run(rays, t_rand, u)
+  f, c = out['fine'], out['coarse']
+  assert all(bool(torch.isfinite(v).all()) for v in f.values())
+  assert float(f['rgb'].min()) >= 0.0 and float(f['rgb'].max()) <= 1.0 + 1e-6
+  assert float(f['acc'].min()) >= 0.0 and float(f['acc'].max()) <= 1.0 + 1e-5
+  z = f['z_vals']
+  assert z.shape == (n, 256) and bool((z[:, 1:] >= z[:, :-1]).all())                      # sortedness
+  assert float(z.min()) >= cfg.near and float(z.max()) <= cfg.far
+  zc = c['z_vals']
+  assert bool((z[:, 0] <= zc[:, 0]).all()) and bool((z[:, -1] >= zc[:, -1]).all())        # the union keeps the coarse depths
+  w = f['weights']
+  assert float(w.min()) >= 0.0
+  # acc sums the weights without the sample at infinity (model_utils.py:143-148); all of them sum to <= 1
+  assert float((w[:, :-1].sum(-1) - f['acc'].reshape(n)).abs().max()) <= 2e-5 and float(w.sum(-1).max()) <= 1.0 + 1e-5
+  d = f['depth'].reshape(n)
+  ws = w.sum(-1)                                                                           # depth = sum(w z), z in [near, far]
+  assert bool((d <= cfg.far * ws + 1e-4).all()) and bool((d >= cfg.near * ws - 1e-4).all())
+  snap = {k: v.clone() for k, v in f.items() if k in ('rgb', 'depth', 'med_depth')}
+  del out, f, c, w, z, zc
+  torch.cuda.empty_cache()
+
+  again = run(rays, t_rand, u)['fine']                                                     # idempotence
+  for k, v in snap.items():
+    assert torch.equal(again[k], v), k
+  del again
+
+  lo, hi = 123_457, 123_457 + 1000                                                         # batch-position independence
+  sub = {'origins': rays['origins'][lo:hi], 'directions': rays['directions'][lo:hi],
+         'metadata': {k: v[lo:hi] for k, v in rays['metadata'].items()}, 'mask': rays['mask'][lo:hi]}
+  part = run(sub, t_rand[lo:hi], u[lo:hi])['fine']
+  for k, v in snap.items():
+    assert torch.equal(part[k], v[lo:hi]), k
+
+  sel = np.linspace(0, n - 1, 48).astype(np.int64)                                         # the oracle on 48 scattered rays
+  pick = {'origins': rays['origins'][sel], 'directions': rays['directions'][sel],
+          'metadata': {k: v[sel] for k, v in rays['metadata'].items()}, 'mask': rays['mask'][sel]}
+  tsel, usel = t_rand[sel].cpu().numpy(), u[sel].cpu().numpy()
+  ref = to_numpy(OracleNerfModel(cfg, params).apply(pick, syn.final_extra_params(), tsel, usel, use_predicted_norm=True,
+                                                    mask_ratio=1, sharp_weights_std=0.1, compute_sigma_gradient=False))
+  err = np.abs(snap['rgb'].cpu().numpy()[sel] - ref['fine']['rgb']).max(-1)
+  assert np.mean(err <= RGB_TOL) >= 0.95 and np.median(err) <= 3e-4, np.sort(err)[-5:]
