@@ -241,6 +241,13 @@ typedef struct ndsr_camera {
 int ndsr_camera_rays(int device, void* stream, const ndsr_camera* camera, float* origins, float* directions,
                      float* pixels);
 
+/* Replaces the two `random.uniform(key, [n_rays, n_samples])` draws of the path (model_utils.py:84 stratified
+ * jitter `t_rand`, model_utils.py:217 inverse-CDF `u`) on the device, bit for bit as jax 0.3.15's default
+ * threefry2x32 generator produces them: out[i] for i in [0, n), n = n_rays * n_samples, row-major.  `key` is the
+ * raw uint32[2] jax key AFTER flax's make_rng folding (models.py:1489, 1524; nerfds_b200/jax_random.py derives it
+ * on the host).  Feed the result to ndsr_render_rays as t_rand / u.  Stateless; n < 2^32 - 1. */
+int ndsr_random_uniform(int device, void* stream, const uint32_t key[2], int64_t n, float* out);
+
 /* Replaces model_utils.volumetric_rendering (model_utils.py:95-159) +
  * compute_depth_map.  rgb [n,S,3], sigma [n,S], z_vals [n,S], dirs [n,3]. */
 int ndsr_volumetric_rendering(ndsr_handle* h, void* stream, int64_t n_rays,

@@ -141,7 +141,7 @@ EXPORTS = ['ndsr_create', 'ndsr_destroy', 'ndsr_last_error', 'ndsr_load_params',
            'ndsr_render_rays_host', 'ndsr_render_samples', 'ndsr_sample_along_rays', 'ndsr_sample_pdf',
            'ndsr_volumetric_rendering', 'ndsr_engine_in_use', 'ndsr_kernel_launches', 'ndsr_abi_version',
            'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense', 'ndsr_profile_enable',
-           'ndsr_profile_read', 'ndsr_camera_rays']
+           'ndsr_profile_read', 'ndsr_camera_rays', 'ndsr_random_uniform']
 
 
 def load_library() -> C.CDLL:
@@ -180,6 +180,7 @@ def load_library() -> C.CDLL:
   lib.ndsr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   lib.ndsr_selftest_tc_dense.argtypes = [C.c_int] * 7 + [vp] * 5
   lib.ndsr_camera_rays.argtypes = [C.c_int, vp, C.POINTER(ndsr_camera), vp, vp, vp]
+  lib.ndsr_random_uniform.argtypes = [C.c_int, vp, C.POINTER(C.c_uint32), i64, vp]
   if lib.ndsr_abi_version() != NDSR_ABI_VERSION:
     raise ImportError('libnerfds_b200.so ABI version mismatch; rebuild')
   a, b, c = i32(), i32(), i32()

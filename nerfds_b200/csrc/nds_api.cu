@@ -790,6 +790,16 @@ extern "C" int ndsr_camera_rays(int device, void* stream, const ndsr_camera* cam
   return launch_camera_rays(*camera, origins, directions, pixels, (cudaStream_t)stream) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
 }
 
+// ------------------------------------------------- jax-compatible uniform draws
+extern "C" int ndsr_random_uniform(int device, void* stream, const uint32_t key[2], int64_t n, float* out) {
+  if (!key || n < 0 || (n > 0 && !out) || n >= (int64_t)0xFFFFFFFFll) return NDSR_ERR_INVALID;
+  if (n == 0) return NDSR_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return NDSR_ERR_CUDA;
+  return launch_uniform_threefry(key[0], key[1], n, out, sms, (cudaStream_t)stream) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
+}
+
 // ------------------------------------------------- stand-alone stage calls
 extern "C" int ndsr_sample_along_rays(ndsr_handle* h, void* stream, int64_t n_rays, int32_t n_samples, float near_,
                                       float far_, int32_t use_linear_disparity, const float* t_rand,

@@ -388,6 +388,49 @@ cudaError_t launch_camera_rays(const ndsr_camera& cam, float* origins, float* di
   return cudaGetLastError();
 }
 
+// ------------------------------------------------- jax.random.uniform
+// Threefry-2x32, 20 rounds, with jax's key schedule and round grouping (jax/_src/prng.py threefry2x32: five groups
+// of four rounds, rotations {13,15,26,6} / {17,29,16,24}, ks2 = k0 ^ k1 ^ 0x1BD11BDA).
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t& x0, uint32_t& x1) {
+  const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+#define NDS_TF_ROUND(r) { x0 += x1; x1 = __funnelshift_l(x1, x1, r); x1 ^= x0; }
+#define NDS_TF_R0 NDS_TF_ROUND(13) NDS_TF_ROUND(15) NDS_TF_ROUND(26) NDS_TF_ROUND(6)
+#define NDS_TF_R1 NDS_TF_ROUND(17) NDS_TF_ROUND(29) NDS_TF_ROUND(16) NDS_TF_ROUND(24)
+  x0 += k0; x1 += k1;
+  NDS_TF_R0 x0 += k1; x1 += k2 + 1u;
+  NDS_TF_R1 x0 += k2; x1 += k0 + 2u;
+  NDS_TF_R0 x0 += k0; x1 += k1 + 3u;
+  NDS_TF_R1 x0 += k1; x1 += k2 + 4u;
+  NDS_TF_R0 x0 += k2; x1 += k0 + 5u;
+#undef NDS_TF_R1
+#undef NDS_TF_R0
+#undef NDS_TF_ROUND
+}
+
+// random.uniform(key, shape) for float32 in [0, 1): counters iota(n) (padded with one 0 when n is odd) are split in
+// two halves that form the two words of each block; block j yields elements j and j + half; 23 random mantissa bits
+// under exponent 0 give [1, 2), minus 1.  One thread per block: both stores are coalesced.
+__global__ void __launch_bounds__(256) uniform_threefry_kernel(uint32_t k0, uint32_t k1, int64_t n, int64_t half,
+                                                               float* __restrict__ out) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < half; j += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t x0 = (uint32_t)j;
+    uint32_t x1 = (j + half < n) ? (uint32_t)(j + half) : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    out[j] = __uint_as_float((x0 >> 9) | 0x3F800000u) - 1.0f;
+    if (j + half < n) out[j + half] = __uint_as_float((x1 >> 9) | 0x3F800000u) - 1.0f;
+  }
+}
+
+cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* out, int num_sms, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t half = (n + 1) / 2;
+  int64_t blocks = (half + 255) / 256;
+  const int64_t cap = (int64_t)num_sms * 8 * 4;          // 8 resident CTAs per SM, 4 waves, then grid-stride
+  if (blocks > cap) blocks = cap;
+  uniform_threefry_kernel<<<(unsigned)blocks, 256, 0, st>>>(k0, k1, n, half, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_sample_pdf(const SamplePdfArgs& a, int num_sms, cudaStream_t st) {
   if (a.n_rays == 0) return cudaSuccess;
   const size_t smem = (size_t)CW * (2 * a.n_bins + a.n_coarse + a.n_fine) * sizeof(float);

@@ -43,6 +43,7 @@ struct SamplePdfArgs {
   int32_t* src_elem_out;  // optional [B, n_coarse + n_fine]: which element of concat(z_coarse, z_samples) sits at sorted position s
 };
 
+cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* out, int num_sms, cudaStream_t st);
 cudaError_t launch_camera_rays(const ndsr_camera& cam, float* origins, float* dirs, float* pixels, cudaStream_t st);
 cudaError_t launch_sample_along_rays(int64_t n_rays, int S, float near_, float far_, int lindisp,
                                      const float* t_rand, float* z, cudaStream_t st);

@@ -17,7 +17,7 @@ from typing import Callable, Dict, Iterable, Optional
 import numpy as np
 import torch
 
-from . import utils
+from . import jax_random, utils
 from .renderer import RENDER_KEYS
 
 
@@ -55,6 +55,12 @@ def make_model_fn(model, *, use_predicted_norm: bool = True, keys: Iterable[str]
     t_rand = u = None
     if t_rand_fn is not None:
       t_rand, u = t_rand_fn(local)
+    elif not dist and D > 1 and getattr(getattr(model, 'cfg', None), 'use_stratified_sampling', False):
+      # under pmap every device draws its shard's samples from its own key (evaluation.py:83-84)
+      per = rays_dict['origins'].shape[1]
+      draw = lambda ks, S: torch.cat([jax_random.uniform(jax_random.flax_make_rng(ks[d]), (per, S), model.device)
+                                      for d in range(D)], 0)
+      t_rand, u = draw(key_0, model.cfg.num_coarse_samples), draw(key_1, model.cfg.num_fine_samples)
     out = model.apply({'params': params}, local, extra_params, rngs={'coarse': k0, 'fine': k1, 'voxel': key_2},
                       mutable=False, use_predicted_norm=use_predicted_norm, return_points=False,
                       return_nv_details=False, mask_ratio=1, sharp_weights_std=0.1,   # render.py:150-153
@@ -99,9 +105,8 @@ def render_image(state, rays_dict, model_fn, device_count, rng, chunk=8192, defa
       np.int64) if np.asarray(x).dtype == np.uint32 else np.ascontiguousarray(np.asarray(x)))
   rays_dict = utils.tree_map(lambda x: as_t(x).reshape((num_rays, -1)), rays_dict)
   # _, key_0, key_1, key_2 = split(rng, 4); key_i = split(key_i, device_count)  (evaluation.py:81-84)
-  base = np.asarray(rng).astype(np.uint64).reshape(-1)
-  mk = lambda i: np.stack([np.concatenate([base, [i, d]]) for d in range(device_count)])
-  key_0, key_1, key_2 = mk(1), mk(2), mk(3)
+  _, key_0, key_1, key_2 = jax_random.split(rng, 4)
+  key_0, key_1, key_2 = (np.array(jax_random.split(k, device_count), np.uint32) for k in (key_0, key_1, key_2))
   ret_maps = []
   num_batches = int(math.ceil(num_rays / chunk))
   for batch_idx in range(num_batches):

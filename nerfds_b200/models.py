@@ -13,6 +13,7 @@ from typing import Any, Dict, Iterable, Optional
 import numpy as np
 import torch
 
+from . import jax_random
 from .config import NerfDSConfig, nerf_ds_config
 from .params import init_params
 from .renderer import Renderer, RENDER_KEYS  # noqa: F401
@@ -52,21 +53,26 @@ class NerfModel:
     return self.cfg.num_fine_samples
 
   def _draws(self, B, rngs, t_rand, u):
+    """The uniform draws of model_utils.py:84 / 217.
+
+    When the caller does not pass `t_rand` / `u` they are generated on the
+    device from `rngs['coarse']` / `rngs['fine']` exactly as flax + jax do
+    (jax_random.py: the first `make_rng` key of each stream, then
+    `random.uniform(key, [B, S])` under threefry2x32), so a JAX run with the
+    same keys sees the same samples.  Keys are raw uint32[2]
+    jax keys (or python int seeds, as `random.PRNGKey(seed)`).
+    """
     c = self.cfg
     if not c.use_stratified_sampling:
       return None, None
-    # The reference draws these from flax make_rng('coarse'/'fine') streams
-    # (models.py:1489,1524); bit-compatible threefry is SURVEY row f-4, so when
-    # the caller does not pass the draws we derive them from the rng keys with
-    # torch's generator (same distribution, different bits).
     if t_rand is None:
-      g = torch.Generator(device=self.device)
-      g.manual_seed(_key_to_seed((rngs or {}).get('coarse')))
-      t_rand = torch.rand((B, c.num_coarse_samples), generator=g, device=self.device)
+      if not rngs or rngs.get('coarse') is None:
+        raise ValueError("NerfModel needs PRNG for \"coarse\"")          # flax errors.InvalidRngError
+      t_rand = jax_random.uniform(jax_random.flax_make_rng(rngs['coarse']), (B, c.num_coarse_samples), self.device)
     if u is None:
-      g = torch.Generator(device=self.device)
-      g.manual_seed(_key_to_seed((rngs or {}).get('fine')) + 1)
-      u = torch.rand((B, c.num_fine_samples), generator=g, device=self.device)
+      if not rngs or rngs.get('fine') is None:
+        raise ValueError("NerfModel needs PRNG for \"fine\"")
+      u = jax_random.uniform(jax_random.flax_make_rng(rngs['fine']), (B, c.num_fine_samples), self.device)
     return t_rand, u
 
   def apply(self, variables: Dict[str, Any], rays_dict: Dict[str, Any], extra_params: Dict[str, Any], *,
