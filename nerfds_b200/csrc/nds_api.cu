@@ -818,7 +818,7 @@ extern "C" int ndsr_sample_pdf(ndsr_handle* h, void* stream, int64_t n_rays, int
                                int32_t* idx_hi, float* cdf) {
   if (!h || !bins || !weights || !z_vals || !z_out || n_bins < 2 || n_fine < 1 || n_coarse < 0 || n_rays < 0)
     return h ? fail(h, NDSR_ERR_INVALID, "bad argument") : NDSR_ERR_INVALID;
-  if (2 * n_bins + n_coarse + n_fine > 11000) return fail(h, NDSR_ERR_INVALID, "too many bins/samples");
+  if (2 * n_bins + n_coarse + 2 * n_fine > 11000) return fail(h, NDSR_ERR_INVALID, "too many bins/samples");
   NDS_CUDA(h, cudaSetDevice(h->device));
   SamplePdfArgs sa;
   memset(&sa, 0, sizeof sa);

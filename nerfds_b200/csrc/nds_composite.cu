@@ -237,7 +237,7 @@ sample_pdf_kernel(const __grid_constant__ SamplePdfArgs a) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = a.n_bins, nf = a.n_fine, nc = a.n_coarse, nt = nc + nf;
-  float* s_cdf = sm + (size_t)warp * (2 * n + nt);
+  float* s_cdf = sm + (size_t)warp * (2 * n + nt + nf);
   float* s_bins = s_cdf + n;
   float* s_all = s_bins + n;
   const float eps = 1e-5f;
@@ -278,16 +278,58 @@ sample_pdf_kernel(const __grid_constant__ SamplePdfArgs a) {
       if (a.idx_hi) a.idx_hi[ray * nf + j] = hi;
     }
     __syncwarp();
-    // jnp.sort(concat([z_vals, z_samples])) by stable rank counting
-    for (int i = lane; i < nt; i += 32) {
-      const float v = s_all[i];
-      int rank = 0;
-      for (int j = 0; j < nt; ++j) {
-        const float o = s_all[j];
-        rank += (o < v || (o == v && j < i)) ? 1 : 0;
+    // jnp.sort(concat([z_vals, z_samples])), stable.  The coarse depths normally arrive sorted (stratified bins), so
+    // the union is a merge: rank the nf new samples among themselves (counting, 4 values per lane against one
+    // broadcast read per step), then two binary searches give every element's place.  Ties keep concat order:
+    // coarse before new, lower index first.  Unsorted coarse depths fall back to counting over the whole union.
+    bool sorted = true;
+    for (int i = lane; i + 1 < nc; i += 32) sorted = sorted && (s_all[i] <= s_all[i + 1]);
+    sorted = __all_sync(0xffffffffu, sorted);
+    if (sorted) {
+      float* s_new = s_all + nt;                          // the new samples in sorted order
+      constexpr int PER = 4;
+      for (int i0 = 0; i0 < nf; i0 += 32 * PER) {
+        float v[PER]; int rk[PER];
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { const int i = i0 + q * 32 + lane; v[q] = i < nf ? s_all[nc + i] : 0.f; rk[q] = 0; }
+        for (int j = 0; j < nf; ++j) {
+          const float o = s_all[nc + j];
+#pragma unroll
+          for (int q = 0; q < PER; ++q) rk[q] += (o < v[q] || (o == v[q] && j < i0 + q * 32 + lane)) ? 1 : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+          const int i = i0 + q * 32 + lane;
+          if (i < nf) {
+            int lo_b = 0, hi_b = nc;                      // #{coarse <= v}
+            while (lo_b < hi_b) { const int mid = (lo_b + hi_b) >> 1; if (s_all[mid] <= v[q]) lo_b = mid + 1; else hi_b = mid; }
+            const int rank = rk[q] + lo_b;
+            a.z_out[ray * nt + rank] = v[q];
+            if (a.src_elem_out) a.src_elem_out[ray * nt + rank] = nc + i;
+            s_new[rk[q]] = v[q];
+          }
+        }
       }
-      a.z_out[ray * nt + rank] = v;
-      if (a.src_elem_out) a.src_elem_out[ray * nt + rank] = i;
+      __syncwarp();
+      for (int i = lane; i < nc; i += 32) {
+        const float v = s_all[i];
+        int lo_b = 0, hi_b = nf;                          // #{new < v}
+        while (lo_b < hi_b) { const int mid = (lo_b + hi_b) >> 1; if (s_new[mid] < v) lo_b = mid + 1; else hi_b = mid; }
+        a.z_out[ray * nt + i + lo_b] = v;
+        if (a.src_elem_out) a.src_elem_out[ray * nt + i + lo_b] = i;
+      }
+    } else {
+      for (int i = lane; i < nt; i += 32) {
+        const float v = s_all[i];
+        int rank = 0;
+        for (int j = 0; j < nt; ++j) {
+          const float o = s_all[j];
+          rank += (o < v || (o == v && j < i)) ? 1 : 0;
+        }
+        a.z_out[ray * nt + rank] = v;
+        if (a.src_elem_out) a.src_elem_out[ray * nt + rank] = i;
+      }
     }
     __syncwarp();
   }
@@ -363,6 +405,10 @@ cudaError_t launch_sample_along_rays(int64_t n_rays, int S, float near_, float f
 cudaError_t launch_composite(const CompositeArgs& a, int num_sms, cudaStream_t st) {
   if (a.n_rays == 0) return cudaSuccess;
   const size_t smem = (size_t)CW * 3 * a.S * sizeof(float);
+  if (smem > 48 * 1024) {     // long rays: opt in to the large carve-out (up to 227 KB)
+    cudaError_t e = cudaFuncSetAttribute(composite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   composite_kernel<<<grid_for(a.n_rays, num_sms), CW * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
@@ -433,7 +479,11 @@ cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* 
 
 cudaError_t launch_sample_pdf(const SamplePdfArgs& a, int num_sms, cudaStream_t st) {
   if (a.n_rays == 0) return cudaSuccess;
-  const size_t smem = (size_t)CW * (2 * a.n_bins + a.n_coarse + a.n_fine) * sizeof(float);
+  const size_t smem = (size_t)CW * (2 * a.n_bins + a.n_coarse + 2 * a.n_fine) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   sample_pdf_kernel<<<grid_for(a.n_rays, num_sms), CW * 32, smem, st>>>(a);
   return cudaGetLastError();
 }

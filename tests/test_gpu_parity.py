@@ -438,3 +438,41 @@ def test_full_frame_properties_at_baseline_size(cuda_device):
                                                     mask_ratio=1, sharp_weights_std=0.1, compute_sigma_gradient=False))
   err = np.abs(snap['rgb'].cpu().numpy()[sel] - ref['fine']['rgb']).max(-1)
   assert np.mean(err <= RGB_TOL) >= 0.95 and np.median(err) <= 3e-4, np.sort(err)[-5:]
+
+
+def test_maximum_sample_counts(cuda_device):
+  """The largest per-ray sample counts the ABI admits (1024 coarse + 1024 fine = 2048): the compositing and
+  resampling kernels need the opt-in shared-memory carve-out there; results still follow the oracle."""
+  cfg, params, rays, t_rand, u = make_case('tiny', image=3, seed=8, num_coarse_samples=1024, num_fine_samples=1024)
+  m = _model(cfg, cuda_device, engine='simt')
+  out = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u,
+                keys=('rgb', 'acc', 'z_vals'), coarse_keys=('rgb', 'weights'))
+  ref = run_oracle(cfg, params, rays, t_rand, u, compute_sigma_gradient=False)
+  assert linf(_np(out['coarse'])['rgb'], ref['coarse']['rgb']) <= RGB_TOL
+  z = _np(out['fine'])['z_vals']
+  assert z.shape == (9, 2048) and np.all(z[:, 1:] >= z[:, :-1])
+  assert np.median(np.abs(_np(out['fine'])['rgb'] - ref['fine']['rgb'])) <= RGB_TOL
+  from nerfds_b200.config import tiny_config
+  with pytest.raises(Exception):
+    _model(tiny_config(num_coarse_samples=2000, num_fine_samples=100), cuda_device, engine='simt')
+
+
+def test_sample_pdf_unsorted_coarse_depths(cuda_device):
+  """The stand-alone resampling entry point sorts the union even when the caller's z_vals are not sorted
+  (the merge shortcut only applies to sorted coarse depths)."""
+  from oracle import nerfds_oracle as O
+  rng = np.random.default_rng(5)
+  B, nb, nf = 33, 20, 24
+  bins = np.sort(rng.uniform(0.1, 2.5, (B, nb)).astype(np.float32), -1)
+  w = rng.uniform(0, 1, (B, nb - 1)).astype(np.float32)
+  u = rng.uniform(0, 1, (B, nf)).astype(np.float32)
+  zc = rng.uniform(0.1, 2.5, (B, nb + 1)).astype(np.float32)         # deliberately unsorted
+  zc[::2] = np.sort(zc[::2], -1)                                      # ... on every other ray
+  zc[4, 3] = zc[4, 4]                                                 # ties
+  cfg, *_ = make_case('tiny', image=2)
+  m = _model(cfg, cuda_device)
+  z = m.renderer.sample_pdf(bins, w, u, zc)
+  z = (z[0] if isinstance(z, (tuple, list)) else z).cpu().numpy()
+  o = torch.zeros(B, 3); d = torch.ones(B, 3)
+  ref, _ = O.sample_pdf(torch.from_numpy(u), torch.from_numpy(bins), torch.from_numpy(w), o, d, torch.from_numpy(zc))
+  np.testing.assert_array_equal(z, ref.numpy())
