@@ -34,10 +34,13 @@ class _Jnp(types.ModuleType):
     return getattr(np, name)
 
 
+_WIDE = [False]   # True while a finite-difference probe runs: keep float64 instead of jax's float32 defaults
+
+
 def _f32_default(fn):
   def wrapped(*a, dtype=None, **k):
     out = fn(*a, **k) if dtype is None else fn(*a, dtype=dtype, **k)
-    if dtype is None and np.issubdtype(np.asarray(out).dtype, np.floating):
+    if dtype is None and not _WIDE[0] and np.issubdtype(np.asarray(out).dtype, np.floating):
       out = np.asarray(out, np.float32)
     return out
   return wrapped
@@ -45,7 +48,7 @@ def _f32_default(fn):
 
 def _array(x, dtype=None):
   a = np.asarray(x, dtype=dtype)
-  if dtype is None and a.dtype == np.float64:
+  if dtype is None and a.dtype == np.float64 and not _WIDE[0]:
     a = a.astype(np.float32)
   if dtype is None and a.dtype == np.int64:
     a = a.astype(np.int32)
@@ -135,13 +138,36 @@ def _vmap(fn, in_axes=0, out_axes=0):
 
 
 def _value_and_grad(f, argnums=0, has_aux=False):
-  """No autodiff here: the VALUE is the reference's, the gradient is zeros.  Only `target_norm` (and `ray_norm`
-  without predicted normals) depend on it; the golden vectors omit those keys."""
-  return lambda *a: (f(*a), np.zeros_like(np.asarray(a[argnums])))
+  """No autodiff here: the VALUE is the reference's float32 evaluation; the GRADIENT is a central difference of the
+  same reference function re-evaluated in float64 (`_WIDE`: float32 parameters, double arithmetic, h = 1e-6), i.e.
+  the derivative of the reference's function to ~1e-8 relative -- what jax's autodiff returns up to float32
+  rounding.  The reference only differentiates per-point scalar functions of a 3-vector (models.py:1063-1069)."""
+  def run(*a):
+    val = f(*a)
+    x = np.asarray(a[argnums], np.float64)
+    g = np.zeros(x.shape, np.float64)
+    h = 1e-6
+    _WIDE[0] = True
+    try:
+      for i in range(x.size):
+        probe = []
+        for sgn in (+1.0, -1.0):
+          xi = x.copy().reshape(-1)
+          xi[i] += sgn * h
+          out = f(*(tuple(a[:argnums]) + (xi.reshape(x.shape),) + tuple(a[argnums + 1:])))
+          out = out[0] if has_aux else out
+          assert np.asarray(out).dtype == np.float64, 'the finite-difference probe fell back to float32'
+          probe.append(float(np.asarray(out)))
+        g.reshape(-1)[i] = (probe[0] - probe[1]) / (2 * h)
+    finally:
+      _WIDE[0] = False
+    return val, g.astype(np.float32)
+  return run
 
 
 def _grad(f, argnums=0, has_aux=False):
-  return lambda *a: np.zeros_like(np.asarray(a[argnums]))
+  vg = _value_and_grad(f, argnums, has_aux)
+  return lambda *a: vg(*a)[1]
 
 
 # ------------------------------------------------------------------ flax.linen stand-in
@@ -572,7 +598,7 @@ def main():
                     use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.1)
   for lvl in ('coarse', 'fine'):
     for k, v in res[lvl].items():
-      if k != 'target_norm' and v is not None:          # gradient-derived: no autodiff under the stand-in
+      if v is not None:
         G[f'model_{lvl}_{k}'] = f32(v)
 
   # ------------------------------------------------------------------ ray generation
