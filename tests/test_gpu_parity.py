@@ -476,3 +476,46 @@ def test_sample_pdf_unsorted_coarse_depths(cuda_device):
   o = torch.zeros(B, 3); d = torch.ones(B, 3)
   ref, _ = O.sample_pdf(torch.from_numpy(u), torch.from_numpy(bins), torch.from_numpy(w), o, d, torch.from_numpy(zc))
   np.testing.assert_array_equal(z, ref.numpy())
+
+
+def test_training_batch_at_baseline_size(cuda_device):
+  """BASELINE configs[2]: a train.py ray batch of 4096 under nerf_ds.gin (64 + 64 samples) with the surface-aware
+  branch and every training-forward key (incl. `target_norm`, i.e. d(sigma)/dx through warp + template), mid-schedule
+  extra_params and a mask_ratio that blends the ground-truth mask: properties at the full size, the oracle on a
+  scattered subset."""
+  import time
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=64, seed=12, num_coarse_samples=64, num_fine_samples=64)
+  n = rays['origins'].shape[0]
+  assert n == 4096
+  ep = dict(syn.final_extra_params(), warp_alpha=2.5, norm_input_alpha=1.5)
+  m = _model(cfg, cuda_device, engine='auto')
+  kw = dict(use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.3)
+  run = lambda r, t, uu: m.apply({'params': params}, r, ep, t_rand=t, u=uu, **kw)
+  run(rays, t_rand, u)
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  out = run(rays, t_rand, u)
+  torch.cuda.synchronize()
+  dt = time.perf_counter() - t0
+  print(f'configs[2] training forward, 4096 rays 64+64 with target_norm: {dt * 1e3:.1f} ms')
+  for lvl, S in (('coarse', 64), ('fine', 128)):
+    o = out[lvl]
+    for k in ('rgb', 'weights', 'sigma', 'predicted_mask', 'predicted_norm', 'target_norm', 'back_facing', 'warped_points',
+              'ray_predicted_mask', 'ray_norm', 'sharp_weights'):
+      assert k in o, (lvl, k)
+    assert tuple(o['target_norm'].shape) == (n, S, 3) and bool(torch.isfinite(o['target_norm']).all())
+    nrm = o['target_norm'].norm(dim=-1)
+    assert float((nrm - 1).abs().max()) <= 1e-4 or float(nrm.min()) >= 0.0       # unit vectors (or eps-normalised zeros)
+    assert float(o['back_facing'].min()) >= 0.0
+  sel = np.linspace(0, n - 1, 24).astype(np.int64)
+  pick = {'origins': rays['origins'][sel], 'directions': rays['directions'][sel],
+          'metadata': {k: v[sel] for k, v in rays['metadata'].items()}, 'mask': rays['mask'][sel]}
+  ref = to_numpy(OracleNerfModel(cfg, params).apply(pick, ep, t_rand[sel], u[sel], return_points=True, return_weights=True,
+                                                    keep_internal=True, **{k: v for k, v in kw.items() if k not in ('return_points', 'return_weights')}))
+  c = {k: v.cpu().numpy()[sel] for k, v in out['coarse'].items() if k != 'sharp_weights'}
+  for k in ('rgb', 'ray_predicted_mask', 'ray_delta_x'):
+    assert linf(c[k].reshape(ref['coarse'][k].shape), ref['coarse'][k]) <= RGB_TOL, k
+  e = np.abs(c['target_norm'] - ref['coarse']['target_norm']).max(-1)
+  assert np.median(e) <= 1e-4 and np.mean(e <= GRAD_TOL) >= 0.97, np.sort(e.reshape(-1))[-5:]
+  e = np.abs(c['predicted_norm'] - ref['coarse']['predicted_norm']).max()
+  assert e <= 2e-4
