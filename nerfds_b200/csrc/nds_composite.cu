@@ -49,7 +49,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 constexpr int CW = 4;   // warps per CTA
 
-__global__ void __launch_bounds__(CW * 32)
+__global__ void __launch_bounds__(CW * 32, 8)
 composite_kernel(const __grid_constant__ CompositeArgs a) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
