@@ -349,7 +349,9 @@ def from_gin_bindings(bindings: dict, base: Optional[NerfDSConfig] = None
     if key in _GIN_MAP:
       kw[_GIN_MAP[key]] = value
     elif key == 'MaskMLP.output_activation':
-      kw['mask_output_relu'] = value in ('@jax.nn.relu', 'relu')
+      kw['mask_output_relu'] = value in ('@jax.nn.relu', '@flax.nn.relu', '@nn.relu', '@relu', 'relu')
+      if not kw['mask_output_relu'] and value not in (None, 'identity'):
+        raise NotImplementedError(f'MaskMLP.output_activation = {value}: only relu / identity are built')
     elif key.split('.')[0] in ('NerfModel',):
       field = key.split('.', 1)[1]
       if field in NerfDSConfig.__dataclass_fields__:

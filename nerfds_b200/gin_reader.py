@@ -222,8 +222,9 @@ def parse_config_file(path: str, search_paths: Optional[Iterable[str]] = None,
 # NerfModel attributes a gin file may bind that do not change the path built here (when they
 # hold the listed values); anything else unknown raises in from_gin_bindings.
 _EXPECTED_REFS = {
-    'NerfModel.activation': ('@jax.nn.relu', '@nn.relu', '@flax.linen.relu'),
-    'NerfModel.sigma_activation': ('@jax.nn.softplus', '@nn.softplus', '@flax.linen.softplus'),
+    # hypernerf/configs.py:29-40 registers flax.nn.* and jax.nn.* activations as gin configurables
+    'NerfModel.activation': ('@jax.nn.relu', '@flax.nn.relu', '@nn.relu', '@relu'),
+    'NerfModel.sigma_activation': ('@flax.nn.softplus', '@nn.softplus', '@softplus'),
     'NerfModel.warp_field_cls': ('@SE3Field',),
     'NerfModel.hyper_sheet_mlp_cls': ('@HyperSheetMLP',),
     'NerfModel.hyper_c_mlp_cls': ('@HyperSheetMLP',),
@@ -233,7 +234,7 @@ _EXPECTED_REFS = {
     'NerfModel.hyper_c_embed_cls': ('@hyper_c/GLOEmbed', '@hyper/GLOEmbed'),
     'NerfModel.mask_embed_cls': ('@mask/GLOEmbed', '@warp/GLOEmbed'),
     'NerfModel.bone_warp_field_cls': ('@BoneSE3Field',),
-    'SE3Field.activation': ('@jax.nn.relu', '@nn.relu'),
+    'SE3Field.activation': ('@jax.nn.relu', '@flax.nn.relu', '@nn.relu', '@relu'),
 }
 _EXPECTED_VALUES = {
     'NerfModel.nerf_embed_key': ('appearance', 'camera', 'time', 'warp'),   # unused: use_nerf_embed is fenced off
