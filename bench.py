@@ -167,7 +167,9 @@ def workload_config(args, world):
   return {'workload': f'single {args.image}x{args.image} frame render, nerf_ds.gin nets (SE3 warp + hyper sheet + mask MLP '
                       f'+ template NeRF, predicted normals), {args.coarse}+{args.fine} coarse/fine stratified samples',
           'rays_per_step': args.image * args.image * world, 'chunk_rays': args.chunk,
-          'parallelism': f'rays block-sharded over {world} GPU(s), 1 all-gather/frame' if world > 1 else 'single GPU',
+          'parallelism': (f'rays block-sharded over {world} GPU(s), ' + (
+              'frame reassembled by peer-memory stores of the compositing kernel (no data-path collective, 1 barrier/frame)'
+              if getattr(args, 'gather', 'peer') == 'peer' else '1 NCCL all-gather/frame')) if world > 1 else 'single GPU',
           'l2': 'per-step inputs + per-sample scratch (>1 GB) exceed the 126 MB L2; a 256 MB buffer is also '
                 'rewritten between steps'}
 
@@ -217,14 +219,29 @@ def run_ours(args):
         'hu': u.cpu().pin_memory()})
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+  # frame reassembly at N > 1: the compositing kernels store every rank's rays into every GPU's frame buffer
+  # (peer.PeerFrames, NVLink stores; two buffers alternate so a frame can be read while the next one is written);
+  # --gather nccl keeps the one all-gather per frame instead
+  peer = None
+  if world > 1 and args.gather == 'peer':
+    from nerfds_b200.peer import PeerFrames
+    peer = [PeerFrames(R, n_frame, RENDER_KEYS), PeerFrames(R, n_frame, RENDER_KEYS)]
+
+  def render_frame(i, o, d, w, t, uu):
+    if peer is not None:
+      pf = peer[i & 1]
+      pf.activate()
+      R.render_rays(o, d, warp_id=w, t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS,
+                    fine_ptrs=pf.shard_ptrs(lo))
+      pf.wait()
+      return pf.frame()
+    out = R.render_rays(o, d, warp_id=w, t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS)['fine']
+    return all_gather_level(out) if world > 1 else out
+
   def step_device():
     outs = None
-    for fr in frames:
-      out = R.render_rays(fr['o'], fr['d'], warp_id=fr['w'], t_rand=fr['t'], u=fr['u'], extra=extra,
-                          coarse_keys=(), fine_keys=RENDER_KEYS)['fine']
-      if world > 1:
-        out = all_gather_level(out)
-      outs = out
+    for i, fr in enumerate(frames):
+      outs = render_frame(i, fr['o'], fr['d'], fr['w'], fr['t'], fr['u'])
     flush.fill_(1)
     return outs
 
@@ -241,8 +258,7 @@ def run_ours(args):
       else:
         o, d, w = (fr[k].to(dev, non_blocking=True) for k in ('ho', 'hd', 'hw'))
         t, uu = fr['ht'].to(dev, non_blocking=True), fr['hu'].to(dev, non_blocking=True)
-        out = R.render_rays(o, d, warp_id=w, t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS)['fine']
-        out = all_gather_level(out)
+        out = render_frame(i, o, d, w, t, uu)
         hb = host_out.setdefault(i, {})
         for k, v in out.items():
           if k not in hb:
@@ -347,6 +363,9 @@ def run_ours(args):
                     'ms_per_step': ms_h / e2e_steps},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line), flush=True)
+  if peer is not None:
+    for pf in peer:
+      pf.close()
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
@@ -374,6 +393,7 @@ def main():
   ap.add_argument('--chunk', type=int, default=65536)
   ap.add_argument('--cpu-rays', type=int, default=None)
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='frame reassembly at N > 1')
   ap.add_argument('--traffic', type=float, default=None, help='DRAM bytes/launch of the dominant kernel from ncu')
   args = ap.parse_args()
   if args.cpu_rays is None:

@@ -241,6 +241,22 @@ typedef struct ndsr_camera {
 int ndsr_camera_rays(int device, void* stream, const ndsr_camera* camera, float* origins, float* directions,
                      float* pixels);
 
+/* ---- multi-GPU frame reassembly over peer memory (replaces `jax.lax.all_gather(out, 'batch')`, render.py:155) ----
+ * One process per GPU.  Every rank allocates the same packed frame buffer with ndsr_peer_alloc, the 64-byte handles
+ * are exchanged by the host (any transport), every rank maps the others' buffers with ndsr_peer_open and registers
+ * the address differences with ndsr_set_output_mirrors.  From then on the compositing kernel of a fine-level
+ * ndsr_render_rays / ndsr_render_samples call stores every PER-RAY result both at the output pointer it was given
+ * (inside the rank's own frame buffer) and at the same offset of every mirror: when all ranks' streams have
+ * drained, every GPU holds the whole frame -- the all-gather happened inside the kernel, as NVLink stores. */
+#define NDSR_MAX_MIRRORS 15
+typedef struct ndsr_ipc_handle { unsigned char bytes[64]; } ndsr_ipc_handle;
+int ndsr_peer_alloc(int device, size_t bytes, void** ptr, ndsr_ipc_handle* handle);
+int ndsr_peer_free(int device, void* ptr);
+int ndsr_peer_open(int device, const ndsr_ipc_handle* handle, void** ptr);
+int ndsr_peer_close(int device, void* ptr);
+/* byte_deltas[m] = (mapped address of mirror m) - (address of this rank's own buffer); n = 0 switches mirroring off */
+int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_deltas);
+
 /* Replaces the two `random.uniform(key, [n_rays, n_samples])` draws of the path (model_utils.py:84 stratified
  * jitter `t_rand`, model_utils.py:217 inverse-CDF `u`) on the device, bit for bit as jax 0.3.15's default
  * threefry2x32 generator produces them: out[i] for i in [0, n), n = n_rays * n_samples, row-major.  `key` is the

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libnerfds_b200.so')
 
 NDSR_ABI_VERSION = 1
+NDSR_MAX_MIRRORS = 15
 ENGINES = {'auto': 0, 'simt': 1, 'tc': 2}
 ENGINE_NAMES = {v: k for k, v in ENGINES.items()}
 PRECISIONS = {'mixed': 0, 'fp16': 1, 'split3': 2}
@@ -141,7 +142,8 @@ EXPORTS = ['ndsr_create', 'ndsr_destroy', 'ndsr_last_error', 'ndsr_load_params',
            'ndsr_render_rays_host', 'ndsr_render_samples', 'ndsr_sample_along_rays', 'ndsr_sample_pdf',
            'ndsr_volumetric_rendering', 'ndsr_engine_in_use', 'ndsr_kernel_launches', 'ndsr_abi_version',
            'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense', 'ndsr_profile_enable',
-           'ndsr_profile_read', 'ndsr_camera_rays', 'ndsr_random_uniform']
+           'ndsr_profile_read', 'ndsr_camera_rays', 'ndsr_random_uniform', 'ndsr_peer_alloc', 'ndsr_peer_free',
+           'ndsr_peer_open', 'ndsr_peer_close', 'ndsr_set_output_mirrors']
 
 
 def load_library() -> C.CDLL:
@@ -181,6 +183,11 @@ def load_library() -> C.CDLL:
   lib.ndsr_selftest_tc_dense.argtypes = [C.c_int] * 7 + [vp] * 5
   lib.ndsr_camera_rays.argtypes = [C.c_int, vp, C.POINTER(ndsr_camera), vp, vp, vp]
   lib.ndsr_random_uniform.argtypes = [C.c_int, vp, C.POINTER(C.c_uint32), i64, vp]
+  lib.ndsr_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
+  lib.ndsr_peer_free.argtypes = [C.c_int, vp]
+  lib.ndsr_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+  lib.ndsr_peer_close.argtypes = [C.c_int, vp]
+  lib.ndsr_set_output_mirrors.argtypes = [vp, i32, C.POINTER(i64)]
   if lib.ndsr_abi_version() != NDSR_ABI_VERSION:
     raise ImportError('libnerfds_b200.so ABI version mismatch; rebuild')
   a, b, c = i32(), i32(), i32()

@@ -530,6 +530,10 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   ca.out = o;
   ca.src_elem = (h->engine == NDSR_ENGINE_TC && !need_grad) ? src_elem : nullptr; ca.n_carried = n_carried;
   if (weights_keep) ca.out.weights = weights_keep;   // coarse weights feed sample_pdf
+  if (level == 1 && h->n_mirror > 0) {
+    ca.n_mirror = h->n_mirror;
+    for (int m = 0; m < h->n_mirror; ++m) ca.mirror_delta[m] = h->mirror_delta[m];
+  }
   const bool sharp = c.use_mask_sharp_weights && o.sharp_weights;
   ca.argmax_idx = sharp ? h->argmax : nullptr;
   ca.weights_sg = sharp ? h->w_sg : nullptr;
@@ -788,6 +792,50 @@ extern "C" int ndsr_camera_rays(int device, void* stream, const ndsr_camera* cam
   if (!camera || !origins || !directions || camera->image_size[0] < 0 || camera->image_size[1] < 0) return NDSR_ERR_INVALID;
   if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
   return launch_camera_rays(*camera, origins, directions, pixels, (cudaStream_t)stream) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
+}
+
+// ------------------------------------------------- peer-memory frame buffers (multi-GPU reassembly)
+extern "C" int ndsr_peer_alloc(int device, size_t bytes, void** ptr, ndsr_ipc_handle* handle) {
+  if (!ptr || !handle || bytes == 0) return NDSR_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(ndsr_ipc_handle), "ipc handle size");
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NDSR_ERR_CUDA; }
+  cudaIpcMemHandle_t hd;
+  if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&hd, p) != cudaSuccess) { cudaFree(p); return NDSR_ERR_CUDA; }
+  memcpy(handle->bytes, &hd, sizeof hd);
+  *ptr = p;
+  return NDSR_OK;
+}
+extern "C" int ndsr_peer_free(int device, void* ptr) {
+  if (!ptr) return NDSR_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  return cudaFree(ptr) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
+}
+extern "C" int ndsr_peer_open(int device, const ndsr_ipc_handle* handle, void** ptr) {
+  if (!handle || !ptr) return NDSR_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle->bytes, sizeof hd);
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return NDSR_ERR_CUDA; }
+  *ptr = p;
+  return NDSR_OK;
+}
+extern "C" int ndsr_peer_close(int device, void* ptr) {
+  if (!ptr) return NDSR_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
+}
+extern "C" int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_deltas) {
+  if (!h) return NDSR_ERR_INVALID;
+  if (n < 0 || n > NDSR_MAX_MIRRORS || (n > 0 && !byte_deltas)) return fail(h, NDSR_ERR_INVALID, "0 <= mirrors <= NDSR_MAX_MIRRORS");
+  for (int m = 0; m < n; ++m) {
+    if (byte_deltas[m] % 4) return fail(h, NDSR_ERR_INVALID, "mirror offsets must keep float alignment");
+    h->mirror_delta[m] = byte_deltas[m];
+  }
+  h->n_mirror = n;
+  return NDSR_OK;
 }
 
 // ------------------------------------------------- jax-compatible uniform draws

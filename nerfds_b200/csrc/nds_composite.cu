@@ -173,19 +173,24 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
     rh[0] = warp_sum(rh[0]); rh[1] = warp_sum(rh[1]);
     if (lane == 0) {
       const ndsr_outputs& o = a.out;
+      // per-ray results go to the caller's buffer and to its mirrors on the peer GPUs
+      auto put = [&](float* dst, float v) {
+        *dst = v;
+        for (int m = 0; m < a.n_mirror; ++m) *reinterpret_cast<float*>(reinterpret_cast<char*>(dst) + a.mirror_delta[m]) = v;
+      };
       if (a.white_bkgd) for (int i = 0; i < 3; ++i) r[i] = r[i] + (1.f - acc);
-      if (o.rgb) for (int i = 0; i < 3; ++i) o.rgb[ray * 3 + i] = r[i];
-      if (o.depth) o.depth[ray] = depth;
-      if (o.med_depth) o.med_depth[ray] = med_found != 0.f ? a.z[base + med_idx] : 0.f;
-      if (o.acc) o.acc[ray] = a.sample_at_infinity ? acc_m1 : acc;
-      if (o.ray_norm && (a.has_norm || a.has_grad)) for (int i = 0; i < 3; ++i) o.ray_norm[ray * 3 + i] = rn[i];
-      if (o.ray_rotation_field && a.has_warp) for (int i = 0; i < 3; ++i) o.ray_rotation_field[ray * 3 + i] = rr[i];
-      if (o.ray_translation_field && a.has_warp) for (int i = 0; i < 3; ++i) o.ray_translation_field[ray * 3 + i] = rt[i];
-      if (o.ray_delta_x) for (int i = 0; i < 3; ++i) o.ray_delta_x[ray * 3 + i] = rdx[i];
-      if (o.ray_hyper_points) for (int i = 0; i < a.H; ++i) o.ray_hyper_points[ray * a.H + i] = rh[i];
-      if (o.ray_predicted_mask && a.has_mask) o.ray_predicted_mask[ray] = rm;
+      if (o.rgb) for (int i = 0; i < 3; ++i) put(o.rgb + ray * 3 + i, r[i]);
+      if (o.depth) put(o.depth + ray, depth);
+      if (o.med_depth) put(o.med_depth + ray, med_found != 0.f ? a.z[base + med_idx] : 0.f);
+      if (o.acc) put(o.acc + ray, a.sample_at_infinity ? acc_m1 : acc);
+      if (o.ray_norm && (a.has_norm || a.has_grad)) for (int i = 0; i < 3; ++i) put(o.ray_norm + ray * 3 + i, rn[i]);
+      if (o.ray_rotation_field && a.has_warp) for (int i = 0; i < 3; ++i) put(o.ray_rotation_field + ray * 3 + i, rr[i]);
+      if (o.ray_translation_field && a.has_warp) for (int i = 0; i < 3; ++i) put(o.ray_translation_field + ray * 3 + i, rt[i]);
+      if (o.ray_delta_x) for (int i = 0; i < 3; ++i) put(o.ray_delta_x + ray * 3 + i, rdx[i]);
+      if (o.ray_hyper_points) for (int i = 0; i < a.H; ++i) put(o.ray_hyper_points + ray * a.H + i, rh[i]);
+      if (o.ray_predicted_mask && a.has_mask) put(o.ray_predicted_mask + ray, rm);
       if (o.med_points) for (int i = 0; i < 3 + a.H; ++i)
-        o.med_points[ray * (3 + a.H) + i] = a.planes[(P_WARPED + i) * ps + pidx(med_idx)];
+        put(o.med_points + ray * (3 + a.H) + i, a.planes[(P_WARPED + i) * ps + pidx(med_idx)]);
       if (a.argmax_idx) a.argmax_idx[ray] = (float)best_i;
     }
     __syncwarp();

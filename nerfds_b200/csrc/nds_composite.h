@@ -25,6 +25,10 @@ struct CompositeArgs {
   // B n_carried + r (S - n_carried) + (e - n_carried).  null: planes are in sample order.
   const int32_t* src_elem;
   int n_carried;
+  // multi-GPU frame reassembly without a collective: every per-ray result is also stored at the same address plus
+  // mirror_delta[m] bytes -- the peer-mapped copies of the caller's frame buffer on the other GPUs (NVLink stores)
+  int n_mirror;
+  int64_t mirror_delta[NDSR_MAX_MIRRORS];
 };
 
 struct SamplePdfArgs {

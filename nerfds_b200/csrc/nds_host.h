@@ -49,6 +49,8 @@ struct ndsr_handle {
   std::vector<void*> scratch_allocs;
   int64_t cap_rays = 0, cap_samples = 0, max_samples_seen = 0;
   int64_t max_chunk = 65536;
+  int n_mirror = 0;                        // peer copies of the caller's frame buffer (ndsr_set_output_mirrors)
+  int64_t mirror_delta[NDSR_MAX_MIRRORS] = {0};
   float* carry = nullptr;      // C_COUNT planes of the coarse samples (tensor-core engine: split fine pass)
   int32_t* src_elem = nullptr; // [rays, S_c + S_f] from sample_pdf: element of concat(coarse, new) at each sorted position
   float* z_new = nullptr;      // [rays, S_f] the new depths in draw order

@@ -138,7 +138,7 @@ def render_image(state, rays_dict, model_fn, device_count, rng, chunk=8192, defa
 
 def render_image_sharded(model, params, rays_dict, extra_params, *, t_rand=None, u=None, chunk=65536,
                          keys: Iterable[str] = RENDER_KEYS, use_predicted_norm=True, group=None,
-                         gather=True) -> Dict[str, torch.Tensor]:
+                         gather=True, peer_frames=None) -> Dict[str, torch.Tensor]:
   """Block-partition one frame over the process group, render, all-gather once.
 
   Every rank passes the same full-frame ``rays_dict``; rank r renders rays
@@ -146,6 +146,10 @@ def render_image_sharded(model, params, rays_dict, extra_params, *, t_rand=None,
   to a multiple of W as evaluation.py:100-107 does) in chunks of ``chunk`` and
   a single all-gather of the packed per-ray outputs reassembles the frame on
   every rank.  Without an initialised process group this is a 1-rank render.
+
+  peer_frames: a `peer.PeerFrames` built for this frame size and these keys -- the compositing kernels then store
+  every rank's rays straight into every GPU's frame buffer (NVLink peer stores) and no collective moves data;
+  the returned tensors are views of this rank's buffer, valid until the next frame is rendered into it.
   """
   dist = _dist()
   W = dist.get_world_size(group) if dist else 1
@@ -167,6 +171,19 @@ def render_image_sharded(model, params, rays_dict, extra_params, *, t_rand=None,
   else:
     ext = lambda x: None if x is None else torch.as_tensor(x)[lo:hi]
   model.renderer.set_max_chunk(chunk)
+  if peer_frames is not None:
+    if peer_frames.n != n or tuple(peer_frames.keys) != tuple(keys):
+      raise ValueError('peer_frames was built for another frame size / key set')
+    if pad > 0:       # the padded tail of the last shard must not be written past the frame: render the real rays only
+      local = utils.tree_map(lambda x: x[:hi - lo], local)
+      ext = lambda x: None if x is None else torch.as_tensor(x)[lo:hi]
+    peer_frames.activate()
+    if hi > lo:
+      model.apply({'params': params}, local, extra_params, use_predicted_norm=use_predicted_norm, mask_ratio=1,
+                  sharp_weights_std=0.1, keys=tuple(keys), coarse_keys=(), t_rand=ext(t_rand), u=ext(u),
+                  fine_ptrs=peer_frames.shard_ptrs(lo))
+    peer_frames.wait()
+    return {k: v.reshape(batch_shape + tuple(v.shape[1:])) for k, v in peer_frames.frame().items()}
   out = model.apply({'params': params}, local, extra_params, use_predicted_norm=use_predicted_norm, mask_ratio=1,
                     sharp_weights_std=0.1, keys=tuple(keys), coarse_keys=(), t_rand=ext(t_rand), u=ext(u))
   fine = out['fine']

@@ -84,13 +84,15 @@ class NerfModel:
             use_sigma_gradient: bool = False, use_predicted_norm: bool = False, mask_ratio=1,
             sharp_weights_std=1.0, x_for_rgb_alpha=4.0, norm_override=None,
             t_rand=None, u=None, keys: Optional[Iterable[str]] = None,
-            coarse_keys: Optional[Iterable[str]] = None) -> Dict[str, Dict[str, torch.Tensor]]:
+            coarse_keys: Optional[Iterable[str]] = None,
+            fine_ptrs: Optional[Dict[str, int]] = None) -> Dict[str, Dict[str, torch.Tensor]]:
     """models.py:1419-1565.  Extra (non-reference) keyword arguments:
 
     t_rand / u   explicit uniform draws of model_utils.py:84,217
     keys         subset of level-dict keys to produce for 'fine' (output mask);
                  default = every key the reference returns under this config
     coarse_keys  same for 'coarse' (default = ``keys``)
+    fine_ptrs    {key: device address} for the fine level's results (peer.PeerFrames)
     """
     c = self.cfg
     if metadata_encoded:
@@ -126,7 +128,7 @@ class NerfModel:
     ck = fine_keys if coarse_keys is None else list(coarse_keys)
     out = self.renderer.render_rays(origins, rays_dict['directions'], viewdirs=rays_dict.get('viewdirs'),
                                     warp_id=warp_id, gt_mask=mask, t_rand=t_rand, u=u, extra=extra,
-                                    coarse_keys=ck, fine_keys=fine_keys)
+                                    coarse_keys=ck, fine_keys=fine_keys, fine_ptrs=fine_ptrs)
     for lvl in out.values():
       if 'ray_hyper_points' in lvl:     # models.py:1384
         lvl['ray_hyper_c'] = torch.zeros_like(lvl['ray_hyper_points'])

@@ -201,8 +201,12 @@ class Renderer:
 
   # ----------------------------------------------------------------- calls
   def render_rays(self, origins, directions, *, viewdirs=None, warp_id=None, gt_mask=None, t_rand=None, u=None,
-                  extra: _lib.ndsr_extra_params, coarse_keys=(), fine_keys=RENDER_KEYS):
-    """NerfModel.__call__ (models.py:1419-1565) on device tensors."""
+                  extra: _lib.ndsr_extra_params, coarse_keys=(), fine_keys=RENDER_KEYS,
+                  fine_ptrs: Optional[Dict[str, int]] = None):
+    """NerfModel.__call__ (models.py:1419-1565) on device tensors.
+
+    fine_ptrs: {key: device address} -- write the fine level's results there instead of into fresh tensors
+    (peer.PeerFrames.shard_ptrs: this rank's rows of a frame buffer); the returned fine dict is then empty."""
     dev = self.device
     o = _as_dev(origins, dev).reshape(-1, 3)
     d = _as_dev(directions, dev).reshape(-1, 3)
@@ -219,7 +223,12 @@ class Renderer:
       raise ValueError('u must be [B, num_fine_samples]')
     Sc, Sf = c.num_coarse_samples, c.num_coarse_samples + c.num_fine_samples
     ct, co = self.alloc_outputs(B, Sc, coarse_keys)
-    ft, fo = self.alloc_outputs(B, Sf, fine_keys)
+    if fine_ptrs is None:
+      ft, fo = self.alloc_outputs(B, Sf, fine_keys)
+    else:
+      ft, fo = {}, _lib.ndsr_outputs()
+      for k in fine_keys:
+        setattr(fo, k, int(fine_ptrs[k]))
     ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
     with torch.cuda.device(dev):
       rc = self.lib.ndsr_render_rays(self._h, self._stream(), B, ptr(o), ptr(d), ptr(v), ptr(w), ptr(m), ptr(tr),
