@@ -225,7 +225,20 @@ def run_ours(args):
   peer = None
   if world > 1 and args.gather == 'peer':
     from nerfds_b200.peer import PeerFrames
-    peer = [PeerFrames(R, n_frame, RENDER_KEYS), PeerFrames(R, n_frame, RENDER_KEYS)]
+    why = ''
+    try:
+      peer = [PeerFrames(R, n_frame, RENDER_KEYS), PeerFrames(R, n_frame, RENDER_KEYS)]
+    except RuntimeError as e:        # no peer mapping between these GPUs: every rank must take the same path
+      peer, why = None, str(e)
+    ok = torch.tensor([0 if peer is None else 1], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+      if peer is not None:
+        R._check(R.lib.ndsr_set_output_mirrors(R._h, 0, None), 'ndsr_set_output_mirrors')
+        peer = None
+      args.gather = 'nccl'
+      sys.stderr.write(f'[bench] rank {rank}: peer-memory reassembly unavailable ({why or "another rank failed"}); '
+                       'using the NCCL all-gather\n')
 
   def render_frame(i, o, d, w, t, uu):
     if peer is not None:
