@@ -242,3 +242,91 @@ def test_config_checkpoint_mismatch_is_reported(tmp_path):
     ckpt.check_params(cfg, params)
   with pytest.raises(ValueError):
     ckpt.train_state_from_dict({'params': {}})
+
+
+OPERATIVE = r'''
+import hypernerf.configs
+
+# Macros:
+# ==============================================================================
+hyper_point_max_deg = 1
+hyper_sheet_max_deg = 6
+warp_max_deg = 4
+warp_min_deg = 0
+
+# Parameters for warp/GLOEmbed:
+# ==============================================================================
+warp/GLOEmbed.num_dims = 8
+
+# Parameters for HyperSheetMLP:
+# ==============================================================================
+HyperSheetMLP.depth = 6
+HyperSheetMLP.max_deg = %hyper_sheet_max_deg
+HyperSheetMLP.min_deg = 0
+HyperSheetMLP.output_channels = 2
+HyperSheetMLP.skips = (4,)
+HyperSheetMLP.width = 64
+
+# Parameters for MaskMLP:
+# ==============================================================================
+MaskMLP.depth = 8
+MaskMLP.output_activation = @jax.nn.relu
+MaskMLP.width = 128
+
+# Parameters for NerfModel:
+# ==============================================================================
+NerfModel.activation = @jax.nn.relu
+NerfModel.hyper_embed_cls = @hyper/GLOEmbed
+NerfModel.hyper_point_max_deg = %hyper_point_max_deg
+NerfModel.hyper_point_min_deg = 0
+NerfModel.hyper_sheet_mlp_cls = @HyperSheetMLP
+NerfModel.hyper_slice_method = 'bendy_sheet'
+NerfModel.hyper_use_warp_embed = True
+NerfModel.nerf_skips = (4,)
+NerfModel.norm_type = 'none'
+NerfModel.num_coarse_samples = 64
+NerfModel.num_fine_samples = 64
+NerfModel.predict_norm = True
+NerfModel.sigma_activation = @flax.nn.softplus
+NerfModel.spatial_point_max_deg = 8
+NerfModel.spatial_point_min_deg = 0
+NerfModel.use_3d_mask = True
+NerfModel.use_mask_in_hyper = True
+NerfModel.use_mask_in_warp = True
+NerfModel.use_mask_sharp_weights = True
+NerfModel.use_posenc_identity = False
+NerfModel.use_predicted_mask = True
+NerfModel.use_warp = True
+NerfModel.use_x_in_rgb_condition = True
+NerfModel.warp_embed_cls = @warp/GLOEmbed
+NerfModel.warp_field_cls = @SE3Field
+
+# Parameters for SE3Field:
+# ==============================================================================
+SE3Field.activation = @jax.nn.relu
+SE3Field.max_deg = %warp_max_deg
+SE3Field.min_deg = %warp_min_deg
+SE3Field.skips = (4,)
+SE3Field.trunk_depth = 6
+SE3Field.trunk_width = 128
+SE3Field.use_posenc_identity = False
+
+# Parameters for TrainConfig:
+# ==============================================================================
+TrainConfig.warp_alpha_schedule = \
+    {'final_value': %warp_max_deg,
+     'initial_value': %warp_min_deg,
+     'num_steps': 50000,
+     'type': 'linear'}
+TrainConfig.hyper_sheet_alpha_schedule = ('constant', %hyper_sheet_max_deg)
+'''
+
+
+def test_operative_config_dump_format():
+  """The layout `gin.operative_config_str()` writes to <exp_dir>/config.gin (train.py:335-338): section comments,
+  alphabetical bindings, macros first, backslash-continued multi-line literals."""
+  b = gin_reader.parse_config(OPERATIVE)
+  cfg = gin_reader.model_config(b, near=0.1, far=2.5, num_warp_embeds=100)
+  assert cfg == nerf_ds_config(num_coarse_samples=64, num_fine_samples=64, near=0.1, far=2.5, num_warp_embeds=100)
+  assert schedules.from_config(b['TrainConfig.warp_alpha_schedule'])(25000) == 2.0
+  assert schedules.extra_params_at(b, 10)['nerf_alpha'] is None          # schedule not in the dump -> disabled
