@@ -161,6 +161,11 @@ PATH_SCHEDULES = {
 }
 
 
+# class defaults of the schedule attributes (configs.py:65-68, 219-225): used when the gin file does not bind them
+SCHEDULE_DEFAULTS = {'SpecularConfig.norm_input_alpha_schedule': {'type': 'constant', 'value': 4}}
+
+
 def extra_params_at(bindings: Mapping, step: int) -> Dict[str, Optional[float]]:
   """The scheduled scalars of `TrainState.extra_params` at `step`, from parsed gin bindings."""
-  return {name: from_config(bindings.get(key)).get(step) for key, name in PATH_SCHEDULES.items()}
+  return {name: from_config(bindings.get(key, SCHEDULE_DEFAULTS.get(key))).get(step)
+          for key, name in PATH_SCHEDULES.items()}

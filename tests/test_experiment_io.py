@@ -329,4 +329,5 @@ def test_operative_config_dump_format():
   cfg = gin_reader.model_config(b, near=0.1, far=2.5, num_warp_embeds=100)
   assert cfg == nerf_ds_config(num_coarse_samples=64, num_fine_samples=64, near=0.1, far=2.5, num_warp_embeds=100)
   assert schedules.from_config(b['TrainConfig.warp_alpha_schedule'])(25000) == 2.0
-  assert schedules.extra_params_at(b, 10)['nerf_alpha'] is None          # schedule not in the dump -> disabled
+  ep = schedules.extra_params_at(b, 10)
+  assert ep['nerf_alpha'] is None and ep['norm_input_alpha'] == 4.0     # not in the dump -> the class defaults (configs.py:65-68, 219)
