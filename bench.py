@@ -346,7 +346,7 @@ def run_ours(args):
     peak = float(pk.get('bf16_tflops_sustained') or pk.get('bf16_tflops') or 1400.0)
     burst = pk.get('bf16_tflops', peak)
     roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                # DRAM bytes per fine-level pass, from the ncu capture of the same command (profiles/): 397 B per
+                # DRAM bytes per fine-level pass, from the ncu capture of the same command (profiles/): 371 B per
                 # sample evaluation (planes written once, carry planes read once, plus write-backs of the previous
                 # kernel's dirty L2 lines that ncu attributes to this one); --traffic overrides
                 'traffic': args.traffic if args.traffic is not None else (
@@ -389,7 +389,7 @@ def ALL_SHAPES_local(k, S, H):
   return ALL_SHAPES[k](S, H) or (1,)
 
 
-NCU_DRAM_BYTES_PER_EVAL = 397.0   # profiles/r1_field_tc_fine_ncu_full.txt
+NCU_DRAM_BYTES_PER_EVAL = 371.0   # profiles/r1_field_tc_fine_ncu_full.txt
 
 
 def main():
