@@ -79,6 +79,12 @@ def render_scene(exp_dir: str, data_dir: str, camera_path_name: str = 'vrig_came
   dev = model.device
   gen = torch.Generator(device=dev)
   results = []
+  # one process per GPU: frames are assembled in every GPU's frame buffer by peer stores of the compositing kernel;
+  # two buffer sets per image size alternate so that frame f can be copied out while frame f + 1 is written
+  import torch.distributed as dist
+  multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+  rank = dist.get_rank() if multi else 0
+  peer_sets, n_rendered = {}, 0
   for i in range(0, len(cameras), interval):
     if cfg.use_warp and i >= cfg.num_warp_embeds:
       raise IndexError(f'camera {i} has no warp embedding (the checkpoint holds {cfg.num_warp_embeds})')
@@ -95,10 +101,21 @@ def render_scene(exp_dir: str, data_dir: str, camera_path_name: str = 'vrig_came
     gen.manual_seed(seed * 1000003 + i)
     t_rand = torch.rand((H * W, cfg.num_coarse_samples), generator=gen, device=dev) if cfg.use_stratified_sampling else None
     u = torch.rand((H * W, cfg.num_fine_samples), generator=gen, device=dev) if cfg.use_stratified_sampling else None
+    pf = None
+    if multi:
+      from .peer import PeerFrames
+      sets = peer_sets.setdefault((H, W), [])
+      if len(sets) < 2:
+        sets.append(PeerFrames(model.renderer, H * W, tuple(keys)))
+      pf = sets[n_rendered % len(sets)] if len(sets) == 2 else sets[-1]
     out = render_image_sharded(model, params, rays, extra, t_rand=t_rand, u=u, chunk=chunk_size, keys=tuple(keys),
-                               use_predicted_norm=use_predicted_norm)
+                               use_predicted_norm=use_predicted_norm, peer_frames=pf)
     results.append({k: v.cpu().numpy() for k, v in out.items()})
-  if save:
+    n_rendered += 1
+  for sets in peer_sets.values():
+    for pf in sets:
+      pf.close()
+  if save and rank == 0:
     name = camera_path_name + ('_full' if interval == 1 else '')                             # render.py:193-194
     with open(os.path.join(exp_dir, f'render_result_{name}'), 'wb+') as f:
       np.save(f, np.array(results, dtype=object), allow_pickle=True)
