@@ -284,3 +284,60 @@ def test_camera_rays_oracle(G):
     assert np.allclose(np.linalg.norm(out['directions'], axis=-1), 1.0, atol=1e-6)
     n += 1
   assert n == 3
+
+
+def test_whole_forward_variant_with_flipped_sampling_switches(G):
+  """The reference's NerfModel.__call__ once more, at render.py's inference settings (mask_ratio 1, end-of-schedule
+  alphas) with deterministic depths (no stratified jitter, u = linspace), linear disparity, white background and no
+  sample at infinity: every key of both level dicts.  No draws -> the end-to-end fine level is compared directly."""
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import unflatten_params
+  small = {str(k): int(v) for k, v in zip(G['model_cfg_keys'], G['model_cfg_vals'])}
+  cfg = nerf_ds_config(**small).replace(use_stratified_sampling=False, use_white_background=True,
+                                        use_linear_disparity=True, use_sample_at_infinity=False)
+  P = unflatten_params({k[3:]: v for k, v in G.items() if k.startswith('MP/')})
+  ep = {'nerf_alpha': 8.0, 'warp_alpha': 4.0, 'hyper_alpha': 1.0, 'hyper_sheet_alpha': 6.0, 'norm_input_alpha': 4.0}
+  rays = {'origins': G['model_origins'], 'directions': G['model_dirs'], 'metadata': {'warp': G['model_warp']},
+          'mask': G['model_gt_mask']}
+  om = O.OracleNerfModel(cfg, P)
+  out = O.to_numpy(om.apply(rays, ep, None, None, return_points=True, return_weights=True, use_predicted_norm=True,
+                            compute_sigma_gradient=True, keep_internal=True, mask_ratio=1, sharp_weights_std=0.1))
+  o3, d3 = G['model_origins'], G['model_dirs']
+  depth_of = lambda pts: (((pts - o3[:, None]) * d3[:, None]).sum(-1) / (d3 ** 2).sum(-1)[:, None]).astype(np.float32)
+  # coarse depths: linear in disparity between near and far, identical for every ray
+  zc = depth_of(G['modelB_coarse_points'])
+  S = zc.shape[1]
+  t = np.arange(S, dtype=np.float32) / np.float32(S - 1)
+  np.testing.assert_allclose(zc, np.broadcast_to(1.0 / (1.0 / cfg.near * (1 - t) + 1.0 / cfg.far * t), zc.shape), rtol=2e-5)
+  np.testing.assert_allclose(out['coarse']['z_vals'], zc, rtol=2e-5, atol=2e-6)
+  zf = depth_of(G['modelB_fine_points'])
+  fine_on_ref = O.to_numpy(om.render_samples(
+      'fine', T(G['modelB_fine_points']), T(zf), T(d3), T(d3), rays['metadata'], ep, G['model_gt_mask'],
+      use_sample_at_infinity=False, use_predicted_norm=True, compute_sigma_gradient=True, mask_ratio=1,
+      sharp_weights_std=0.1))
+  checked = 0
+  for lvl, res in (('coarse', out['coarse']), ('fine', fine_on_ref)):
+    gold = {k[len(f'modelB_{lvl}_'):]: v for k, v in G.items() if k.startswith(f'modelB_{lvl}_')}
+    assert {'rgb', 'depth', 'acc', 'weights', 'sigma', 'warped_points', 'predicted_mask', 'predicted_norm', 'target_norm',
+            'ray_norm', 'ray_delta_x', 'med_points'} <= set(gold)
+    for k, g in gold.items():
+      if k == 'sharp_weights':
+        continue                              # ill-conditioned rows, covered by the first variant
+      o = np.asarray(res[k]).reshape(g.shape)
+      if k == 'target_norm':
+        e = np.abs(o - g).max(-1)
+        assert np.median(e) <= 2e-6 and np.mean(e <= 1e-4) >= 0.98, (lvl, np.sort(e.reshape(-1))[-4:])
+      elif k == 'sigma':
+        # (full-frequency posenc: a logit of size 30 carries 4e-6 of float32 noise, 4e-4 of a sigma of 0.1)
+        np.testing.assert_allclose(o, g, rtol=5e-4, atol=2e-5, err_msg=f'{lvl}/{k}')
+      elif k in ('med_depth', 'med_points'):
+        np.testing.assert_allclose(o, g, rtol=1e-5, atol=1e-5, err_msg=f'{lvl}/{k}')
+      else:
+        np.testing.assert_allclose(o, g, rtol=1e-4, atol=2e-5, equal_nan=True, err_msg=f'{lvl}/{k}')
+      checked += 1
+  assert checked >= 40
+  # end to end (deterministic u): the resampled depths and the fine colours follow the reference's
+  dz = np.abs(np.sort(out['fine']['z_vals'], -1) - zf)          # (near-empty bins: the inverse CDF amplifies 1e-7 of weight)
+  assert np.mean(dz <= 2e-4) >= 0.98 and dz.max() <= 2e-2, np.sort(dz.reshape(-1))[-4:]
+  e = np.abs(out['fine']['rgb'] - G['modelB_fine_rgb']).max(-1)    # one moved sample on a sharp edge moves a 16-sample ray
+  assert np.median(e) <= 1e-5 and np.mean(e <= 1e-3) >= 0.89, np.sort(e)[-3:]

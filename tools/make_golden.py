@@ -561,7 +561,7 @@ def main():
   G['model_cfg_vals'] = np.array([msmall[k] for k in sorted(msmall.keys())], np.int32)
   modules.MaskMLP = functools.partial(modules.MaskMLP, depth=mcfg.mask_depth, width=mcfg.mask_width,
                                       output_activation=jx.nn.relu)                       # nerf_ds.gin:116-118
-  model = models.NerfModel(
+  model_kw = dict(
       embeddings_dict={'warp': list(range(mcfg.num_warp_embeds)), 'appearance': [0], 'camera': [0]},
       near=mcfg.near, far=mcfg.far, num_coarse_samples=mcfg.num_coarse_samples, num_fine_samples=mcfg.num_fine_samples,
       use_viewdirs=True, use_stratified_sampling=True, norm_type='none', activation=jx.nn.relu, use_posenc_identity=False,
@@ -578,6 +578,7 @@ def main():
       use_x_in_rgb_condition=True, use_hyper_c=False, hyper_c_hyper_input=True, use_hyper_c_embed=False,
       use_mask_in_warp=True, use_mask_in_hyper=True, use_mask_in_rgb=False, use_predicted_mask=True, use_3d_mask=True,
       use_mask_sharp_weights=True, nerf_trunk_width=mcfg.nerf_trunk_width, nerf_rgb_branch_width=mcfg.nerf_rgb_branch_width)
+  model = models.NerfModel(**model_kw)
   MB = 19
   mo = f32(rng.normal(size=(MB, 3)) * 0.3)
   md = f32(rng.normal(size=(MB, 3)))
@@ -600,6 +601,20 @@ def main():
     for k, v in res[lvl].items():
       if v is not None:
         G[f'model_{lvl}_{k}'] = f32(v)
+
+  # Second variant: the inference settings of render.py (mask_ratio 1, end-of-schedule alphas) with the sampling /
+  # compositing switches flipped -- deterministic depths (no stratified jitter, u = linspace), linear disparity,
+  # white background, no sample at infinity.  Same rays and parameters.
+  modelB = models.NerfModel(**dict(model_kw, use_stratified_sampling=False, use_white_background=True,
+                                   use_linear_disparity=True, use_sample_at_infinity=False))
+  mepB = {'nerf_alpha': 8.0, 'warp_alpha': 4.0, 'hyper_alpha': 1.0, 'hyper_sheet_alpha': 6.0, 'norm_loss_weight': 1.0,
+          'norm_input_alpha': 4.0, 'norm_voxel_lr': 0.0, 'norm_voxel_ratio': 0.0}
+  resB = modelB.apply({'params': MP}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mepB,
+                      use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=1, sharp_weights_std=0.1)
+  for lvl in ('coarse', 'fine'):
+    for k, v in resB[lvl].items():
+      if v is not None:
+        G[f'modelB_{lvl}_{k}'] = f32(v)
 
   # ------------------------------------------------------------------ ray generation
   # hypernerf/camera.py is plain numpy; its module imports gpath -> tensorflow, stubbed out
