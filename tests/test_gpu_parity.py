@@ -519,3 +519,53 @@ def test_training_batch_at_baseline_size(cuda_device):
   assert np.median(e) <= 1e-4 and np.mean(e <= GRAD_TOL) >= 0.97, np.sort(e.reshape(-1))[-5:]
   e = np.abs(c['predicted_norm'] - ref['coarse']['predicted_norm']).max()
   assert e <= 2e-4
+
+
+@pytest.mark.parametrize('variant', ['A', 'B'])
+def test_cuda_path_against_reference_goldens(cuda_device, variant):
+  """The CUDA path against vectors produced by the REFERENCE'S OWN SOURCE (tests/golden/reference_shim.npz, whole
+  NerfModel.__call__ with every network 32 wide, the narrowest shape the engines build): no oracle in between.  Variant A: mid-schedule alphas, mask_ratio 0.7, stratified draws;
+  variant B: inference settings, deterministic depths, linear disparity, white background, no sample at infinity.
+  Coarse level end to end; fine level on the reference's own fine samples."""
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import unflatten_params
+  from tests.test_oracle_golden import GOLDEN
+  G = dict(np.load(GOLDEN))
+  small = {str(k): int(v) for k, v in zip(G['model32_cfg_keys'], G['model32_cfg_vals'])}
+  cfg = nerf_ds_config(**small)
+  P = unflatten_params({k[5:]: v for k, v in G.items() if k.startswith('MP32/')})
+  if variant == 'A':
+    pre, ratio = 'model32', float(G['model_mask_ratio'])
+    ep = {str(k): float(v) for k, v in zip(G['model_extra_keys'], G['model_extra_vals'])}
+    t_rand, u = G['model_t_rand'], G['model_u']
+  else:
+    pre, ratio = 'model32B', 1.0
+    cfg = cfg.replace(use_stratified_sampling=False, use_white_background=True, use_linear_disparity=True,
+                      use_sample_at_infinity=False)
+    ep = {'nerf_alpha': 8.0, 'warp_alpha': 4.0, 'hyper_alpha': 1.0, 'hyper_sheet_alpha': 6.0, 'norm_input_alpha': 4.0}
+    t_rand = u = None
+  rays = {'origins': G['model_origins'], 'directions': G['model_dirs'], 'metadata': {'warp': G['model_warp']},
+          'mask': G['model_gt_mask']}
+  m = _model(cfg, cuda_device, engine='auto')
+  out = m.apply({'params': P}, rays, ep, t_rand=t_rand, u=u, use_predicted_norm=True, return_points=True,
+                return_weights=True, mask_ratio=ratio, sharp_weights_std=0.1)
+  o3, d3 = G['model_origins'], G['model_dirs']
+  zf = (((G[f'{pre}_fine_points'] - o3[:, None]) * d3[:, None]).sum(-1) / (d3 ** 2).sum(-1)[:, None]).astype(np.float32)
+  extra = m.renderer.make_extra(ep, use_predicted_norm=True, mask_ratio=ratio, sharp_weights_std=0.1)
+  keys = m.renderer.level_keys(return_points=True, return_weights=True)
+  fine = m.renderer.render_samples(1, zf, d3, points=G[f'{pre}_fine_points'], warp_id=G['model_warp'],
+                                   gt_mask=G['model_gt_mask'], extra=extra,
+                                   use_sample_at_infinity=cfg.use_sample_at_infinity, keys=keys)
+  checked = 0
+  for lvl, res in (('coarse', _np(out['coarse'])), ('fine', _np(fine))):
+    for k in ('rgb', 'depth', 'acc', 'weights', 'alpha', 'warped_points', 'predicted_mask', 'predicted_norm',
+              'ray_norm', 'ray_delta_x', 'ray_hyper_points', 'ray_predicted_mask', 'ray_rotation_field',
+              'ray_translation_field', 'delta_x', 'back_facing'):
+      g = G[f'{pre}_{lvl}_{k}']
+      assert linf(res[k].reshape(g.shape), g) <= RGB_TOL, (variant, lvl, k, linf(res[k].reshape(g.shape), g))
+      checked += 1
+    g = G[f'{pre}_{lvl}_sigma']
+    np.testing.assert_allclose(res['sigma'].reshape(g.shape), g, rtol=1e-3, atol=1e-3)
+    e = np.abs(res['target_norm'].reshape(-1, 3) - G[f'{pre}_{lvl}_target_norm'].reshape(-1, 3)).max(-1)
+    assert np.median(e) <= 1e-5 and np.mean(e <= 1e-3) >= 0.97, (variant, lvl, np.sort(e)[-4:])
+  assert checked == 32

@@ -559,7 +559,8 @@ def main():
     G['MP/' + name] = f32(arr)
   G['model_cfg_keys'] = np.array(sorted(msmall.keys()))
   G['model_cfg_vals'] = np.array([msmall[k] for k in sorted(msmall.keys())], np.int32)
-  modules.MaskMLP = functools.partial(modules.MaskMLP, depth=mcfg.mask_depth, width=mcfg.mask_width,
+  MaskMLP_cls = modules.MaskMLP
+  modules.MaskMLP = functools.partial(MaskMLP_cls, depth=mcfg.mask_depth, width=mcfg.mask_width,
                                       output_activation=jx.nn.relu)                       # nerf_ds.gin:116-118
   model_kw = dict(
       embeddings_dict={'warp': list(range(mcfg.num_warp_embeds)), 'appearance': [0], 'camera': [0]},
@@ -615,6 +616,35 @@ def main():
     for k, v in resB[lvl].items():
       if v is not None:
         G[f'modelB_{lvl}_{k}'] = f32(v)
+
+  # Third / fourth set: the same two call variants with every network 32 wide -- the narrowest shape the CUDA
+  # engines build -- so that tests/test_gpu_parity.py can compare the CUDA path with the reference's output directly.
+  w32 = dict(nerf_trunk_width=32, nerf_rgb_branch_width=32, mask_width=32, warp_trunk_width=32, hyper_sheet_width=32,
+             num_warp_embeds=5, num_coarse_samples=8, num_fine_samples=8)
+  cfg32 = nerf_ds_config(**w32)
+  MP32 = init_params(cfg32, 12)
+  for name, arr in flatten_params(MP32):
+    G['MP32/' + name] = f32(arr)
+  G['model32_cfg_keys'] = np.array(sorted(w32.keys()))
+  G['model32_cfg_vals'] = np.array([w32[k] for k in sorted(w32.keys())], np.int32)
+  modules.MaskMLP = functools.partial(MaskMLP_cls, depth=cfg32.mask_depth, width=32, output_activation=jx.nn.relu)
+  kw32 = dict(model_kw, nerf_trunk_width=32, nerf_rgb_branch_width=32,
+              hyper_sheet_mlp_cls=functools.partial(modules.HyperSheetMLP, min_deg=0, max_deg=6, output_channels=2, width=32),
+              warp_field_cls=functools.partial(warping.SE3Field, min_deg=0, max_deg=4, use_posenc_identity=False,
+                                               trunk_width=32))
+  _DRAWS.extend([mt, mu_])
+  res32 = models.NerfModel(**kw32).apply(
+      {'params': MP32}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mep,
+      use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.1)
+  res32B = models.NerfModel(**dict(kw32, use_stratified_sampling=False, use_white_background=True,
+                                   use_linear_disparity=True, use_sample_at_infinity=False)).apply(
+      {'params': MP32}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mepB,
+      use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=1, sharp_weights_std=0.1)
+  for tag, res_ in (('model32', res32), ('model32B', res32B)):
+    for lvl in ('coarse', 'fine'):
+      for k, v in res_[lvl].items():
+        if v is not None and k != 'sharp_weights':
+          G[f'{tag}_{lvl}_{k}'] = f32(v)
 
   # ------------------------------------------------------------------ ray generation
   # hypernerf/camera.py is plain numpy; its module imports gpath -> tensorflow, stubbed out
