@@ -646,6 +646,28 @@ def main():
         if v is not None and k != 'sharp_weights':
           G[f'{tag}_{lvl}_{k}'] = f32(v)
 
+  # Fifth set: nerf_ds.gin's FULL widths (the shape the tensor-core engine builds), variant-A call.  The 1.5 M
+  # parameters are not stored: init_params(cfg, seed) regenerates them (numpy Generator streams are stable).
+  full = dict(num_warp_embeds=5, num_coarse_samples=8, num_fine_samples=8)
+  cfgF = nerf_ds_config(**full)
+  MPF = init_params(cfgF, 13)
+  G['modelF_seed'] = np.array(13, np.int32)
+  G['modelF_param_checksum'] = np.array(sum(float(np.abs(a).sum()) for _, a in flatten_params(MPF)), np.float64)
+  modules.MaskMLP = functools.partial(MaskMLP_cls, depth=cfgF.mask_depth, width=cfgF.mask_width, output_activation=jx.nn.relu)
+  kwF = dict(model_kw, nerf_trunk_width=cfgF.nerf_trunk_width, nerf_rgb_branch_width=cfgF.nerf_rgb_branch_width,
+             hyper_sheet_mlp_cls=functools.partial(modules.HyperSheetMLP, min_deg=0, max_deg=6, output_channels=2,
+                                                   width=cfgF.hyper_sheet_width),
+             warp_field_cls=functools.partial(warping.SE3Field, min_deg=0, max_deg=4, use_posenc_identity=False,
+                                              trunk_width=cfgF.warp_trunk_width))
+  _DRAWS.extend([mt, mu_])
+  resF = models.NerfModel(**kwF).apply(
+      {'params': MPF}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mep,
+      use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.1)
+  for lvl in ('coarse', 'fine'):
+    for k, v in resF[lvl].items():
+      if v is not None and k not in ('sharp_weights', 'target_norm'):
+        G[f'modelF_{lvl}_{k}'] = f32(v)
+
   # ------------------------------------------------------------------ ray generation
   # hypernerf/camera.py is plain numpy; its module imports gpath -> tensorflow, stubbed out
   tf = types.ModuleType('tensorflow')
