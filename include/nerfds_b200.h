@@ -13,6 +13,7 @@
 #ifndef NERFDS_B200_H_
 #define NERFDS_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

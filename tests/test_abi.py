@@ -69,3 +69,19 @@ def test_product_never_imports_oracle():
       if f.endswith(('.py', '.cu', '.cuh', '.h')):
         txt = open(os.path.join(dirpath, f)).read()
         assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def test_header_is_plain_c(tmp_path):
+  """include/nerfds_b200.h is a C header (C99, no C++ or CUDA types): it must compile on its own with gcc."""
+  import shutil
+  import subprocess
+  gcc = shutil.which('gcc')
+  if gcc is None:
+    pytest.skip('no gcc')
+  src = tmp_path / 't.c'
+  src.write_text('#include "nerfds_b200.h"\nint main(void) { ndsr_config c; ndsr_outputs o; ndsr_extra_params e; ndsr_camera cam;\n'
+                 '  ndsr_ipc_handle h; (void)c; (void)o; (void)e; (void)cam; (void)h; return sizeof(ndsr_tensor) > 0 ? 0 : 1; }\n')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-I',
+                      os.path.join(root, 'include'), str(src)], capture_output=True, text=True)
+  assert r.returncode == 0, r.stderr
