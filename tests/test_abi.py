@@ -85,3 +85,23 @@ def test_header_is_plain_c(tmp_path):
   r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-I',
                       os.path.join(root, 'include'), str(src)], capture_output=True, text=True)
   assert r.returncode == 0, r.stderr
+
+
+def test_c_client_links_and_runs(tmp_path):
+  """examples/abi_probe.c: a C99 program linked against the shared library alone (no CUDA, no C++ headers) sees the
+  declared ABI version / struct sizes and the error path of ndsr_create -- runs without a GPU."""
+  import shutil
+  import subprocess
+  from nerfds_b200 import _lib
+  gcc = shutil.which('gcc')
+  if gcc is None or not os.path.exists(_lib.LIB_PATH):
+    pytest.skip('no gcc or library not built')
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  libdir = os.path.dirname(_lib.LIB_PATH)
+  exe = str(tmp_path / 'abi_probe')
+  r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-Werror', '-I', os.path.join(root, 'include'),
+                      os.path.join(root, 'examples', 'abi_probe.c'), '-L', libdir, '-lnerfds_b200',
+                      f'-Wl,-rpath,{libdir}', '-o', exe], capture_output=True, text=True)
+  assert r.returncode == 0, r.stderr
+  r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+  assert r.returncode == 0 and 'abi 1 ok' in r.stdout, r.stdout + r.stderr
