@@ -24,5 +24,8 @@ int main(void) {
     return 2;
   }
   printf("abi %d ok; ndsr_create on an empty config: %d (%s)\n", ndsr_abi_version(), rc, ndsr_last_error(NULL));
+  printf("sizeof config=%u extra_params=%u outputs=%u camera=%u tensor=%u ipc_handle=%u\n", (unsigned)sizeof(ndsr_config),
+         (unsigned)sizeof(ndsr_extra_params), (unsigned)sizeof(ndsr_outputs), (unsigned)sizeof(ndsr_camera),
+         (unsigned)sizeof(ndsr_tensor), (unsigned)sizeof(ndsr_ipc_handle));
   return 0;
 }

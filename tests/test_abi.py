@@ -105,3 +105,10 @@ def test_c_client_links_and_runs(tmp_path):
   assert r.returncode == 0, r.stderr
   r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
   assert r.returncode == 0 and 'abi 1 ok' in r.stdout, r.stdout + r.stderr
+  # the ctypes mirrors have the C compiler's sizes (layout drift would shift every later field)
+  sizes = dict(kv.split('=') for kv in r.stdout.splitlines()[-1].split()[1:])
+  want = {'config': _lib.ndsr_config, 'extra_params': _lib.ndsr_extra_params, 'outputs': _lib.ndsr_outputs,
+          'camera': _lib.ndsr_camera, 'tensor': _lib.ndsr_tensor}
+  for k, t in want.items():
+    assert int(sizes[k]) == ctypes.sizeof(t), (k, sizes[k], ctypes.sizeof(t))
+  assert int(sizes['ipc_handle']) == 64
