@@ -331,3 +331,33 @@ def test_operative_config_dump_format():
   assert schedules.from_config(b['TrainConfig.warp_alpha_schedule'])(25000) == 2.0
   ep = schedules.extra_params_at(b, 10)
   assert ep['nerf_alpha'] is None and ep['norm_input_alpha'] == 4.0     # not in the dump -> the class defaults (configs.py:65-68, 219)
+
+
+def test_msgpack_round_trip_property():
+  """Random state trees (nested dicts of float / int arrays of any rank, numpy scalars, None, python scalars)
+  survive serialize -> restore exactly, whatever the chunk threshold."""
+  from hypothesis import given, settings, strategies as st
+  from hypothesis.extra import numpy as hnp
+  leaf = st.one_of(
+      hnp.arrays(dtype=st.sampled_from([np.float32, np.int32, np.uint32, np.float64, np.uint8]),
+                 shape=hnp.array_shapes(min_dims=0, max_dims=3, min_side=0, max_side=5),
+                 elements=st.integers(0, 100)),
+      st.none(), st.integers(-2 ** 31, 2 ** 31), st.booleans(),
+      st.floats(allow_nan=False, allow_infinity=False, width=32).map(np.float32))
+  tree = st.recursive(leaf, lambda c: st.dictionaries(st.text('abc/_0', min_size=1, max_size=4), c, max_size=4), max_leaves=12)
+
+  def same(a, b):
+    if isinstance(a, dict):
+      return isinstance(b, dict) and a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+    if isinstance(a, np.ndarray):
+      return isinstance(b, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+    if isinstance(a, np.generic):
+      return type(a) is type(b) and a == b
+    return type(a) is type(b) and a == b
+
+  @settings(max_examples=60, deadline=None)
+  @given(tree.filter(lambda t: isinstance(t, dict)), st.sampled_from([8, 64, 2 ** 30]))
+  def check(t, chunk):
+    assert same(t, ckpt.msgpack_restore(ckpt.msgpack_serialize(t, max_chunk_bytes=chunk)))
+
+  check()
