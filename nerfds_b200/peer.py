@@ -14,6 +14,11 @@ is used for the 64-byte handle exchange and the barrier only.
     out = model.apply(..., fine_ptrs=frames.shard_ptrs(lo)) # this rank's rays [lo, hi)
     frames.wait()                                           # stream sync + barrier
     full = frames.frame()                                   # {key: [n_rays, ...]} on this GPU
+    frames.close()                                          # unregisters the mirrors, unmaps, frees
+
+While a PeerFrames is active the renderer's fine-level per-ray stores are mirrored at fixed address offsets, so
+every fine-level call must write into the frame buffer (`fine_ptrs=frames.shard_ptrs(...)`); `close()` (or
+`ndsr_set_output_mirrors(h, 0, NULL)`) switches mirroring off again before ordinary calls.
 """
 from __future__ import annotations
 
