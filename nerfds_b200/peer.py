@@ -82,6 +82,7 @@ class PeerFrames:
     """Make this buffer set the mirror target of the renderer's next calls (several PeerFrames can alternate,
     e.g. to let a consumer read frame f while frame f + 1 is being written)."""
     self.R._check(self.lib.ndsr_set_output_mirrors(self.R._h, len(self.mapped), self._deltas), 'ndsr_set_output_mirrors')
+    self.R._mirrors_active = True        # Renderer.render_rays refuses fine-level calls without fine_ptrs from now on
 
   @staticmethod
   def _check(rc, what):
@@ -110,6 +111,7 @@ class PeerFrames:
     self.closed = True
     idx = self.dev.index or 0
     self.R._check(self.lib.ndsr_set_output_mirrors(self.R._h, 0, None), 'ndsr_set_output_mirrors')
+    self.R._mirrors_active = False
     self.wait()                                          # nobody still writes into a buffer about to go away
     for p in self.mapped.values():
       self.lib.ndsr_peer_close(idx, C.c_void_p(p))

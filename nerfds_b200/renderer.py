@@ -223,6 +223,9 @@ class Renderer:
       raise ValueError('u must be [B, num_fine_samples]')
     Sc, Sf = c.num_coarse_samples, c.num_coarse_samples + c.num_fine_samples
     ct, co = self.alloc_outputs(B, Sc, coarse_keys)
+    if fine_ptrs is None and fine_keys and getattr(self, '_mirrors_active', False):
+      raise NdsrError('a peer.PeerFrames is active on this renderer: fine-level results must go into its frame '
+                      'buffer (fine_ptrs=frames.shard_ptrs(...)), or close() it first')
     if fine_ptrs is None:
       ft, fo = self.alloc_outputs(B, Sf, fine_keys)
     else:

@@ -37,6 +37,11 @@ def main():
       a, b = got[k].reshape(ref[k].shape), ref[k]
       assert torch.equal(a, b), (rank, rep, k, float((a - b).abs().max()))
     dist.barrier()
+  try:                                                   # an ordinary call while mirrors are registered is refused
+    model.apply({'params': params}, rays, ep, t_rand=t_rand, u=u, use_predicted_norm=True, keys=('rgb',), coarse_keys=())
+    raise SystemExit('expected NdsrError')
+  except Exception as e:
+    assert 'PeerFrames is active' in str(e), e
   frames.close()
   # mirrors are off again: a plain call writes only locally
   out = model.apply({'params': params}, rays, ep, t_rand=t_rand, u=u, use_predicted_norm=True, mask_ratio=1,
