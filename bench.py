@@ -234,7 +234,7 @@ def run_ours(args):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if int(ok.item()) == 0:
       if peer is not None:
-        R._check(R.lib.ndsr_set_output_mirrors(R._h, 0, None), 'ndsr_set_output_mirrors')
+        R._check(R.lib.ndsr_set_output_mirrors(R._h, 0, None, None, 0), 'ndsr_set_output_mirrors')
         peer = None
       args.gather = 'nccl'
       sys.stderr.write(f'[bench] rank {rank}: peer-memory reassembly unavailable ({why or "another rank failed"}); '

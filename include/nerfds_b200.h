@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define NDSR_ABI_VERSION 1
+#define NDSR_ABI_VERSION 2
 #define NDSR_MAX_DEPTH 8      /* hidden layers per MLP */
 #define NDSR_MAX_BANDS 12     /* posenc frequency bands per encoder */
 
@@ -113,6 +113,15 @@ typedef struct ndsr_extra_params {
   int32_t use_sigma_gradient;            /* models.py:1437 */
   int32_t sample_at_infinity_override;   /* -1 = configured, 0/1 = override (fine level only,
                                             models.py:1509 vs 1544) */
+  /* render_opts of filter_sigma (models.py:38-66), applied where the reference applies it: ndsr_render_rays on the
+   * FINE level only (models.py:1545; the coarse call gets no render_opts), ndsr_render_samples on the level it is
+   * called for.  Bit 0: dust_threshold present, bit 1: bounding_box present.  The compositing density is
+   * [sigma >= dust] * [x in box] * sigma on the ACTIVATED sigma and the observation-space point (models.py:1288);
+   * `sharp_weights` filters the RAW sigma before the activation (models.py:1236-1237); the `sigma` output stays
+   * unfiltered (models.py:1271). */
+  int32_t filter_flags;
+  float dust_threshold;
+  float bounding_box[6];                 /* xmin, xmax, ymin, ymax, zmin, zmax (models.py:60) */
 } ndsr_extra_params;
 
 /* Output buffers of one level dict.  Every member is a
@@ -246,17 +255,22 @@ int ndsr_camera_rays(int device, void* stream, const ndsr_camera* camera, float*
  * One process per GPU.  Every rank allocates the same packed frame buffer with ndsr_peer_alloc, the 64-byte handles
  * are exchanged by the host (any transport), every rank maps the others' buffers with ndsr_peer_open and registers
  * the address differences with ndsr_set_output_mirrors.  From then on the compositing kernel of a fine-level
- * ndsr_render_rays / ndsr_render_samples call stores every PER-RAY result both at the output pointer it was given
- * (inside the rank's own frame buffer) and at the same offset of every mirror: when all ranks' streams have
- * drained, every GPU holds the whole frame -- the all-gather happened inside the kernel, as NVLink stores. */
+ * ndsr_render_rays call whose per-ray output pointers ALL lie inside the registered frame buffer
+ * [frame_base, frame_base + frame_bytes) stores every PER-RAY result both at the output pointer it was given and at
+ * the same offset of every mirror: when all ranks' streams have drained, every GPU holds the whole frame -- the
+ * all-gather happened inside the kernel, as NVLink stores.  Calls whose per-ray outputs all lie OUTSIDE the frame
+ * buffer (ordinary tensors, ndsr_render_samples, ndsr_render_rays_host staging) are not mirrored; a call with
+ * pointers on both sides fails with NDSR_ERR_INVALID. */
 #define NDSR_MAX_MIRRORS 15
 typedef struct ndsr_ipc_handle { unsigned char bytes[64]; } ndsr_ipc_handle;
 int ndsr_peer_alloc(int device, size_t bytes, void** ptr, ndsr_ipc_handle* handle);
 int ndsr_peer_free(int device, void* ptr);
 int ndsr_peer_open(int device, const ndsr_ipc_handle* handle, void** ptr);
 int ndsr_peer_close(int device, void* ptr);
-/* byte_deltas[m] = (mapped address of mirror m) - (address of this rank's own buffer); n = 0 switches mirroring off */
-int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_deltas);
+/* byte_deltas[m] = (mapped address of mirror m) - (address of this rank's own buffer); frame_base / frame_bytes =
+ * this rank's own buffer (the only address range whose stores are mirrored); n = 0 switches mirroring off */
+int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_deltas, const void* frame_base,
+                            size_t frame_bytes);
 
 /* Replaces the two `random.uniform(key, [n_rays, n_samples])` draws of the path (model_utils.py:84 stratified
  * jitter `t_rand`, model_utils.py:217 inverse-CDF `u`) on the device, bit for bit as jax 0.3.15's default

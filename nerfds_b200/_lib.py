@@ -13,7 +13,7 @@ from .config import NerfDSConfig
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libnerfds_b200.so')
 
-NDSR_ABI_VERSION = 1
+NDSR_ABI_VERSION = 2
 NDSR_MAX_MIRRORS = 15
 ENGINES = {'auto': 0, 'simt': 1, 'tc': 2}
 ENGINE_NAMES = {v: k for k, v in ENGINES.items()}
@@ -60,7 +60,8 @@ class ndsr_extra_params(C.Structure):
               ('norm_input_alpha', _f32), ('mask_ratio', _f32), ('sharp_weights_std', _f32),
               ('near_override', _f32), ('far_override', _f32),
               ('use_predicted_norm', _i32), ('use_sigma_gradient', _i32),
-              ('sample_at_infinity_override', _i32)]
+              ('sample_at_infinity_override', _i32),
+              ('filter_flags', _i32), ('dust_threshold', _f32), ('bounding_box', _f32 * 6)]
 
 
 OUTPUT_FIELDS = ['rgb', 'depth', 'med_depth', 'acc', 'ray_norm', 'ray_rotation_field', 'ray_translation_field',
@@ -187,7 +188,7 @@ def load_library() -> C.CDLL:
   lib.ndsr_peer_free.argtypes = [C.c_int, vp]
   lib.ndsr_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
   lib.ndsr_peer_close.argtypes = [C.c_int, vp]
-  lib.ndsr_set_output_mirrors.argtypes = [vp, i32, C.POINTER(i64)]
+  lib.ndsr_set_output_mirrors.argtypes = [vp, i32, C.POINTER(i64), vp, C.c_size_t]
   if lib.ndsr_abi_version() != NDSR_ABI_VERSION:
     raise ImportError('libnerfds_b200.so ABI version mismatch; rebuild')
   a, b, c = i32(), i32(), i32()

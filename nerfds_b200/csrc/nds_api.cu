@@ -483,7 +483,8 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
                      const float* z, const float* origins, const float* dirs, const float* viewdirs,
                      const uint32_t* warp_id, const float* gt_mask, const ndsr_extra_params& ep,
                      const CallParams& cp, int sample_at_infinity, const ndsr_outputs* out, float* weights_keep,
-                     bool need_rgb, float* carry_out = nullptr, const int32_t* src_elem = nullptr, int n_carried = 0) {
+                     bool need_rgb, float* carry_out = nullptr, const int32_t* src_elem = nullptr, int n_carried = 0,
+                     bool apply_filter = true) {
   const ndsr_config& c = h->cfg;
   ndsr_outputs o;
   memset(&o, 0, sizeof o);
@@ -527,12 +528,30 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   ca.viewdirs = viewdirs ? viewdirs : dirs; ca.origins = origins; ca.points = points;
   ca.sigma_is_activated = 0; ca.white_bkgd = c.use_white_background; ca.sample_at_infinity = sample_at_infinity;
   ca.has_norm = c.predict_norm; ca.has_warp = c.use_warp; ca.has_mask = c.use_predicted_mask; ca.has_grad = need_grad;
+  if (apply_filter && (ep.filter_flags & 3)) {      // filter_sigma (models.py:38-66)
+    ca.filter_flags = ep.filter_flags & 3;
+    ca.dust_threshold = ep.dust_threshold;
+    for (int i = 0; i < 6; ++i) ca.bbox[i] = ep.bounding_box[i];
+  }
   ca.out = o;
   ca.src_elem = (h->engine == NDSR_ENGINE_TC && !need_grad) ? src_elem : nullptr; ca.n_carried = n_carried;
   if (weights_keep) ca.out.weights = weights_keep;   // coarse weights feed sample_pdf
   if (level == 1 && h->n_mirror > 0) {
-    ca.n_mirror = h->n_mirror;
-    for (int m = 0; m < h->n_mirror; ++m) ca.mirror_delta[m] = h->mirror_delta[m];
+    // mirrored stores add fixed address offsets: only legal when the destination is the registered frame buffer
+    const float* per_ray[] = {o.rgb, o.depth, o.med_depth, o.acc, o.ray_norm, o.ray_rotation_field, o.ray_translation_field,
+                              o.ray_delta_x, o.ray_hyper_points, o.ray_predicted_mask, o.med_points};
+    int inside = 0, outside = 0;
+    for (const float* p : per_ray) {
+      if (!p) continue;
+      const char* q = reinterpret_cast<const char*>(p);
+      (q >= h->mirror_base && q < h->mirror_base + h->mirror_bytes) ? ++inside : ++outside;
+    }
+    if (inside && outside)
+      return fail(h, NDSR_ERR_INVALID, "per-ray outputs lie partly inside and partly outside the mirrored frame buffer");
+    if (inside) {
+      ca.n_mirror = h->n_mirror;
+      for (int m = 0; m < h->n_mirror; ++m) ca.mirror_delta[m] = h->mirror_delta[m];
+    }
   }
   const bool sharp = c.use_mask_sharp_weights && o.sharp_weights;
   ca.argmax_idx = sharp ? h->argmax : nullptr;
@@ -612,7 +631,7 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
                      getenv("NDS_TC_NO_SPLIT") == nullptr;
   int rc = run_level(h, st, 0, B, Sc, nullptr, h->z_coarse, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
                      c.use_sample_at_infinity, coarse, h->w_coarse, coarse_rgb || coarse != nullptr,
-                     split ? h->carry : nullptr);
+                     split ? h->carry : nullptr, nullptr, 0, /*apply_filter=*/false);   // models.py:1493-1516: no render_opts
   if (rc) return rc;
   SamplePdfArgs sa;
   memset(&sa, 0, sizeof sa);
@@ -827,14 +846,18 @@ extern "C" int ndsr_peer_close(int device, void* ptr) {
   if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
   return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
 }
-extern "C" int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_deltas) {
+extern "C" int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_deltas, const void* frame_base,
+                                       size_t frame_bytes) {
   if (!h) return NDSR_ERR_INVALID;
   if (n < 0 || n > NDSR_MAX_MIRRORS || (n > 0 && !byte_deltas)) return fail(h, NDSR_ERR_INVALID, "0 <= mirrors <= NDSR_MAX_MIRRORS");
+  if (n > 0 && (!frame_base || frame_bytes == 0)) return fail(h, NDSR_ERR_INVALID, "mirrors need the frame buffer's address range");
   for (int m = 0; m < n; ++m) {
     if (byte_deltas[m] % 4) return fail(h, NDSR_ERR_INVALID, "mirror offsets must keep float alignment");
     h->mirror_delta[m] = byte_deltas[m];
   }
   h->n_mirror = n;
+  h->mirror_base = n > 0 ? static_cast<const char*>(frame_base) : nullptr;
+  h->mirror_bytes = n > 0 ? frame_bytes : 0;
   return NDSR_OK;
 }
 

@@ -71,13 +71,54 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);   // jnp.linalg.norm(dirs)
     const float last = a.sample_at_infinity ? 1e10f : 1e-19f;
     float alpha_inf_last = 0.f;
+    const float fox = a.origins ? a.origins[ray * 3] : 0.f, foy = a.origins ? a.origins[ray * 3 + 1] : 0.f,
+                foz = a.origins ? a.origins[ray * 3 + 2] : 0.f;
+    // filter_sigma's keep factor (1 or 0) of sample s for the value v it thresholds (models.py:56-63)
+    auto keep = [&](int s, float v) -> float {
+      float m = 1.f;
+      if (a.filter_flags & 1) m = (v >= a.dust_threshold) ? 1.f : 0.f;
+      if (a.filter_flags & 2) {
+        float px, py, pz;
+        if (a.points) { px = a.points[(base + s) * 3]; py = a.points[(base + s) * 3 + 1]; pz = a.points[(base + s) * 3 + 2]; }
+        else { const float zs = a.z[base + s]; px = fox + zs * dx; py = foy + zs * dy; pz = foz + zs * dz; }
+        const bool in = px >= a.bbox[0] && px <= a.bbox[1] && py >= a.bbox[2] && py <= a.bbox[3] && pz >= a.bbox[4] && pz <= a.bbox[5];
+        m = in ? m : 0.f;
+      }
+      return m;
+    };
+    bool sg_done = false;
+    float best_w = -1.f; int best_i = 0;
+    if (a.filter_flags && a.weights_sg && !a.sigma_is_activated) {
+      // sharp weights under render_opts: the RAW sigma is filtered, then activated (models.py:1236-1237), and
+      // cal_weights always places the last sample at infinity (model_utils.py:162)
+      for (int s = lane; s < S; s += 32) {
+        const float raw = a.planes[P_SIGMA_RAW * ps + pidx(s)];
+        const float sg = softplus_f(keep(s, raw) * raw);
+        const float dist = ((s == S - 1) ? 1e10f : (a.z[base + s + 1] - a.z[base + s])) * dnorm;
+        s_alpha[s] = 1.f - expf(-sg * dist);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        float T = 1.f;
+        for (int s = 0; s < S; ++s) { const float al = s_alpha[s]; s_w[s] = al * T; T = T * (1.f - al + 1e-10f); }
+      }
+      __syncwarp();
+      for (int s = lane; s < S; s += 32) {
+        const float wsg = s_w[s];
+        a.weights_sg[base + s] = wsg;
+        if (wsg > best_w) { best_w = wsg; best_i = s; }
+      }
+      __syncwarp();
+      sg_done = true;
+    }
     for (int s = lane; s < S; s += 32) {
       const float raw = a.planes[P_SIGMA_RAW * ps + pidx(s)];
       const float sigma = a.sigma_is_activated ? raw : softplus_f(raw);
       const float zs = a.z[base + s];
       const float dist = ((s == S - 1) ? last : (a.z[base + s + 1] - zs)) * dnorm;
-      s_alpha[s] = 1.f - expf(-sigma * dist);
-      if (s == S - 1) alpha_inf_last = 1.f - expf(-sigma * (1e10f * dnorm));
+      const float sig_f = a.filter_flags ? keep(s, sigma) * sigma : sigma;      // models.py:1288
+      s_alpha[s] = 1.f - expf(-sig_f * dist);
+      if (s == S - 1) alpha_inf_last = 1.f - expf(-sig_f * (1e10f * dnorm));
       if (a.out.sigma) a.out.sigma[base + s] = sigma;
     }
     __syncwarp();
@@ -104,7 +145,6 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
     // per-ray reductions
     float r[3] = {0, 0, 0}, depth = 0, acc = 0, acc_m1 = 0, rn[3] = {0, 0, 0}, rr[3] = {0, 0, 0},
           rt[3] = {0, 0, 0}, rdx[3] = {0, 0, 0}, rh[2] = {0, 0}, rm = 0;
-    float best_w = -1.f; int best_i = 0;
     const float vx = a.viewdirs[ray * 3], vy = a.viewdirs[ray * 3 + 1], vz = a.viewdirs[ray * 3 + 2];
     const float ox = a.origins ? a.origins[ray * 3] : 0.f, oy = a.origins ? a.origins[ray * 3 + 1] : 0.f,
                 oz = a.origins ? a.origins[ray * 3 + 2] : 0.f;
@@ -156,9 +196,11 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       if (a.out.accum_prod) a.out.accum_prod[n] = s_T[s];
       if (a.out.z_vals) a.out.z_vals[n] = zs;
       // cal_weights() weights (always sample_at_infinity, model_utils.py:162) for sharpen_weights
-      const float wsg = (s == S - 1) ? alpha_inf_last * s_T[s] : w;
-      if (a.weights_sg) a.weights_sg[n] = wsg;
-      if (wsg > best_w) { best_w = wsg; best_i = s; }
+      if (!sg_done) {
+        const float wsg = (s == S - 1) ? alpha_inf_last * s_T[s] : w;
+        if (a.weights_sg) a.weights_sg[n] = wsg;
+        if (wsg > best_w) { best_w = wsg; best_i = s; }
+      }
     }
     // argmax (first occurrence) across lanes
 #pragma unroll

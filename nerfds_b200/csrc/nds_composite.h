@@ -25,6 +25,9 @@ struct CompositeArgs {
   // B n_carried + r (S - n_carried) + (e - n_carried).  null: planes are in sample order.
   const int32_t* src_elem;
   int n_carried;
+  // filter_sigma (models.py:38-66): bit 0 dust threshold, bit 1 bounding box on the observation-space points
+  int filter_flags;
+  float dust_threshold, bbox[6];
   // multi-GPU frame reassembly without a collective: every per-ray result is also stored at the same address plus
   // mirror_delta[m] bytes -- the peer-mapped copies of the caller's frame buffer on the other GPUs (NVLink stores)
   int n_mirror;

@@ -112,9 +112,11 @@ struct alignas(16) Burst {
   uint32_t idesc;        // tcgen05 instruction descriptor (M = 128, N = rows)
   uint32_t b0, b1;       // B_hi / B_lo image: descriptor low words
   uint32_t ctl;          // [0,13) BurstFlags | [13,15) pat | [15,18) steps | [18] tile slot | [19,21) ring unit |
-                         // [21,24) 1 + ring unit the NEXT burst acquires (0: none) | [24] that next burst is burst 0
+                         // [21,24) 1 + ring unit the NEXT burst acquires (0: none) | [24] that next burst is burst 0 |
+                         // [25] PAIR burst: two groups of four MMAs, (a_hi, b0) then (a_lo, b1) -- see make_bursts
   uint32_t bars;         // Ctrl barrier indices (0xff: none): [0,8) commit on release | [8,16) commit when the
-                         // accumulators are complete | [16,24) weight barrier of the next burst (probe)
+                         // accumulators are complete | [16,24) weight barrier of the next burst (probe) |
+                         // [24,32) commit on release of a second ring unit
 };
 static_assert(sizeof(Burst) == 32, "Burst is read as two uint4");
 // host-side description of a burst (encode_burst() makes the device form)
@@ -122,6 +124,10 @@ struct BurstH {
   uint32_t a_hi = 0, a_lo = 0, src = 0;
   uint16_t d_col = 0, rows = 0, flags = 0, rows128 = 0;
   uint8_t steps = 4, pat = 0, unit = 0, tslot = 0;
+  // PAIR bursts (cross-first ops): group 1 = (a_hi, image b_sel[0] of K-chunk kc), group 2 = (a_lo, image b_sel[1]
+  // of K-chunk kc2 or kc); b_sel: 0 = B_hi image, 1 = B_lo image
+  uint8_t pair = 0, b_sel[2] = {0, 1}, unit2 = 0xff, release2 = 0;
+  int16_t kc = 0, kc2 = -1;           // K-chunks of the op whose weight images the burst reads
 };
 
 enum StepKind : uint8_t { STEP_EPI = 0, STEP_HEAD = 1, STEP_VIEW = 2, STEP_PREP = 3, STEP_OUT = 4 };
@@ -129,7 +135,7 @@ struct Step { uint8_t kind, tslot, op, arg; };
 
 constexpr int MAX_OPS = 80;
 constexpr int MAX_STEPS = 128;
-constexpr int MAX_BURST = 256;
+constexpr int MAX_BURST = 320;
 struct TcProgram {       // passed by value as a __grid_constant__ kernel parameter (constant bank)
   int n_ops, n_burst, n_steps, full;     // full: rgb branch present (else sigma-only)
   int carried;           // the program has no N phase: the narrow networks' results are read from the carry planes
@@ -243,6 +249,25 @@ __device__ __forceinline__ uint32_t issue_burst(uint32_t pat, bool two, uint32_t
   return ok;
 }
 
+// PAIR burst: D (+)= A1 B1 ; D += A2 B2 (four K-steps each).  Cross-first ops issue their small terms
+// (A_lo B_hi, A_hi B_lo) of every K-chunk before any main term (A_hi B_hi): the tensor core's fp32 accumulator
+// TRUNCATES at every accumulating MMA, one ulp of the running sum each, so the small terms are summed while the
+// accumulator is still small and the large running sum takes 4 truncations per K-chunk instead of 12.
+__device__ __forceinline__ uint32_t issue_pair(uint32_t pat, uint32_t steps, uint32_t d, uint32_t a1, uint32_t a2, uint32_t b1,
+                                               uint32_t b2, uint32_t idesc, uint32_t acc, uint32_t pbar, uint32_t ppar,
+                                               uint32_t do_probe) {
+  uint32_t ok;
+  if (pat == PAT_SS) {
+    ok = mma4_ss(d, a1, b1, idesc, acc, steps, pbar, ppar, do_probe);
+    mma4_ss(d, a2, b2, idesc, 1u, steps, 0u, 0u, 0u);
+    return ok;
+  }
+  const uint32_t s1 = pat == PAT_16 ? 16u : 8u, s2 = pat == PAT_8 ? 16u : 32u, s3 = pat == PAT_32 ? 40u : (pat == PAT_16 ? 48u : 24u);
+  ok = mma4_ts(d, a1, a1 + s1, a1 + s2, a1 + s3, b1, idesc, acc, 4u, pbar, ppar, do_probe);
+  mma4_ts(d, a2, a2 + s1, a2 + s2, a2 + s3, b2, idesc, 1u, 4u, 0u, 0u, 0u);
+  return ok;
+}
+
 // Ctrl barrier index -> shared-window address (all barriers are the leading uint64 array of Ctrl)
 __device__ __forceinline__ uint32_t bar_addr(uint32_t ctl_addr, uint32_t idx) { return ctl_addr + 8u * idx; }
 
@@ -285,11 +310,13 @@ __device__ __forceinline__ void issue_program(const TcProgram& P, Ctrl* ctl, uin
     const uint32_t acc = (c & B_FIRST) ? 0u : 1u, pat = (c >> 13) & 3u;
     const bool two = (c & B_TWO) != 0;
     uint32_t ok;
-    if (two && pat == PAT_32) ok = burst12_ts32(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
+    if (c & (1u << 25)) ok = issue_pair(pat, (c >> 15) & 7u, q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
+    else if (two && pat == PAT_32) ok = burst12_ts32(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
     else if (two && pat == PAT_16) ok = burst12_ts16(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
     else ok = issue_burst(pat, two, (c >> 15) & 7u, q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
-    const uint32_t eb = q1.w & 0xffu, db = (q1.w >> 8) & 0xffu;
+    const uint32_t eb = q1.w & 0xffu, db = (q1.w >> 8) & 0xffu, eb2 = q1.w >> 24;
     if (eb != 0xffu) umma_commit_a(bar_addr(ctl_addr, eb));
+    if (eb2 != 0xffu) umma_commit_a(bar_addr(ctl_addr, eb2));
     if (db != 0xffu) umma_commit_a(bar_addr(ctl_addr, db));
     if (do_probe) {
       if (!ok) { mbar_wait_a(pbar, ppar); tc_fence_after_sync(); }
@@ -953,6 +980,8 @@ struct OpBuild {
   int terms = 3, relu = 0, epi_kind = EPI_INPLACE, glue = GLUE_NONE;
   int prev_produces = 0;              // the op before this one is a hidden layer (its epilogue signals part)
   int interleave = 0;                 // order the bursts K-range-major so that chunk 1's epilogue stays hidden
+  int cross_first = 0;                // 3-term op whose weight images are all resident (N phase): issue the small
+                                      // terms of every K-chunk before any main term (see issue_pair)
   uint16_t first_flags = 0;           // B_WAIT_* of the first burst
   uint16_t first_part_waits = 0;      // bit c: the first burst waits for part c of the previous op
   int signal_glue = 0;
@@ -1124,6 +1153,59 @@ static TcOp make_tcop(const OpBuild& ob, const OpWeights& ow) {
 static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
   const int nc_rows = ob.N / ob.n_nc;
   const int n_kc = (int)ob.kcs.size();
+  auto steps_of = [&](const KChunkMap& km) {
+    int last = -1;
+    for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
+    return (uint8_t)(km.pat == PAT_SS ? std::max(1, (last + 16) / 16) : 4);
+  };
+  std::vector<BurstH> out;
+  int waited = 0;    // bit 0 / 1: part c, bit 2: glue (of the per-sample stage feeding a K-chunk)
+  auto wait_flags = [&](int need, bool first) {
+    uint16_t fl = 0;
+    if (first) { fl |= ob.first_flags; need |= ob.first_part_waits; if (ob.first_flags & B_WAIT_GLUE) waited |= 4; }
+    need &= ~waited;
+    if (need & 1) fl |= B_WAIT_P0;
+    if (need & 2) fl |= B_WAIT_P1;
+    if (need & 4) fl |= B_WAIT_GLUE;
+    waited |= need;
+    return fl;
+  };
+  bool cross_first = ob.cross_first && ob.n_nc == 1 && ob.terms == 3;
+  for (const KChunkMap& km : ob.kcs) if (km.terms && km.terms != 3) cross_first = false;
+  if (cross_first) {
+    // X(kc) for every K-chunk: A_lo B_hi + A_hi B_lo; then the main terms A_hi B_hi, two K-chunks per burst where
+    // the operand patterns agree
+    struct Item { int kc, kc2; bool cross; };
+    std::vector<Item> items;
+    for (int kc = 0; kc < n_kc; ++kc) items.push_back({kc, -1, true});
+    for (int kc = 0; kc < n_kc;) {
+      const bool pairable = kc + 1 < n_kc && ob.kcs[kc].pat != PAT_SS && ob.kcs[kc + 1].pat == ob.kcs[kc].pat;
+      items.push_back({kc, pairable ? kc + 1 : -1, false});
+      kc += pairable ? 2 : 1;
+    }
+    for (size_t i = 0; i < items.size(); ++i) {
+      const Item& it = items[i];
+      const KChunkMap& km = ob.kcs[it.kc];
+      BurstH e;
+      e.pat = km.pat; e.rows = (uint16_t)nc_rows; e.steps = steps_of(km); e.d_col = (uint16_t)ob.d_col[0];
+      e.tslot = (uint8_t)ob.tslot; e.kc = (int16_t)it.kc; e.kc2 = (int16_t)it.kc2;
+      e.src = ow.src[(size_t)it.kc]; e.rows128 = (uint16_t)(nc_rows * 2);
+      int need = km.wait | (km.wait_glue ? 4 : 0);
+      uint16_t fl = 0;
+      if (it.cross) { e.pair = 1; e.a_hi = km.a_lo; e.a_lo = km.a_hi; e.b_sel[0] = 0; e.b_sel[1] = 1; }
+      else if (it.kc2 >= 0) {
+        const KChunkMap& k2 = ob.kcs[it.kc2];
+        e.pair = 1; e.a_hi = km.a_hi; e.a_lo = k2.a_hi; e.b_sel[0] = 0; e.b_sel[1] = 0;
+        need |= k2.wait | (k2.wait_glue ? 4 : 0);
+      } else { e.a_hi = km.a_hi; e.a_lo = km.a_lo; }     // plain 1-term burst: A_hi B_hi
+      if (i == 0) fl |= B_FIRST;
+      if (i + 1 == items.size()) { fl |= B_LAST; if (ob.prev_produces) fl |= B_PART_NEXT; }
+      fl |= wait_flags(need, i == 0);
+      e.flags = fl;
+      out.push_back(e);
+    }
+    return out;
+  }
   std::vector<std::pair<int, int>> order;
   if (ob.n_nc == 2 && ob.interleave) {
     for (int late = 0; late < 2; ++late)
@@ -1133,8 +1215,6 @@ static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
   } else {
     for (int nc = 0; nc < ob.n_nc; ++nc) for (int kc = 0; kc < n_kc; ++kc) order.push_back({nc, kc});
   }
-  std::vector<BurstH> out;
-  int waited = 0;    // bit 0 / 1: part c, bit 2: glue (of the per-sample stage feeding a K-chunk)
   int seen[2] = {0, 0};
   int left[2] = {n_kc, n_kc};
   for (size_t i = 0; i < order.size(); ++i) {
@@ -1143,11 +1223,10 @@ static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
     BurstH e;
     e.a_hi = km.a_hi; e.a_lo = km.a_lo; e.pat = km.pat;
     e.rows = (uint16_t)nc_rows;
-    int last = -1;
-    for (int c = 0; c < 64; ++c) if (km.rows[c] >= 0) last = c;
-    e.steps = (uint8_t)(km.pat == PAT_SS ? std::max(1, (last + 16) / 16) : 4);
+    e.steps = steps_of(km);
     e.d_col = (uint16_t)ob.d_col[nc];
     e.tslot = (uint8_t)ob.tslot;
+    e.kc = (int16_t)(nc * n_kc + kc);                    // one weight image pair per (N-chunk, K-chunk)
     e.src = ow.src[(size_t)nc * n_kc + kc];
     const int kterms = km.terms ? km.terms : ob.terms;
     e.rows128 = (uint16_t)(nc_rows * (kterms == 3 ? 2 : 1));
@@ -1156,18 +1235,37 @@ static std::vector<BurstH> make_bursts(const OpBuild& ob, const OpWeights& ow) {
     if (!seen[nc]) { fl |= B_FIRST; seen[nc] = 1; }
     if (--left[nc] == 0) fl |= B_LAST;
     if (nc == 1) fl |= B_NC1;
-    int need = km.wait | (km.wait_glue ? 4 : 0);
-    if (i == 0) { fl |= ob.first_flags; need |= ob.first_part_waits; if (ob.first_flags & B_WAIT_GLUE) waited |= 4; }
-    need &= ~waited;
-    if (need & 1) fl |= B_WAIT_P0;
-    if (need & 2) fl |= B_WAIT_P1;
-    if (need & 4) fl |= B_WAIT_GLUE;
-    waited |= need;
+    fl |= wait_flags(km.wait | (km.wait_glue ? 4 : 0), i == 0);
     if (i + 1 == order.size() && ob.prev_produces) fl |= B_PART_NEXT;
     e.flags = fl;
     out.push_back(e);
   }
   return out;
+}
+
+// Ring units of the weight images a list of bursts reads: one unit per distinct K-chunk id, taken round-robin
+// from `cursor`.  `acquire` / `release`: flag the first / last burst that touches a unit (the N phase lets tile
+// slot 0 acquire and tile slot 1 release the units both slots read).
+static void assign_units(std::vector<BurstH>& b, int& cursor, int* unit_of /*[64], -1 = unassigned*/, bool acquire, bool release) {
+  for (auto& e : b) {
+    for (int16_t kc : {e.kc, e.kc2}) {
+      if (kc < 0) continue;
+      if (unit_of[kc] < 0) { unit_of[kc] = cursor; cursor = (cursor + 1) % NUNIT; }
+    }
+    e.unit = (uint8_t)unit_of[e.kc];
+    e.unit2 = e.kc2 >= 0 ? (uint8_t)unit_of[e.kc2] : (uint8_t)0xff;
+  }
+  if (acquire) {
+    bool seen[64] = {false};
+    for (auto& e : b) if (!seen[e.kc]) { seen[e.kc] = true; e.flags |= B_ACQUIRE; }      // X bursts come first: kc2 never opens a unit
+  }
+  if (release) {
+    bool seen[64] = {false};
+    for (auto it = b.rbegin(); it != b.rend(); ++it) {
+      if (it->kc2 >= 0 && !seen[it->kc2]) { seen[it->kc2] = true; it->release2 = 1; }
+      if (!seen[it->kc]) { seen[it->kc] = true; it->flags |= B_RELEASE; }
+    }
+  }
 }
 
 // shared-window address of the 1024-aligned dynamic shared memory of the engine's kernels (none of them has
@@ -1211,15 +1309,21 @@ static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, uint32_t s
     b.idesc = make_idesc_f16(e.rows);
     b.b0 = desc_lo(OFF_RING + (uint32_t)e.unit * UNIT_BYTES);
     b.b1 = b.b0 + (uint32_t)e.rows * 8u;
+    if (e.pair) {        // group 1 reads image b_sel[0] of `unit`, group 2 image b_sel[1] of `unit2` (or `unit`)
+      const uint32_t u2 = desc_lo(OFF_RING + (uint32_t)(e.unit2 != 0xff ? e.unit2 : e.unit) * UNIT_BYTES);
+      b.b0 += e.b_sel[0] ? (uint32_t)e.rows * 8u : 0u;
+      b.b1 = u2 + (e.b_sel[1] ? (uint32_t)e.rows * 8u : 0u);
+    }
     uint32_t nu = 0, wrap = 0;
     if (i + 1 < n) { if (hb[i + 1].flags & B_ACQUIRE) nu = 1u + hb[i + 1].unit; }
     else if (cyclic && (hb[0].flags & B_ACQUIRE)) { nu = 1u + hb[0].unit; wrap = 1; }
     b.ctl = (uint32_t)(e.flags & 0x1fffu) | ((uint32_t)e.pat << 13) | ((uint32_t)e.steps << 15) | ((uint32_t)e.tslot << 18) |
-            ((uint32_t)e.unit << 19) | (nu << 21) | (wrap << 24);
+            ((uint32_t)e.unit << 19) | (nu << 21) | (wrap << 24) | ((uint32_t)(e.pair ? 1u : 0u) << 25);
     const uint32_t eb = (e.flags & B_RELEASE) ? NDS_BAR_IDX(empty) + e.unit : 0xffu;
     const uint32_t db = (e.flags & B_LAST) ? NDS_BAR_IDX(d_full) + 2u * e.tslot + ((e.flags & B_NC1) ? 1u : 0u) : 0xffu;
     const uint32_t pb = nu ? NDS_BAR_IDX(full) + (nu - 1u) : 0xffu;
-    b.bars = eb | (db << 8) | (pb << 16);
+    const uint32_t eb2 = e.release2 ? NDS_BAR_IDX(empty) + e.unit2 : 0xffu;
+    b.bars = eb | (db << 8) | (pb << 16) | (eb2 << 24);
     out[i] = b;
     src[i] = (e.src & 0xfffffu) | ((uint32_t)e.rows128 << 20) | ((uint32_t)e.unit << 29) | ((e.flags & B_ACQUIRE) ? (1u << 31) : 0u);
   }
@@ -1230,7 +1334,8 @@ static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, uint32_t s
 //   wide   (T phase): regions of 256 columns at {0, 256}, two N-chunks; layer l accumulates into region (l even ? 0 : 1)
 // Returns the last layer's layout.
 static ActLayout build_mlp_ops(const HostMlp& m, int terms, bool wide, int tslot, const KChunkMap& in0,
-                               const KChunkMap& in_skip, uint16_t first_flags, std::vector<OpBuild>& ops) {
+                               const KChunkMap& in_skip, uint16_t first_flags, std::vector<OpBuild>& ops,
+                               bool cross_first = false) {
   ActLayout prev;
   for (int l = 0; l < m.depth; ++l) {
     OpBuild ob;
@@ -1246,6 +1351,7 @@ static ActLayout build_mlp_ops(const HostMlp& m, int terms, bool wide, int tslot
       region = (l % 2 == 0) ? 1 : 0;
       ob.n_nc = 1;
       ob.d_col[0] = ob.d_col[1] = 256 * tslot + 128 * region;
+      ob.cross_first = cross_first ? 1 : 0;
     }
     ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE; ob.epi_kind = EPI_INPLACE;
     ob.prev_produces = l > 0;
@@ -1267,7 +1373,7 @@ static ActLayout build_mlp_ops(const HostMlp& m, int terms, bool wide, int tslot
 
 // head over the layer output `in`; accumulators at the start of the other region
 static void build_head_op(const std::vector<const HostDense*>& heads, const ActLayout& in, int terms, int glue,
-                          bool wide, int tslot, int signal_glue, std::vector<OpBuild>& ops) {
+                          bool wide, int tslot, int signal_glue, std::vector<OpBuild>& ops, bool cross_first = false) {
   OpBuild ob;
   int n = 0;
   for (auto* h : heads) n += h->N;
@@ -1278,6 +1384,7 @@ static void build_head_op(const std::vector<const HostDense*>& heads, const ActL
   ob.d_col[0] = ob.d_col[1] = wide ? (1 - in.region) * 256 : 256 * tslot + 128 * (1 - in.region);
   ob.terms = terms; ob.relu = 0; ob.epi_kind = EPI_HEAD; ob.glue = glue; ob.prev_produces = 1;
   ob.signal_glue = signal_glue;
+  ob.cross_first = (!wide && cross_first) ? 1 : 0;
   ob.W_own.assign((size_t)in.N * n, 0.f);
   int c0 = 0;
   for (auto* h : heads) {
@@ -1346,12 +1453,12 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
   for (int i = 0; i < (carried ? 0 : LB.n_narrow); ++i) {
     std::vector<BurstH> b0 = make_bursts(LB.ops[0][i], LB.weights[i]);
     std::vector<BurstH> b1 = make_bursts(LB.ops[1][i], LB.weights[i]);
-    if ((int)b0.size() > NUNIT - 1) { err = "tensor-core engine: narrow layer with too many K-chunks for the weight ring"; return false; }
-    for (size_t j = 0; j < b0.size(); ++j) {
-      b0[j].unit = b1[j].unit = (uint8_t)cursor;
-      cursor = (cursor + 1) % NUNIT;
-      b0[j].flags |= B_ACQUIRE;
-      b1[j].flags |= B_RELEASE;
+    if ((int)LB.ops[0][i].kcs.size() > NUNIT - 1) { err = "tensor-core engine: narrow layer with too many K-chunks for the weight ring"; return false; }
+    {
+      int unit_of[64];
+      std::fill(unit_of, unit_of + 64, -1);
+      assign_units(b0, cursor, unit_of, true, false);
+      assign_units(b1, cursor, unit_of, false, true);
     }
     bursts.insert(bursts.end(), b0.begin(), b0.end());
     bursts.insert(bursts.end(), b1.begin(), b1.end());
@@ -1366,10 +1473,10 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
       if (carried && i == LB.trunk_first)       // inputs come from the PREP steps; the other slot must have left the T phase
         b[0].flags = (uint16_t)((b[0].flags & ~B_WAIT_GLUE) | B_WAIT_PREP | B_WAIT_DONE_OTHER);
       if (carried && i == LB.trunk_first + 1) b[0].flags &= (uint16_t)~B_PEEK_GLUE_OTHER;
-      for (auto& e : b) {
-        e.unit = (uint8_t)cursor;
-        cursor = (cursor + 1) % NUNIT;
-        e.flags |= B_ACQUIRE | B_RELEASE;
+      {
+        int unit_of[64];
+        std::fill(unit_of, unit_of + 64, -1);
+        assign_units(b, cursor, unit_of, true, true);
       }
       bursts.insert(bursts.end(), b.begin(), b.end());
       steps.push_back(step_of(s, i));
@@ -1409,7 +1516,9 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
           if (held[e.unit] || released[e.unit] > gi - 2) { err = "tensor-core engine: weight ring too small for this layer program"; return false; }
           held[e.unit] = 1;
         } else if (!held[e.unit]) { err = "tensor-core engine: internal ring schedule error"; return false; }
+        if (e.unit2 != 0xff && !held[e.unit2]) { err = "tensor-core engine: internal ring schedule error (second unit)"; return false; }
         if (e.flags & B_RELEASE) { held[e.unit] = 0; released[e.unit] = gi; }
+        if (e.release2) { held[e.unit2] = 0; released[e.unit2] = gi; }
       }
   }
   prog.n_burst = (int)bursts.size();
@@ -1440,6 +1549,16 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
   const int t_rgb = prec == NDSR_PREC_SPLIT3 ? 3 : 1;     // mixed: 1-term rgb branch (median rgb error ~2e-4)
   if (h->max_in > 64) { h->err = "tensor-core engine: MLP inputs wider than 64 features"; return NDSR_ERR_UNSUPPORTED; }
   if (h->dim_view + (c.predict_norm ? h->dim_norm : 0) > 64) { h->err = "tensor-core engine: rgb side inputs wider than 64"; return NDSR_ERR_UNSUPPORTED; }
+  // Which narrow networks issue their small split terms first (see issue_pair): the tensor core's accumulator
+  // truncates, and the error that matters for the 1e-3 RGB bound is the one the SE(3) field makes -- a 1e-6 error
+  // of the warped point is multiplied by 2^7 pi in the trunk's positional encoding (tools/tc_emulation.py:
+  // truncation in the warp field alone gives 9e-4 of the 8e-4..9e-4 total on the worst rays of 16 384; in the mask
+  // / hyper-sheet / trunk networks 1.5e-4 / 3e-5 / 1.3e-4).  Each cross-first layer costs one more burst per tile.
+  int xf_warp = 1, xf_mask = 0, xf_hyper = 0;
+  if (const char* e = getenv("NDS_TC_CROSS_FIRST")) {       // experiments: none | warp | all
+    const std::string v(e);
+    xf_warp = v != "none"; xf_mask = xf_hyper = v == "all";
+  }
   // ---- shared feature block of the narrow networks
   FLayout& F = LB.F;
   {
@@ -1468,19 +1587,19 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
     if (c.use_predicted_mask) {
       const KChunkMap k0 = kc_features(F, in_off, 0, 0, c.mask_min_deg, c.mask_max_deg, 0, F.col_membed, c.mask_embed_dims, false);
       const KChunkMap ks = kc_features(F, in_off, HM.mask.width, 0, c.mask_min_deg, c.mask_max_deg, 0, F.col_membed, c.mask_embed_dims, false);
-      build_head_op({&HM.mask.logit}, build_mlp_ops(HM.mask, t_sigma, false, s, k0, ks, first_flags(), ops), t_sigma, GLUE_MASK, false, s, 1, ops);
+      build_head_op({&HM.mask.logit}, build_mlp_ops(HM.mask, t_sigma, false, s, k0, ks, first_flags(), ops, xf_mask), t_sigma, GLUE_MASK, false, s, 1, ops, xf_mask);
     }
     if (c.use_hyper_sheet) {
       const bool wm = c.use_mask_in_hyper != 0;
       const KChunkMap k0 = kc_features(F, in_off, 0, 2, c.hyper_sheet_min_deg, c.hyper_sheet_max_deg, 0, F.col_wembed, c.warp_embed_dims, wm);
       const KChunkMap ks = kc_features(F, in_off, HM.hyper.width, 2, c.hyper_sheet_min_deg, c.hyper_sheet_max_deg, 0, F.col_wembed, c.warp_embed_dims, wm);
-      build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, false, s, k0, ks, first_flags(), ops), t_sigma, GLUE_HYPER, false, s, 1, ops);
+      build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, false, s, k0, ks, first_flags(), ops, xf_hyper), t_sigma, GLUE_HYPER, false, s, 1, ops, xf_hyper);
     }
     {
       const bool wm = c.use_mask_in_warp != 0;
       const KChunkMap k0 = kc_features(F, in_off, 0, 1, c.warp_min_deg, c.warp_max_deg, c.warp_use_posenc_identity, F.col_wembed, c.warp_embed_dims, wm);
       const KChunkMap ks = kc_features(F, in_off, HM.warp.width, 1, c.warp_min_deg, c.warp_max_deg, c.warp_use_posenc_identity, F.col_wembed, c.warp_embed_dims, wm);
-      build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, false, s, k0, ks, first_flags(), ops), t_sigma, GLUE_WARP, false, s, 1, ops);
+      build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, false, s, k0, ks, first_flags(), ops, xf_warp), t_sigma, GLUE_WARP, false, s, 1, ops, xf_warp);
     }
     LB.n_narrow = (int)ops.size();
     // ---- template NeRF
@@ -1729,7 +1848,11 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   prog.n_ops = 1;
   prog.ops[0] = make_tcop(ob, ow);
   int cursor = 0;
-  for (auto& e : bursts) { e.unit = (uint8_t)cursor; cursor = (cursor + 1) % NUNIT; e.flags |= B_ACQUIRE | B_RELEASE; }
+  {
+    int unit_of[64];
+    std::fill(unit_of, unit_of + 64, -1);
+    assign_units(bursts, cursor, unit_of, true, true);
+  }
   prog.n_burst = (int)bursts.size();
   {
     std::string perr;

@@ -51,6 +51,8 @@ struct ndsr_handle {
   int64_t max_chunk = 65536;
   int n_mirror = 0;                        // peer copies of the caller's frame buffer (ndsr_set_output_mirrors)
   int64_t mirror_delta[NDSR_MAX_MIRRORS] = {0};
+  const char* mirror_base = nullptr;       // this rank's own frame buffer: only stores inside it are mirrored
+  size_t mirror_bytes = 0;
   float* carry = nullptr;      // C_COUNT planes of the coarse samples (tensor-core engine: split fine pass)
   int32_t* src_elem = nullptr; // [rays, S_c + S_f] from sample_pdf: element of concat(coarse, new) at each sorted position
   float* z_new = nullptr;      // [rays, S_f] the new depths in draw order

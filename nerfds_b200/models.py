@@ -99,8 +99,6 @@ class NerfModel:
       raise NotImplementedError('metadata_encoded=True')
     if return_warp_jacobian or return_hyper_jacobian or return_hyper_c_jacobian:
       raise NotImplementedError('jacobian outputs (elastic loss) are outside the built path')
-    if render_opts is not None:
-      raise NotImplementedError('render_opts (filter_sigma) is None in train.py / render.py')
     if screw_input_mode not in (None, 'none', 'None'):
       raise NotImplementedError       # models.py:554-561
     if norm_override is not None:
@@ -120,7 +118,8 @@ class NerfModel:
     t_rand, u = self._draws(B, rngs, t_rand, u)
     extra = self.renderer.make_extra(extra_params, mask_ratio=mask_ratio, sharp_weights_std=sharp_weights_std,
                                      use_predicted_norm=use_predicted_norm, use_sigma_gradient=use_sigma_gradient,
-                                     near=near, far=far, use_sample_at_infinity=use_sample_at_infinity)
+                                     near=near, far=far, use_sample_at_infinity=use_sample_at_infinity,
+                                     render_opts=render_opts)
     if keys is None:
       fine_keys = self.renderer.level_keys(return_points=return_points, return_weights=return_weights)
     else:

@@ -16,9 +16,13 @@ is used for the 64-byte handle exchange and the barrier only.
     full = frames.frame()                                   # {key: [n_rays, ...]} on this GPU
     frames.close()                                          # unregisters the mirrors, unmaps, frees
 
-While a PeerFrames is active the renderer's fine-level per-ray stores are mirrored at fixed address offsets, so
-every fine-level call must write into the frame buffer (`fine_ptrs=frames.shard_ptrs(...)`); `close()` (or
-`ndsr_set_output_mirrors(h, 0, NULL)`) switches mirroring off again before ordinary calls.
+The library mirrors a fine-level call only when ALL its per-ray output pointers lie inside the registered frame
+buffer (`fine_ptrs=frames.shard_ptrs(...)`); ordinary calls (fresh tensors, render_samples, render_rays_host) made
+while a PeerFrames is active are left alone, and a call with pointers on both sides is refused.
+
+Lifetime: `close()` is collective.  It unregisters the mirrors, waits until no rank still stores into any buffer
+(stream sync + barrier), unmaps the peers' buffers, and only after a SECOND barrier frees its own exported buffer
+(freeing exported memory that an importer still maps is undefined behaviour).
 """
 from __future__ import annotations
 
@@ -81,8 +85,8 @@ class PeerFrames:
   def activate(self):
     """Make this buffer set the mirror target of the renderer's next calls (several PeerFrames can alternate,
     e.g. to let a consumer read frame f while frame f + 1 is being written)."""
-    self.R._check(self.lib.ndsr_set_output_mirrors(self.R._h, len(self.mapped), self._deltas), 'ndsr_set_output_mirrors')
-    self.R._mirrors_active = True        # Renderer.render_rays refuses fine-level calls without fine_ptrs from now on
+    self.R._check(self.lib.ndsr_set_output_mirrors(self.R._h, len(self.mapped), self._deltas, C.c_void_p(self.base),
+                                                   self.bytes), 'ndsr_set_output_mirrors')
 
   @staticmethod
   def _check(rc, what):
@@ -110,9 +114,11 @@ class PeerFrames:
       return
     self.closed = True
     idx = self.dev.index or 0
-    self.R._check(self.lib.ndsr_set_output_mirrors(self.R._h, 0, None), 'ndsr_set_output_mirrors')
-    self.R._mirrors_active = False
+    import torch.distributed as dist
+    self.R._check(self.lib.ndsr_set_output_mirrors(self.R._h, 0, None, None, 0), 'ndsr_set_output_mirrors')
     self.wait()                                          # nobody still writes into a buffer about to go away
     for p in self.mapped.values():
       self.lib.ndsr_peer_close(idx, C.c_void_p(p))
+    if self.world > 1:
+      dist.barrier(group=self.group)                     # every importer has unmapped before any exporter frees
     self.lib.ndsr_peer_free(idx, C.c_void_p(self.base))

@@ -70,7 +70,7 @@ class Renderer:
     if rc != 0:
       raise NdsrError(f'ndsr_create failed ({rc}): {self.lib.ndsr_last_error(None).decode()}')
     self._h = h
-    self._params_id = None
+    self._params_ref = None        # strong reference to the params object whose values are on the device
     self.H = cfg.hyper_num_dims if (cfg.has_hyper_sheet and cfg.use_hyper_for_sigma) else 0
 
   # ------------------------------------------------------------------ misc
@@ -129,16 +129,19 @@ class Renderer:
       arr[i].rows, arr[i].cols = v2.shape
     with torch.cuda.device(self.device):
       self._check(self.lib.ndsr_load_params(self._h, arr, len(flat)), 'ndsr_load_params')
-    self._params_id = id(params)
+    self._params_ref = params
 
   def ensure_params(self, params: Dict) -> None:
-    if self._params_id != id(params):
+    """Upload `params` unless this very object is the one already on the device.  Identity, not id(): the renderer
+    keeps the object alive, so a new dict can never be mistaken for it.  Arrays mutated IN PLACE inside the same
+    dict are not detected -- call load_params() after such an update."""
+    if self._params_ref is not params:
       self.load_params(params)
 
   # --------------------------------------------------------------- helpers
   def make_extra(self, extra_params: Optional[Dict] = None, *, mask_ratio=1.0, sharp_weights_std=1.0,
                  use_predicted_norm=False, use_sigma_gradient=False, near=None, far=None,
-                 use_sample_at_infinity=None) -> _lib.ndsr_extra_params:
+                 use_sample_at_infinity=None, render_opts: Optional[Dict] = None) -> _lib.ndsr_extra_params:
     ep = _lib.ndsr_extra_params()
     x = extra_params or {}
 
@@ -163,6 +166,18 @@ class Renderer:
     ep.use_predicted_norm = int(bool(use_predicted_norm))
     ep.use_sigma_gradient = int(bool(use_sigma_gradient))
     ep.sample_at_infinity_override = -1 if use_sample_at_infinity is None else int(bool(use_sample_at_infinity))
+    ep.filter_flags = 0
+    if render_opts is not None:            # filter_sigma (models.py:52-63): keys other than these two are ignored
+      if 'dust_threshold' in render_opts:
+        ep.filter_flags |= 1
+        ep.dust_threshold = float(render_opts.get('dust_threshold', 0.0))
+      if 'bounding_box' in render_opts:
+        box = [float(v) for v in render_opts['bounding_box']]
+        if len(box) != 6:
+          raise ValueError('bounding_box = (xmin, xmax, ymin, ymax, zmin, zmax)')
+        ep.filter_flags |= 2
+        for i, v in enumerate(box):
+          ep.bounding_box[i] = v
     return ep
 
   def alloc_outputs(self, B: int, S: int, keys: Iterable[str]):
@@ -223,9 +238,6 @@ class Renderer:
       raise ValueError('u must be [B, num_fine_samples]')
     Sc, Sf = c.num_coarse_samples, c.num_coarse_samples + c.num_fine_samples
     ct, co = self.alloc_outputs(B, Sc, coarse_keys)
-    if fine_ptrs is None and fine_keys and getattr(self, '_mirrors_active', False):
-      raise NdsrError('a peer.PeerFrames is active on this renderer: fine-level results must go into its frame '
-                      'buffer (fine_ptrs=frames.shard_ptrs(...)), or close() it first')
     if fine_ptrs is None:
       ft, fo = self.alloc_outputs(B, Sf, fine_keys)
     else:

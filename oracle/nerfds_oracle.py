@@ -298,6 +298,23 @@ def se3_apply(R, p, x, rotation_only=False, inverse=False):
   return (R @ x[..., None])[..., 0] + p
 
 
+def filter_sigma(points, sigma, render_opts):
+  """models.filter_sigma (hypernerf/models.py:38-66): dust threshold and
+  bounding box as 0/1 factors on sigma; keys other than these are ignored."""
+  if render_opts is None:
+    return sigma
+  if 'dust_threshold' in render_opts:
+    dust_thres = render_opts.get('dust_threshold', 0.0)
+    sigma = (sigma >= dust_thres).to(sigma.dtype) * sigma
+  if 'bounding_box' in render_opts:
+    xmin, xmax, ymin, ymax, zmin, zmax = render_opts['bounding_box']
+    render_mask = ((points[..., 0] >= xmin) & (points[..., 0] <= xmax)
+                   & (points[..., 1] >= ymin) & (points[..., 1] <= ymax)
+                   & (points[..., 2] >= zmin) & (points[..., 2] <= zmax))
+    sigma = render_mask.to(sigma.dtype) * sigma
+  return sigma
+
+
 # --------------------------------------------------------------------------
 # modules.py
 # --------------------------------------------------------------------------
@@ -424,8 +441,8 @@ class OracleNerfModel:
                      metadata, extra_params, gt_mask, *, use_warp=True,
                      use_sample_at_infinity=False, use_sigma_gradient=False,
                      use_predicted_norm=False, mask_ratio=1,
-                     sharp_weights_std=1.0, compute_sigma_gradient=True
-                     ) -> Dict[str, torch.Tensor]:
+                     sharp_weights_std=1.0, compute_sigma_gradient=True,
+                     render_opts=None) -> Dict[str, torch.Tensor]:
     """hypernerf/models.py:867-1417 under the flags NerfDSConfig admits."""
     c = self.cfg
     dt = self.dtype
@@ -541,7 +558,8 @@ class OracleNerfModel:
 
       # sharp weights (models.py:1235-1246)
       sigma_raw_bs = sigma_raw.reshape(B, S)
-      sigmoid_sigma = torch.nn.functional.softplus(sigma_raw_bs)
+      filtered_sigma = filter_sigma(points, sigma_raw_bs, render_opts)   # the RAW sigma (models.py:1236)
+      sigmoid_sigma = torch.nn.functional.softplus(filtered_sigma)
       weights_sg = cal_weights(sigmoid_sigma, z_vals, directions)
       if c.use_mask_sharp_weights:
         out['sharp_weights'] = sharpen_weights(weights_sg, z_vals, std=sharp_weights_std)
@@ -566,6 +584,8 @@ class OracleNerfModel:
         translation_field = se3_apply(R, p, torch.zeros_like(x))
       else:
         rotation_field = translation_field = None
+
+      sigma = filter_sigma(points, sigma, render_opts)           # models.py:1288
 
       D = warped_points.shape[-1]
       warped_points = warped_points.reshape(B, S, D)
@@ -611,7 +631,7 @@ class OracleNerfModel:
             near=None, far=None, use_sample_at_infinity=None,
             use_sigma_gradient=False, use_predicted_norm=False, mask_ratio=1,
             sharp_weights_std=1.0, compute_sigma_gradient=True,
-            keep_internal=False):
+            keep_internal=False, render_opts=None):
     """hypernerf/models.py:1419-1565."""
     c = self.cfg
     origins = self._t(rays_dict['origins'])
@@ -646,7 +666,8 @@ class OracleNerfModel:
                                   origins, directions, z_vals)
     out['fine'] = self.render_samples(
         'fine', points_f, z_fine, directions, viewdirs, metadata, extra_params,
-        mask, use_sample_at_infinity=use_sample_at_infinity, **kw)
+        mask, use_sample_at_infinity=use_sample_at_infinity,
+        render_opts=render_opts, **kw)                           # models.py:1545 (fine level only)
     if keep_internal:
       out['coarse']['z_vals'] = z_vals
       out['fine']['z_vals'] = z_fine

@@ -104,7 +104,7 @@ def test_c_client_links_and_runs(tmp_path):
                       f'-Wl,-rpath,{libdir}', '-o', exe], capture_output=True, text=True)
   assert r.returncode == 0, r.stderr
   r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-  assert r.returncode == 0 and 'abi 1 ok' in r.stdout, r.stdout + r.stderr
+  assert r.returncode == 0 and f'abi {_lib.NDSR_ABI_VERSION} ok' in r.stdout, r.stdout + r.stderr
   # the ctypes mirrors have the C compiler's sizes (layout drift would shift every later field)
   sizes = dict(kv.split('=') for kv in r.stdout.splitlines()[-1].split()[1:])
   want = {'config': _lib.ndsr_config, 'extra_params': _lib.ndsr_extra_params, 'outputs': _lib.ndsr_outputs,

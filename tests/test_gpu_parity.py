@@ -571,6 +571,45 @@ def test_cuda_path_against_reference_goldens(cuda_device, variant):
   assert checked == 32
 
 
+def test_filter_sigma_against_reference_goldens(cuda_device):
+  """render_opts (models.filter_sigma, models.py:38-66, applied at 1236 and 1288 on the fine level only) against the
+  reference's own output: coarse level end to end (no render_opts there), fine level on the reference's samples."""
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import unflatten_params
+  from tests.test_oracle_golden import GOLDEN
+  G = dict(np.load(GOLDEN))
+  small = {str(k): int(v) for k, v in zip(G['model32_cfg_keys'], G['model32_cfg_vals'])}
+  cfg = nerf_ds_config(**small)
+  P = unflatten_params({k[5:]: v for k, v in G.items() if k.startswith('MP32/')})
+  ep = {str(k): float(v) for k, v in zip(G['model_extra_keys'], G['model_extra_vals'])}
+  ratio = float(G['model_mask_ratio'])
+  ropts = {'dust_threshold': float(G['model32R_dust']), 'bounding_box': tuple(float(v) for v in G['model32R_bbox'])}
+  rays = {'origins': G['model_origins'], 'directions': G['model_dirs'], 'metadata': {'warp': G['model_warp']},
+          'mask': G['model_gt_mask']}
+  m = _model(cfg, cuda_device, engine='auto')
+  keys = m.renderer.level_keys(return_points=True, return_weights=True, want_target_norm=False)
+  out = m.apply({'params': P}, rays, ep, t_rand=G['model_t_rand'], u=G['model_u'], use_predicted_norm=True,
+                mask_ratio=ratio, sharp_weights_std=0.1, render_opts=ropts, keys=keys)
+  o3, d3 = G['model_origins'], G['model_dirs']
+  pts = G['model32R_fine_points']
+  zf = (((pts - o3[:, None]) * d3[:, None]).sum(-1) / (d3 ** 2).sum(-1)[:, None]).astype(np.float32)
+  extra = m.renderer.make_extra(ep, use_predicted_norm=True, mask_ratio=ratio, sharp_weights_std=0.1, render_opts=ropts)
+  fine = m.renderer.render_samples(1, zf, d3, points=pts, warp_id=G['model_warp'], gt_mask=G['model_gt_mask'],
+                                   extra=extra, use_sample_at_infinity=True, keys=keys)
+  for lvl, res in (('coarse', _np(out['coarse'])), ('fine', _np(fine))):
+    for k in ('rgb', 'depth', 'acc', 'weights', 'alpha', 'accum_prod', 'ray_norm', 'ray_delta_x', 'ray_predicted_mask',
+              'ray_rotation_field', 'predicted_mask', 'warped_points'):
+      g = G[f'model32R_{lvl}_{k}']
+      assert linf(res[k].reshape(g.shape), g) <= RGB_TOL, (lvl, k, linf(res[k].reshape(g.shape), g))
+    g = G[f'model32R_{lvl}_sigma']                       # out['sigma'] is NOT filtered (models.py:1271)
+    np.testing.assert_allclose(res['sigma'].reshape(g.shape), g, rtol=1e-3, atol=1e-3)
+  assert np.abs(G['model32R_fine_weights'] - G['model32_fine_weights']).max() > 0.1
+  g = G['model32R_fine_sharp_weights']
+  ok = np.isfinite(g).all(-1)
+  big = np.abs(_np(fine)['sharp_weights'][ok] - g[ok]).max(-1)
+  assert np.median(big) <= 5e-3, np.sort(big)[-4:]
+
+
 def test_tensor_core_engine_against_reference_goldens(cuda_device):
   """The TENSOR-CORE engine against the reference's own output at nerf_ds.gin's full widths (256 / 128 / 128 / 64;
   mid-schedule alphas, mask_ratio 0.7, stratified draws): no oracle in between.  The 1.5 M parameters are

@@ -341,3 +341,42 @@ def test_whole_forward_variant_with_flipped_sampling_switches(G):
   assert np.mean(dz <= 2e-4) >= 0.98 and dz.max() <= 2e-2, np.sort(dz.reshape(-1))[-4:]
   e = np.abs(out['fine']['rgb'] - G['modelB_fine_rgb']).max(-1)    # one moved sample on a sharp edge moves a 16-sample ray
   assert np.median(e) <= 1e-5 and np.mean(e <= 1e-3) >= 0.89, np.sort(e)[-3:]
+
+
+def test_filter_sigma_render_opts(G):
+  """render_opts (models.filter_sigma, models.py:38-66): the reference's NerfModel.__call__ with a dust threshold and a
+  bounding box.  The coarse level receives no render_opts (models.py:1493-1516): identical to the unfiltered run.  The
+  fine level on the reference's fine samples: sigma stays unfiltered, weights / rgb / sharp_weights are filtered."""
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import unflatten_params
+  small = {str(k): int(v) for k, v in zip(G['model32_cfg_keys'], G['model32_cfg_vals'])}
+  cfg = nerf_ds_config(**small)
+  P = unflatten_params({k[5:]: v for k, v in G.items() if k.startswith('MP32/')})
+  ep = {str(k): float(v) for k, v in zip(G['model_extra_keys'], G['model_extra_vals'])}
+  ropts = {'dust_threshold': float(G['model32R_dust']), 'bounding_box': tuple(float(v) for v in G['model32R_bbox'])}
+  for k in ('rgb', 'weights', 'sigma'):
+    np.testing.assert_array_equal(G[f'model32R_coarse_{k}'], G[f'model32_coarse_{k}'])
+  assert np.abs(G['model32R_fine_weights'] - G['model32_fine_weights']).max() > 0.1        # the options do something
+  np.testing.assert_allclose(G['model32R_fine_sigma'], G['model32_fine_sigma'], rtol=1e-6)  # ... but not to out['sigma']
+  o3, d3 = G['model_origins'], G['model_dirs']
+  pts = G['model32R_fine_points']
+  zf = (((pts - o3[:, None]) * d3[:, None]).sum(-1) / (d3 ** 2).sum(-1)[:, None]).astype(np.float32)
+  om = O.OracleNerfModel(cfg, P)
+  res = O.to_numpy(om.render_samples('fine', T(pts), T(zf), T(d3), T(d3), {'warp': G['model_warp']}, ep, G['model_gt_mask'],
+                                     use_sample_at_infinity=True, use_predicted_norm=True, compute_sigma_gradient=False,
+                                     mask_ratio=float(G['model_mask_ratio']), sharp_weights_std=0.1, render_opts=ropts))
+  n = 0
+  for k in ('rgb', 'depth', 'acc', 'weights', 'alpha', 'accum_prod', 'ray_norm', 'ray_delta_x', 'ray_predicted_mask',
+            'ray_rotation_field', 'med_depth'):
+    g = G[f'model32R_fine_{k}']
+    np.testing.assert_allclose(np.asarray(res[k]).reshape(g.shape), g, rtol=1e-4, atol=2e-5, err_msg=k)
+    n += 1
+  np.testing.assert_allclose(res['sigma'], G['model32R_fine_sigma'], rtol=5e-4, atol=2e-5)
+  g = G['model32R_fine_sharp_weights']
+  ok = np.isfinite(g).all(-1) & np.isfinite(res['sharp_weights']).all(-1)
+  assert ok.sum() >= 3
+  # (ill-conditioned rows as in the first variant: only rows whose Gaussian normaliser is healthy are compared)
+  w = G['model32R_fine_weights'].astype(np.float64)
+  big = np.abs(res['sharp_weights'][ok] - g[ok]).max(-1)
+  assert np.median(big) <= 5e-3, np.sort(big)[-4:]
+  assert n == 11

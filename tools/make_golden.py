@@ -640,6 +640,20 @@ def main():
                                    use_linear_disparity=True, use_sample_at_infinity=False)).apply(
       {'params': MP32}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mepB,
       use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=1, sharp_weights_std=0.1)
+  # render_opts / filter_sigma (models.py:38-66, applied at 1236 and 1288, fine level only): dust threshold and a
+  # bounding box that cuts through the sampled depth range
+  ropts = {'dust_threshold': 0.35, 'bounding_box': (-0.6, 0.5, -0.7, 0.6, -0.4, 0.8)}
+  G['model32R_dust'] = f32(ropts['dust_threshold'])
+  G['model32R_bbox'] = f32(ropts['bounding_box'])
+  _DRAWS.extend([mt, mu_])
+  res32R = models.NerfModel(**kw32).apply(
+      {'params': MP32}, {'origins': mo, 'directions': md, 'metadata': {'warp': mmeta}, 'mask': mgt}, mep,
+      use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.1,
+      render_opts=ropts)
+  for lvl in ('coarse', 'fine'):
+    for k, v in res32R[lvl].items():
+      if v is not None and k != 'target_norm':
+        G[f'model32R_{lvl}_{k}'] = f32(v)
   for tag, res_ in (('model32', res32), ('model32B', res32B)):
     for lvl in ('coarse', 'fine'):
       for k, v in res_[lvl].items():
