@@ -8,12 +8,15 @@ one 800x800 frame (640 000 rays) of a synthetic orbit through the nerf_ds.gin
 networks (SE3 warp + hyper sheet + mask MLP + template NeRF, predicted
 normals) at 128 coarse + 128 fine samples ("256 samples/ray"), stratified
 draws, render-mode outputs (render.py:192-193).  At N > 1 every step renders N
-frames, each block-partitioned over the N ranks (utils.shard order) and
-reassembled with one NCCL all-gather per frame: per-GPU work is fixed (weak).
+frames (--scaling weak, per-GPU work fixed; --scaling strong: one frame), each
+block-partitioned over the N ranks (utils.shard order) and reassembled inside
+the compositing kernel by peer-memory stores (--gather nccl: one all-gather).
 
-Prints ONE JSON line (rank 0).  `value` = rays/s with inputs resident in HBM;
-`e2e` = the same frames through the host-buffer C-ABI call
-(ndsr_render_rays_host: pinned host rays in, pinned host image out).
+Prints ONE JSON line (rank 0).  `value` = rays/s with the rays resident in HBM;
+`e2e` = the same frames from pinned host rays to the frame in pinned host
+memory (N = 1: one ndsr_render_rays_host_rng call; N > 1: per-rank upload,
+rank 0 reads the assembled frame back).  The uniform draws are generated on
+the device from jax keys inside the timed region in both.
 `--impl reference` times the CPU oracle (the restatement of the reference's
 JAX path; jax itself is not installable here) on the host cores.
 """
@@ -156,17 +159,19 @@ def run_reference(args):
   line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
           'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-          'config': workload_config(args, 1),
+          'config': dict(workload_config(args, 1, 1, rays_per_step=n),
+                         note=f'each timed step is a bounded sample of the frame: {n} of its {args.image * args.image} rays'),
           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
           'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
           'gpu_launches': 0}
   print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
+def workload_config(args, n_frames, world, rays_per_step=None):
   return {'workload': f'single {args.image}x{args.image} frame render, nerf_ds.gin nets (SE3 warp + hyper sheet + mask MLP '
                       f'+ template NeRF, predicted normals), {args.coarse}+{args.fine} coarse/fine stratified samples',
-          'rays_per_step': args.image * args.image * world, 'chunk_rays': args.chunk,
+          'rays_per_step': args.image * args.image * n_frames if rays_per_step is None else rays_per_step,
+          'frames_per_step': n_frames, 'chunk_rays': args.chunk,
           'parallelism': (f'rays block-sharded over {world} GPU(s), ' + (
               'frame reassembled by peer-memory stores of the compositing kernel (no data-path collective, 1 barrier/frame)'
               if getattr(args, 'gather', 'peer') == 'peer' else '1 NCCL all-gather/frame')) if world > 1 else 'single GPU',
@@ -175,6 +180,17 @@ def workload_config(args, world):
 
 
 # ---------------------------------------------------------------------------
+def traffic_per_eval():
+  """DRAM bytes per fine-level sample evaluation, from the committed ncu capture of this command (profiles/):
+  (dram__bytes_read.sum + dram__bytes_write.sum) of the fine-level field launches / evaluations."""
+  p = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
+  if os.path.exists(p):
+    with open(p) as f:
+      d = json.load(f)
+    return float(d['dram_bytes_per_eval']), d.get('source', 'profiles/r2_traffic.json')
+  return None, None
+
+
 def run_ours(args):
   import torch
   import torch.distributed as dist
@@ -185,12 +201,22 @@ def run_ours(args):
     raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
+  cfg, params, syn = build_case(args)
+  # CPU baseline: rank 0 of a single-GPU run only, before anything else competes for the host cores (under torchrun
+  # the other ranks would be spinning in a barrier and OMP_NUM_THREADS is 1)
+  cpu = None
+  if world == 1 and not args.no_cpu:
+    threads = os.cpu_count() or 1
+    v, dt = cpu_sample(args, cfg, params, syn, args.cpu_rays, threads)
+    cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+           'sample': f'{args.cpu_rays} rays spread over frame 0, {args.coarse}+{args.fine} samples, {dt:.1f} s, PyTorch-CPU fp32 '
+                     f'restatement of the reference JAX path incl. autograd d(sigma)/dx (jax not installable here)'}
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
+  from nerfds_b200 import jax_random as jr
   from nerfds_b200.models import NerfModel
-  from nerfds_b200.renderer import RENDER_KEYS
+  from nerfds_b200.renderer import RENDER_KEYS, ALL_SHAPES
   from nerfds_b200.evaluation import all_gather_level
-  cfg, params, syn = build_case(args)
   model = NerfModel(cfg, device=dev, engine=args.engine, precision=args.precision)
   R = model.renderer
   R.load_params(params)
@@ -199,24 +225,26 @@ def run_ours(args):
   Sc, Sf = cfg.num_coarse_samples, cfg.num_fine_samples
   n_frame = args.image * args.image
   per = (n_frame + world - 1) // world
-  lo, hi = rank * per, min(n_frame, (rank + 1) * per)
+  bounds = [(r * per, min(n_frame, (r + 1) * per)) for r in range(world)]
+  lo, hi = bounds[rank]
+  n_frames = world if args.scaling == 'weak' else 1     # frames per step; every frame is sharded over all ranks
 
-  # ---- inputs: `world` frames per step, this rank's block of each; device-resident + pinned host copies
+  # ---- inputs.  Rays: device-resident copy (`value`) and pinned host copy (`e2e`).  The two uniform draws of the path
+  # are generated on the device from jax keys inside the timed region, as the reference does inside its jitted call
+  # (model_utils.py:84, 217; one key pair per device and frame, evaluation.py:81-84).
+  def frame_keys(f, r):
+    ks = jr.split(jr.fold_in(jr.PRNGKey(20230601), f), 2 * world)
+    return np.asarray(ks[2 * r], np.uint32), np.asarray(ks[2 * r + 1], np.uint32)
+
   frames = []
-  g = torch.Generator(device=dev)
-  g.manual_seed(1234 + rank)
-  for f in range(world):
+  for f in range(n_frames):
     o, d, w = frame_inputs(syn, args, f)
     blk = lambda a: np.ascontiguousarray(a[lo:hi])
     ho, hd, hw = blk(o), blk(d), blk(w)
-    t_rand = torch.rand((hi - lo, Sc), generator=g, device=dev)
-    u = torch.rand((hi - lo, Sf), generator=g, device=dev)
     frames.append({
-        'o': torch.from_numpy(ho).to(dev), 'd': torch.from_numpy(hd).to(dev),
-        'w': torch.from_numpy(hw.view(np.int32)).to(dev), 't': t_rand, 'u': u,
+        'o': torch.from_numpy(ho).to(dev), 'd': torch.from_numpy(hd).to(dev), 'w': torch.from_numpy(hw.view(np.int32)).to(dev),
         'ho': torch.from_numpy(ho).pin_memory(), 'hd': torch.from_numpy(hd).pin_memory(),
-        'hw': torch.from_numpy(hw.view(np.int32)).pin_memory(), 'ht': t_rand.cpu().pin_memory(),
-        'hu': u.cpu().pin_memory()})
+        'hw': torch.from_numpy(hw.view(np.int32)).pin_memory(), 'keys': frame_keys(f, rank)})
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
   # frame reassembly at N > 1: the compositing kernels store every rank's rays into every GPU's frame buffer
@@ -240,53 +268,57 @@ def run_ours(args):
       sys.stderr.write(f'[bench] rank {rank}: peer-memory reassembly unavailable ({why or "another rank failed"}); '
                        'using the NCCL all-gather\n')
 
-  def render_frame(i, o, d, w, t, uu):
+  def render_shard(o, d, w, keys, fine_ptrs=None):
+    n = o.shape[0]
+    t = R.random_uniform(keys[0], n, Sc)
+    uu = R.random_uniform(keys[1], n, Sf)
+    return R.render_rays(o, d, warp_id=w, t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS,
+                         fine_ptrs=fine_ptrs)['fine']
+
+  def render_frame(i, o, d, w, keys):
     if peer is not None:
       pf = peer[i & 1]
       pf.activate()
-      R.render_rays(o, d, warp_id=w, t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS,
-                    fine_ptrs=pf.shard_ptrs(lo))
+      render_shard(o, d, w, keys, fine_ptrs=pf.shard_ptrs(lo))
       pf.wait()
       return pf.frame()
-    out = R.render_rays(o, d, warp_id=w, t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS)['fine']
+    out = render_shard(o, d, w, keys)
     return all_gather_level(out) if world > 1 else out
 
   def step_device():
     outs = None
     for i, fr in enumerate(frames):
-      outs = render_frame(i, fr['o'], fr['d'], fr['w'], fr['t'], fr['u'])
+      outs = render_frame(i, fr['o'], fr['d'], fr['w'], fr['keys'])
     flush.fill_(1)
     return outs
 
   host_out = {}
-
-  def step_host():
-    """End to end through the host-buffer entry point: pinned host rays in, pinned host image block out."""
-    res = None
-    for i, fr in enumerate(frames):
-      if world == 1:
-        res = R.render_rays_host(fr['ho'].numpy(), fr['hd'].numpy(), warp_id=fr['hw'].numpy().view(np.uint32),
-                                 t_rand=fr['ht'].numpy(), u=fr['hu'].numpy(), extra=extra, fine_keys=RENDER_KEYS,
-                                 out=host_out.setdefault(i, {}))
-      else:
-        o, d, w = (fr[k].to(dev, non_blocking=True) for k in ('ho', 'hd', 'hw'))
-        t, uu = fr['ht'].to(dev, non_blocking=True), fr['hu'].to(dev, non_blocking=True)
-        out = render_frame(i, o, d, w, t, uu)
-        hb = host_out.setdefault(i, {})
-        for k, v in out.items():
-          if k not in hb:
-            hb[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
-          hb[k].copy_(v, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        res = hb
-    flush.fill_(1)
-    return res
-
-  if rank == 0 and world == 1:      # make the render_rays_host output buffers pinned too
-    from nerfds_b200.renderer import ALL_SHAPES
+  if world == 1:                    # pinned destination of ndsr_render_rays_host_rng
     for i in range(len(frames)):
       host_out[i] = {k: torch.empty((hi - lo,) + tuple(ALL_SHAPES[k](Sc + Sf, R.H)), dtype=torch.float32).pin_memory().numpy()
                      for k in RENDER_KEYS}
+
+  def step_host():
+    """End to end: pinned host rays in, the frame in pinned host memory out (rank 0), every step."""
+    res = None
+    for i, fr in enumerate(frames):
+      if world == 1:
+        # one C-ABI call: chunked, input copies of chunk k + 1 overlap the compute of chunk k, draws generated on the device
+        res = R.render_rays_host(fr['ho'].numpy(), fr['hd'].numpy(), warp_id=fr['hw'].numpy().view(np.uint32),
+                                 extra=extra, fine_keys=RENDER_KEYS, out=host_out[i], rng_keys=fr['keys'])
+      else:
+        o, d, w = (fr[k].to(dev, non_blocking=True) for k in ('ho', 'hd', 'hw'))
+        out = render_frame(i, o, d, w, fr['keys'])
+        if rank == 0:               # like render.py: process 0 keeps the image
+          hb = host_out.setdefault(i, {})
+          for k, v in out.items():
+            if k not in hb:
+              hb[k] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+            hb[k].copy_(v, non_blocking=True)
+          res = hb
+        torch.cuda.current_stream().synchronize()
+    flush.fill_(1)
+    return res
 
   def barrier():
     if world > 1:
@@ -320,61 +352,85 @@ def run_ours(args):
   sampler.start()
   ms, launches, prof = timed(step_device, args.steps, profile=True)
   clocks = sampler.result()
-  rays_step = n_frame * world      # whole job: `world` frames per step
+  rays_step = n_frame * n_frames      # whole job
   value = rays_step * args.steps / (ms * 1e-3)
 
-  # ---- end to end (host buffers)
+  # ---- end to end (host buffers), timed over the same number of steps
   for _ in range(min(args.warmup, 2)):
     step_host()
-  e2e_steps = max(1, min(args.steps, 3))
-  ms_h, _, _ = timed(step_host, e2e_steps)
-  e2e_value = rays_step * e2e_steps / (ms_h * 1e-3)
+  ms_h, _, _ = timed(step_host, args.steps)
+  e2e_value = rays_step * args.steps / (ms_h * 1e-3)
   fr = frames[0]
-  h2d = sum(fr[k].numel() * fr[k].element_size() for k in ('ho', 'hd', 'hw', 'ht', 'hu')) * world
-  per_ray_out = sum(int(np.prod(ALL_SHAPES_local(k, Sc + Sf, R.H))) for k in RENDER_KEYS) * 4
-  d2h = per_ray_out * (n_frame if world > 1 else (hi - lo)) * world
+  h2d = sum(fr[k].numel() * fr[k].element_size() for k in ('ho', 'hd', 'hw')) * world * n_frames
+  per_ray_out = sum(int(np.prod(ALL_SHAPES[k](Sc + Sf, R.H) or (1,))) for k in RENDER_KEYS) * 4
+  d2h = per_ray_out * n_frame * n_frames          # the assembled frame(s), once (rank 0)
+
+  # ---- N > 1: the last assembled frame against a single-GPU render of the same rays, shards and keys
+  frame_check = None
+  if world > 1:
+    last = n_frames - 1
+    got = {k: v.clone() for k, v in step_device().items()}
+    barrier()
+    if rank == 0:
+      o, d, w = frame_inputs(syn, args, last)
+      same = True
+      if peer is not None:
+        R._check(R.lib.ndsr_set_output_mirrors(R._h, 0, None, None, 0), 'ndsr_set_output_mirrors')
+      for r, (a, b) in enumerate(bounds):
+        ref = render_shard(torch.from_numpy(np.ascontiguousarray(o[a:b])).to(dev), torch.from_numpy(np.ascontiguousarray(d[a:b])).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(w[a:b]).view(np.int32)).to(dev), frame_keys(last, r))
+        for k, v in ref.items():
+          same = same and bool(torch.equal(v.reshape(b - a, -1), got[k].reshape(n_frame, -1)[a:b]))
+      frame_check = same
+    barrier()
 
   if rank == 0:
     pk, pk_kind = peaks()
     # dominant kernel: the fine-level field kernel; algorithmic FLOPs per launch / measured duration
     f_ms, f_n = prof['field_fine']
     c_ms, c_n = prof['field_coarse']
-    rays_local_total = (hi - lo) * world * args.steps
+    rays_local_total = (hi - lo) * n_frames * args.steps
     fine_flops = 2.0 * MAC_FINE * (Sc + Sf) * rays_local_total
     coarse_flops = 2.0 * MAC_COARSE * Sc * rays_local_total
     ach = fine_flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
     peak = float(pk.get('bf16_tflops_sustained') or pk.get('bf16_tflops') or 1400.0)
     burst = pk.get('bf16_tflops', peak)
+    tpe, tsrc = traffic_per_eval()
+    if args.traffic is not None:
+      traffic, tsrc = args.traffic, '--traffic'
+    else:
+      traffic = tpe * (Sc + Sf) * rays_local_total / max(f_n, 1) if (tpe is not None and R.engine == 'tc') else None
+    issued = None
+    if R.engine == 'tc':
+      im = R.tc_issued_macs()
+      issued = {'coarse_per_eval': im[(0, 'sigma')], 'fine_new_per_eval': im[(1, 'full')], 'fine_carried_per_eval': im[(1, 'carried')],
+                'per_ray': Sc * im[(0, 'sigma')] + Sf * im[(1, 'full')] + Sc * im[(1, 'carried')],
+                'algorithmic_per_ray': Sc * MAC_COARSE + (Sc + Sf) * MAC_FINE}
+      issued['issued_over_algorithmic'] = issued['per_ray'] / issued['algorithmic_per_ray']
     roofline = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                # DRAM bytes per fine-level pass, from the ncu capture of the same command (profiles/): 371 B per
-                # sample evaluation (planes written once, carry planes read once, plus write-backs of the previous
-                # kernel's dirty L2 lines that ncu attributes to this one); --traffic overrides
-                'traffic': args.traffic if args.traffic is not None else (
-                    NCU_DRAM_BYTES_PER_EVAL * (Sc + Sf) * rays_local_total / max(f_n, 1) if R.engine == 'tc' else None),
+                'traffic': traffic, 'traffic_source': tsrc,
                 'kernel': (f'field_tc_kernel x2 (fine level: {Sf} new depths per ray through every network + {Sc} coarse depths '
                            'through the template NeRF on carried warp/hyper/mask results)') if R.engine == 'tc'
                 else f'field_{R.engine}_kernel (fine level)',
                 'peak_kind': f'{pk_kind} sustained bf16 (burst {burst})',
                 'launches': f_n, 'avg_launch_ms': f_ms / max(f_n, 1),
                 'flops_per_launch': fine_flops / max(f_n, 1),
-                'whole_step_tflops': (fine_flops + coarse_flops) / (ms * 1e-3) / 1e12,
+                'coarse_level_frac': (coarse_flops / (c_ms * 1e-3) / 1e12 / peak) if c_ms > 0 else None,
+                'whole_step_tflops': (fine_flops + coarse_flops) * world / (ms * 1e-3) / 1e12,
+                'issued_macs': issued,
                 'stage_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
                 'hbm_gbs_of_peak': None}
-    cpu = None
-    if not args.no_cpu:
-      threads = os.cpu_count() or 1
-      v, dt = cpu_sample(args, cfg, params, syn, args.cpu_rays, threads)
-      cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-             'sample': f'{args.cpu_rays} rays spread over frame 0, {Sc}+{Sf} samples, {dt:.1f} s, PyTorch-CPU fp32 '
-                       f'restatement of the reference JAX path incl. autograd d(sigma)/dx (jax not installable here)'}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
             'dtype': 'f32 (tensor-core layers: split-fp16 operands, fp32 accumulate)' if R.engine == 'tc' else 'f32',
-            'data': 'synthetic', 'config': dict(workload_config(args, world), engine=R.engine, precision=args.precision),
+            'data': 'synthetic', 'config': dict(workload_config(args, n_frames, world), engine=R.engine, precision=args.precision),
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'ms_per_step': ms_h / e2e_steps},
+                    'ms_per_step': ms_h / args.steps, 'steps': args.steps,
+                    'draws': 'generated on the device from jax keys inside the timed region (threefry2x32)'},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
+    if frame_check is not None:
+      line['frame_matches_single_gpu'] = frame_check
     print(json.dumps(line), flush=True)
   if peer is not None:
     for pf in peer:
@@ -382,14 +438,6 @@ def run_ours(args):
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
-
-
-def ALL_SHAPES_local(k, S, H):
-  from nerfds_b200.renderer import ALL_SHAPES
-  return ALL_SHAPES[k](S, H) or (1,)
-
-
-NCU_DRAM_BYTES_PER_EVAL = 371.0   # profiles/r1_field_tc_fine_ncu_full.txt
 
 
 def main():
@@ -407,6 +455,8 @@ def main():
   ap.add_argument('--cpu-rays', type=int, default=None)
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='frame reassembly at N > 1')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help='weak: N frames per step (per-GPU work fixed); strong: one frame per step over N ranks')
   ap.add_argument('--traffic', type=float, default=None, help='DRAM bytes/launch of the dominant kernel from ncu')
   args = ap.parse_args()
   if args.cpu_rays is None:

@@ -201,6 +201,18 @@ int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_rays,
                           const ndsr_extra_params* ep,
                           const ndsr_outputs* coarse, const ndsr_outputs* fine);
 
+/* ndsr_render_rays_host with the two uniform draws of the path generated ON THE DEVICE from jax keys, as the
+ * reference does inside its jitted call (model_utils.py:84 `random.uniform(key, [n_rays, S_c])`, :217
+ * `[n_rays, S_f]`): t_rand = uniform(key_coarse, [n_rays, S_c]), u = uniform(key_fine, [n_rays, S_f]) over the WHOLE
+ * call's rays (threefry2x32, bit for bit what ndsr_random_uniform writes), whatever the internal ray chunking.  The
+ * host then only supplies the rays: 28 B/ray instead of 28 + 4 (S_c + S_f). */
+int ndsr_render_rays_host_rng(ndsr_handle* h, void* stream, int64_t n_rays,
+                              const float* origins, const float* directions,
+                              const float* viewdirs, const uint32_t* warp_id,
+                              const float* gt_mask, const uint32_t key_coarse[2], const uint32_t key_fine[2],
+                              const ndsr_extra_params* ep,
+                              const ndsr_outputs* coarse, const ndsr_outputs* fine);
+
 /* Replaces NerfModel.render_samples (models.py:867-1417): one level on
  * caller-provided samples.  level 0 = 'coarse', 1 = 'fine' (selects the
  * NerfMLP).  points [n,S,3] may be NULL (= origins + z_vals * directions). */
@@ -278,6 +290,9 @@ int ndsr_set_output_mirrors(ndsr_handle* h, int32_t n, const int64_t* byte_delta
  * raw uint32[2] jax key AFTER flax's make_rng folding (models.py:1489, 1524; nerfds_b200/jax_random.py derives it
  * on the host).  Feed the result to ndsr_render_rays as t_rand / u.  Stateless; n < 2^32 - 1. */
 int ndsr_random_uniform(int device, void* stream, const uint32_t key[2], int64_t n, float* out);
+/* Elements [first, first + count) of the same n-draw stream (a block of rows of the [n_rays, n_samples] array). */
+int ndsr_random_uniform_range(int device, void* stream, const uint32_t key[2], int64_t n, int64_t first, int64_t count,
+                              float* out);
 
 /* Replaces model_utils.volumetric_rendering (model_utils.py:95-159) +
  * compute_depth_map.  rgb [n,S,3], sigma [n,S], z_vals [n,S], dirs [n,3]. */
@@ -292,6 +307,9 @@ int ndsr_volumetric_rendering(ndsr_handle* h, void* stream, int64_t n_rays,
 int ndsr_engine_in_use(const ndsr_handle* h);             /* ndsr_engine actually selected */
 int64_t ndsr_kernel_launches(const ndsr_handle* h);       /* kernels launched so far */
 int ndsr_abi_version(void);
+/* Tensor-core engine: MACs the layer programs ISSUE per sample evaluation (split-fp16 terms and padding included),
+ * out[level * 3 + mode], mode 0 = sigma-only, 1 = full, 2 = full on carried warp / hyper / mask results (6 doubles). */
+int ndsr_tc_issued_macs(const ndsr_handle* h, double* out);
 /* sizeof(ndsr_config), sizeof(ndsr_extra_params), sizeof(ndsr_outputs): lets a
  * foreign-language binding assert its struct mirrors before the first call. */
 void ndsr_struct_sizes(int32_t* config, int32_t* extra_params, int32_t* outputs);

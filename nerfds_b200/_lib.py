@@ -144,7 +144,8 @@ EXPORTS = ['ndsr_create', 'ndsr_destroy', 'ndsr_last_error', 'ndsr_load_params',
            'ndsr_volumetric_rendering', 'ndsr_engine_in_use', 'ndsr_kernel_launches', 'ndsr_abi_version',
            'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense', 'ndsr_profile_enable',
            'ndsr_profile_read', 'ndsr_camera_rays', 'ndsr_random_uniform', 'ndsr_peer_alloc', 'ndsr_peer_free',
-           'ndsr_peer_open', 'ndsr_peer_close', 'ndsr_set_output_mirrors']
+           'ndsr_peer_open', 'ndsr_peer_close', 'ndsr_set_output_mirrors', 'ndsr_render_rays_host_rng',
+           'ndsr_random_uniform_range', 'ndsr_tc_issued_macs']
 
 
 def load_library() -> C.CDLL:
@@ -168,6 +169,8 @@ def load_library() -> C.CDLL:
               C.POINTER(ndsr_outputs), C.POINTER(ndsr_outputs)]
   lib.ndsr_render_rays.argtypes = rays_sig
   lib.ndsr_render_rays_host.argtypes = rays_sig
+  lib.ndsr_render_rays_host_rng.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                            C.POINTER(ndsr_extra_params), C.POINTER(ndsr_outputs), C.POINTER(ndsr_outputs)]
   lib.ndsr_render_samples.argtypes = [vp, vp, C.c_int, i64, i32, vp, vp, vp, vp, vp, vp, vp,
                                       C.POINTER(ndsr_extra_params), i32, C.POINTER(ndsr_outputs)]
   lib.ndsr_sample_along_rays.argtypes = [vp, vp, i64, i32, C.c_float, C.c_float, i32, vp, vp]
@@ -179,11 +182,13 @@ def load_library() -> C.CDLL:
   lib.ndsr_struct_sizes.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
   lib.ndsr_struct_sizes.restype = None
   lib.ndsr_set_max_chunk.argtypes = [vp, i64]
+  lib.ndsr_tc_issued_macs.argtypes = [vp, C.POINTER(C.c_double)]
   lib.ndsr_profile_enable.argtypes = [vp, C.c_int]
   lib.ndsr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   lib.ndsr_selftest_tc_dense.argtypes = [C.c_int] * 7 + [vp] * 5
   lib.ndsr_camera_rays.argtypes = [C.c_int, vp, C.POINTER(ndsr_camera), vp, vp, vp]
   lib.ndsr_random_uniform.argtypes = [C.c_int, vp, C.POINTER(C.c_uint32), i64, vp]
+  lib.ndsr_random_uniform_range.argtypes = [C.c_int, vp, C.POINTER(C.c_uint32), i64, i64, i64, vp]
   lib.ndsr_peer_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]
   lib.ndsr_peer_free.argtypes = [C.c_int, vp]
   lib.ndsr_peer_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]

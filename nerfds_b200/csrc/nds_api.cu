@@ -715,11 +715,11 @@ static size_t stage_outputs(const ndsr_outputs* host, int64_t B, int S, int H, n
 // Host buffers in, host buffers out (what a ctypes caller of the reference's render_image chunk loop has).  The
 // rays are processed in chunks of max_chunk; the inputs of chunk k + 1 are copied on a second stream while chunk k
 // computes (pinned host memory makes the copies asynchronous), the outputs come back in one copy per key at the end.
-extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,
-                                     const float* directions, const float* viewdirs, const uint32_t* warp_id,
-                                     const float* gt_mask, const float* t_rand, const float* u,
-                                     const ndsr_extra_params* ep, const ndsr_outputs* coarse,
-                                     const ndsr_outputs* fine) {
+static int render_rays_host_impl(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,
+                                 const float* directions, const float* viewdirs, const uint32_t* warp_id,
+                                 const float* gt_mask, const float* t_rand, const float* u, const uint32_t* key_coarse,
+                                 const uint32_t* key_fine, const ndsr_extra_params* ep, const ndsr_outputs* coarse,
+                                 const ndsr_outputs* fine) {
   if (!h) return NDSR_ERR_INVALID;
   if (n_rays == 0) return NDSR_OK;
   if (n_rays < 0 || !origins || !directions) return fail(h, NDSR_ERR_INVALID, "origins/directions required");
@@ -737,7 +737,9 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
       NDS_CUDA(h, cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
     }
   }
-  // persistent staging (grown on demand, reused across calls)
+  // persistent staging (grown on demand, reused across calls); with keys the draws are generated on the device
+  // straight into the staging half (the reference draws them inside the jitted call too: model_utils.py:84, 217)
+  const bool gen = key_coarse && key_fine && c.use_stratified_sampling;
   const size_t per_ray = (size_t)(3 + 3 + 3 + 1 + 1 + Sc + Sf) * sizeof(float);
   const size_t half = ((size_t)chunk * per_ray + 255) & ~(size_t)255;
   if (2 * half > h->in_stage_bytes) {
@@ -784,8 +786,18 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
     NDS_CUDA(h, up(viewdirs, 3, &d_v));
     NDS_CUDA(h, up(warp_id, 1, &d_w));
     NDS_CUDA(h, up(gt_mask, 1, &d_m));
-    NDS_CUDA(h, up(t_rand, (size_t)Sc, &d_t));
-    NDS_CUDA(h, up(u, (size_t)Sf, &d_u));
+    if (gen) {
+      // rows [r0, r0 + B) of random.uniform(key, [n_rays, S]): generated on the copy stream as well, so that they are
+      // ready together with the rays
+      d_t = p; p += (size_t)B * Sc;
+      d_u = p; p += (size_t)B * Sf;
+      NDS_CUDA(h, launch_uniform_threefry_range(key_coarse[0], key_coarse[1], n_rays * Sc, r0 * Sc, B * Sc, d_t, h->num_sms, cs));
+      NDS_CUDA(h, launch_uniform_threefry_range(key_fine[0], key_fine[1], n_rays * Sf, r0 * Sf, B * Sf, d_u, h->num_sms, cs));
+      h->launches += 2;
+    } else {
+      NDS_CUDA(h, up(t_rand, (size_t)Sc, &d_t));
+      NDS_CUDA(h, up(u, (size_t)Sf, &d_u));
+    }
     NDS_CUDA(h, cudaEventRecord(h->ev_in[b], cs));
     NDS_CUDA(h, cudaStreamWaitEvent(st, h->ev_in[b], 0));
     ndsr_outputs oc = offset_outputs(coarse ? &dc : nullptr, r0, Sc, h->H), of = offset_outputs(fine ? &df : nullptr, r0, Sc + Sf, h->H);
@@ -803,6 +815,38 @@ extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_ray
   cudaError_t se = cudaStreamSynchronize(st);
   if (!rc && se != cudaSuccess) { h->err = cudaGetErrorString(se); rc = NDSR_ERR_CUDA; }
   return rc;
+}
+
+extern "C" int ndsr_render_rays_host(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,
+                                     const float* directions, const float* viewdirs, const uint32_t* warp_id,
+                                     const float* gt_mask, const float* t_rand, const float* u,
+                                     const ndsr_extra_params* ep, const ndsr_outputs* coarse,
+                                     const ndsr_outputs* fine) {
+  return render_rays_host_impl(h, stream, n_rays, origins, directions, viewdirs, warp_id, gt_mask, t_rand, u, nullptr,
+                               nullptr, ep, coarse, fine);
+}
+
+extern "C" int ndsr_render_rays_host_rng(ndsr_handle* h, void* stream, int64_t n_rays, const float* origins,
+                                         const float* directions, const float* viewdirs, const uint32_t* warp_id,
+                                         const float* gt_mask, const uint32_t key_coarse[2], const uint32_t key_fine[2],
+                                         const ndsr_extra_params* ep, const ndsr_outputs* coarse,
+                                         const ndsr_outputs* fine) {
+  if (!h) return NDSR_ERR_INVALID;
+  if (!key_coarse || !key_fine) return fail(h, NDSR_ERR_INVALID, "ndsr_render_rays_host_rng needs both keys");
+  if ((int64_t)n_rays * (h->cfg.num_coarse_samples > h->cfg.num_fine_samples ? h->cfg.num_coarse_samples : h->cfg.num_fine_samples) >= (int64_t)0xFFFFFFFFll)
+    return fail(h, NDSR_ERR_INVALID, "too many draws for one 32-bit counter stream");
+  return render_rays_host_impl(h, stream, n_rays, origins, directions, viewdirs, warp_id, gt_mask, nullptr, nullptr,
+                               key_coarse, key_fine, ep, coarse, fine);
+}
+
+extern "C" int ndsr_random_uniform_range(int device, void* stream, const uint32_t key[2], int64_t n, int64_t first,
+                                         int64_t count, float* out) {
+  if (!key || n < 0 || first < 0 || count < 0 || first + count > n || (count > 0 && !out) || n >= (int64_t)0xFFFFFFFFll) return NDSR_ERR_INVALID;
+  if (count == 0) return NDSR_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return NDSR_ERR_CUDA;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) return NDSR_ERR_CUDA;
+  return launch_uniform_threefry_range(key[0], key[1], n, first, count, out, sms, (cudaStream_t)stream) == cudaSuccess ? NDSR_OK : NDSR_ERR_CUDA;
 }
 
 // ------------------------------------------------- ray generation

@@ -514,6 +514,30 @@ __global__ void __launch_bounds__(256) uniform_threefry_kernel(uint32_t k0, uint
   }
 }
 
+// elements [first, first + count) of the same stream of n draws (a ray chunk's rows of a [n_rays, S] array): element i
+// is word 0 of block i (i < half) or word 1 of block i - half
+__global__ void __launch_bounds__(256) uniform_threefry_range_kernel(uint32_t k0, uint32_t k1, int64_t n, int64_t half,
+                                                                     int64_t first, int64_t count, float* __restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = first + t, j = i < half ? i : i - half;
+    uint32_t x0 = (uint32_t)j;
+    uint32_t x1 = (j + half < n) ? (uint32_t)(j + half) : 0u;
+    threefry2x32(k0, k1, x0, x1);
+    out[t] = __uint_as_float(((i < half ? x0 : x1) >> 9) | 0x3F800000u) - 1.0f;
+  }
+}
+
+cudaError_t launch_uniform_threefry_range(uint32_t k0, uint32_t k1, int64_t n, int64_t first, int64_t count, float* out,
+                                          int num_sms, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  const int64_t half = (n + 1) / 2;
+  int64_t blocks = (count + 255) / 256;
+  const int64_t cap = (int64_t)num_sms * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  uniform_threefry_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(k0, k1, n, half, first, count, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* out, int num_sms, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   const int64_t half = (n + 1) / 2;

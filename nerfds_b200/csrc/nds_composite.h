@@ -51,6 +51,8 @@ struct SamplePdfArgs {
 };
 
 cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* out, int num_sms, cudaStream_t st);
+cudaError_t launch_uniform_threefry_range(uint32_t k0, uint32_t k1, int64_t n, int64_t first, int64_t count, float* out,
+                                          int num_sms, cudaStream_t st);
 cudaError_t launch_camera_rays(const ndsr_camera& cam, float* origins, float* dirs, float* pixels, cudaStream_t st);
 cudaError_t launch_sample_along_rays(int64_t n_rays, int S, float near_, float far_, int lindisp,
                                      const float* t_rand, float* z, cudaStream_t st);

@@ -1808,6 +1808,28 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
 
 }  // namespace nds
 
+// tensor-core MACs the programs ISSUE per sample evaluation (split terms and padding included): out[level * 3 + mode],
+// mode 0 sigma-only | 1 full | 2 full, carried
+extern "C" int ndsr_tc_issued_macs(const ndsr_handle* h, double* out) {
+  using namespace nds;
+  if (!h || !out) return NDSR_ERR_INVALID;
+  if (!h->tc) return NDSR_ERR_NOT_LOADED;
+  for (int lv = 0; lv < 2; ++lv)
+    for (int mode = 0; mode < 3; ++mode) {
+      const TcProgram& P = h->tc->prog[lv][mode];
+      double macs = 0;
+      for (int i = 0; i < P.n_burst; ++i) {
+        const Burst& b = P.burst[i];
+        const int steps = (b.ctl >> 15) & 7, pat = (b.ctl >> 13) & 3, per = pat == PAT_SS ? steps : 4;
+        const int groups = (b.ctl & (1u << 25)) ? 2 : ((b.ctl & B_TWO) ? 3 : 1);
+        const double rows = (double)(((b.idesc >> 17) & 63u) * 8u);
+        macs += (double)groups * per * rows * TM * 16.0;
+      }
+      out[lv * 3 + mode] = macs / (2.0 * TM);       // a program covers a pair of tiles
+    }
+  return NDSR_OK;
+}
+
 // ---------------------------------------------------------------------------
 // diagnostics entry point: one Dense layer through the tensor-core machinery
 // ---------------------------------------------------------------------------

@@ -97,6 +97,12 @@ class Renderer:
   def kernel_launches(self) -> int:
     return int(self.lib.ndsr_kernel_launches(self._h))
 
+  def tc_issued_macs(self):
+    """{(level, mode): tensor-core MACs issued per sample evaluation}; mode in 'sigma', 'full', 'carried'."""
+    out = (C.c_double * 6)()
+    self._check(self.lib.ndsr_tc_issued_macs(self._h, out), 'ndsr_tc_issued_macs')
+    return {(lv, m): float(out[lv * 3 + i]) for lv in (0, 1) for i, m in enumerate(('sigma', 'full', 'carried'))}
+
   def set_max_chunk(self, rays: int):
     self._check(self.lib.ndsr_set_max_chunk(self._h, int(rays)), 'ndsr_set_max_chunk')
 
@@ -253,8 +259,12 @@ class Renderer:
     return {'coarse': ct, 'fine': ft}
 
   def render_rays_host(self, origins, directions, *, viewdirs=None, warp_id=None, gt_mask=None, t_rand=None,
-                       u=None, extra: _lib.ndsr_extra_params, fine_keys=RENDER_KEYS, out: Optional[Dict] = None):
-    """Host-buffer entry point: numpy (ideally pinned) in, numpy out; H2D/D2H inside the call."""
+                       u=None, extra: _lib.ndsr_extra_params, fine_keys=RENDER_KEYS, out: Optional[Dict] = None,
+                       rng_keys=None):
+    """Host-buffer entry point: numpy (ideally pinned) in, numpy out; H2D/D2H inside the call.
+
+    rng_keys: (key_coarse, key_fine), two raw uint32[2] jax keys -- the draws are then generated on the device
+    (t_rand = uniform(key_coarse, [B, S_c]), u = uniform(key_fine, [B, S_f])) instead of being uploaded."""
     c = self.cfg
     f32 = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float32))
     o, d, v = f32(origins).reshape(-1, 3), f32(directions).reshape(-1, 3), f32(viewdirs)
@@ -271,10 +281,28 @@ class Renderer:
       setattr(fo, k, res[k].ctypes.data if res[k].size else None)
     ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
     with torch.cuda.device(self.device):
-      rc = self.lib.ndsr_render_rays_host(self._h, self._stream(), B, ptr(o), ptr(d), ptr(v), ptr(w), ptr(m),
-                                          ptr(tr), ptr(uu), C.byref(extra), None, C.byref(fo))
+      if rng_keys is not None:
+        kc = (C.c_uint32 * 2)(*[int(x) for x in np.asarray(rng_keys[0]).reshape(2)])
+        kf = (C.c_uint32 * 2)(*[int(x) for x in np.asarray(rng_keys[1]).reshape(2)])
+        rc = self.lib.ndsr_render_rays_host_rng(self._h, self._stream(), B, ptr(o), ptr(d), ptr(v), ptr(w), ptr(m),
+                                                kc, kf, C.byref(extra), None, C.byref(fo))
+      else:
+        rc = self.lib.ndsr_render_rays_host(self._h, self._stream(), B, ptr(o), ptr(d), ptr(v), ptr(w), ptr(m),
+                                            ptr(tr), ptr(uu), C.byref(extra), None, C.byref(fo))
     self._check(rc, 'ndsr_render_rays_host')
     return res
+
+  def random_uniform(self, key, n_rays: int, n_samples: int, first_ray: int = 0, rays: Optional[int] = None):
+    """Rows [first_ray, first_ray + rays) of jax.random.uniform(key, [n_rays, n_samples]) on this device."""
+    rays = n_rays - first_ray if rays is None else rays
+    t = torch.empty((rays, n_samples), dtype=torch.float32, device=self.device)
+    k = (C.c_uint32 * 2)(*[int(x) for x in np.asarray(key).reshape(2)])
+    with torch.cuda.device(self.device):
+      rc = self.lib.ndsr_random_uniform_range(self.device.index or 0, self._stream(), k, n_rays * n_samples,
+                                              first_ray * n_samples, rays * n_samples, C.c_void_p(t.data_ptr()))
+    if rc != 0:
+      raise NdsrError(f'ndsr_random_uniform_range failed ({rc})')
+    return t
 
   def render_samples(self, level: int, z_vals, directions, *, points=None, origins=None, viewdirs=None,
                      warp_id=None, gt_mask=None, extra: _lib.ndsr_extra_params, use_sample_at_infinity=False,

@@ -37,11 +37,31 @@ def main():
       a, b = got[k].reshape(ref[k].shape), ref[k]
       assert torch.equal(a, b), (rank, rep, k, float((a - b).abs().max()))
     dist.barrier()
-  try:                                                   # an ordinary call while mirrors are registered is refused
-    model.apply({'params': params}, rays, ep, t_rand=t_rand, u=u, use_predicted_norm=True, keys=('rgb',), coarse_keys=())
-    raise SystemExit('expected NdsrError')
+  # An ordinary call while mirrors are registered: its outputs lie outside the frame buffer, so the library does not
+  # mirror them (no store into a peer's mapping) and the frame buffers keep the last frame.
+  snap = {k: v.clone() for k, v in frames.frame().items()}
+  plain = model.apply({'params': params}, rays, ep, t_rand=t_rand, u=u, use_predicted_norm=True, mask_ratio=1,
+                      sharp_weights_std=0.1, keys=('rgb',), coarse_keys=())
+  assert torch.equal(plain['fine']['rgb'], ref['rgb'])
+  extra = model.renderer.make_extra(ep, use_predicted_norm=True, mask_ratio=1, sharp_weights_std=0.1)
+  host = model.renderer.render_rays_host(rays['origins'], rays['directions'], warp_id=rays['metadata']['warp'].reshape(-1),
+                                         gt_mask=rays['mask'].reshape(-1), t_rand=t_rand, u=u, extra=extra, fine_keys=('rgb',))
+  assert np.array_equal(host['rgb'], ref['rgb'].cpu().numpy())
+  torch.cuda.synchronize()
+  dist.barrier()
+  for k, v in frames.frame().items():
+    assert torch.equal(v, snap[k]), (rank, k)
+  # ... and a call with per-ray outputs on both sides of the frame buffer is refused
+  ptrs = frames.shard_ptrs(0)
+  bad = dict(ptrs, depth=int(plain['fine']['rgb'].data_ptr()))
+  try:
+    model.renderer.render_rays(rays['origins'][:8], rays['directions'][:8], warp_id=rays['metadata']['warp'][:8],
+                               gt_mask=rays['mask'][:8], t_rand=t_rand[:8], u=u[:8], extra=extra, coarse_keys=(),
+                               fine_keys=('rgb', 'depth'), fine_ptrs=bad)
+    refused = world == 1                                   # a single rank registers no mirrors: nothing to refuse
   except Exception as e:
-    assert 'PeerFrames is active' in str(e), e
+    refused = 'partly inside' in str(e)
+  assert refused
   frames.close()
   # mirrors are off again: a plain call writes only locally
   out = model.apply({'params': params}, rays, ep, t_rand=t_rand, u=u, use_predicted_norm=True, mask_ratio=1,

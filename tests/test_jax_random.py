@@ -114,3 +114,34 @@ def test_render_image_draws_per_device_keys(cuda_device):
   ref = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True,
                 mask_ratio=1, sharp_weights_std=0.1, keys=('rgb',), coarse_keys=())
   assert torch.equal(out['rgb'].reshape(-1, 3), ref['fine']['rgb'].cpu())
+
+
+@pytest.mark.gpu
+def test_device_uniform_row_ranges_and_host_call_with_keys(cuda_device):
+  """ndsr_random_uniform_range: any block of rows of uniform(key, [n, S]) equals the same rows of the whole array
+  (even and odd totals).  ndsr_render_rays_host_rng (draws generated on the device, per internal ray chunk) gives the
+  same frame, bit for bit, as ndsr_render_rays_host fed those draws from the host."""
+  from nerfds_b200 import synthetic as syn
+  from nerfds_b200.models import NerfModel
+  from tests.common import make_case
+  cfg, params, rays, _, _ = make_case('nerf_ds', image=9, seed=1, num_coarse_samples=16, num_fine_samples=8)
+  m = NerfModel(cfg, device=cuda_device)
+  R = m.renderer
+  key = jr.flax_make_rng(jr.split(jr.PRNGKey(7), 2)[0])
+  for n, S in ((81, 16), (33, 7)):
+    full = oj.uniform(key, (n, S))
+    for first, rows in ((0, n), (5, 11), (n - 3, 3), (n // 2 - 1, 4)):
+      got = R.random_uniform(key, n, S, first, rows).cpu().numpy()
+      np.testing.assert_array_equal(got, full[first:first + rows])
+  R.load_params(params)
+  R.set_max_chunk(32)                                                   # 81 rays -> 3 internal chunks
+  B = rays['origins'].shape[0]
+  extra = R.make_extra(syn.final_extra_params(), use_predicted_norm=True)
+  kc, kf = np.array([11, 22], np.uint32), np.array([33, 44], np.uint32)
+  wid = rays['metadata']['warp'].reshape(-1)
+  a = R.render_rays_host(rays['origins'], rays['directions'], warp_id=wid, gt_mask=rays['mask'].reshape(-1), extra=extra,
+                         fine_keys=('rgb', 'depth'), rng_keys=(kc, kf))
+  b = R.render_rays_host(rays['origins'], rays['directions'], warp_id=wid, gt_mask=rays['mask'].reshape(-1), extra=extra,
+                         fine_keys=('rgb', 'depth'), t_rand=oj.uniform(kc, (B, 16)), u=oj.uniform(kf, (B, 8)))
+  for k in a:
+    np.testing.assert_array_equal(a[k], b[k])

@@ -24,43 +24,7 @@ PER_RAY = ('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'ray_hyper_points',
            'ray_rotation_field', 'ray_translation_field', 'med_points')
 
 
-def scene(n_rays, coarse, fine, seed=0):
-  cfg = nerf_ds_config(num_coarse_samples=coarse, num_fine_samples=fine, near=0.1, far=2.5, num_warp_embeds=100)
-  params = init_params(cfg, 0)
-  rng = np.random.default_rng(seed)
-  per = (n_rays + 3) // 4
-  parts = []
-  for f in range(4):                      # four frames of the orbit, rays spread over each
-    r = syn.frame_rays(800, 800, frame=7 * f, num_frames=30, focal=800.)
-    sel = np.sort(rng.choice(640000, size=per, replace=False))
-    parts.append({'origins': r['origins'][sel], 'directions': r['directions'][sel]})
-  o = np.concatenate([p['origins'] for p in parts])[:n_rays]
-  d = np.concatenate([p['directions'] for p in parts])[:n_rays]
-  rays = {'origins': o, 'directions': d,
-          'metadata': {'warp': rng.integers(0, cfg.num_warp_embeds, size=(n_rays, 1)).astype(np.uint32)},
-          'mask': np.zeros((n_rays, 1), np.float32)}
-  t_rand, u = syn.uniform_draws(n_rays, coarse, fine, seed)
-  return cfg, params, rays, t_rand, u
-
-
-def take(rays, sl):
-  return {'origins': rays['origins'][sl], 'directions': rays['directions'][sl],
-          'metadata': {k: v[sl] for k, v in rays['metadata'].items()}, 'mask': rays['mask'][sl]}
-
-
-def run_oracle_chunks(cfg, params, rays, t_rand, u, chunk=1024):
-  m = OracleNerfModel(cfg, params)
-  outs = {'coarse': {}, 'fine': {}}
-  n = rays['origins'].shape[0]
-  for r0 in range(0, n, chunk):
-    sl = slice(r0, min(n, r0 + chunk))
-    o = to_numpy(m.apply(take(rays, sl), syn.final_extra_params(), t_rand[sl], u[sl], use_predicted_norm=True,
-                         mask_ratio=1, sharp_weights_std=0.1, return_weights=True, return_points=True,
-                         keep_internal=True, compute_sigma_gradient=False))
-    for lvl in outs:
-      for k, v in o[lvl].items():
-        outs[lvl].setdefault(k, []).append(v)
-  return {lvl: {k: np.concatenate(v) for k, v in d.items()} for lvl, d in outs.items()}
+from tests.common import bench_scene as scene, run_oracle_chunks, take_rays as take
 
 
 def main():
