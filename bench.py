@@ -440,6 +440,183 @@ def run_ours(args):
     dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------
+# BASELINE configs[2]: train.py ray batch of 4096, nerf_ds.gin (64+64), surface-aware branch + mask: the training
+# FORWARD with every level-dict key training.py consumes, incl. target_norm = R normalize(-d sigma / dx) on both levels
+MAC_TRAIN = 1_470_720     # forward + reverse sweep
+
+
+def train_case(args):
+  from nerfds_b200 import synthetic as syn
+  from nerfds_b200.config import nerf_ds_config
+  from nerfds_b200.params import init_params
+  cfg = nerf_ds_config(num_coarse_samples=args.coarse, num_fine_samples=args.fine, near=0.1, far=2.5, num_warp_embeds=100)
+  params = init_params(cfg, 0)
+  rays = syn.train_batch(args.batch, cfg.num_warp_embeds, seed=3)
+  t_rand, u = syn.uniform_draws(args.batch, args.coarse, args.fine, 3)
+  return cfg, params, syn, rays, t_rand, u
+
+
+def train_cpu(args, cfg, params, syn, rays, t_rand, u, n, threads):
+  import torch
+  from oracle.nerfds_oracle import OracleNerfModel
+  torch.set_num_threads(threads)
+  m = OracleNerfModel(cfg, params)
+  sub = {'origins': rays['origins'][:n], 'directions': rays['directions'][:n],
+         'metadata': {'warp': rays['metadata']['warp'][:n]}, 'mask': rays['mask'][:n]}
+  run = lambda: m.apply(sub, syn.final_extra_params(), t_rand[:n], u[:n], use_predicted_norm=True, mask_ratio=0.7,
+                        sharp_weights_std=0.1, return_points=True, return_weights=True, compute_sigma_gradient=True)
+  t0 = time.perf_counter()
+  run()
+  return n / (time.perf_counter() - t0)
+
+
+def train_config(args, n=None):
+  return {'workload': f'train.py ray batch {args.batch}, nerf_ds.gin ({args.coarse}+{args.fine} samples), training forward with every '
+                      'level-dict key incl. target_norm (surface-aware branch, mask MLP) on both levels (BASELINE configs[2])',
+          'rays_per_step': args.batch if n is None else n,
+          'l2': 'a 256 MB buffer is rewritten between steps (the batch itself fits the L2)'}
+
+
+def run_train(args):
+  import torch
+  if args.impl == 'reference':
+    if int(os.environ.get('RANK', '0')) != 0:
+      return
+    cfg, params, syn, rays, t_rand, u = train_case(args)
+    threads = os.cpu_count() or 1
+    n = args.cpu_rays
+    train_cpu(args, cfg, params, syn, rays, t_rand, u, min(32, n), threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+      train_cpu(args, cfg, params, syn, rays, t_rand, u, n, threads)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    print(json.dumps({'impl': 'reference', 'metric': METRIC_TRAIN, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+                      'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+                      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': dict(train_config(args, n), note=f'each timed step is a bounded sample: {n} of the {args.batch} rays'),
+                      'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                       'sample': f'{n} rays of the batch per step, PyTorch-CPU fp32 restatement incl. autograd d(sigma)/dx'},
+                      'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}), flush=True)
+    return
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  cfg, params, syn, rays, t_rand, u = train_case(args)
+  cpu = None
+  if world == 1 and not args.no_cpu:
+    threads = os.cpu_count() or 1
+    n = min(args.cpu_rays, args.batch)
+    train_cpu(args, cfg, params, syn, rays, t_rand, u, min(32, n), threads)
+    cpu = {'value': train_cpu(args, cfg, params, syn, rays, t_rand, u, n, threads), 'unit': UNIT, 'cores': threads, 'kind': 'port',
+           'sample': f'{n} rays of the batch, PyTorch-CPU fp32 restatement of the reference JAX path incl. autograd d(sigma)/dx'}
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=dev)       # replicas: every rank runs its own batch (data parallel, no exchange in the forward)
+  from nerfds_b200.models import NerfModel
+  model = NerfModel(cfg, device=dev, engine=args.engine, precision=args.precision)
+  R = model.renderer
+  R.load_params(params)
+  extra = R.make_extra(syn.final_extra_params(), mask_ratio=0.7, sharp_weights_std=0.1, use_predicted_norm=True)
+  keys = R.level_keys(return_points=True, return_weights=True, want_target_norm=True)
+  Sc, Sf = cfg.num_coarse_samples, cfg.num_fine_samples
+  d_in = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in
+          (('o', rays['origins']), ('d', rays['directions']), ('m', rays['mask'].reshape(-1)), ('t', t_rand), ('u', u))}
+  d_in['w'] = torch.from_numpy(rays['metadata']['warp'].reshape(-1).astype(np.uint32).view(np.int32)).to(dev)
+  h_in = {k: v.cpu().pin_memory() for k, v in d_in.items()}
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  h_out = {}
+
+  def step_device():
+    out = R.render_rays(d_in['o'], d_in['d'], warp_id=d_in['w'], gt_mask=d_in['m'], t_rand=d_in['t'], u=d_in['u'], extra=extra,
+                        coarse_keys=keys, fine_keys=keys)
+    flush.fill_(1)
+    return out
+
+  def step_host():
+    g = {k: v.to(dev, non_blocking=True) for k, v in h_in.items()}
+    out = R.render_rays(g['o'], g['d'], warp_id=g['w'], gt_mask=g['m'], t_rand=g['t'], u=g['u'], extra=extra,
+                        coarse_keys=keys, fine_keys=keys)
+    for lvl in ('coarse', 'fine'):                       # what the loss reads per ray; the per-sample keys stay on the device
+      for k in ('rgb', 'ray_predicted_mask'):
+        dst = h_out.setdefault((lvl, k), torch.empty(out[lvl][k].shape, dtype=torch.float32).pin_memory())
+        dst.copy_(out[lvl][k], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    flush.fill_(1)
+
+  def timed(fn, steps, profile=False):
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = R.kernel_launches
+    if profile:
+      R.profile_enable(True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    prof = R.profile_read() if profile else None
+    if profile:
+      R.profile_enable(False)
+    return float(ms.item()), (R.kernel_launches - l0) * world, prof
+
+  for _ in range(args.warmup):
+    step_device()
+  sampler = ClockSampler(local)
+  sampler.start()
+  ms, launches, prof = timed(step_device, args.steps, profile=True)
+  clocks = sampler.result()
+  for _ in range(min(args.warmup, 2)):
+    step_host()
+  ms_h, _, _ = timed(step_host, args.steps)
+  if rank == 0:
+    pk, pk_kind = peaks()
+    peak = float(pk.get('bf16_tflops_sustained') or pk.get('bf16_tflops') or 1400.0)
+    f_ms = prof['field_coarse'][0] + prof['field_fine'][0]
+    f_n = prof['field_coarse'][1] + prof['field_fine'][1]
+    flops = 2.0 * MAC_TRAIN * (2 * Sc + Sf) * args.batch * args.steps
+    ach = flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else 0.0
+    issued = None
+    if R.engine == 'tc':
+      im = R.tc_issued_macs()
+      issued = {'coarse_per_eval': im[(0, 'grad')], 'fine_per_eval': im[(1, 'grad')], 'algorithmic_per_eval': MAC_TRAIN}
+    h2d = sum(v.numel() * v.element_size() for v in h_in.values())
+    d2h = 2 * args.batch * 4 * 4
+    line = {'metric': METRIC_TRAIN, 'value': args.batch * world * args.steps / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (tensor-core layers: split-fp16 operands, fp32 accumulate)' if R.engine == 'tc' else 'f32',
+            'data': 'synthetic', 'config': dict(train_config(args), engine=R.engine, precision=args.precision,
+                                                parallelism='single GPU' if world == 1 else f'{world} independent replicas of the batch'),
+            'clocks': clocks,
+            'e2e': {'value': args.batch * world * args.steps / (ms_h * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d) * world,
+                    'd2h_bytes_per_step': int(d2h) * world, 'ms_per_step': ms_h / args.steps, 'steps': args.steps},
+            'gpu_launches': launches,
+            'roofline': {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
+                         'kernel': f'field_{R.engine}_kernel (both levels: forward + reverse sweep for d sigma / dx)',
+                         'peak_kind': f'{pk_kind} sustained bf16', 'launches': f_n, 'avg_launch_ms': f_ms / max(f_n, 1),
+                         'flops_per_launch': flops / max(f_n, 1), 'issued_macs': issued,
+                         'stage_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()}},
+            'cpu_baseline': cpu}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+METRIC_TRAIN = 'rays/sec, training forward of a 4096-ray batch (all level-dict keys incl. target_norm)'
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -449,18 +626,30 @@ def main():
   ap.add_argument('--engine', default='auto', choices=['auto', 'tc', 'simt'])
   ap.add_argument('--precision', default='split3', choices=['mixed', 'fp16', 'split3'])
   ap.add_argument('--image', type=int, default=800)
-  ap.add_argument('--coarse', type=int, default=128)
-  ap.add_argument('--fine', type=int, default=128)
+  ap.add_argument('--coarse', type=int, default=None)
+  ap.add_argument('--fine', type=int, default=None)
   ap.add_argument('--chunk', type=int, default=65536)
   ap.add_argument('--cpu-rays', type=int, default=None)
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='frame reassembly at N > 1')
+  ap.add_argument('--workload', default='frame', choices=['frame', 'train4096'],
+                  help='frame: BASELINE configs[1] (the headline); train4096: configs[2], the training forward of a ray batch')
+  ap.add_argument('--batch', type=int, default=4096)
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='weak: N frames per step (per-GPU work fixed); strong: one frame per step over N ranks')
   ap.add_argument('--traffic', type=float, default=None, help='DRAM bytes/launch of the dominant kernel from ncu')
   args = ap.parse_args()
+  train = args.workload == 'train4096'
+  if args.coarse is None:
+    args.coarse = 64 if train else 128        # nerf_ds.gin's literal 64+64 for the train batch, 128+128 for the headline
+  if args.fine is None:
+    args.fine = 64 if train else 128
   if args.cpu_rays is None:
-    args.cpu_rays = 1024 if args.impl == 'ours' else 512
+    args.cpu_rays = (256 if train else 1024) if args.impl == 'ours' else (256 if train else 512)
+  if train:
+    if args.steps == 3 and '--steps' not in sys.argv:
+      args.steps = 50
+    return run_train(args)
   world = int(os.environ.get('WORLD_SIZE', '1'))
   if world != args.gpus and args.impl == 'ours':
     if world == 1 and args.gpus > 1:

@@ -308,7 +308,8 @@ int ndsr_engine_in_use(const ndsr_handle* h);             /* ndsr_engine actuall
 int64_t ndsr_kernel_launches(const ndsr_handle* h);       /* kernels launched so far */
 int ndsr_abi_version(void);
 /* Tensor-core engine: MACs the layer programs ISSUE per sample evaluation (split-fp16 terms and padding included),
- * out[level * 3 + mode], mode 0 = sigma-only, 1 = full, 2 = full on carried warp / hyper / mask results (6 doubles). */
+ * out[level * 4 + mode], mode 0 = sigma-only, 1 = full, 2 = full on carried warp / hyper / mask results, 3 = full +
+ * reverse sweep for d(sigma)/dx (8 doubles). */
 int ndsr_tc_issued_macs(const ndsr_handle* h, double* out);
 /* sizeof(ndsr_config), sizeof(ndsr_extra_params), sizeof(ndsr_outputs): lets a
  * foreign-language binding assert its struct mirrors before the first call. */

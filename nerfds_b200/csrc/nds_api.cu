@@ -513,8 +513,11 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
       fb.carry = h->carry; fb.carry_stride = B * n_carried;
       rc = tc_engine_field(h, cp, fb, st);
       if (rc) return rc;
-    } else if (h->engine == NDSR_ENGINE_TC && !need_grad) {
-      fa.carry_out = carry_out; fa.carry_stride = B * S;
+    } else if (h->engine == NDSR_ENGINE_TC && (!need_grad || !ep.use_sigma_gradient)) {
+      // (with d(sigma)/dx: one launch of the program that ends every tile with the reverse sweep; only
+      //  use_sigma_gradient -- the gradient as the rgb branch's normal input -- stays on the CUDA-core engine)
+      if (need_grad) fa.sigma_only = 0;
+      else { fa.carry_out = carry_out; fa.carry_stride = B * S; }
       int rc = tc_engine_field(h, cp, fa, st);
       if (rc) return rc;
     } else {

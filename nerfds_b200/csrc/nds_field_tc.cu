@@ -30,12 +30,14 @@
 
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "nds_dual.cuh"
 #include "nds_host.h"
 #include "nds_tc.cuh"
 
@@ -58,7 +60,9 @@ constexpr uint32_t OFF_RING = 5 * KBLK;
 constexpr uint32_t UNIT_BYTES = 32768;  // one ring unit: a B_hi image followed by its B_lo image (<= 2 x 16 KB)
 constexpr int NUNIT = 4;
 constexpr uint32_t OFF_CTRL = OFF_RING + NUNIT * UNIT_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = OFF_CTRL + 11264 + 1024;  // Ctrl + manual 1024-byte alignment slack
+constexpr uint32_t CTRL_HDR = 256;      // barriers + TMEM base; the program copies (ops | steps | bursts) follow
+constexpr uint32_t TC_SMEM_MAX = 232448;                     // 227 KB opt-in limit of sm_100
+constexpr uint32_t TC_SMEM_PROBE = OFF_CTRL + 1024;          // any size: only the base address matters
 constexpr int NPREP = 3;                // the shared feature block of the next pair is written in 3 parts
 #ifndef NDS_EPI_RZ
 #define NDS_EPI_RZ 0    // 1: ReLU folded into cvt.rz.relu (2 instructions fewer per pair, hi truncated -> lo twice as large)
@@ -68,8 +72,13 @@ enum EpiKind : uint8_t {
   EPI_INPLACE = 0,      // slice of CW accumulator columns -> hi (CW/2 columns) | lo (CW/2 columns) over the same slice
   EPI_INPLACE_HI = 1,   // hi only (consumer is a 1-term layer)
   EPI_COMPACT_HI = 2,   // hi only, compacted to the first half of the chunk (frees the second half for accumulators)
-  EPI_HEAD = 4          // <= 16 outputs consumed by the per-sample stage
+  EPI_HEAD = 4,         // <= 16 outputs consumed by the per-sample stage
+  EPI_INGRAD = 5        // reverse sweep: 64 input-gradient columns, accumulated per thread (16 columns each)
 };
+// ReLU masks of the reverse sweep (d sigma / dx, models.py:1035-1077): one 32-bit word per (layer, N-chunk) and
+// thread, bit i = pre-activation of the thread's i-th column > 0 (jax.nn.relu's derivative is x > 0)
+enum MaskMode : uint8_t { MASK_NONE = 0, MASK_RECORD = 1, MASK_APPLY = 2 };
+constexpr int MASK_TRUNK = 0, MASK_WARP = 16, MASK_HYPER = 24, MASK_WORDS = 32;
 enum Glue : uint8_t { GLUE_NONE = 0, GLUE_MASK = 1, GLUE_WARP = 2, GLUE_HYPER = 3, GLUE_ALPHA = 4, GLUE_BOTTLENECK = 5,
                       GLUE_RGB = 6, GLUE_SELFTEST = 7 };
 // A-operand addressing pattern of a burst: 0 = shared memory (IN block), else tensor memory with the K-step
@@ -86,8 +95,10 @@ struct TcOp {
   uint16_t d_col[2];     // tensor-memory column of accumulator chunk c
   uint8_t signal_glue;   // the per-sample stage after this head arrives on glue[tile slot]
   uint8_t signal_done;   // last tensor-memory read of the tile slot: arrive on done[tile slot] right after it
-  uint8_t pad[2];
+  uint8_t mask_idx;      // first mask word of the op (+ N-chunk)
+  uint8_t mask_mode;     // MaskMode
 };
+static_assert(sizeof(TcOp) == 24, "TcOp layout");
 
 // One burst of the MMA issuer = one K-chunk (<= 4 K-steps) of one N-chunk of one op of one tile slot:
 // 12 tcgen05.mma for a 3-term layer (B_hi and B_lo images), 4 for a 1-term layer.
@@ -101,6 +112,8 @@ enum BurstFlags : uint16_t {
   B_ACQUIRE = 2048,          // first use of a ring unit: wait for the TMA
   B_RELEASE = 4096           // last use: commit to the unit's empty barrier
 };
+constexpr uint32_t CTL_PAIR = 1u << 25;             // Burst::ctl: PAIR burst
+constexpr uint32_t CTL_WAIT_DONE_SELF = 1u << 26;   // Burst::ctl: this tile slot's previous done phase (reverse sweep)
 constexpr uint16_t B_WAIT_ANY = B_WAIT_P0 | B_WAIT_P1 | B_WAIT_GLUE | B_PEEK_GLUE_OTHER | B_WAIT_PREP | B_WAIT_DONE_OTHER;
 // Device encoding, everything the issuer needs as FINAL values (it is read as two uint4 from the constant bank):
 // the issuing thread shares its warp scheduler with four epilogue warps, so its instruction count per burst is
@@ -128,17 +141,24 @@ struct BurstH {
   // of K-chunk kc2 or kc); b_sel: 0 = B_hi image, 1 = B_lo image
   uint8_t pair = 0, b_sel[2] = {0, 1}, unit2 = 0xff, release2 = 0;
   int16_t kc = 0, kc2 = -1;           // K-chunks of the op whose weight images the burst reads
+  uint32_t ctl_extra = 0;             // CTL_WAIT_DONE_SELF
 };
 
-enum StepKind : uint8_t { STEP_EPI = 0, STEP_HEAD = 1, STEP_VIEW = 2, STEP_PREP = 3, STEP_OUT = 4 };
+enum StepKind : uint8_t { STEP_EPI = 0, STEP_HEAD = 1, STEP_VIEW = 2, STEP_PREP = 3, STEP_OUT = 4,
+                          STEP_INGRAD = 5,   // reverse sweep: accumulate an input-gradient op (arg 1: first of its sum)
+                          STEP_SEED = 6,     // reverse sweep: write the gradient seed of a network (arg: SeedKind)
+                          STEP_PEB = 7 };    // reverse sweep: positional-encoding backward (arg 0: trunk input, 1: feature block)
+enum SeedKind : uint8_t { SEED_TRUNK = 0, SEED_HYPER = 1, SEED_WARP = 2 };
 struct Step { uint8_t kind, tslot, op, arg; };
 
-constexpr int MAX_OPS = 80;
-constexpr int MAX_STEPS = 128;
-constexpr int MAX_BURST = 320;
+constexpr int MAX_OPS = 120;
+constexpr int MAX_STEPS = 200;
+constexpr int MAX_BURST = 448;
 struct TcProgram {       // passed by value as a __grid_constant__ kernel parameter (constant bank)
   int n_ops, n_burst, n_steps, full;     // full: rgb branch present (else sigma-only)
   int carried;           // the program has no N phase: the narrow networks' results are read from the carry planes
+  int grad;              // the program ends every tile with the reverse sweep for -d(sigma_raw)/dx
+  uint32_t smem_bytes;   // dynamic shared memory of the launch (the control block is sized for this program)
   // shared feature block: [identity x (3)] [sin/cos of bands f_kmin .. f_kmin + f_nb) (6 each)] [warp embed]
   // [mask embed] [mask]; t_cols = width of the trunk input that later overwrites it
   int f_col_ident, f_col_bands, f_kmin, f_nb, f_col_wembed, f_col_membed, f_col_mask, f_cols, t_cols;
@@ -149,7 +169,7 @@ struct TcProgram {       // passed by value as a __grid_constant__ kernel parame
   uint32_t src[MAX_BURST];   // producer: [0,20) weight stream offset in 128-byte rows | [20,29) rows to load |
                              // [29,31) ring unit | [31] the burst acquires (loads) its unit
 };
-static_assert(sizeof(TcProgram) < 16384, "kernel parameter budget");
+static_assert(sizeof(TcProgram) < 24576, "kernel parameter budget (32 764 bytes with the other arguments)");
 
 constexpr int TRACE_WORDS = 3 * MAX_BURST + 2 * MAX_STEPS + 8;
 
@@ -171,12 +191,13 @@ struct Ctrl {     // the barriers come first, in this order: Burst::bars holds i
   uint64_t d_full[2][2];    // MMA -> compute: accumulators of N-chunk c complete
   uint32_t tmem_base;
   uint32_t pad[3];
-  // the compute warps' view of the program, copied here once: a dynamically indexed constant-bank read costs a
-  // few hundred cycles, a shared-memory read ~30
-  TcOp ops[MAX_OPS];
-  Step steps[MAX_STEPS];
-  alignas(16) Burst burst[MAX_BURST];   // the issuer's copy of the burst program
+  // The program copies follow at CTRL_HDR (ops | steps | bursts, each 16-byte aligned, sized for THIS program): a
+  // dynamically indexed constant-bank read costs a few hundred cycles, a shared-memory read ~30.
 };
+static_assert(sizeof(Ctrl) <= CTRL_HDR, "control header");
+__host__ __device__ __forceinline__ uint32_t ctrl_off_steps(int n_ops) { return CTRL_HDR + (((uint32_t)n_ops * (uint32_t)sizeof(TcOp) + 15u) & ~15u); }
+__host__ __device__ __forceinline__ uint32_t ctrl_off_burst(int n_ops, int n_steps) { return ctrl_off_steps(n_ops) + (((uint32_t)n_steps * 4u + 15u) & ~15u); }
+__host__ __device__ __forceinline__ uint32_t ctrl_bytes(int n_ops, int n_steps, int n_burst) { return ctrl_off_burst(n_ops, n_steps) + (uint32_t)n_burst * 32u; }
 
 __device__ __forceinline__ void ctrl_init(Ctrl* ctl) {
   for (int i = 0; i < NUNIT; ++i) { mbar_init(&ctl->full[i], 1); mbar_init(&ctl->empty[i], 1); }
@@ -282,7 +303,7 @@ __device__ __forceinline__ void issue_program(const TcProgram& P, Ctrl* ctl, uin
   uint32_t bits = bits_io;
   // program entries come from the shared-memory copy (a dynamically indexed constant-bank read misses the small
   // immediate-constant cache and costs a few hundred cycles), fetched one burst ahead
-  const uint4* bp = reinterpret_cast<const uint4*>(ctl->burst);
+  const uint4* bp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(ctl) + ctrl_off_burst(P.n_ops, P.n_steps));
   uint4 q0 = bp[0];
   uint4 q1 = bp[1];
   for (int i = 0; i < n; ++i) {
@@ -291,10 +312,11 @@ __device__ __forceinline__ void issue_program(const TcProgram& P, Ctrl* ctl, uin
     const uint4 n1 = bp[2 * ni + 1];
     const uint32_t c = q1.z, s = (c >> 18) & 1u;
     if (trace) trace[i] = clock64();
-    if (c & B_WAIT_ANY) {
+    if (c & (B_WAIT_ANY | CTL_WAIT_DONE_SELF)) {
       const uint32_t o = s ^ 1u;
       if (c & B_WAIT_PREP) { mbar_wait(&ctl->prep[s], (bits >> (4 + s)) & 1u); bits ^= 1u << (4 + s); }
       if (c & B_WAIT_DONE_OTHER) { mbar_wait(&ctl->done[o], (bits >> (6 + o)) & 1u); bits ^= 1u << (6 + o); }
+      if (c & CTL_WAIT_DONE_SELF) { mbar_wait(&ctl->done[s], (bits >> (6 + s)) & 1u); bits ^= 1u << (6 + s); }
       if (c & B_WAIT_GLUE) { mbar_wait(&ctl->glue[s], (bits >> (2 + s)) & 1u); bits ^= 1u << (2 + s); }
       if (c & B_PEEK_GLUE_OTHER) mbar_wait(&ctl->glue[o], (bits >> (2 + o)) & 1u);
       if (c & B_WAIT_P0) mbar_wait(&ctl->part[s][0], (bits >> s) & 1u);
@@ -310,7 +332,7 @@ __device__ __forceinline__ void issue_program(const TcProgram& P, Ctrl* ctl, uin
     const uint32_t acc = (c & B_FIRST) ? 0u : 1u, pat = (c >> 13) & 3u;
     const bool two = (c & B_TWO) != 0;
     uint32_t ok;
-    if (c & (1u << 25)) ok = issue_pair(pat, (c >> 15) & 7u, q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
+    if (c & CTL_PAIR) ok = issue_pair(pat, (c >> 15) & 7u, q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
     else if (two && pat == PAT_32) ok = burst12_ts32(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
     else if (two && pat == PAT_16) ok = burst12_ts16(q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
     else ok = issue_burst(pat, two, (c >> 15) & 7u, q0.z, q0.x, q0.y, q1.x, q1.y, q0.w, acc, pbar, ppar, do_probe);
@@ -365,7 +387,7 @@ __device__ __forceinline__ void store_in_hi(uint8_t* blk, uint32_t r, uint32_t c
 template <int CW>
 __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const float* __restrict__ bias_base,
                                                uint32_t tmem_lane, uint32_t row, int sub, int q, float* dbg_out,
-                                               int dbg_ld, uint64_t* bar, uint32_t parity) {
+                                               int dbg_ld, uint64_t* bar, uint32_t parity, uint32_t* mask_word = nullptr) {
   const uint32_t oc0 = (uint32_t)nc * op.nc_rows + (uint32_t)sub * CW;   // first output column of this slice
   const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off + oc0);
   float b[CW];
@@ -384,7 +406,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
   uint32_t hi[CW / 2], lo[CW / 2];
-  if (NDS_EPI_RZ && relu && !dbg_out) {
+  uint32_t mword = (mask_word && op.mask_mode == MASK_APPLY) ? *mask_word : 0u;
+  if (NDS_EPI_RZ && relu && !dbg_out && !mask_word) {
     // ReLU folded into the conversions: hi = relu(x) truncated to fp16 (round toward zero, so the residual of a
     // positive x is never negative), lo = relu(x - hi) -- for x < 0 both come out 0.  hi + lo still carries 21+ bits.
 #pragma unroll
@@ -404,6 +427,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
       float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
       float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
       if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      if (mask_word) {
+        if (op.mask_mode == MASK_RECORD) mword |= (x0 > 0.f ? 1u : 0u) << (2 * i) | (x1 > 0.f ? 1u : 0u) << (2 * i + 1);
+        else { x0 = ((mword >> (2 * i)) & 1u) ? x0 : 0.f; x1 = ((mword >> (2 * i + 1)) & 1u) ? x1 : 0.f; }
+      }
       if (dbg_out) { dbg_out[row * dbg_ld + oc0 + 2 * i] = x0; dbg_out[row * dbg_ld + oc0 + 2 * i + 1] = x1; }
       const __half2 h = __floats2half2_rn(x0, x1);
       const float2 hf = __half22float2(h);
@@ -412,6 +439,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
       lo[i] = *reinterpret_cast<const uint32_t*>(&l);
     }
   }
+  if (mask_word && op.mask_mode == MASK_RECORD) *mask_word = mword;
   const uint8_t kind = op.epi_kind;
   if (kind == EPI_COMPACT_HI) {
     // the compacted slice overlaps columns other warps of this lane quarter are still reading
@@ -428,9 +456,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
 // waits for the chunk's accumulators (bar / parity) inside, after the bias prefetch
 __device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint32_t tmem_lane,
                                                   uint32_t row, int sub, int q, float* dbg, int dbg_ld, uint64_t* bar,
-                                                  uint32_t parity) {
-  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity);
-  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity);
+                                                  uint32_t parity, uint32_t* mask_word = nullptr) {
+  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, mask_word);
+  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, mask_word);
 }
 
 // head (<= 16 outputs): every compute warp of the lane quarter reads all of them
@@ -462,6 +490,24 @@ __device__ __forceinline__ float pe_sin(float x) {
   cs = fmaf(cs * r2, r2, fmaf(r2, -0.5f, 1.0f));
   const float v = (q & 1) ? cs : sn;
   return (q & 2) ? -v : v;
+}
+
+// cos(x), same reduction (the reverse sweep's derivative of the encodings)
+__device__ __forceinline__ float pe_cos(float x) {
+  const float j = rintf(x * 0.636619772367581343f);
+  float r = fmaf(j, -1.57079601287841796875f, x);
+  r = fmaf(j, -3.1391647326017846e-07f, r);
+  r = fmaf(j, -5.390302529957764e-15f, r);
+  const int q = (int)j;
+  const float r2 = r * r;
+  float sn = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sn = fmaf(sn, r2, -1.6666654611e-1f);
+  sn = fmaf(sn * r2, r, r);
+  float cs = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cs = fmaf(cs, r2, 4.166664568298827e-2f);
+  cs = fmaf(cs * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const float v = (q & 1) ? sn : cs;             // cos(r + q pi/2): cos, -sin, -cos, sin
+  return ((q + 1) & 2) ? -v : v;
 }
 
 // positional encoding (model_utils.py:398-417): feature layout (F, 2, C) flattened, identity first.  The
@@ -496,6 +542,12 @@ struct TcKernelArgs {
   TcLevel lvl;
   const float* warp_embed;
   const float* mask_embed;
+  // reverse sweep seeds (fp32, Flax layout): column 0 of the sigma head [trunk width], hyper-sheet logit kernel
+  // [width, H], SE(3) branch kernels [width, 3] each
+  const float* alpha_col0;
+  const float* hyper_logit_w;
+  const float* warp_w_w;
+  const float* warp_v_w;
   unsigned long long* trace;   // diagnostics (NDS_TC_TRACE): clock64 stamps of CTA 0's second pair, else null
 };
 // trace layout: [i] burst i reached | [MAX_BURST + i] its dependencies satisfied | [2 MAX_BURST + i] issued |
@@ -510,6 +562,14 @@ struct TileState {
   float xw[3], om[2], maskv, pmask, sigma_raw, nrm[3], rgb[3];
   float R[9], p[3];
 };
+// reverse-sweep state of one tile slot (only in the kernel instantiation that runs the reverse sweep)
+struct GradState {
+  float wv[6];            // raw SE(3) branch outputs (w, v)
+  float fb[16];           // this thread's 16 columns of the input gradient being accumulated
+  float gxw[3], gom[2];   // d sigma_raw / d (warped point, hyper coordinates)
+  uint32_t masks[MASK_WORDS];
+};
+struct NoGradState {};
 struct NextSample {
   float x[3], vd[3], gt;
   uint32_t wid;
@@ -518,6 +578,7 @@ struct NextSample {
   float xw[3], om[2], pmask, R[9], p[3];   // carried launches only
 };
 
+template <bool GRAD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcKernelArgs K,
                 const __grid_constant__ CallParams cp, const __grid_constant__ FieldArgs a,
@@ -532,12 +593,15 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
   // input blocks start as zeros: columns beyond the written features multiply zero weight rows, but 0 x garbage
   // could be NaN
   for (uint32_t i = threadIdx.x; i < OFF_RING / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  TcOp* c_ops = reinterpret_cast<TcOp*>(reinterpret_cast<uint8_t*>(ctl) + CTRL_HDR);
+  Step* c_steps = reinterpret_cast<Step*>(reinterpret_cast<uint8_t*>(ctl) + ctrl_off_steps(P.n_ops));
+  uint32_t* c_burst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ctl) + ctrl_off_burst(P.n_ops, P.n_steps));
   for (int i = threadIdx.x; i < P.n_ops * (int)(sizeof(TcOp) / 4); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ctl->ops)[i] = reinterpret_cast<const uint32_t*>(P.ops)[i];
+    reinterpret_cast<uint32_t*>(c_ops)[i] = reinterpret_cast<const uint32_t*>(P.ops)[i];
   for (int i = threadIdx.x; i < P.n_steps; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ctl->steps)[i] = reinterpret_cast<const uint32_t*>(P.steps)[i];
+    reinterpret_cast<uint32_t*>(c_steps)[i] = reinterpret_cast<const uint32_t*>(P.steps)[i];
   for (int i = threadIdx.x; i < P.n_burst * 8; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ctl->burst)[i] = reinterpret_cast<const uint32_t*>(P.burst)[i];
+    c_burst[i] = reinterpret_cast<const uint32_t*>(P.burst)[i];
   if (threadIdx.x == 0) ctrl_init(ctl);
   if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   fence_proxy_async_smem();
@@ -582,6 +646,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     uint32_t dc = 0;      // parity of d_full[s][c]: bit 2 s + c
     TileState cur[2];
     NextSample nxt[2];
+    typename std::conditional<GRAD, GradState, NoGradState>::type gst[2];
     // per-sample inputs are fetched one pair ahead, so their global-memory latency hides behind the T phase
     auto load_next = [&](int64_t pair_, int s_) {
       NextSample& ns = nxt[s_];
@@ -696,6 +761,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     load_next(blockIdx.x, 1);
     for (int s = 0; s < 2; ++s) for (int part = 0; part < NPREP; ++part) prep_part(s, part);
     warp_arrive(&ctl->done[1], lane);     // nothing occupies tensor memory before the first pair
+    if (GRAD) warp_arrive(&ctl->done[0], lane);     // (reverse-sweep programs also wait for this slot's previous pair)
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       for (int s = 0; s < 2; ++s) {
@@ -724,7 +790,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
       unsigned long long* tr = (K.trace && pair == (int64_t)gridDim.x && threadIdx.x == CWARP0 * 32) ? K.trace + 3 * MAX_BURST : nullptr;
       if (tr) tr[2 * MAX_STEPS] = clock64();
       for (int si = 0; si < P.n_steps; ++si) {
-        const Step sp = ctl->steps[si];
+        const Step sp = c_steps[si];
         const int s = sp.tslot;
         TileState& T = cur[s];
         uint8_t* blk = smem + OFF_IN + (uint32_t)s * 2u * KBLK;
@@ -732,16 +798,18 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         auto st_in2 = [&](int c, float v) { store_in_hi(smem + OFF_IN2, row, (uint32_t)c, v); };
         if (tr) tr[2 * si] = clock64();
         if (sp.kind == STEP_EPI) {
-          const TcOp& op = ctl->ops[sp.op];
+          const TcOp& op = c_ops[sp.op];
           for (int nc = 0; nc < op.n_nc; ++nc) {
             const uint32_t par = (dc >> (2 * s + nc)) & 1u;
             dc ^= 1u << (2 * s + nc);
-            epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par);
+            uint32_t* mw = nullptr;
+            if constexpr (GRAD) { if (op.mask_mode != MASK_NONE) mw = &gst[s].masks[op.mask_idx + nc]; }
+            epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par, mw);
             warp_arrive(&ctl->part[s][nc], lane);
             if (op.n_nc == 1) warp_arrive(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
           }
         } else if (sp.kind == STEP_HEAD) {
-          const TcOp& op = ctl->ops[sp.op];
+          const TcOp& op = c_ops[sp.op];
           mbar_wait(&ctl->d_full[s][0], (dc >> (2 * s)) & 1u);
           dc ^= 1u << (2 * s);
           tc_fence_after_sync();
@@ -764,6 +832,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
               for (int c = 0; c < 3; ++c) xw[c] = se.R[c * 3 + 0] * T.x[0] + se.R[c * 3 + 1] * T.x[1] + se.R[c * 3 + 2] * T.x[2] + se.p[c];
               for (int i = 0; i < 9; ++i) T.R[i] = se.R[i];
               for (int c = 0; c < 3; ++c) { T.p[c] = se.p[c]; T.xw[c] = xw[c]; }
+              if constexpr (GRAD) { for (int i = 0; i < 6; ++i) gst[s].wv[i] = hv[i]; }
               // trunk input over the feature block, which the narrow networks are done with
               trunk_input(blk, xw, T.om, -1);
             } break;
@@ -799,6 +868,129 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           }
         } else if (sp.kind == STEP_PREP) {
           prep_part(s, sp.arg);
+        } else if (GRAD && sp.kind >= STEP_INGRAD) {
+         if constexpr (GRAD) {
+          GradState& GS = gst[s];
+          if (sp.kind == STEP_INGRAD) {
+          // ---- reverse sweep: 64 input-gradient columns, 16 per thread, summed over the ops of a network ----
+          const TcOp& op = c_ops[sp.op];
+          mbar_wait(&ctl->d_full[s][0], (dc >> (2 * s)) & 1u);
+          dc ^= 1u << (2 * s);
+          tc_fence_after_sync();
+          uint32_t v[16];
+          tmem_ld16(tmem_lane + op.d_col[0] + (uint32_t)sub * 16u, v);
+          tmem_ld_wait();
+          if (op.signal_done) warp_arrive(&ctl->done[s], lane);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float g = __uint_as_float(v[i]) * op.inv_scale;
+            GS.fb[i] = sp.arg ? g : GS.fb[i] + g;
+          }
+          if (op.signal_glue) warp_arrive(&ctl->glue[s], lane);
+          } else if (sp.kind == STEP_SEED) {
+          // ---- reverse sweep: gradient at the last hidden layer of a network, masked by its ReLU, as the operand
+          //      image an epilogue of that width would leave (App. E steps 1, 4, 5) ----
+          const TcOp& op = c_ops[sp.op];            // the first backward op of the network: reads what is written here
+          const int width = op.N, n_nc = op.n_nc, cw = (op.N / op.n_nc) / NSUB;
+          float gwv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (sp.arg == SEED_WARP) {
+            // x' = R(w, v) x + p(w, v): forward-mode over the 6 raw screw outputs of the closed-form exponential
+            Dual6 dw[3], dv[3];
+            for (int i = 0; i < 3; ++i) { dw[i] = Dual6::var(GS.wv[i], i); dv[i] = Dual6::var(GS.wv[3 + i], 3 + i); }
+            SE3<Dual6> TD;
+            exp_se3<Dual6>(dw, dv, TD);
+            for (int i = 0; i < 3; ++i) {
+              const Dual6 xi = TD.R[i * 3 + 0] * T.x[0] + TD.R[i * 3 + 1] * T.x[1] + TD.R[i * 3 + 2] * T.x[2] + TD.p[i];
+              for (int k = 0; k < 6; ++k) gwv[k] += GS.gxw[i] * xi.d[k];
+            }
+          }
+          // the operand region of that op = the region it does NOT accumulate into
+          const uint32_t seed_col = n_nc == 2 ? 256u - op.d_col[0] : 256u * (uint32_t)s + (128u - (op.d_col[0] - 256u * (uint32_t)s));
+          for (int nc = 0; nc < n_nc; ++nc) {
+            const int oc0 = nc * (width / n_nc) + sub * cw;
+            const uint32_t mword = GS.masks[op.mask_idx + n_nc + nc];     // ReLU of the network's LAST hidden layer (the op applies the one before)
+            uint32_t hi[16], lo[16];
+            for (int i = 0; i < cw / 2; ++i) {
+              float x2[2];
+              for (int e = 0; e < 2; ++e) {
+                const int k = oc0 + 2 * i + e;
+                float g;
+                if (sp.arg == SEED_TRUNK) g = __ldg(K.alpha_col0 + k);
+                else if (sp.arg == SEED_HYPER) { g = 0.f; for (int o = 0; o < H; ++o) g = fmaf(GS.gom[o], __ldg(K.hyper_logit_w + (size_t)k * H + o), g); }
+                else {
+                  g = 0.f;
+                  for (int o = 0; o < 3; ++o) { g = fmaf(gwv[o], __ldg(K.warp_w_w + (size_t)k * 3 + o), g); g = fmaf(gwv[3 + o], __ldg(K.warp_v_w + (size_t)k * 3 + o), g); }
+                }
+                x2[e] = ((mword >> (2 * i + e)) & 1u) ? g : 0.f;
+              }
+              const __half2 h = __floats2half2_rn(x2[0], x2[1]);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(x2[0] - hf.x, x2[1] - hf.y);
+              hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            const uint32_t col = tmem_lane + seed_col + (uint32_t)nc * 128u + (uint32_t)sub * (uint32_t)cw;
+            if (cw == 32) { tmem_st<16>(col, reinterpret_cast<const uint32_t(&)[16]>(hi)); tmem_st<16>(col + 16, reinterpret_cast<const uint32_t(&)[16]>(lo)); }
+            else { tmem_st<8>(col, reinterpret_cast<const uint32_t(&)[8]>(hi)); tmem_st<8>(col + 8, reinterpret_cast<const uint32_t(&)[8]>(lo)); }
+          }
+          warp_arrive(&ctl->part[s][0], lane);
+          warp_arrive(&ctl->part[s][1], lane);
+          } else if (sp.kind == STEP_PEB) {
+          // ---- reverse sweep: positional-encoding backward (App. E step 3) of this thread's 16 feature columns, summed
+          //      over the 4 warps that share the sample through the (idle) rgb side-input block ----
+          float part5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};       // d/d(x0, x1, x2) and, trunk input only, d/d(hyper 0, 1)
+          auto band_grad = [&](float xv, int deg, float w, bool is_cos, float g) {
+            const float xb = xv * __int_as_float((127 + deg) << 23);
+            return w * __int_as_float((127 + deg) << 23) * pe_cos(is_cos ? xb + NDS_HALF_PI_F : xb) * g;
+          };
+          if (sp.arg == 0) {
+            const PosencSpec& ps = cp.pe_spatial;
+            const PosencSpec& ph = cp.pe_hyperpt;
+            const int o_sp = ps.identity ? 3 : 0, n_sp = ps.num_bands * 6;
+            const int o_h0 = o_sp + n_sp, o_hy = o_h0 + ((H > 0 && ph.identity) ? H : 0), n_hy = H > 0 ? ph.num_bands * 2 * H : 0;
+            for (int i = 0; i < 16; ++i) {
+              const int j = sub * 16 + i;
+              const float g = GS.fb[i];
+              if (j < o_sp) part5[j] += g;
+              else if (j < o_h0) { const int jj = j - o_sp, k = jj / 6, r = jj - 6 * k, c = r % 3; part5[c] += band_grad(T.xw[c], ps.min_deg + k, ps.window[k], r >= 3, g); }
+              else if (j < o_hy) part5[3 + (j - o_h0)] += g;
+              else if (j < o_hy + n_hy) { const int jj = j - o_hy, k = jj / (2 * H), r = jj - 2 * H * k, c = r % H; part5[3 + c] += band_grad(T.om[c], ph.min_deg + k, ph.window[k], r >= H, g); }
+            }
+          } else {
+            for (int i = 0; i < 16; ++i) {
+              const int j = sub * 16 + i;
+              const float g = GS.fb[i];
+              if (P.f_col_ident >= 0 && j >= P.f_col_ident && j < P.f_col_ident + 3) part5[j - P.f_col_ident] += g;
+              else if (j >= P.f_col_bands && j < P.f_col_bands + 6 * P.f_nb) {
+                const int jj = j - P.f_col_bands, k = jj / 6, r = jj - 6 * k, c = r % 3;
+                part5[c] += band_grad(T.x[c], P.f_kmin + k, 1.f, r >= 3, g);       // windows are folded into the weights
+              }
+            }
+          }
+          float* scr = reinterpret_cast<float*>(smem + OFF_IN2) + ((size_t)row * NSUB + sub) * 8;
+          for (int i = 0; i < 5; ++i) scr[i] = part5[i];
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+          float tot[5];
+          for (int i = 0; i < 5; ++i) {
+            const float* r4 = reinterpret_cast<const float*>(smem + OFF_IN2) + (size_t)row * NSUB * 8 + i;
+            tot[i] = (r4[0] + r4[8]) + (r4[16] + r4[24]);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the block is re-used by the next reduction
+          if (sp.arg == 0) { for (int c = 0; c < 3; ++c) GS.gxw[c] = tot[c]; GS.gom[0] = tot[3]; GS.gom[1] = tot[4]; }
+          else if (sub == 0 && T.valid) {
+            // d sigma_raw / dx = (feature-block path of the warp field and the hyper sheet) + R^T (d / d x')
+            float gx[3], gn[3], tn[3], tnn[3];
+            for (int c = 0; c < 3; ++c)
+              gx[c] = -(tot[c] + (cfg.use_warp ? (T.R[0 * 3 + c] * GS.gxw[0] + T.R[1 * 3 + c] * GS.gxw[1] + T.R[2 * 3 + c] * GS.gxw[2]) : GS.gxw[c]));
+            normalize3(gx, gn);                                             // models.py:1070, 1077
+            for (int c = 0; c < 3; ++c) tn[c] = cfg.use_warp ? (T.R[c * 3 + 0] * gn[0] + T.R[c * 3 + 1] * gn[1] + T.R[c * 3 + 2] * gn[2]) : gn[c];
+            normalize3(tn, tnn);                                            // models.py:1273-1277
+            float* PL = a.planes;
+            const int64_t ps = a.plane_stride, n = T.n_out;
+            for (int c = 0; c < 3; ++c) { PL[(P_GRAD + c) * ps + n] = gn[c]; PL[(P_TNORM + c) * ps + n] = tnn[c]; }
+          }
+          }
+         }
         } else {
           // ---- STEP_OUT: write planes (the warps sharing a sample take different planes) ----
           const int64_t n = T.n_out;
@@ -853,8 +1045,10 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   Ctrl* ctl = reinterpret_cast<Ctrl*>(smem + OFF_CTRL);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < P.n_burst * 8; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ctl->burst)[i] = reinterpret_cast<const uint32_t*>(P.burst)[i];
+  {
+    uint32_t* c_burst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ctl) + ctrl_off_burst(P.n_ops, P.n_steps));
+    for (int i = threadIdx.x; i < P.n_burst * 8; i += blockDim.x) c_burst[i] = reinterpret_cast<const uint32_t*>(P.burst)[i];
+  }
   if (threadIdx.x == 0) ctrl_init(ctl);
   if (warp == WARP_MMA) tmem_alloc(&ctl->tmem_base, 512);
   tc_fence_before_sync();
@@ -982,6 +1176,10 @@ struct OpBuild {
   int interleave = 0;                 // order the bursts K-range-major so that chunk 1's epilogue stays hidden
   int cross_first = 0;                // 3-term op whose weight images are all resident (N phase): issue the small
                                       // terms of every K-chunk before any main term (see issue_pair)
+  int mask_idx = 0, mask_mode = MASK_NONE;   // ReLU mask words the epilogue records (forward) / applies (reverse sweep)
+  int row_band[64];                   // reverse sweep, input-gradient ops of the narrow networks: output row n is feature-
+  int row_pe = -1;                    // block column n; >= 0: its weights carry posenc window row_band[n] of encoder row_pe
+  OpBuild() { for (int i = 0; i < 64; ++i) row_band[i] = -1; }
   uint16_t first_flags = 0;           // B_WAIT_* of the first burst
   uint16_t first_part_waits = 0;      // bit c: the first burst waits for part c of the previous op
   int signal_glue = 0;
@@ -996,7 +1194,8 @@ struct WindowedImage {
   size_t stream_off;                  // byte offset of the B_hi image (B_lo follows when terms == 3)
   int rows, terms, pe;
   std::vector<float> w;               // [rows][64] scaled weights without the window
-  int band[64];
+  int band[64];                       // per K column
+  int row_band[128];                  // per output row (input-gradient ops), -1 = none
 };
 
 struct Packed {
@@ -1074,11 +1273,12 @@ static float op_scale(const OpBuild& ob, int& e_out) {
   return std::ldexp(1.f, e);
 }
 
-static void write_image(uint8_t* dst, const float* w /*[rows][64]*/, const float* colscale, int rows, int terms) {
+static void write_image(uint8_t* dst, const float* w /*[rows][64]*/, const float* colscale, int rows, int terms,
+                        const float* rowscale = nullptr) {
   const size_t img = (size_t)rows * 128;
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < 64; ++c) {
-      const float v = w[(size_t)r * 64 + c] * (colscale ? colscale[c] : 1.f);
+      const float v = w[(size_t)r * 64 + c] * (colscale ? colscale[c] : 1.f) * (rowscale ? rowscale[r] : 1.f);
       const __half hi = __float2half_rn(v);
       const __half lo = __float2half_rn(v - __half2float(hi));
       const uint32_t o = kblock_offset((uint32_t)r, (uint32_t)c);
@@ -1122,10 +1322,14 @@ static OpWeights pack_weights(const OpBuild& ob, Packed& out) {
       out.stream.resize(base + img * (kterms == 3 ? 2 : 1), 0);
       write_image(&out.stream[base], w.data(), nullptr, nc_rows, kterms);
       ow.src.push_back((uint32_t)(base / 128));
+      if (ob.row_pe >= 0) {
+        for (int r = 0; r < nc_rows && r < 64; ++r) if (ob.row_band[r] >= 0) windowed = true;
+      }
       if (windowed) {
         WindowedImage wi;
-        wi.stream_off = base; wi.rows = nc_rows; wi.terms = kterms; wi.pe = km.pe; wi.w = w;
+        wi.stream_off = base; wi.rows = nc_rows; wi.terms = kterms; wi.pe = ob.row_pe >= 0 ? ob.row_pe : km.pe; wi.w = w;
         memcpy(wi.band, km.band, sizeof wi.band);
+        for (int r = 0; r < 128; ++r) wi.row_band[r] = (ob.row_pe >= 0 && r < 64) ? ob.row_band[r] : -1;
         out.windowed.push_back(std::move(wi));
       }
     }
@@ -1146,6 +1350,8 @@ static TcOp make_tcop(const OpBuild& ob, const OpWeights& ow) {
   op.d_col[0] = (uint16_t)ob.d_col[0];
   op.d_col[1] = (uint16_t)ob.d_col[1];
   op.signal_glue = (uint8_t)ob.signal_glue;
+  op.mask_idx = (uint8_t)ob.mask_idx;
+  op.mask_mode = (uint8_t)ob.mask_mode;
   return op;
 }
 
@@ -1281,8 +1487,8 @@ static bool query_smem_base(uint32_t& base, std::string& err) {
   if (!have) {
     uint32_t* d = nullptr;
     cudaError_t e = cudaMalloc(&d, 4);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (e == cudaSuccess) { smem_base_probe_kernel<<<1, 32, TC_SMEM_BYTES>>>(d); e = cudaDeviceSynchronize(); }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_PROBE);
+    if (e == cudaSuccess) { smem_base_probe_kernel<<<1, 32, TC_SMEM_PROBE>>>(d); e = cudaDeviceSynchronize(); }
     if (e == cudaSuccess) e = cudaMemcpy(&cached, d, 4, cudaMemcpyDeviceToHost);
     if (d) cudaFree(d);
     if (e != cudaSuccess) { err = std::string("tensor-core engine: shared-memory base probe: ") + cudaGetErrorString(e); return false; }
@@ -1318,7 +1524,7 @@ static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, uint32_t s
     if (i + 1 < n) { if (hb[i + 1].flags & B_ACQUIRE) nu = 1u + hb[i + 1].unit; }
     else if (cyclic && (hb[0].flags & B_ACQUIRE)) { nu = 1u + hb[0].unit; wrap = 1; }
     b.ctl = (uint32_t)(e.flags & 0x1fffu) | ((uint32_t)e.pat << 13) | ((uint32_t)e.steps << 15) | ((uint32_t)e.tslot << 18) |
-            ((uint32_t)e.unit << 19) | (nu << 21) | (wrap << 24) | ((uint32_t)(e.pair ? 1u : 0u) << 25);
+            ((uint32_t)e.unit << 19) | (nu << 21) | (wrap << 24) | (e.pair ? CTL_PAIR : 0u) | e.ctl_extra;
     const uint32_t eb = (e.flags & B_RELEASE) ? NDS_BAR_IDX(empty) + e.unit : 0xffu;
     const uint32_t db = (e.flags & B_LAST) ? NDS_BAR_IDX(d_full) + 2u * e.tslot + ((e.flags & B_NC1) ? 1u : 0u) : 0xffu;
     const uint32_t pb = nu ? NDS_BAR_IDX(full) + (nu - 1u) : 0xffu;
@@ -1335,7 +1541,7 @@ static void encode_bursts(const std::vector<BurstH>& hb, bool cyclic, uint32_t s
 // Returns the last layer's layout.
 static ActLayout build_mlp_ops(const HostMlp& m, int terms, bool wide, int tslot, const KChunkMap& in0,
                                const KChunkMap& in_skip, uint16_t first_flags, std::vector<OpBuild>& ops,
-                               bool cross_first = false) {
+                               bool cross_first = false, int mask_base = -1) {
   ActLayout prev;
   for (int l = 0; l < m.depth; ++l) {
     OpBuild ob;
@@ -1354,6 +1560,7 @@ static ActLayout build_mlp_ops(const HostMlp& m, int terms, bool wide, int tslot
       ob.cross_first = cross_first ? 1 : 0;
     }
     ob.terms = terms; ob.relu = 1; ob.glue = GLUE_NONE; ob.epi_kind = EPI_INPLACE;
+    if (mask_base >= 0) { ob.mask_mode = MASK_RECORD; ob.mask_idx = mask_base + l * ob.n_nc; }
     ob.prev_produces = l > 0;
     if (l == 0) ob.first_flags = first_flags;
     // the second trunk layer of tile slot 0 accumulates over the columns of tile slot 1's narrow networks
@@ -1395,6 +1602,66 @@ static void build_head_op(const std::vector<const HostDense*>& heads, const ActL
   for (int j = 0; j < in.N / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, true));
   ops.push_back(ob);
 }
+// Reverse sweep of one modules.MLP (App. E): with zbar_l = (d sigma / d h_l) masked by layer l's ReLU, appends
+//   bwd(L-1) ... bwd(skip+1), INGRAD(skip), bwd(skip), ..., bwd(1), INGRAD(0)
+// where bwd(l): zbar_{l-1} = (zbar_l W_l[h rows]^T) masked by layer l-1, and INGRAD(l): 64 columns of
+// zbar_l W_l[input rows]^T in the layout of the network's input block (`in0` / `in_skip`: column -> W row, windows).
+// The seed zbar_{L-1} is written by the compute warps (STEP_SEED) into region 0; regions alternate from there.
+static void build_mlp_backward(const HostMlp& m, int terms, bool wide, int tslot, const KChunkMap& in0,
+                               const KChunkMap& in_skip, int mask_base, bool cross_first, std::vector<OpBuild>& ops) {
+  const int L = m.depth, W = m.width, n_nc = wide ? 2 : 1;
+  auto layout = [&](int region) {
+    ActLayout a;
+    a.N = W; a.n_nc = n_nc; a.region = region;
+    if (wide) { a.d_col[0] = region * 256; a.d_col[1] = a.d_col[0] + 128; }
+    else a.d_col[0] = a.d_col[1] = 256 * tslot + 128 * region;
+    return a;
+  };
+  int region = 0;                      // where zbar_l lives
+  auto ingrad = [&](int l, const KChunkMap& map) {
+    OpBuild ob;
+    ob.N_logical = ob.N = 64; ob.n_nc = 1; ob.tslot = tslot;
+    const ActLayout out = layout(1 - region);
+    ob.d_col[0] = ob.d_col[1] = out.d_col[0];
+    ob.terms = terms; ob.relu = 0; ob.epi_kind = EPI_INGRAD; ob.glue = GLUE_NONE; ob.prev_produces = 1;
+    ob.signal_glue = l != 0 ? 1 : 0;   // a hidden op overwrites these accumulators next
+    ob.cross_first = (!wide && cross_first) ? 1 : 0;
+    const std::vector<float>& Wl = m.hidden[l].W;      // [K_l][W]
+    ob.W_own.assign((size_t)W * 64, 0.f);
+    ob.b_own.assign(64, 0.f);
+    for (int n = 0; n < 64; ++n) {
+      if (map.rows[n] < 0) continue;
+      for (int k = 0; k < W; ++k) ob.W_own[(size_t)k * 64 + n] = Wl[(size_t)map.rows[n] * W + k];
+      ob.row_band[n] = map.band[n];
+    }
+    ob.row_pe = map.pe;
+    const ActLayout in = layout(region);
+    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, true));
+    ops.push_back(ob);
+  };
+  for (int l = L - 1; l >= 1; --l) {
+    const bool after_ingrad = l == m.skip;
+    if (after_ingrad) ingrad(l, in_skip);
+    OpBuild ob;
+    ob.N_logical = ob.N = W; ob.n_nc = n_nc; ob.tslot = tslot; ob.interleave = wide ? 1 : 0;
+    const ActLayout out = layout(1 - region), in = layout(region);
+    ob.d_col[0] = out.d_col[0]; ob.d_col[1] = out.d_col[1];
+    ob.terms = terms; ob.relu = 0; ob.epi_kind = EPI_INPLACE; ob.glue = GLUE_NONE;
+    ob.mask_mode = MASK_APPLY; ob.mask_idx = mask_base + (l - 1) * n_nc;
+    ob.cross_first = (!wide && cross_first) ? 1 : 0;
+    ob.prev_produces = after_ingrad ? 0 : 1;           // the INGRAD op before it consumed the phase
+    if (after_ingrad) ob.first_flags = B_WAIT_GLUE;    // ... and its accumulators must have been read
+    const std::vector<float>& Wl = m.hidden[l].W;      // [W (+ in_dim)][W], h rows first
+    ob.W_own.assign((size_t)W * W, 0.f);
+    ob.b_own.assign(W, 0.f);
+    for (int k = 0; k < W; ++k) for (int n = 0; n < W; ++n) ob.W_own[(size_t)k * W + n] = Wl[(size_t)n * W + k];
+    for (int j = 0; j < W / 64; ++j) ob.kcs.push_back(kc_hidden(in, j, 0, !after_ingrad));
+    ops.push_back(ob);
+    region = 1 - region;
+  }
+  ingrad(0, in0);
+}
+
 static void fix_own(std::vector<OpBuild>& ops) {
   for (auto& ob : ops) if (!ob.W) { ob.W = &ob.W_own; ob.b = &ob.b_own; }
 }
@@ -1406,12 +1673,15 @@ struct LevelBuild {
   int trunk_first = 0, trunk_skip_op = -1;
   FLayout F;
   int t_cols = 0;
+  // reverse sweep (appended after the forward ops): [tb_first, tb_first + tb_count) trunk, then the hyper sheet
+  // [hb_first, + hb_count) and the SE(3) field [wb_first, + wb_count)
+  int n_fwd = 0, tb_first = 0, tb_count = 0, hb_first = 0, hb_count = 0, wb_first = 0, wb_count = 0;
 };
 
 struct TcEngine {
   Packed packed[2];
   LevelBuild lb[2];
-  TcProgram prog[2][3];               // [level][0 sigma-only | 1 full | 2 full, carried (no N phase)]
+  TcProgram prog[2][4];               // [level][0 sigma-only | 1 full | 2 full, carried (no N phase) | 3 full + reverse sweep]
   uint8_t* d_stream[2] = {nullptr, nullptr};
   float* d_bias[2] = {nullptr, nullptr};
   float win[2][3][NDSR_MAX_BANDS];    // windows currently folded into the streams, per level
@@ -1421,11 +1691,14 @@ struct TcEngine {
 // Merges the per-slot op lists into the pair program: bursts (issuer / producer) and steps (compute warps).
 // `carried`: no N phase -- the narrow networks' results come from the carry planes, the trunk input is written by
 // the PREP steps and the first trunk layer waits for them.
-static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t smem_base, TcProgram& prog, std::string& err) {
+static bool assemble(const LevelBuild& LB, bool full, bool carried, bool grad, uint32_t smem_base, TcProgram& prog, std::string& err) {
   memset(&prog, 0, sizeof prog);
   prog.smem_base = smem_base;
   prog.carried = carried ? 1 : 0;
-  const int n_ops = full ? (int)LB.ops[0].size() : LB.n_sigma;
+  prog.grad = grad ? 1 : 0;
+  if (grad && (!full || carried)) { err = "tensor-core engine: the reverse sweep is built for the full program"; return false; }
+  const int n_fwd = full ? LB.n_fwd : LB.n_sigma;
+  const int n_ops = grad ? (int)LB.ops[0].size() : n_fwd;       // per tile slot
   if (2 * n_ops > MAX_OPS) { err = "tensor-core engine: too many layers"; return false; }
   prog.n_ops = 2 * n_ops;
   prog.full = full ? 1 : 0;
@@ -1438,14 +1711,24 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
   for (int s = 0; s < 2; ++s)
     for (int i = 0; i < n_ops; ++i) {
       OpBuild ob = LB.ops[s][i];
-      if (!full && i == n_ops - 1) ob.signal_glue = 0;      // nothing follows the sigma head
+      if (!full && i == n_fwd - 1) ob.signal_glue = 0;      // nothing follows the sigma head
+      if (!grad) ob.mask_mode = MASK_NONE;
       prog.ops[op_index(s, i)] = make_tcop(ob, LB.weights[i]);
-      prog.ops[op_index(s, i)].signal_done = (i == n_ops - 1) ? 1 : 0;
+      // the tile slot's tensor-memory columns are free again: after the T phase (slot 1 may start its own; with a
+      // reverse sweep only slot 0 signals here, see the N-phase sweep below) and after the whole program of the slot
+      const bool t_end = grad ? (s == 0 && i == LB.tb_first + LB.tb_count - 1) : (i == n_fwd - 1);
+      prog.ops[op_index(s, i)].signal_done = (t_end || (grad && i == n_ops - 1)) ? 1 : 0;
     }
   auto step_of = [&](int s, int i) {
     Step st;
-    st.kind = LB.ops[s][i].epi_kind == EPI_HEAD ? STEP_HEAD : STEP_EPI;
+    const int ek = LB.ops[s][i].epi_kind;
+    st.kind = ek == EPI_HEAD ? STEP_HEAD : (ek == EPI_INGRAD ? STEP_INGRAD : STEP_EPI);
     st.tslot = (uint8_t)s; st.op = (uint8_t)op_index(s, i); st.arg = 0;
+    return st;
+  };
+  auto aux_step = [&](int kind, int s, int op, int arg) {
+    Step st;
+    st.kind = (uint8_t)kind; st.tslot = (uint8_t)s; st.op = (uint8_t)op; st.arg = (uint8_t)arg;
     return st;
   };
   // ---- N phase: both tile slots op by op; slot 0 acquires the weights, slot 1 releases them
@@ -1468,7 +1751,7 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
   // ---- T phase: tile slot 0, then tile slot 1
   for (int s = 0; s < 2; ++s) {
     int prep_next = 0;
-    for (int i = LB.n_narrow; i < n_ops; ++i) {
+    for (int i = LB.n_narrow; i < n_fwd; ++i) {
       std::vector<BurstH> b = make_bursts(LB.ops[s][i], LB.weights[i]);
       if (carried && i == LB.trunk_first)       // inputs come from the PREP steps; the other slot must have left the T phase
         b[0].flags = (uint16_t)((b[0].flags & ~B_WAIT_GLUE) | B_WAIT_PREP | B_WAIT_DONE_OTHER);
@@ -1498,8 +1781,59 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
       Step p; p.kind = STEP_PREP; p.tslot = (uint8_t)s; p.op = 0; p.arg = (uint8_t)prep_next;
       steps.push_back(p);
     }
+    if (grad) {
+      // reverse sweep through the trunk: seed = column 0 of the sigma head under the last layer's ReLU, then the
+      // transposed-weight chain; the two input-gradient ops sum into the thread's 16 columns
+      steps.push_back(aux_step(STEP_SEED, s, op_index(s, LB.tb_first), SEED_TRUNK));
+      bool first_ingrad = true;
+      for (int i = LB.tb_first; i < LB.tb_first + LB.tb_count; ++i) {
+        std::vector<BurstH> b = make_bursts(LB.ops[s][i], LB.weights[i]);
+        int unit_of[64];
+        std::fill(unit_of, unit_of + 64, -1);
+        assign_units(b, cursor, unit_of, true, true);
+        bursts.insert(bursts.end(), b.begin(), b.end());
+        Step st = step_of(s, i);
+        if (st.kind == STEP_INGRAD) { st.arg = first_ingrad ? 1 : 0; first_ingrad = false; }
+        steps.push_back(st);
+      }
+      steps.push_back(aux_step(STEP_PEB, s, 0, 0));
+    }
     Step o; o.kind = STEP_OUT; o.tslot = (uint8_t)s; o.op = 0; o.arg = 0;
     steps.push_back(o);
+  }
+  if (grad) {
+    // ---- reverse sweep through the narrow networks, both tile slots op by op like the N phase (slot 0 acquires the
+    // weights, slot 1 releases them).  Tile slot 0's columns were last used by slot 1's T phase, which the compute
+    // warps have left before they write the seeds the first bursts wait for.
+    bool first_ingrad = true;
+    auto sweep = [&](int first, int count, int seed) {
+      if (count == 0) return true;
+      for (int s = 0; s < 2; ++s) steps.push_back(aux_step(STEP_SEED, s, op_index(s, first), seed));
+      for (int i = first; i < first + count; ++i) {
+        std::vector<BurstH> b0 = make_bursts(LB.ops[0][i], LB.weights[i]);
+        std::vector<BurstH> b1 = make_bursts(LB.ops[1][i], LB.weights[i]);
+        if ((int)LB.ops[0][i].kcs.size() > NUNIT - 1) { err = "tensor-core engine: narrow layer with too many K-chunks for the weight ring"; return false; }
+        int unit_of[64];
+        std::fill(unit_of, unit_of + 64, -1);
+        assign_units(b0, cursor, unit_of, true, false);
+        assign_units(b1, cursor, unit_of, false, true);
+        bursts.insert(bursts.end(), b0.begin(), b0.end());
+        bursts.insert(bursts.end(), b1.begin(), b1.end());
+        for (int s = 0; s < 2; ++s) {
+          Step st = step_of(s, i);
+          if (st.kind == STEP_INGRAD) st.arg = first_ingrad ? 1 : 0;
+          steps.push_back(st);
+        }
+        if (LB.ops[0][i].epi_kind == EPI_INGRAD) first_ingrad = false;
+      }
+      return true;
+    };
+    if (!sweep(LB.hb_first, LB.hb_count, SEED_HYPER)) return false;
+    if (!sweep(LB.wb_first, LB.wb_count, SEED_WARP)) return false;
+    for (int s = 0; s < 2; ++s) steps.push_back(aux_step(STEP_PEB, s, 0, 1));
+    // the next pair's N phase accumulates over BOTH slots' columns: besides slot 1 (B_WAIT_DONE_OTHER) it waits for
+    // slot 0's reverse sweep
+    bursts[0].ctl_extra |= CTL_WAIT_DONE_SELF;
   }
   if ((int)bursts.size() > MAX_BURST || (int)steps.size() > MAX_STEPS) { err = "tensor-core engine: layer program too long"; return false; }
   // ring safety: a unit is re-acquired only if its previous occupant was released at least two bursts earlier
@@ -1523,6 +1857,8 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, uint32_t sme
   }
   prog.n_burst = (int)bursts.size();
   prog.n_steps = (int)steps.size();
+  prog.smem_bytes = OFF_CTRL + ctrl_bytes(prog.n_ops, prog.n_steps, prog.n_burst) + 1024;    // + manual 1024-byte alignment slack
+  if (prog.smem_bytes > TC_SMEM_MAX) { err = "tensor-core engine: layer program does not fit the shared-memory control block"; return false; }
   encode_bursts(bursts, true, smem_base, prog.burst, prog.src);
   std::copy(steps.begin(), steps.end(), prog.steps);
   return true;
@@ -1579,6 +1915,7 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
     std::vector<OpBuild>& ops = LB.ops[s];
     const uint32_t in_off = OFF_IN + (uint32_t)s * 2u * KBLK;
     bool first_net = true;
+    KChunkMap hyper_k0, hyper_ks, warp_k0, warp_ks;     // kept for the reverse sweep
     auto first_flags = [&]() {
       uint16_t f = first_net ? (uint16_t)(B_WAIT_PREP | (s == 0 ? B_WAIT_DONE_OTHER : 0)) : (uint16_t)B_WAIT_GLUE;
       first_net = false;
@@ -1593,13 +1930,15 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
       const bool wm = c.use_mask_in_hyper != 0;
       const KChunkMap k0 = kc_features(F, in_off, 0, 2, c.hyper_sheet_min_deg, c.hyper_sheet_max_deg, 0, F.col_wembed, c.warp_embed_dims, wm);
       const KChunkMap ks = kc_features(F, in_off, HM.hyper.width, 2, c.hyper_sheet_min_deg, c.hyper_sheet_max_deg, 0, F.col_wembed, c.warp_embed_dims, wm);
-      build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, false, s, k0, ks, first_flags(), ops, xf_hyper), t_sigma, GLUE_HYPER, false, s, 1, ops, xf_hyper);
+      build_head_op({&HM.hyper.logit}, build_mlp_ops(HM.hyper, t_sigma, false, s, k0, ks, first_flags(), ops, xf_hyper, MASK_HYPER), t_sigma, GLUE_HYPER, false, s, 1, ops, xf_hyper);
+      hyper_k0 = k0; hyper_ks = ks;
     }
     {
       const bool wm = c.use_mask_in_warp != 0;
       const KChunkMap k0 = kc_features(F, in_off, 0, 1, c.warp_min_deg, c.warp_max_deg, c.warp_use_posenc_identity, F.col_wembed, c.warp_embed_dims, wm);
       const KChunkMap ks = kc_features(F, in_off, HM.warp.width, 1, c.warp_min_deg, c.warp_max_deg, c.warp_use_posenc_identity, F.col_wembed, c.warp_embed_dims, wm);
-      build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, false, s, k0, ks, first_flags(), ops, xf_warp), t_sigma, GLUE_WARP, false, s, 1, ops, xf_warp);
+      build_head_op({&HM.warp_w, &HM.warp_v}, build_mlp_ops(HM.warp, t_sigma, false, s, k0, ks, first_flags(), ops, xf_warp, MASK_WARP), t_sigma, GLUE_WARP, false, s, 1, ops, xf_warp);
+      warp_k0 = k0; warp_ks = ks;
     }
     LB.n_narrow = (int)ops.size();
     // ---- template NeRF
@@ -1608,7 +1947,7 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
     LB.trunk_skip_op = LB.trunk_first + (TR.skip > 0 ? TR.skip : 0);
     const KChunkMap t0 = kc_input(in_off, 0, TR.in_dim), tsk = kc_input(in_off, TR.width, TR.in_dim);
     const uint16_t tflags = (uint16_t)(B_WAIT_GLUE | (s == 1 ? B_WAIT_DONE_OTHER : 0));
-    const ActLayout trunk = build_mlp_ops(TR, t_sigma, true, s, t0, tsk, tflags, ops);
+    const ActLayout trunk = build_mlp_ops(TR, t_sigma, true, s, t0, tsk, tflags, ops, false, MASK_TRUNK);
     build_head_op({&HM.alpha[lv]}, trunk, t_sigma, GLUE_ALPHA, true, s, 1, ops);
     LB.n_sigma = (int)ops.size();
     // ---- rgb branch (modules.py:288-313).  Flax input order of its Dense(560 -> 128):
@@ -1682,6 +2021,17 @@ static int build_level(ndsr_handle* h, int lv, LevelBuild& LB, Packed& P) {
       for (int j = 0; j < R.width / 64; ++j) hb.kcs.push_back(kc_hidden(rgbh, j, 0, true));
       ops.push_back(hb);
     }
+    // ---- reverse sweep for -d(sigma_raw)/dx (models.py:1035-1077): trunk, then hyper sheet and SE(3) field
+    LB.n_fwd = (int)ops.size();
+    LB.tb_first = (int)ops.size();
+    build_mlp_backward(TR, t_sigma, true, s, t0, tsk, MASK_TRUNK, false, ops);
+    LB.tb_count = (int)ops.size() - LB.tb_first;
+    LB.hb_first = (int)ops.size();
+    if (c.use_hyper_sheet) build_mlp_backward(HM.hyper, t_sigma, false, s, hyper_k0, hyper_ks, MASK_HYPER, xf_hyper, ops);
+    LB.hb_count = (int)ops.size() - LB.hb_first;
+    LB.wb_first = (int)ops.size();
+    build_mlp_backward(HM.warp, t_sigma, false, s, warp_k0, warp_ks, MASK_WARP, xf_warp, ops);
+    LB.wb_count = (int)ops.size() - LB.wb_first;
     fix_own(ops);
   }
   for (size_t i = 0; i < LB.ops[0].size(); ++i) LB.weights.push_back(pack_weights(LB.ops[0][i], P));
@@ -1698,8 +2048,8 @@ int tc_engine_load(ndsr_handle* h) {
     int rc = build_level(h, lv, E->lb[lv], E->packed[lv]);
     if (rc) return rc;
     Packed& P = E->packed[lv];
-    for (int mode = 0; mode < 3; ++mode)
-      if (!assemble(E->lb[lv], mode != 0, mode == 2, smem_base, E->prog[lv][mode], h->err)) return NDSR_ERR_UNSUPPORTED;
+    for (int mode = 0; mode < 4; ++mode)
+      if (!assemble(E->lb[lv], mode != 0, mode == 2, mode == 3, smem_base, E->prog[lv][mode], h->err)) return NDSR_ERR_UNSUPPORTED;
     cudaError_t e;
     if ((e = cudaMalloc(&E->d_stream[lv], P.stream.size())) != cudaSuccess ||
         (e = cudaMalloc(&E->d_bias[lv], P.bias.size() * sizeof(float))) != cudaSuccess ||
@@ -1712,7 +2062,8 @@ int tc_engine_load(ndsr_handle* h) {
     for (int p = 0; p < 3; ++p) for (int k = 0; k < NDSR_MAX_BANDS; ++k) E->win[lv][p][k] = 1.f;
     E->win_valid[lv] = true;
   }
-  cudaError_t e = cudaFuncSetAttribute(field_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(field_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(field_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX);
   if (e != cudaSuccess) { h->err = std::string("tc smem attribute: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
   return NDSR_OK;
 }
@@ -1739,10 +2090,11 @@ static int fold_windows(ndsr_handle* h, int lv, const CallParams& cp, cudaStream
   if (same) return NDSR_OK;
   Packed& P = E->packed[lv];
   for (const WindowedImage& wi : P.windowed) {
-    float colscale[64];
+    float colscale[64], rowscale[128];
     for (int c = 0; c < 64; ++c) colscale[c] = wi.band[c] >= 0 ? pes[wi.pe]->window[wi.band[c]] : 1.f;
+    for (int r = 0; r < 128; ++r) rowscale[r] = wi.row_band[r] >= 0 ? pes[wi.pe]->window[wi.row_band[r]] : 1.f;
     const size_t bytes = (size_t)wi.rows * 128 * (wi.terms == 3 ? 2 : 1);
-    write_image(&P.stream[wi.stream_off], wi.w.data(), colscale, wi.rows, wi.terms);
+    write_image(&P.stream[wi.stream_off], wi.w.data(), colscale, wi.rows, wi.terms, rowscale);
     cudaError_t e = cudaMemcpyAsync(E->d_stream[lv] + wi.stream_off, &P.stream[wi.stream_off], bytes, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { h->err = std::string("fold_windows: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
   }
@@ -1760,11 +2112,16 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
   if (rc) return rc;
   TcKernelArgs K;
   if (fa.carry && fa.sigma_only) { h->err = "tensor-core engine: carried launches are built for the full program"; return NDSR_ERR_INVALID; }
-  const TcProgram& prog = E->prog[fa.level][fa.carry ? 2 : (fa.sigma_only ? 0 : 1)];
+  if (fa.need_grad && (fa.carry || fa.carry_out)) { h->err = "tensor-core engine: the reverse sweep runs in a single launch"; return NDSR_ERR_INVALID; }
+  const TcProgram& prog = E->prog[fa.level][fa.need_grad ? 3 : (fa.carry ? 2 : (fa.sigma_only ? 0 : 1))];
   K.lvl.weights = E->d_stream[fa.level];
   K.lvl.bias = E->d_bias[fa.level];
   K.warp_embed = h->M.warp_embed;
   K.mask_embed = h->M.mask_embed;
+  K.alpha_col0 = h->M.alpha_col0[fa.level];
+  K.hyper_logit_w = h->cfg.use_hyper_sheet ? h->M.hyper.logit.W : nullptr;
+  K.warp_w_w = h->M.warp_w.W;
+  K.warp_v_w = h->M.warp_v.W;
   K.trace = nullptr;
   const char* trace_path = getenv("NDS_TC_TRACE");
   if (trace_path && !fa.sigma_only) {
@@ -1774,7 +2131,8 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
   const int64_t pairs = (tiles + 1) / 2;
   int grid = (int)(pairs < h->num_sms ? pairs : h->num_sms);
   if (const char* g = getenv("NDS_TC_GRID")) { const int v = atoi(g); if (v > 0 && v < grid) grid = v; }   // experiments
-  field_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(prog, K, cp, fa, h->cfg);
+  if (prog.grad) field_tc_kernel<true><<<grid, TC_THREADS, prog.smem_bytes, st>>>(prog, K, cp, fa, h->cfg);
+  else field_tc_kernel<false><<<grid, TC_THREADS, prog.smem_bytes, st>>>(prog, K, cp, fa, h->cfg);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string("field_tc_kernel launch: ") + cudaGetErrorString(e); return NDSR_ERR_CUDA; }
   if (K.trace) {   // diagnostics only: synchronous dump of the stamps, relative to the pair start
@@ -1808,14 +2166,14 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
 
 }  // namespace nds
 
-// tensor-core MACs the programs ISSUE per sample evaluation (split terms and padding included): out[level * 3 + mode],
-// mode 0 sigma-only | 1 full | 2 full, carried
+// tensor-core MACs the programs ISSUE per sample evaluation (split terms and padding included): out[level * 4 + mode],
+// mode 0 sigma-only | 1 full | 2 full, carried | 3 full + reverse sweep
 extern "C" int ndsr_tc_issued_macs(const ndsr_handle* h, double* out) {
   using namespace nds;
   if (!h || !out) return NDSR_ERR_INVALID;
   if (!h->tc) return NDSR_ERR_NOT_LOADED;
   for (int lv = 0; lv < 2; ++lv)
-    for (int mode = 0; mode < 3; ++mode) {
+    for (int mode = 0; mode < 4; ++mode) {
       const TcProgram& P = h->tc->prog[lv][mode];
       double macs = 0;
       for (int i = 0; i < P.n_burst; ++i) {
@@ -1825,7 +2183,7 @@ extern "C" int ndsr_tc_issued_macs(const ndsr_handle* h, double* out) {
         const double rows = (double)(((b.idesc >> 17) & 63u) * 8u);
         macs += (double)groups * per * rows * TM * 16.0;
       }
-      out[lv * 3 + mode] = macs / (2.0 * TM);       // a program covers a pair of tiles
+      out[lv * 4 + mode] = macs / (2.0 * TM);       // a program covers a pair of tiles
     }
   return NDSR_OK;
 }
@@ -1876,6 +2234,7 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
     assign_units(bursts, cursor, unit_of, true, true);
   }
   prog.n_burst = (int)bursts.size();
+  prog.smem_bytes = OFF_CTRL + ctrl_bytes(prog.n_ops, prog.n_steps, prog.n_burst) + 1024;
   {
     std::string perr;
     if (!query_smem_base(prog.smem_base, perr)) { fprintf(stderr, "%s\n", perr.c_str()); return NDSR_ERR_CUDA; }
@@ -1890,9 +2249,9 @@ extern "C" int ndsr_selftest_tc_dense(int device, int k_hid, int k_in, int n_out
   cudaMemcpy(d_bias, P.bias.data(), P.bias.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_A, A, (size_t)TM * K * 4, cudaMemcpyHostToDevice);
   cudaMemset(d_out, 0, (size_t)TM * N * 4); cudaMemset(d_rb, 0, (size_t)TM * N * 4);
-  cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+  cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_MAX);
   TcLevel L; L.weights = d_stream; L.bias = d_bias;
-  tc_selftest_kernel<<<1, TC_THREADS, TC_SMEM_BYTES>>>(prog, L, d_A, k_hid, k_in, d_out, d_rb);
+  tc_selftest_kernel<<<1, TC_THREADS, prog.smem_bytes>>>(prog, L, d_A, k_hid, k_in, d_out, d_rb);
   cudaError_t e = cudaDeviceSynchronize();
   int rc = NDSR_OK;
   if (e != cudaSuccess) { fprintf(stderr, "ndsr_selftest_tc_dense: %s\n", cudaGetErrorString(e)); rc = NDSR_ERR_CUDA; }

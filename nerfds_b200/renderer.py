@@ -99,9 +99,9 @@ class Renderer:
 
   def tc_issued_macs(self):
     """{(level, mode): tensor-core MACs issued per sample evaluation}; mode in 'sigma', 'full', 'carried'."""
-    out = (C.c_double * 6)()
+    out = (C.c_double * 8)()
     self._check(self.lib.ndsr_tc_issued_macs(self._h, out), 'ndsr_tc_issued_macs')
-    return {(lv, m): float(out[lv * 3 + i]) for lv in (0, 1) for i, m in enumerate(('sigma', 'full', 'carried'))}
+    return {(lv, m): float(out[lv * 4 + i]) for lv in (0, 1) for i, m in enumerate(('sigma', 'full', 'carried', 'grad'))}
 
   def set_max_chunk(self, rays: int):
     self._check(self.lib.ndsr_set_max_chunk(self._h, int(rays)), 'ndsr_set_max_chunk')

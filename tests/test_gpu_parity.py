@@ -274,6 +274,40 @@ def test_tc_strict_parity_at_scale(cuda_device):
     assert e.max() <= 6e-4, (name, float(e.max()))
 
 
+def test_tc_reverse_sweep_target_norm(cuda_device):
+  """-d(sigma_raw)/dx on the tensor cores (transposed-weight chain with ReLU masks, models.py:1035-1077):
+  `target_norm` of both levels against the oracle's autograd and against the fp32 CUDA-core engine (itself pinned to the
+  reference goldens), on the oracle's samples at nerf_ds.gin widths.  The forward results of the program that carries
+  the reverse sweep are bit-identical to those of the plain program."""
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=12, seed=5)
+  ref = run_oracle(cfg, params, rays, t_rand, u, compute_sigma_gradient=True)
+  res = {}
+  for eng in ('simt', 'tc'):
+    m = _model(cfg, cuda_device, engine=eng)
+    assert m.renderer.engine == eng
+    m.renderer.ensure_params(params)
+    extra = m.renderer.make_extra(syn.final_extra_params(), use_predicted_norm=True)
+    for want in (True, False):
+      keys = [k for k in m.renderer.level_keys(return_points=True, return_weights=True, want_target_norm=want)]
+      for lvl, name in ((0, 'coarse'), (1, 'fine')):
+        r = ref[name]
+        res[eng, want, name] = _np(m.renderer.render_samples(
+            lvl, r['z_vals'], rays['directions'], origins=rays['origins'], warp_id=rays['metadata']['warp'],
+            gt_mask=rays['mask'], extra=extra, use_sample_at_infinity=cfg.use_sample_at_infinity, keys=keys))
+  for name in ('coarse', 'fine'):
+    r = ref[name]
+    tc, simt, plain = res['tc', True, name], res['simt', True, name], res['tc', False, name]
+    for k in plain:                                   # same forward arithmetic, same MMA order
+      assert np.array_equal(tc[k], plain[k]), (name, k)
+    tn = tc['target_norm'].reshape(-1, 3)
+    assert np.isfinite(tn).all()
+    for other, tag in ((r['target_norm'].reshape(-1, 3), 'oracle'), (simt['target_norm'].reshape(-1, 3), 'simt')):
+      e = np.abs(tn - other).max(-1)
+      assert np.median(e) <= 1e-4 and np.mean(e <= GRAD_TOL) >= 0.97, (name, tag, float(np.median(e)), np.sort(e)[-5:])
+    nrm = np.linalg.norm(tn, axis=-1)
+    assert np.all((np.abs(nrm - 1) <= 1e-4) | (nrm <= 1e-3))
+
+
 def test_tc_end_to_end_matches_simt(cuda_device):
   """Whole NerfModel.__call__ on both engines: same sampling code, so the
   resampled depths agree except where 1e-6 weight differences flip a bin."""

@@ -65,20 +65,33 @@ int main(int argc, char** argv) {
     int r = build_level(h, lv, LB, P);
     if (r) { printf("level %d: build_level failed: %s\n", lv, h->err.c_str()); return 1; }
     static TcProgram prog;
-    const char* names[3] = {"sigma-only", "full", "full carried"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char* names[4] = {"sigma-only", "full", "full carried", "full + grad"};
+    for (int mode = 0; mode < 4; ++mode) {
       std::string err;
-      if (!assemble(LB, mode != 0, mode == 2, 1024u, prog, err)) { printf("level %d %s: assemble failed: %s\n", lv, names[mode], err.c_str()); rc = 1; continue; }
+      if (!assemble(LB, mode != 0, mode == 2, mode == 3, 1024u, prog, err)) { printf("level %d %s: assemble failed: %s\n", lv, names[mode], err.c_str()); rc = 1; continue; }
       long mmas = 0, pair = 0;
       for (int i = 0; i < prog.n_burst; ++i) {
         const uint32_t ctl = prog.burst[i].ctl;
         const int steps = (ctl >> 15) & 7, pat = (ctl >> 13) & 3;
         const int per = pat == PAT_SS ? steps : 4;
-        if (ctl & (1u << 25)) { mmas += 2 * per; ++pair; }
+        if (ctl & CTL_PAIR) { mmas += 2 * per; ++pair; }
         else mmas += per * ((ctl & B_TWO) ? 3 : 1);
       }
-      printf("level %d %-13s ops %3d bursts %3d (pair %3ld) steps %3d mma/pair-of-tiles %ld  stream %.2f MB\n", lv, names[mode], prog.n_ops,
-             prog.n_burst, pair, prog.n_steps, mmas, P.stream.size() / 1e6);
+      printf("level %d %-13s ops %3d bursts %3d (pair %3ld) steps %3d mma/pair-of-tiles %ld  stream %.2f MB  smem %u B\n", lv, names[mode], prog.n_ops,
+             prog.n_burst, pair, prog.n_steps, mmas, P.stream.size() / 1e6, prog.smem_bytes);
+      if (getenv("DUMP") && mode == atoi(getenv("DUMP")) && lv == 1) {
+        for (int i = 0; i < prog.n_burst; ++i) {
+          const Burst& b = prog.burst[i];
+          printf("  burst %3d slot %d rows %3d pat %d fl %04x pair %d dself %d unit %d d %3u a %u/%u\n", i, (b.ctl >> 18) & 1, ((b.idesc >> 17) & 63) * 8,
+                 (b.ctl >> 13) & 3, b.ctl & 0x1fff, (b.ctl >> 25) & 1, (b.ctl >> 26) & 1, (b.ctl >> 19) & 3, b.d, b.a_hi, b.a_lo);
+        }
+        for (int i = 0; i < prog.n_steps; ++i) {
+          const Step& st = prog.steps[i];
+          const TcOp& op = prog.ops[st.op];
+          printf("  step %3d kind %d slot %d op %3d arg %d | N %3d nnc %d epi %d dcol %3d mask %d/%d sg %d sd %d\n", i, st.kind, st.tslot, st.op, st.arg, op.N, op.n_nc, op.epi_kind,
+                 op.d_col[0], op.mask_idx, op.mask_mode, op.signal_glue, op.signal_done);
+        }
+      }
     }
   }
   printf(rc ? "FAILED\n" : "ok\n");
