@@ -708,7 +708,7 @@ def test_tensor_core_engine_against_reference_goldens(cuda_device):
           'mask': G['model_gt_mask']}
   m = _model(cfg, cuda_device, engine='tc')
   assert m.renderer.engine == 'tc'
-  keys = [k for k in m.renderer.level_keys(return_points=True, return_weights=True, want_target_norm=False)]
+  keys = [k for k in m.renderer.level_keys(return_points=True, return_weights=True, want_target_norm=True)]
   out = m.apply({'params': P}, rays, ep, t_rand=G['model_t_rand'], u=G['model_u'], use_predicted_norm=True,
                 mask_ratio=ratio, sharp_weights_std=0.1, keys=keys)
   o3, d3 = G['model_origins'], G['model_dirs']
@@ -726,3 +726,7 @@ def test_tensor_core_engine_against_reference_goldens(cuda_device):
       assert linf(res[k].reshape(g.shape), g) <= tol.get(k, RGB_TOL), (lvl, k, linf(res[k].reshape(g.shape), g))
     g = G[f'modelF_{lvl}_sigma']
     np.testing.assert_allclose(res['sigma'].reshape(g.shape), g, rtol=2e-3, atol=5e-3)
+    # target_norm from the tensor-core reverse sweep against the reference's own (float64 central differences of its
+    # per-point sigma function, rotated and normalised by its own code, models.py:1063-1077, 1273-1283)
+    e = np.abs(res['target_norm'].reshape(-1, 3) - G[f'modelF_{lvl}_target_norm'].reshape(-1, 3)).max(-1)
+    assert np.median(e) <= 2e-5 and np.mean(e <= 1e-3) >= 0.97, (lvl, float(np.median(e)), np.sort(e)[-4:])

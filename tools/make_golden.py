@@ -679,7 +679,7 @@ def main():
       use_predicted_norm=True, return_points=True, return_weights=True, mask_ratio=0.7, sharp_weights_std=0.1)
   for lvl in ('coarse', 'fine'):
     for k, v in resF[lvl].items():
-      if v is not None and k not in ('sharp_weights', 'target_norm'):
+      if v is not None and k != 'sharp_weights':
         G[f'modelF_{lvl}_{k}'] = f32(v)
 
   # ------------------------------------------------------------------ ray generation
