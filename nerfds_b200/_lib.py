@@ -11,7 +11,7 @@ import os
 from .config import NerfDSConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libnerfds_b200.so')
+LIB_PATH = os.environ.get('NDSR_LIBRARY') or os.path.join(_HERE, 'lib', 'libnerfds_b200.so')   # (override: A/B experiments)
 
 NDSR_ABI_VERSION = 2
 NDSR_MAX_MIRRORS = 15
