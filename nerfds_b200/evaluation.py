@@ -93,6 +93,31 @@ def all_gather_level(level: Dict[str, torch.Tensor], group=None) -> Dict[str, to
   return out
 
 
+def reference_draws(rng, num_rays: int, chunk: int, device_count: int, num_coarse: int, num_fine: int, device):
+  """The stratified / inverse-CDF draws of a whole frame exactly as `render_image` + a pmapped model make them
+  (evaluation.py:81-84, 94-120; models.py:1489, 1524): every chunk of `chunk` rays is edge-padded to a multiple of
+  `device_count` and sharded, device d draws `uniform(make_rng(key_i[d]), [rows, S])` for its rows -- the SAME keys
+  for every chunk.  Returns (t_rand [num_rays, num_coarse], u [num_rays, num_fine]) in frame order."""
+  _, key_0, key_1, _ = jax_random.split(rng, 4)
+  key_0, key_1 = jax_random.split(key_0, device_count), jax_random.split(key_1, device_count)
+  tables = {}
+
+  def table(rows):
+    if rows not in tables:
+      tables[rows] = tuple(torch.cat([jax_random.uniform(jax_random.flax_make_rng(ks[d]), (rows, S), device)
+                                      for d in range(device_count)], 0)
+                           for ks, S in ((key_0, num_coarse), (key_1, num_fine)))
+    return tables[rows]
+
+  ts, us = [], []
+  for ray_idx in range(0, num_rays, chunk):
+    n = min(chunk, num_rays - ray_idx)
+    t, u = table((n + device_count - 1) // device_count)
+    ts.append(t[:n])
+    us.append(u[:n])
+  return torch.cat(ts, 0), torch.cat(us, 0)
+
+
 def render_image(state, rays_dict, model_fn, device_count, rng, chunk=8192, default_ret_key=None):
   """hypernerf/evaluation.py:53-149 (same arguments, same chunk/pad/shard logic).
 

@@ -26,7 +26,8 @@ import torch
 
 from . import checkpoints
 from .camera import Camera, camera_to_rays, load_camera
-from .evaluation import render_image_sharded
+from . import jax_random
+from .evaluation import reference_draws, render_image_sharded
 from .models import NerfModel
 
 # render.py:189-190
@@ -58,9 +59,15 @@ def load_mask(path: str) -> np.ndarray:
 
 def render_scene(exp_dir: str, data_dir: str, camera_path_name: str = 'vrig_camera', interval: int = 1,
                  chunk_size: int = 65536, *, device=None, keys: Iterable[str] = RELEVANT_KEYS, seed: Optional[int] = None,
-                 save: bool = True, precision: str = 'split3', step: Optional[int] = None) -> List[Dict[str, np.ndarray]]:
+                 save: bool = True, precision: str = 'split3', step: Optional[int] = None,
+                 device_count: Optional[int] = None) -> List[Dict[str, np.ndarray]]:
   """render.py:36-243.  Returns (and, like the reference, np.save's under
-  `<exp_dir>/render_result_<camera_path_name>`) one dict of (H, W, .) maps per rendered camera."""
+  `<exp_dir>/render_result_<camera_path_name>`) one dict of (H, W, .) maps per rendered camera.
+
+  The stratified draws are the ones the reference makes: `rng = PRNGKey(random_seed); rng, _ = split(rng)`
+  (render.py:85, 100), the same `rng` for every frame (render.py:218), split per device and drawn per chunk as
+  evaluation.py:81-120 does for `device_count` devices (default: the size of the process group) -- generated on the
+  device by the threefry kernel."""
   cfg, params, extra, state, bindings = checkpoints.load_experiment(exp_dir, data_dir=data_dir, step=step)
   image_scale = bindings.get('ExperimentConfig.image_scale', bindings.get('image_scale', 1))
   with open(os.path.join(data_dir, 'scene.json')) as f:
@@ -77,7 +84,8 @@ def render_scene(exp_dir: str, data_dir: str, camera_path_name: str = 'vrig_came
 
   model = NerfModel(cfg, device=device, precision=precision)
   dev = model.device
-  gen = torch.Generator(device=dev)
+  rng, _ = jax_random.split(jax_random.PRNGKey(seed))          # render.py:85, 100
+  draws = {}
   results = []
   # one process per GPU: frames are assembled in every GPU's frame buffer by peer stores of the compositing kernel;
   # two buffer sets per image size alternate so that frame f can be copied out while frame f + 1 is written
@@ -98,9 +106,12 @@ def render_scene(exp_dir: str, data_dir: str, camera_path_name: str = 'vrig_came
     rays = {'origins': batch['origins'], 'directions': batch['directions'],
             'metadata': {'warp': torch.full((H, W, 1), i, dtype=torch.int64, device=dev)},   # render.py:203-216
             'mask': mask}
-    gen.manual_seed(seed * 1000003 + i)
-    t_rand = torch.rand((H * W, cfg.num_coarse_samples), generator=gen, device=dev) if cfg.use_stratified_sampling else None
-    u = torch.rand((H * W, cfg.num_fine_samples), generator=gen, device=dev) if cfg.use_stratified_sampling else None
+    t_rand = u = None
+    if cfg.use_stratified_sampling:
+      if (H, W) not in draws:
+        D = device_count or (dist.get_world_size() if multi else 1)
+        draws[(H, W)] = reference_draws(rng, H * W, chunk_size, D, cfg.num_coarse_samples, cfg.num_fine_samples, dev)
+      t_rand, u = draws[(H, W)]
     pf = None
     if multi:
       from .peer import PeerFrames

@@ -145,3 +145,22 @@ def test_device_uniform_row_ranges_and_host_call_with_keys(cuda_device):
                          fine_keys=('rgb', 'depth'), t_rand=oj.uniform(kc, (B, 16)), u=oj.uniform(kf, (B, 8)))
   for k in a:
     np.testing.assert_array_equal(a[k], b[k])
+
+
+@pytest.mark.gpu
+def test_reference_draws_follow_render_image_layout(cuda_device):
+  """evaluation.reference_draws: the draws of a whole frame laid out as evaluation.py:81-120 produces them under pmap
+  (same per-device keys for every chunk, edge-padded last chunk sharded over the devices)."""
+  from nerfds_b200.evaluation import reference_draws
+  rng, n, chunk, D, Sc, Sf = np.array([3, 9], np.uint32), 23, 10, 2, 6, 5
+  t, u = reference_draws(rng, n, chunk, D, Sc, Sf, cuda_device)
+  _, k0, k1, _ = jr.split(rng, 4)
+  k0, k1 = jr.split(k0, D), jr.split(k1, D)
+  want_t, want_u = [], []
+  for ray in range(0, n, chunk):
+    m = min(chunk, n - ray)
+    rows = -(-m // D)
+    want_t.append(np.concatenate([oj.uniform(jr.flax_make_rng(k0[d]), (rows, Sc)) for d in range(D)])[:m])
+    want_u.append(np.concatenate([oj.uniform(jr.flax_make_rng(k1[d]), (rows, Sf)) for d in range(D)])[:m])
+  np.testing.assert_array_equal(t.cpu().numpy(), np.concatenate(want_t))
+  np.testing.assert_array_equal(u.cpu().numpy(), np.concatenate(want_u))
