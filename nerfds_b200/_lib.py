@@ -157,6 +157,12 @@ def load_library() -> C.CDLL:
     raise ImportError(
         f'{LIB_PATH} is missing: build it with `python -m nerfds_b200.build` '
         '(nvcc, sm_100a).  There is no CPU fallback.')
+  if not os.environ.get('NDSR_LIBRARY'):
+    # provenance: the binary must have been built from exactly these sources (build.py records their sha256)
+    from . import build as _build
+    if _build.recorded_fingerprint() != _build.source_fingerprint():
+      raise ImportError(f'{LIB_PATH} was not built from the sources in this tree (lib/BUILD_INFO.json disagrees): '
+                        'run `python -m nerfds_b200.build`')
   lib = C.CDLL(LIB_PATH)
   vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
   lib.ndsr_create.argtypes = [C.POINTER(ndsr_config), C.c_int, C.POINTER(vp)]

@@ -33,24 +33,48 @@ def _nvcc() -> str:
   raise RuntimeError('nvcc not found')
 
 
-def _stale(target: str, deps) -> bool:
-  if not os.path.exists(target):
-    return True
-  t = os.path.getmtime(target)
-  return any(os.path.getmtime(d) > t for d in deps)
+BUILD_INFO = os.path.join(LIBDIR, 'BUILD_INFO.json')
+
+
+def source_fingerprint() -> dict:
+  """sha256 of every source the library is built from, plus the compile flags: written next to the .so by `build`
+  and checked by `_lib.load_library`, so that a shipped binary can never silently differ from the tree's sources."""
+  import hashlib
+  files = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h'))] +
+                 [os.path.join(ROOT, 'include', 'nerfds_b200.h')])
+  out = {}
+  for f in files:
+    with open(f, 'rb') as fh:
+      out[os.path.relpath(f, ROOT)] = hashlib.sha256(fh.read()).hexdigest()
+  out['flags'] = hashlib.sha256(repr((COMMON[:-2], SOURCES)).encode()).hexdigest()
+  return out
+
+
+def recorded_fingerprint():
+  import json
+  try:
+    with open(BUILD_INFO) as f:
+      return json.load(f).get('sources')
+  except (OSError, ValueError):
+    return None
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+  """Compile what changed.  Staleness is decided by CONTENT (sha256 of each source and of the flags, recorded in
+  lib/BUILD_INFO.json), not by mtimes -- a snapshot copied to another box keeps its binary only if it matches."""
+  import json
   os.makedirs(LIBDIR, exist_ok=True)
-  headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.h', '.cuh'))]
-  headers.append(os.path.join(ROOT, 'include', 'nerfds_b200.h'))
+  want = source_fingerprint()
+  have = recorded_fingerprint() or {}
+  shared_changed = any(want.get(k) != have.get(k) for k in want if not k.endswith('.cu'))
   objs = []
   procs = []
   for src, extra in SOURCES.items():
     s = os.path.join(CSRC, src)
     o = os.path.join(LIBDIR, src.replace('.cu', '.o'))
     objs.append(o)
-    if force or _stale(o, [s] + headers):
+    key = os.path.relpath(s, ROOT)
+    if force or shared_changed or not os.path.exists(o) or want.get(key) != have.get(key):
       cmd = [_nvcc()] + COMMON + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
       procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
   failed = False
@@ -63,9 +87,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
       sys.stderr.write(f'--- {src} ---\n{out}\n')
   if failed:
     raise RuntimeError('nvcc compilation failed')
-  if force or procs or _stale(LIB, objs):
+  if force or procs or not os.path.exists(LIB):
     cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ARCH + ['-lcudart_static', '-lpthread', '-ldl', '-lrt']
     subprocess.check_call(cmd)
+  if force or procs or recorded_fingerprint() != want:
+    with open(BUILD_INFO, 'w') as f:
+      json.dump({'sources': want, 'compiled': [src for src, _ in procs], 'nvcc': _nvcc(),
+                 'arch': 'compute_100a,sm_100a'}, f, indent=1)
   return LIB
 
 
