@@ -17,4 +17,6 @@ def cuda_device():
   import torch
   if not torch.cuda.is_available():
     pytest.skip('no CUDA device')
+  from nerfds_b200 import build
+  build.build()          # no-op when lib/BUILD_INFO.json matches the sources; compiles (nvcc, sm_100a) otherwise
   return torch.device('cuda', 0)
