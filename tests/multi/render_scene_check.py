@@ -36,7 +36,9 @@ def main():
       f.write(GIN_BASE + GIN_MAIN.replace("include 'base.gin'", '') +
               "\nExperimentConfig.image_scale = 2\nSpecularConfig.use_predicted_norm = True\n")
     ckpt.save_checkpoint(os.path.join(exp, 'checkpoints'), state, 7)
-  single = render_scene(exp, data, chunk_size=100, device=dev, save=False) if rank == 0 else None     # before the group exists
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  # (the draws follow the reference's per-device keys, evaluation.py:81-84: same device_count in both runs)
+  single = render_scene(exp, data, chunk_size=100, device=dev, save=False, device_count=world) if rank == 0 else None     # before the group exists
   dist.init_process_group('nccl', device_id=dev)
   dist.barrier()
   multi = render_scene(exp, data, chunk_size=100, device=dev, save=True)
