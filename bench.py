@@ -211,7 +211,7 @@ def run_ours(args):
     cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
            'sample': f'{args.cpu_rays} rays spread over frame 0, {args.coarse}+{args.fine} samples, {dt:.1f} s, PyTorch-CPU fp32 '
                      f'restatement of the reference JAX path incl. autograd d(sigma)/dx (jax not installable here)'}
-  if world > 1:
+  if world > 1 and not dist.is_initialized():
     dist.init_process_group('nccl', device_id=dev)
   from nerfds_b200 import jax_random as jr
   from nerfds_b200.models import NerfModel
@@ -435,9 +435,11 @@ def run_ours(args):
   if peer is not None:
     for pf in peer:
       pf.close()
+  model.renderer.close()
   if world > 1:
     dist.barrier()
-    dist.destroy_process_group()
+    if not getattr(args, 'keep_group', False):
+      dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------
@@ -632,6 +634,7 @@ def main():
   ap.add_argument('--cpu-rays', type=int, default=None)
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--gather', default='peer', choices=['peer', 'nccl'], help='frame reassembly at N > 1')
+  ap.add_argument('--sweep', default=None, help="sample-count sweep, e.g. '32+32,64+64,128+128,256+256' (BASELINE configs[4])")
   ap.add_argument('--workload', default='frame', choices=['frame', 'train4096'],
                   help='frame: BASELINE configs[1] (the headline); train4096: configs[2], the training forward of a ray batch')
   ap.add_argument('--batch', type=int, default=4096)
@@ -656,6 +659,14 @@ def main():
       raise SystemExit(f'--gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...)')
   if args.impl == 'reference':
     run_reference(args)
+  elif args.sweep:
+    # BASELINE configs[4]: sample-count sweep, one JSON line per point, one process group for all of them
+    points = [tuple(int(v) for v in p.split('+')) for p in args.sweep.split(',')]
+    for i, (c, f) in enumerate(points):
+      args.coarse, args.fine = c, f
+      args.keep_group = i + 1 < len(points)
+      args.no_cpu = True
+      run_ours(args)
   else:
     run_ours(args)
 

@@ -46,7 +46,8 @@ def source_fingerprint() -> dict:
   for f in files:
     with open(f, 'rb') as fh:
       out[os.path.relpath(f, ROOT)] = hashlib.sha256(fh.read()).hexdigest()
-  out['flags'] = hashlib.sha256(repr((COMMON[:-2], SOURCES)).encode()).hexdigest()
+  flags = [a.replace(ROOT, '.') for a in COMMON]           # (paths relative: the tree may live anywhere)
+  out['flags'] = hashlib.sha256(repr((flags, SOURCES)).encode()).hexdigest()
   return out
 
 
