@@ -498,6 +498,15 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   fa.origins = origins; fa.dirs = dirs; fa.viewdirs = viewdirs ? viewdirs : dirs; fa.warp_id = warp_id;
   fa.gt_mask = gt_mask; fa.planes = h->planes; fa.plane_stride = B * S;
   fa.sigma_only = need_rgb ? 0 : 1; fa.need_grad = need_grad ? 1 : 0;
+  // planes behind the requested keys only (sigma_raw always): the coarse level of a render call writes one plane
+  uint32_t pm = 0;
+  if (o.rgb) pm |= PG_RGB;
+  if (o.ray_norm || o.predicted_norm || o.back_facing) pm |= PG_NORM;
+  if (o.ray_predicted_mask || o.predicted_mask) pm |= PG_MASK;
+  if (o.med_points || o.ray_delta_x || o.delta_x || o.warped_points || o.ray_hyper_points) pm |= PG_WARPED;
+  if (o.ray_rotation_field) pm |= PG_ROT;
+  if (o.ray_translation_field) pm |= PG_TRANS;
+  fa.plane_mask = pm;
   {
     ProfScope ps(h, st, level == 0 ? NDSR_STAGE_FIELD_COARSE : NDSR_STAGE_FIELD_FINE);
     if (h->engine == NDSR_ENGINE_TC && !need_grad && src_elem) {
@@ -528,6 +537,7 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
   CompositeArgs ca;
   memset(&ca, 0, sizeof ca);
   ca.n_rays = B; ca.S = S; ca.H = h->H; ca.planes = h->planes; ca.plane_stride = B * S; ca.z = z; ca.dirs = dirs;
+  ca.plane_mask = pm;
   ca.viewdirs = viewdirs ? viewdirs : dirs; ca.origins = origins; ca.points = points;
   ca.sigma_is_activated = 0; ca.white_bkgd = c.use_white_background; ca.sample_at_infinity = sample_at_infinity;
   ca.has_norm = c.predict_norm; ca.has_warp = c.use_warp; ca.has_mask = c.use_predicted_mask; ca.has_grad = need_grad;
@@ -967,6 +977,7 @@ extern "C" int ndsr_volumetric_rendering(ndsr_handle* h, void* stream, int64_t n
   memset(&ca, 0, sizeof ca);
   ca.n_rays = n_rays; ca.S = n_samples; ca.H = 0; ca.planes = h->planes; ca.plane_stride = N; ca.z = z_vals;
   ca.dirs = dirs; ca.viewdirs = dirs; ca.origins = nullptr; ca.points = nullptr; ca.sigma_is_activated = 1;
+  ca.plane_mask = PG_RGB;
   ca.white_bkgd = use_white_background; ca.sample_at_infinity = sample_at_infinity;
   memset(&ca.out, 0, sizeof ca.out);
   ca.out.rgb = out->rgb; ca.out.depth = out->depth; ca.out.med_depth = out->med_depth; ca.out.acc = out->acc;

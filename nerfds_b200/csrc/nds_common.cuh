@@ -69,6 +69,10 @@ enum Plane {
   P_COUNT = 25
 };
 
+// which groups of planes a call needs (FieldArgs::plane_mask / CompositeArgs::plane_mask): the field kernel only
+// writes, and the compositing kernel only reads, the planes behind the requested level-dict keys
+enum PlaneGroup : uint32_t { PG_RGB = 1, PG_NORM = 2, PG_MASK = 4, PG_WARPED = 8, PG_ROT = 16, PG_TRANS = 32, PG_ALL = 63 };
+
 struct FieldArgs {
   int64_t n_samples_total;   // B * S
   int S;
@@ -82,6 +86,7 @@ struct FieldArgs {
   const float* gt_mask;      // [B] or null
   float* planes;
   int64_t plane_stride;
+  uint32_t plane_mask;       // PlaneGroup bits (sigma_raw is always written)
   int sigma_only;            // skip bottleneck/rgb/normal-input work
   int need_grad;             // compute P_GRAD / P_TNORM
   // ---- tensor-core engine only: fine pass split into "new" and "carried" samples --------------------------

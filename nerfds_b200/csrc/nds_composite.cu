@@ -153,31 +153,29 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       const float w = s_w[s];
       const float zs = a.z[n];
       const int64_t pn = pidx(s);
-      float c[3], nv[3] = {0, 0, 0}, wp[5], px[3];
-      for (int i = 0; i < 3; ++i) c[i] = a.planes[(P_RGB + i) * ps + pn];
-      for (int i = 0; i < 3 + a.H; ++i) wp[i] = a.planes[(P_WARPED + i) * ps + pn];
+      float c[3] = {0, 0, 0}, nv[3] = {0, 0, 0}, wp[5] = {0, 0, 0, 0, 0}, px[3];
+      if (a.plane_mask & PG_RGB) for (int i = 0; i < 3; ++i) c[i] = a.planes[(P_RGB + i) * ps + pn];
+      if (a.plane_mask & PG_WARPED) for (int i = 0; i < 3 + a.H; ++i) wp[i] = a.planes[(P_WARPED + i) * ps + pn];
       if (a.points) { px[0] = a.points[n * 3]; px[1] = a.points[n * 3 + 1]; px[2] = a.points[n * 3 + 2]; }
       else { px[0] = ox + zs * dx; px[1] = oy + zs * dy; px[2] = oz + zs * dz; }
       for (int i = 0; i < 3; ++i) r[i] += w * c[i];
       depth += w * zs;
       acc += w;
       if (s < S - 1) acc_m1 += w;
-      if (a.has_norm) {
+      if (a.has_norm && (a.plane_mask & PG_NORM)) {
         for (int i = 0; i < 3; ++i) { nv[i] = a.planes[(P_NORM + i) * ps + pn]; rn[i] += w * nv[i]; }
         if (a.out.back_facing) {
           const float bf = fmaxf(nv[0] * vx + nv[1] * vy + nv[2] * vz, 0.f);
           a.out.back_facing[n] = bf * bf;
         }
         if (a.out.predicted_norm) for (int i = 0; i < 3; ++i) a.out.predicted_norm[n * 3 + i] = nv[i];
-      } else if (a.has_grad) {
+      } else if (!a.has_norm && a.has_grad) {
         for (int i = 0; i < 3; ++i) rn[i] += w * a.planes[(P_GRAD + i) * ps + pn];   // models.py:1353
       }
       if (a.has_grad && a.has_norm && a.out.target_norm)
         for (int i = 0; i < 3; ++i) a.out.target_norm[n * 3 + i] = a.planes[(P_TNORM + i) * ps + pn];
-      if (a.has_warp) for (int i = 0; i < 3; ++i) {
-        rr[i] += w * a.planes[(P_ROT + i) * ps + pn];
-        rt[i] += w * a.planes[(P_TRANS + i) * ps + pn];
-      }
+      if (a.has_warp && (a.plane_mask & PG_ROT)) for (int i = 0; i < 3; ++i) rr[i] += w * a.planes[(P_ROT + i) * ps + pn];
+      if (a.has_warp && (a.plane_mask & PG_TRANS)) for (int i = 0; i < 3; ++i) rt[i] += w * a.planes[(P_TRANS + i) * ps + pn];
       for (int i = 0; i < 3; ++i) {
         const float d = wp[i] - px[i];
         rdx[i] += w * d;
@@ -186,7 +184,7 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       }
       for (int i = 0; i < a.H; ++i) rh[i] += w * wp[3 + i];
       if (a.out.warped_points) for (int i = 0; i < 3 + a.H; ++i) a.out.warped_points[n * (3 + a.H) + i] = wp[i];
-      if (a.has_mask) {
+      if (a.has_mask && (a.plane_mask & PG_MASK)) {
         const float m = a.planes[P_MASK * ps + pn];
         rm += w * m;
         if (a.out.predicted_mask) a.out.predicted_mask[n] = m;
@@ -231,7 +229,7 @@ composite_kernel(const __grid_constant__ CompositeArgs a) {
       if (o.ray_delta_x) for (int i = 0; i < 3; ++i) put(o.ray_delta_x + ray * 3 + i, rdx[i]);
       if (o.ray_hyper_points) for (int i = 0; i < a.H; ++i) put(o.ray_hyper_points + ray * a.H + i, rh[i]);
       if (o.ray_predicted_mask && a.has_mask) put(o.ray_predicted_mask + ray, rm);
-      if (o.med_points) for (int i = 0; i < 3 + a.H; ++i)
+      if (o.med_points && (a.plane_mask & PG_WARPED)) for (int i = 0; i < 3 + a.H; ++i)
         put(o.med_points + ray * (3 + a.H) + i, a.planes[(P_WARPED + i) * ps + pidx(med_idx)]);
       if (a.argmax_idx) a.argmax_idx[ray] = (float)best_i;
     }

@@ -10,6 +10,7 @@ struct CompositeArgs {
   int S, H;
   const float* planes;
   int64_t plane_stride;
+  uint32_t plane_mask;   // PlaneGroup bits: which planes the field kernel wrote for this call
   const float* z;        // [B,S]
   const float* dirs;     // [B,3]
   const float* viewdirs; // [B,3]

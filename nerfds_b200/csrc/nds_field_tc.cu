@@ -987,39 +987,47 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
             normalize3(tn, tnn);                                            // models.py:1273-1277
             float* PL = a.planes;
             const int64_t ps = a.plane_stride, n = T.n_out;
-            for (int c = 0; c < 3; ++c) { PL[(P_GRAD + c) * ps + n] = gn[c]; PL[(P_TNORM + c) * ps + n] = tnn[c]; }
+            for (int c = 0; c < 3; ++c) { __stcs(&PL[(P_GRAD + c) * ps + n], gn[c]); __stcs(&PL[(P_TNORM + c) * ps + n], tnn[c]); }
           }
           }
          }
         } else {
-          // ---- STEP_OUT: write planes (the warps sharing a sample take different planes) ----
+          // ---- STEP_OUT: write planes (the warps sharing a sample take different planes; only the groups of planes the
+          //      call's outputs need; streaming stores: nothing in this kernel reads them back, and they must not evict
+          //      the weights or the warps' local memory from the L2) ----
           const int64_t n = T.n_out;
           if (T.valid && a.carry_out) {          // what a later "carried" launch needs of this sample
             float* C = a.carry_out + n;
             const int64_t cs = a.carry_stride;
-            if (sub == 0) { for (int c = 0; c < 3; ++c) C[(C_WARPED + c) * cs] = T.xw[c]; for (int c = 0; c < 2; ++c) C[(C_WARPED + 3 + c) * cs] = c < H ? T.om[c] : 0.f; }
-            else if (sub == 1) { C[C_MASK * cs] = T.pmask; for (int c = 0; c < 3; ++c) C[(C_P + c) * cs] = T.p[c]; }
-            else if (sub == 2) { for (int i = 0; i < 5; ++i) C[(C_R + i) * cs] = T.R[i]; }
-            else { for (int i = 5; i < 9; ++i) C[(C_R + i) * cs] = T.R[i]; }
+            if (sub == 0) { for (int c = 0; c < 3; ++c) __stcs(&C[(C_WARPED + c) * cs], T.xw[c]); for (int c = 0; c < 2; ++c) __stcs(&C[(C_WARPED + 3 + c) * cs], c < H ? T.om[c] : 0.f); }
+            else if (sub == 1) { __stcs(&C[C_MASK * cs], T.pmask); for (int c = 0; c < 3; ++c) __stcs(&C[(C_P + c) * cs], T.p[c]); }
+            else if (sub == 2) { for (int i = 0; i < 5; ++i) __stcs(&C[(C_R + i) * cs], T.R[i]); }
+            else { for (int i = 5; i < 9; ++i) __stcs(&C[(C_R + i) * cs], T.R[i]); }
           }
           if (T.valid) {
             float* PL = a.planes;
             const int64_t ps = a.plane_stride;
+            const uint32_t pm = a.plane_mask;
             if (sub == 0) {
-              PL[P_SIGMA_RAW * ps + n] = T.sigma_raw;
-              for (int c = 0; c < 3; ++c) PL[(P_RGB + c) * ps + n] = T.rgb[c];
+              __stcs(&PL[P_SIGMA_RAW * ps + n], T.sigma_raw);
+              if (pm & PG_RGB) for (int c = 0; c < 3; ++c) __stcs(&PL[(P_RGB + c) * ps + n], T.rgb[c]);
             } else if (sub == 1) {
-              for (int c = 0; c < 3; ++c) PL[(P_NORM + c) * ps + n] = T.nrm[c];
-              PL[P_MASK * ps + n] = T.pmask;
+              if (pm & PG_NORM) for (int c = 0; c < 3; ++c) __stcs(&PL[(P_NORM + c) * ps + n], T.nrm[c]);
+              if (pm & PG_MASK) __stcs(&PL[P_MASK * ps + n], T.pmask);
             } else if (sub == 2) {
-              for (int c = 0; c < 3; ++c) PL[(P_WARPED + c) * ps + n] = T.xw[c];
-              for (int c = 0; c < H; ++c) PL[(P_WARPED + 3 + c) * ps + n] = T.om[c];
-            } else if (cfg.use_warp) {
-              const float r = 0.57735025882720947265625f;
-              float rf[3], rn[3];
-              for (int c = 0; c < 3; ++c) rf[c] = T.R[c * 3 + 0] * r + T.R[c * 3 + 1] * r + T.R[c * 3 + 2] * r;
-              normalize3(rf, rn);
-              for (int c = 0; c < 3; ++c) { PL[(P_ROT + c) * ps + n] = rn[c]; PL[(P_TRANS + c) * ps + n] = T.p[c]; }
+              if (pm & PG_WARPED) {
+                for (int c = 0; c < 3; ++c) __stcs(&PL[(P_WARPED + c) * ps + n], T.xw[c]);
+                for (int c = 0; c < H; ++c) __stcs(&PL[(P_WARPED + 3 + c) * ps + n], T.om[c]);
+              }
+            } else if (cfg.use_warp && (pm & (PG_ROT | PG_TRANS))) {
+              if (pm & PG_ROT) {
+                const float r = 0.57735025882720947265625f;
+                float rf[3], rn[3];
+                for (int c = 0; c < 3; ++c) rf[c] = T.R[c * 3 + 0] * r + T.R[c * 3 + 1] * r + T.R[c * 3 + 2] * r;
+                normalize3(rf, rn);
+                for (int c = 0; c < 3; ++c) __stcs(&PL[(P_ROT + c) * ps + n], rn[c]);
+              }
+              if (pm & PG_TRANS) for (int c = 0; c < 3; ++c) __stcs(&PL[(P_TRANS + c) * ps + n], T.p[c]);
             }
           }
         }

@@ -60,10 +60,10 @@ def test_render_scene_from_experiment_dir(tmp_path, cuda_device):
                     scene_scale=0.5)
   assert cam.image_shape == (H, W) and cam.focal_length == W
   rays = camera_to_rays(cam, cuda_device)
-  g = torch.Generator(device=cuda_device)
-  g.manual_seed(3 * 1000003 + 2)
-  t_rand = torch.rand((H * W, 64), generator=g, device=cuda_device)
-  u = torch.rand((H * W, 32), generator=g, device=cuda_device)
+  # render.py:85, 100, 218: rng = split(PRNGKey(random_seed))[0], the same for every frame; evaluation.py:81-120
+  from nerfds_b200 import jax_random as jr
+  from nerfds_b200.evaluation import reference_draws
+  t_rand, u = reference_draws(jr.split(jr.PRNGKey(3))[0], H * W, 256, 1, 64, 32, cuda_device)
   m = NerfModel(cfg, device=cuda_device)
   out = m.apply({'params': params}, {'origins': rays['origins'].reshape(-1, 3), 'directions': rays['directions'].reshape(-1, 3),
                                      'metadata': {'warp': torch.full((H * W, 1), 2, dtype=torch.int64, device=cuda_device)},
