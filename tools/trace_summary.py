@@ -6,8 +6,9 @@ for l in open(sys.argv[1]):
   d = {t[i]: int(t[i + 1]) for i in range(2, len(t) - 1, 2)}
   d['i'] = int(t[1])
   (bursts if t[0] == 'burst' else steps).append(d)
-kinds = {0: 'EPI', 1: 'HEAD', 2: 'VIEW', 3: 'PREP', 4: 'OUT'}
+kinds = {0: 'EPI', 1: 'HEAD', 2: 'VIEW', 3: 'PREP', 4: 'OUT', 5: 'INGR', 6: 'SEED', 7: 'PEB'}
 print('pair span (cycles):', max(s['end'] for s in steps), ' bursts', len(bursts))
+steps = [s for s in steps if s['start'] >= 0]
 live = [b for b in bursts if b['top'] >= 0]
 print('issuer: sum(top->ready) %d  sum(ready->issued) %d  sum(issued->next top) %d' % (
     sum(b['ready'] - b['top'] for b in live), sum(b['issued'] - b['ready'] for b in live),
