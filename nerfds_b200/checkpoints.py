@@ -110,7 +110,9 @@ def _unchunk_leaves(tree):
 
 
 def to_state_dict(tree) -> Any:
-  """flax.serialization.to_state_dict for the containers this package uses."""
+  """flax.serialization.to_state_dict for the containers this package uses.  A `TrainState` made by
+  `TrainState.create` has no Adam moments: the file it serialises to is an INFERENCE checkpoint (params, step and
+  schedule scalars -- all `render.py` reads); a state restored from a reference checkpoint keeps its `param_states`."""
   if isinstance(tree, TrainState):
     opt = tree.optimizer
     state = getattr(opt, 'state', None)
@@ -212,10 +214,14 @@ def train_state_from_dict(sd: Dict[str, Any]) -> TrainState:
     params = opt['target']['model']
   except (KeyError, TypeError):
     raise ValueError("not a NeRF-DS train state: missing optimizer/target/model") from None
-  step = int(np.asarray(opt.get('state', {}).get('step', 0)).reshape(-1)[0])
+  raw_state = opt.get('state', {}) or {}
+  step = int(np.asarray(raw_state.get('step', 0)).reshape(-1)[0])
   scal = {k: (None if sd.get(k) is None else float(np.asarray(sd[k]).reshape(-1)[0])) for k in _SCALARS}
-  return TrainState(optimizer=SimpleNamespace(target={'model': _f32_tree(params)}, state=SimpleNamespace(step=step)),
-                    **scal)
+  # everything else the optimizer state holds (flax.optim Adam: `param_states` = grad_ema / grad_sq_ema per leaf) is
+  # kept verbatim, so that a state restored here and saved again is still loadable by the reference's
+  # `checkpoints.restore_checkpoint(dir, state)` (from_state_dict raises on a missing `param_states`)
+  state = SimpleNamespace(step=step, **{k: v for k, v in raw_state.items() if k != 'step'})
+  return TrainState(optimizer=SimpleNamespace(target={'model': _f32_tree(params)}, state=state), **scal)
 
 
 def check_params(cfg: NerfDSConfig, params: Dict) -> None:

@@ -155,6 +155,7 @@ extern "C" int ndsr_create(const ndsr_config* cfg, int device, ndsr_handle** out
     return NDSR_ERR_CUDA;
   }
   h->num_sms = prop.multiProcessorCount;
+  h->tc_no_split = getenv("NDS_TC_NO_SPLIT") != nullptr;
   h->cc_major = prop.major;
   const ndsr_config& c = h->cfg;
   h->H = c.use_hyper_sheet ? c.hyper_num_dims : 0;
@@ -641,7 +642,7 @@ static int render_rays_chunk(ndsr_handle* h, cudaStream_t st, int64_t B, const f
   const bool fine_grad = fine && ((c.predict_norm && fine->target_norm) || (!c.predict_norm && fine->ray_norm));
   const bool coarse_grad = coarse && ((c.predict_norm && coarse->target_norm) || (!c.predict_norm && coarse->ray_norm));
   const bool split = h->engine == NDSR_ENGINE_TC && !ep.use_sigma_gradient && !fine_grad && !coarse_grad &&
-                     getenv("NDS_TC_NO_SPLIT") == nullptr;
+                     !h->tc_no_split;
   int rc = run_level(h, st, 0, B, Sc, nullptr, h->z_coarse, origins, dirs, viewdirs, warp_id, gt_mask, ep, cp,
                      c.use_sample_at_infinity, coarse, h->w_coarse, coarse_rgb || coarse != nullptr,
                      split ? h->carry : nullptr, nullptr, 0, /*apply_filter=*/false);   // models.py:1493-1516: no render_opts

@@ -49,6 +49,7 @@ struct ndsr_handle {
   std::vector<void*> scratch_allocs;
   int64_t cap_rays = 0, cap_samples = 0, max_samples_seen = 0;
   int64_t max_chunk = 65536;
+  bool tc_no_split = false;    // NDS_TC_NO_SPLIT (diagnostics), read once at ndsr_create
   int n_mirror = 0;                        // peer copies of the caller's frame buffer (ndsr_set_output_mirrors)
   int64_t mirror_delta[NDSR_MAX_MIRRORS] = {0};
   const char* mirror_base = nullptr;       // this rank's own frame buffer: only stores inside it are mirrored

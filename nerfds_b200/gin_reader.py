@@ -154,6 +154,27 @@ def _parse_value(expr: str, where: str) -> Any:
     raise GinSyntaxError(f'{where}: cannot parse value {expr!r}: {e.msg}') from None
 
 
+_LAZY = [True]
+
+
+class _Unbound:
+  """A binding whose value references a macro nobody defined (e.g. `NerfiesDataSource.data_dir = %data_dir` when the
+  file is parsed without a data_dir binding).  gin raises when such a value is used, not when the file is parsed; any
+  use of this placeholder raises the same KeyError."""
+
+  def __init__(self, name):
+    self.name = name
+
+  def _fail(self, *a, **k):
+    raise KeyError(f'undefined gin macro %{self.name}')
+
+  __str__ = __float__ = __int__ = __bool__ = __iter__ = __len__ = __getitem__ = __call__ = __eq__ = __hash__ = _fail
+  __add__ = __radd__ = __mul__ = __rmul__ = __lt__ = __gt__ = __fspath__ = _fail
+
+  def __repr__(self):
+    return f'<unbound gin macro %{self.name}>'
+
+
 def _resolve(v: Any, raw: Dict[str, Any], stack: Tuple[str, ...] = ()) -> Any:
   if isinstance(v, _Macro):
     if v.name in stack:
@@ -161,6 +182,8 @@ def _resolve(v: Any, raw: Dict[str, Any], stack: Tuple[str, ...] = ()) -> Any:
     for key in (v.name, f'{v.name}/macro.value', f'macro.{v.name}'):
       if key in raw:
         return _resolve(raw[key], raw, stack + (v.name,))
+    if not stack and _LAZY[0]:
+      return _Unbound(v.name)         # gin fails only when the value is USED: keep a placeholder that raises then
     raise KeyError(f'undefined gin macro %{v.name}')
   if isinstance(v, tuple):
     return tuple(_resolve(e, raw, stack) for e in v)

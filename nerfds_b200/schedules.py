@@ -37,6 +37,8 @@ class ConstantSchedule(Schedule):
     self.value = value
 
   def get(self, step):
+    if self.value is None:          # schedules.py:79-81: ('constant', None) disables the scalar
+      return None
     return float(self.value)
 
 

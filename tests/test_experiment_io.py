@@ -93,8 +93,12 @@ def test_gin_reader_syntax(gin_files):
   assert b['SpecularConfig.norm_input_alpha_schedule']['schedules'][1] == (0, ('linear', 0.0, 4, 2000))
   assert b['EvalConfig.num_val_eval'] is None and b['EvalConfig.niter'] == -3
   assert b['NerfiesDataSource.data_dir'] == '/data/x'
+  lazy = gin_reader.parse_config('A.b = %nope\nC.d = 2')          # like gin: an undefined macro fails when USED
+  assert lazy['C.d'] == 2
   with pytest.raises(KeyError):
-    gin_reader.parse_config('A.b = %nope')
+    float(lazy['A.b'])
+  with pytest.raises(KeyError):
+    os.path.join(lazy['A.b'], 'x')
   with pytest.raises(gin_reader.GinSyntaxError):
     gin_reader.parse_config('A.b = (1, 2')
   with pytest.raises(gin_reader.GinSyntaxError):
@@ -361,3 +365,25 @@ def test_msgpack_round_trip_property():
     assert same(t, ckpt.msgpack_restore(ckpt.msgpack_serialize(t, max_chunk_bytes=chunk)))
 
   check()
+
+
+def test_optimizer_state_survives_a_restore_save_round_trip(tmp_path):
+  """A reference checkpoint carries flax.optim Adam moments (`optimizer/state/param_states`); restoring it here and
+  saving it again keeps them, so the file stays loadable upstream.  `('constant', None)` disables a scalar."""
+  cfg = tiny_config()
+  from nerfds_b200.params import init_params
+  params = init_params(cfg, 1)
+  moments = {'model': {'x': {'grad_ema': np.arange(3, dtype=np.float32), 'grad_sq_ema': np.ones(3, np.float32)}}}
+  sd = {'optimizer': {'target': {'model': params}, 'state': {'step': np.int32(9), 'param_states': moments}},
+        'nerf_alpha': 3.0, 'warp_alpha': None}
+  d = tmp_path / 'ck'
+  d.mkdir()
+  with open(d / 'checkpoint_9', 'wb') as f:
+    f.write(ckpt.msgpack_serialize(sd))
+  st = ckpt.restore_checkpoint(str(d), TrainState.create(params, {}))
+  assert st.optimizer.state.step == 9
+  ckpt.save_checkpoint(str(d), st, 10)
+  again = ckpt.restore_checkpoint(str(d))
+  np.testing.assert_array_equal(again['optimizer']['state']['param_states']['model']['x']['grad_ema'], moments['model']['x']['grad_ema'])
+  assert int(again['optimizer']['state']['step']) == 9 and again['nerf_alpha'] == 3.0
+  assert schedules.from_config(('constant', None)).get(5) is None

@@ -379,16 +379,17 @@ def test_tc_split_fine_pass_is_exact(cuda_device, monkeypatch):
   """The fine pass as two launches (new samples: whole chain; coarse depths: template NeRF on the coarse pass's
   carried warp / hyper / mask results) gives the results of the single launch, sample for sample."""
   cfg, params, rays, t_rand, u = make_case('nerf_ds', image=14, seed=5)
-  m = _model(cfg, cuda_device, engine='tc')
   keys = ('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'ray_hyper_points', 'ray_predicted_mask',
           'ray_rotation_field', 'ray_translation_field', 'med_points', 'weights', 'sigma', 'warped_points',
           'predicted_mask', 'predicted_norm')
   outs = []
   for no_split in ('', '1'):
-    if no_split:
+    if no_split:                                   # (diagnostic switch, read when the handle is created)
       monkeypatch.setenv('NDS_TC_NO_SPLIT', '1')
     else:
       monkeypatch.delenv('NDS_TC_NO_SPLIT', raising=False)
+    m = _model(cfg, cuda_device, engine='tc')
+    m.renderer.ensure_params(params)
     l0 = m.renderer.kernel_launches
     o = m.apply({'params': params}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True,
                 keys=keys, coarse_keys=('rgb', 'weights'))
