@@ -80,4 +80,40 @@ __device__ __forceinline__ Dual6 ncos(const Dual6& a) {
   return r;
 }
 
+
+// the same with N tangents (the tensor-core reverse sweep differentiates w.r.t. the 3 rotation inputs only; the
+// translation inputs enter linearly)
+template <int N>
+struct DualN {
+  float v;
+  float d[N];
+  __device__ __forceinline__ DualN() {}
+  __device__ __forceinline__ explicit DualN(float x) : v(x) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) d[i] = 0.f;
+  }
+  __device__ __forceinline__ static DualN var(float x, int idx) {
+    DualN r(x);
+#pragma unroll
+    for (int i = 0; i < N; ++i) r.d[i] = (i == idx) ? 1.f : 0.f;
+    return r;
+  }
+};
+#define NDS_DUALN_LOOP _Pragma("unroll") for (int i = 0; i < N; ++i)
+template <int N> __device__ __forceinline__ DualN<N> operator+(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v + b.v; NDS_DUALN_LOOP r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int N> __device__ __forceinline__ DualN<N> operator-(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v - b.v; NDS_DUALN_LOOP r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int N> __device__ __forceinline__ DualN<N> operator-(const DualN<N>& a) { DualN<N> r; r.v = -a.v; NDS_DUALN_LOOP r.d[i] = -a.d[i]; return r; }
+template <int N> __device__ __forceinline__ DualN<N> operator*(const DualN<N>& a, const DualN<N>& b) { DualN<N> r; r.v = a.v * b.v; NDS_DUALN_LOOP r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+template <int N> __device__ __forceinline__ DualN<N> operator*(const DualN<N>& a, float b) { DualN<N> r; r.v = a.v * b; NDS_DUALN_LOOP r.d[i] = a.d[i] * b; return r; }
+template <int N> __device__ __forceinline__ DualN<N> operator/(const DualN<N>& a, const DualN<N>& b) {
+  DualN<N> r; r.v = a.v / b.v;
+  const float inv = 1.f / b.v;
+  NDS_DUALN_LOOP r.d[i] = (a.d[i] - r.v * b.d[i]) * inv;
+  return r;
+}
+template <int N> __device__ __forceinline__ DualN<N> nsqrt(const DualN<N>& a) { DualN<N> r; r.v = sqrtf(a.v); const float k = 0.5f / r.v; NDS_DUALN_LOOP r.d[i] = a.d[i] * k; return r; }
+template <int N> __device__ __forceinline__ DualN<N> nsin(const DualN<N>& a) { DualN<N> r; r.v = sinf(a.v); const float c = cosf(a.v); NDS_DUALN_LOOP r.d[i] = a.d[i] * c; return r; }
+template <int N> __device__ __forceinline__ DualN<N> ncos(const DualN<N>& a) { DualN<N> r; r.v = cosf(a.v); const float sn = -sinf(a.v); NDS_DUALN_LOOP r.d[i] = a.d[i] * sn; return r; }
+#undef NDS_DUALN_LOOP
+
 }  // namespace nds

@@ -384,7 +384,7 @@ __device__ __forceinline__ void store_in_hi(uint8_t* blk, uint32_t r, uint32_t c
 
 // Epilogue of one N-chunk for this thread's row and its CW-column slice: accumulators -> scale/bias/ReLU ->
 // split fp16 -> written over the very columns just read (hi | lo), the operand of the next layer.
-template <int CW>
+template <int CW, int MM = MASK_NONE>
 __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const float* __restrict__ bias_base,
                                                uint32_t tmem_lane, uint32_t row, int sub, int q, float* dbg_out,
                                                int dbg_ld, uint64_t* bar, uint32_t parity, uint32_t* mask_word = nullptr) {
@@ -406,8 +406,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
   uint32_t hi[CW / 2], lo[CW / 2];
-  uint32_t mword = (mask_word && op.mask_mode == MASK_APPLY) ? *mask_word : 0u;
-  if (NDS_EPI_RZ && relu && !dbg_out && !mask_word) {
+  uint32_t mword = MM == MASK_APPLY ? *mask_word : 0u;
+  if (NDS_EPI_RZ && relu && !dbg_out && MM == MASK_NONE) {
     // ReLU folded into the conversions: hi = relu(x) truncated to fp16 (round toward zero, so the residual of a
     // positive x is never negative), lo = relu(x - hi) -- for x < 0 both come out 0.  hi + lo still carries 21+ bits.
 #pragma unroll
@@ -427,10 +427,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
       float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
       float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
       if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-      if (mask_word) {
-        if (op.mask_mode == MASK_RECORD) mword |= (x0 > 0.f ? 1u : 0u) << (2 * i) | (x1 > 0.f ? 1u : 0u) << (2 * i + 1);
-        else { x0 = ((mword >> (2 * i)) & 1u) ? x0 : 0.f; x1 = ((mword >> (2 * i + 1)) & 1u) ? x1 : 0.f; }
-      }
+      if (MM == MASK_RECORD) mword |= (x0 > 0.f ? 1u : 0u) << (2 * i) | (x1 > 0.f ? 1u : 0u) << (2 * i + 1);
+      if (MM == MASK_APPLY) { x0 = ((mword >> (2 * i)) & 1u) ? x0 : 0.f; x1 = ((mword >> (2 * i + 1)) & 1u) ? x1 : 0.f; }
       if (dbg_out) { dbg_out[row * dbg_ld + oc0 + 2 * i] = x0; dbg_out[row * dbg_ld + oc0 + 2 * i + 1] = x1; }
       const __half2 h = __floats2half2_rn(x0, x1);
       const float2 hf = __half22float2(h);
@@ -439,7 +437,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
       lo[i] = *reinterpret_cast<const uint32_t*>(&l);
     }
   }
-  if (mask_word && op.mask_mode == MASK_RECORD) *mask_word = mword;
+  if (MM == MASK_RECORD) *mask_word = mword;
   const uint8_t kind = op.epi_kind;
   if (kind == EPI_COMPACT_HI) {
     // the compacted slice overlaps columns other warps of this lane quarter are still reading
@@ -457,8 +455,24 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
 __device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint32_t tmem_lane,
                                                   uint32_t row, int sub, int q, float* dbg, int dbg_ld, uint64_t* bar,
                                                   uint32_t parity, uint32_t* mask_word = nullptr) {
-  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, mask_word);
-  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, mask_word);
+  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, nullptr);
+  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, nullptr);
+}
+// reverse-sweep instantiation: the epilogue records (forward) or applies (reverse) a ReLU mask word
+__device__ __forceinline__ void epilogue_dispatch_mask(const TcOp& op, int nc, const float* bias_base, uint32_t tmem_lane,
+                                                       uint32_t row, int sub, int q, uint64_t* bar, uint32_t parity,
+                                                       uint32_t* mask_word) {
+  const bool wide = op.nc_rows == 128;
+  if (op.mask_mode == MASK_RECORD) {
+    if (wide) epilogue_chunk<32, MASK_RECORD>(op, nc, bias_base, tmem_lane, row, sub, q, nullptr, 0, bar, parity, mask_word);
+    else epilogue_chunk<16, MASK_RECORD>(op, nc, bias_base, tmem_lane, row, sub, q, nullptr, 0, bar, parity, mask_word);
+  } else if (op.mask_mode == MASK_APPLY) {
+    if (wide) epilogue_chunk<32, MASK_APPLY>(op, nc, bias_base, tmem_lane, row, sub, q, nullptr, 0, bar, parity, mask_word);
+    else epilogue_chunk<16, MASK_APPLY>(op, nc, bias_base, tmem_lane, row, sub, q, nullptr, 0, bar, parity, mask_word);
+  } else {
+    if (wide) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, nullptr, 0, bar, parity, nullptr);
+    else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, nullptr, 0, bar, parity, nullptr);
+  }
 }
 
 // head (<= 16 outputs): every compute warp of the lane quarter reads all of them
@@ -534,6 +548,33 @@ __device__ __forceinline__ int posenc_emit_sub(float x0, float x1, float x2, int
   return o + 2 * npair;
 }
 
+
+// Reverse sweep: write CW columns of a gradient seed (already masked) as the split-fp16 operand slice an epilogue
+// would leave at `col`: hi halves in the first CW / 2 columns, lo halves after them.
+template <int CW, typename G>
+__device__ __forceinline__ void seed_slice(uint32_t col, uint32_t mword, G g_of) {
+  uint32_t hi[CW / 2], lo[CW / 2];
+#pragma unroll
+  for (int i = 0; i < CW / 2; ++i) {
+    const float x0 = ((mword >> (2 * i)) & 1u) ? g_of(2 * i) : 0.f;
+    const float x1 = ((mword >> (2 * i + 1)) & 1u) ? g_of(2 * i + 1) : 0.f;
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  tmem_st<CW / 2>(col, hi);
+  tmem_st<CW / 2>(col + CW / 2, lo);
+}
+
+// Reverse sweep: one feature column of a positional encoding this thread differentiates (fixed for the whole launch)
+struct PeCol {
+  float scale;     // window x 2^deg (band) | 1 (identity) | 0 (column carries no gradient w.r.t. a coordinate)
+  float freq;      // 2^deg (band), 0 otherwise
+  float phase;     // pi/2 for the cos feature
+  int comp;        // coordinate: 0..2 point, 3..4 hyper; kind in bits 8+: 0 none, 1 identity, 2 band
+};
 
 // ---------------------------------------------------------------------------
 // the field kernel
@@ -757,6 +798,10 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
       if (part == NPREP - 1) warp_arrive(&ctl->prep[s_], lane);
     };
 
+    // reverse sweep: which coordinate each of this thread's 16 feature columns encodes is a function of (column slice,
+    // i) only: decoded on the fly from warp-uniform integers (a per-thread table would live in local memory, and with
+    // 224 KB of shared memory the L1 holds next to nothing: every local access is an L2 round trip)
+    const int sub_u = __shfl_sync(0xffffffffu, sub, 0);
     load_next(blockIdx.x, 0);
     load_next(blockIdx.x, 1);
     for (int s = 0; s < 2; ++s) for (int part = 0; part < NPREP; ++part) prep_part(s, part);
@@ -802,9 +847,8 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           for (int nc = 0; nc < op.n_nc; ++nc) {
             const uint32_t par = (dc >> (2 * s + nc)) & 1u;
             dc ^= 1u << (2 * s + nc);
-            uint32_t* mw = nullptr;
-            if constexpr (GRAD) { if (op.mask_mode != MASK_NONE) mw = &gst[s].masks[op.mask_idx + nc]; }
-            epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par, mw);
+            if constexpr (GRAD) epilogue_dispatch_mask(op, nc, L.bias, tmem_lane, row, sub, q, &ctl->d_full[s][nc], par, &gst[s].masks[(op.mask_idx + nc) & (MASK_WORDS - 1)]);
+            else epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par);
             warp_arrive(&ctl->part[s][nc], lane);
             if (op.n_nc == 1) warp_arrive(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
           }
@@ -891,89 +935,120 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
           // ---- reverse sweep: gradient at the last hidden layer of a network, masked by its ReLU, as the operand
           //      image an epilogue of that width would leave (App. E steps 1, 4, 5) ----
           const TcOp& op = c_ops[sp.op];            // the first backward op of the network: reads what is written here
-          const int width = op.N, n_nc = op.n_nc, cw = (op.N / op.n_nc) / NSUB;
-          float gwv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (sp.arg == SEED_WARP) {
-            // x' = R(w, v) x + p(w, v): forward-mode over the 6 raw screw outputs of the closed-form exponential
-            Dual6 dw[3], dv[3];
-            for (int i = 0; i < 3; ++i) { dw[i] = Dual6::var(GS.wv[i], i); dv[i] = Dual6::var(GS.wv[3 + i], 3 + i); }
-            SE3<Dual6> TD;
-            exp_se3<Dual6>(dw, dv, TD);
-            for (int i = 0; i < 3; ++i) {
-              const Dual6 xi = TD.R[i * 3 + 0] * T.x[0] + TD.R[i * 3 + 1] * T.x[1] + TD.R[i * 3 + 2] * T.x[2] + TD.p[i];
-              for (int k = 0; k < 6; ++k) gwv[k] += GS.gxw[i] * xi.d[k];
+          const int n_nc = op.n_nc;
+          // the operand region of that op = the region it does NOT accumulate into; its mask = the ReLU of the network's
+          // LAST hidden layer (the op itself applies the one before)
+          const uint32_t seed_col = tmem_lane + (n_nc == 2 ? 256u - op.d_col[0] : 256u * (uint32_t)s + (128u - (op.d_col[0] - 256u * (uint32_t)s)));
+          const uint32_t* mw = &GS.masks[(op.mask_idx + n_nc) & (MASK_WORDS - 1)];
+          if (sp.arg == SEED_TRUNK) {
+            // column 0 of the sigma head (App. E step 1)
+            for (int nc = 0; nc < 2; ++nc) {
+              const float* w = K.alpha_col0 + nc * 128 + sub * 32;
+              seed_slice<32>(seed_col + (uint32_t)nc * 128u + (uint32_t)sub * 32u, mw[nc], [&](int i) { return __ldg(w + i); });
             }
-          }
-          // the operand region of that op = the region it does NOT accumulate into
-          const uint32_t seed_col = n_nc == 2 ? 256u - op.d_col[0] : 256u * (uint32_t)s + (128u - (op.d_col[0] - 256u * (uint32_t)s));
-          for (int nc = 0; nc < n_nc; ++nc) {
-            const int oc0 = nc * (width / n_nc) + sub * cw;
-            const uint32_t mword = GS.masks[op.mask_idx + n_nc + nc];     // ReLU of the network's LAST hidden layer (the op applies the one before)
-            uint32_t hi[16], lo[16];
-            for (int i = 0; i < cw / 2; ++i) {
-              float x2[2];
-              for (int e = 0; e < 2; ++e) {
-                const int k = oc0 + 2 * i + e;
-                float g;
-                if (sp.arg == SEED_TRUNK) g = __ldg(K.alpha_col0 + k);
-                else if (sp.arg == SEED_HYPER) { g = 0.f; for (int o = 0; o < H; ++o) g = fmaf(GS.gom[o], __ldg(K.hyper_logit_w + (size_t)k * H + o), g); }
-                else {
-                  g = 0.f;
-                  for (int o = 0; o < 3; ++o) { g = fmaf(gwv[o], __ldg(K.warp_w_w + (size_t)k * 3 + o), g); g = fmaf(gwv[3 + o], __ldg(K.warp_v_w + (size_t)k * 3 + o), g); }
-                }
-                x2[e] = ((mword >> (2 * i + e)) & 1u) ? g : 0.f;
+          } else if (sp.arg == SEED_HYPER) {
+            // d / d(last hidden) = sum_o gom[o] W_logit[:, o] (App. E step 4)
+            const float g0 = GS.gom[0], g1 = H > 1 ? GS.gom[1] : 0.f;
+            const float* w = K.hyper_logit_w + (size_t)(sub * 16) * H;
+            seed_slice<16>(seed_col + (uint32_t)sub * 16u, mw[0], [&](int i) {
+              float g = g0 * __ldg(w + i * H);
+              if (H > 1) g = fmaf(g1, __ldg(w + i * H + 1), g);
+              return g;
+            });
+          } else {
+            // x' = R(w, v) x + p(w, v) (App. E step 5).  The rotation inputs by forward mode over the literal
+            // rigid_body.py expressions (3 tangents); the translation inputs enter linearly, p = M(w) v / theta:
+            // d x' / d v_j = M[:, j] / theta
+            float gwv[6];
+            {
+              DualN<3> dw[3], dv[3];
+              for (int i = 0; i < 3; ++i) { dw[i] = DualN<3>::var(GS.wv[i], i); dv[i] = DualN<3>(GS.wv[3 + i]); }
+              SE3<DualN<3>> TD;
+              exp_se3<DualN<3>>(dw, dv, TD);
+              for (int k = 0; k < 3; ++k) gwv[k] = 0.f;
+              for (int i = 0; i < 3; ++i) {
+                const DualN<3> xi = TD.R[i * 3 + 0] * T.x[0] + TD.R[i * 3 + 1] * T.x[1] + TD.R[i * 3 + 2] * T.x[2] + TD.p[i];
+                for (int k = 0; k < 3; ++k) gwv[k] = fmaf(GS.gxw[i], xi.d[k], gwv[k]);
               }
-              const __half2 h = __floats2half2_rn(x2[0], x2[1]);
-              const float2 hf = __half22float2(h);
-              const __half2 l = __floats2half2_rn(x2[0] - hf.x, x2[1] - hf.y);
-              hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-              lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+              const float a0 = GS.wv[0], a1 = GS.wv[1], a2 = GS.wv[2];
+              const float theta = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+              const float w0 = a0 / theta, w1 = a1 / theta, w2 = a2 / theta;
+              const float W[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+              const float st = sinf(theta), ct = cosf(theta), omc = 1.f - ct, tms = theta - st;
+              for (int j = 0; j < 3; ++j) {
+                float acc = 0.f;
+                for (int i = 0; i < 3; ++i) {
+                  const float ww = W[i * 3 + 0] * W[0 * 3 + j] + W[i * 3 + 1] * W[1 * 3 + j] + W[i * 3 + 2] * W[2 * 3 + j];
+                  const float m = ((i == j) ? theta : 0.f) + omc * W[i * 3 + j] + tms * ww;
+                  acc = fmaf(GS.gxw[i], m, acc);
+                }
+                gwv[3 + j] = acc / theta;
+              }
             }
-            const uint32_t col = tmem_lane + seed_col + (uint32_t)nc * 128u + (uint32_t)sub * (uint32_t)cw;
-            if (cw == 32) { tmem_st<16>(col, reinterpret_cast<const uint32_t(&)[16]>(hi)); tmem_st<16>(col + 16, reinterpret_cast<const uint32_t(&)[16]>(lo)); }
-            else { tmem_st<8>(col, reinterpret_cast<const uint32_t(&)[8]>(hi)); tmem_st<8>(col + 8, reinterpret_cast<const uint32_t(&)[8]>(lo)); }
+            const float* ww = K.warp_w_w + (size_t)(sub * 32) * 3;
+            const float* wv = K.warp_v_w + (size_t)(sub * 32) * 3;
+            seed_slice<32>(seed_col + (uint32_t)sub * 32u, mw[0], [&](int i) {
+              float g = gwv[0] * __ldg(ww + 3 * i);
+              g = fmaf(gwv[1], __ldg(ww + 3 * i + 1), g); g = fmaf(gwv[2], __ldg(ww + 3 * i + 2), g);
+              g = fmaf(gwv[3], __ldg(wv + 3 * i), g); g = fmaf(gwv[4], __ldg(wv + 3 * i + 1), g); g = fmaf(gwv[5], __ldg(wv + 3 * i + 2), g);
+              return g;
+            });
           }
           warp_arrive(&ctl->part[s][0], lane);
           warp_arrive(&ctl->part[s][1], lane);
           } else if (sp.kind == STEP_PEB) {
           // ---- reverse sweep: positional-encoding backward (App. E step 3) of this thread's 16 feature columns, summed
           //      over the 4 warps that share the sample through the (idle) rgb side-input block ----
-          float part5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};       // d/d(x0, x1, x2) and, trunk input only, d/d(hyper 0, 1)
-          auto band_grad = [&](float xv, int deg, float w, bool is_cos, float g) {
-            const float xb = xv * __int_as_float((127 + deg) << 23);
-            return w * __int_as_float((127 + deg) << 23) * pe_cos(is_cos ? xb + NDS_HALF_PI_F : xb) * g;
-          };
-          if (sp.arg == 0) {
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, p4 = 0.f;   // d/d(x0, x1, x2) and, trunk input only, d/d(hyper 0, 1)
+          {
+            const bool trunk = sp.arg == 0;
+            const float c0 = trunk ? T.xw[0] : T.x[0], c1 = trunk ? T.xw[1] : T.x[1], c2 = trunk ? T.xw[2] : T.x[2];
+            const float c3 = T.om[0], c4 = T.om[1];
+            float fbv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) fbv[i] = GS.fb[i];           // all 16 loads in flight together
             const PosencSpec& ps = cp.pe_spatial;
             const PosencSpec& ph = cp.pe_hyperpt;
-            const int o_sp = ps.identity ? 3 : 0, n_sp = ps.num_bands * 6;
-            const int o_h0 = o_sp + n_sp, o_hy = o_h0 + ((H > 0 && ph.identity) ? H : 0), n_hy = H > 0 ? ph.num_bands * 2 * H : 0;
+            // column ranges (warp-uniform): [identity | bands] of the point, then of the hyper coordinates (trunk only)
+            const int o_id = trunk ? (ps.identity ? 0 : -1) : P.f_col_ident, o_b = trunk ? (ps.identity ? 3 : 0) : P.f_col_bands;
+            const int n_b = 6 * (trunk ? ps.num_bands : P.f_nb), deg0 = trunk ? ps.min_deg : P.f_kmin;
+            const int o_hid = (trunk && H > 0 && ph.identity) ? o_b + n_b : -1;
+            const int o_hb = (trunk && H > 0) ? o_b + n_b + (ph.identity ? H : 0) : 1 << 20, n_hb = H > 0 ? 2 * H * ph.num_bands : 0;
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int j = sub * 16 + i;
-              const float g = GS.fb[i];
-              if (j < o_sp) part5[j] += g;
-              else if (j < o_h0) { const int jj = j - o_sp, k = jj / 6, r = jj - 6 * k, c = r % 3; part5[c] += band_grad(T.xw[c], ps.min_deg + k, ps.window[k], r >= 3, g); }
-              else if (j < o_hy) part5[3 + (j - o_h0)] += g;
-              else if (j < o_hy + n_hy) { const int jj = j - o_hy, k = jj / (2 * H), r = jj - 2 * H * k, c = r % H; part5[3 + c] += band_grad(T.om[c], ph.min_deg + k, ph.window[k], r >= H, g); }
-            }
-          } else {
-            for (int i = 0; i < 16; ++i) {
-              const int j = sub * 16 + i;
-              const float g = GS.fb[i];
-              if (P.f_col_ident >= 0 && j >= P.f_col_ident && j < P.f_col_ident + 3) part5[j - P.f_col_ident] += g;
-              else if (j >= P.f_col_bands && j < P.f_col_bands + 6 * P.f_nb) {
-                const int jj = j - P.f_col_bands, k = jj / 6, r = jj - 6 * k, c = r % 3;
-                part5[c] += band_grad(T.x[c], P.f_kmin + k, 1.f, r >= 3, g);       // windows are folded into the weights
+              const int j = sub_u * 16 + i;
+              int comp = -1, deg = 0;
+              float win = 1.f, phase = 0.f;
+              bool band = false;
+              if (o_id >= 0 && j >= o_id && j < o_id + 3) comp = j - o_id;
+              else if (j >= o_b && j < o_b + n_b) {
+                const int jj = j - o_b, k = jj / 6, r = jj - 6 * k;
+                comp = r >= 3 ? r - 3 : r; deg = deg0 + k; band = true; phase = r >= 3 ? NDS_HALF_PI_F : 0.f;
+                if (trunk) win = ps.window[k];            // (the feature block's windows are folded into the weights)
+              } else if (o_hid >= 0 && j >= o_hid && j < o_hid + H) comp = 3 + j - o_hid;
+              else if (j >= o_hb && j < o_hb + n_hb) {
+                const int jj = j - o_hb, k = jj / (2 * H), r = jj - 2 * H * k;
+                comp = 3 + (r >= H ? r - H : r); deg = ph.min_deg + k; band = true; phase = r >= H ? NDS_HALF_PI_F : 0.f;
+                win = ph.window[k];
               }
+              const float xv = comp == 0 ? c0 : (comp == 1 ? c1 : (comp == 2 ? c2 : (comp == 3 ? c3 : c4)));
+              const float f = __int_as_float((127 + deg) << 23);
+              // d/dx [w sin(x 2^deg + phase)] = w 2^deg cos(x 2^deg + phase); identity columns pass the gradient through
+              const float d = band ? win * f * pe_cos(xv * f + phase) : 1.f;
+              const float v = comp >= 0 ? d * fbv[i] : 0.f;
+              p0 += comp == 0 ? v : 0.f; p1 += comp == 1 ? v : 0.f; p2 += comp == 2 ? v : 0.f;
+              p3 += comp == 3 ? v : 0.f; p4 += comp == 4 ? v : 0.f;
             }
           }
-          float* scr = reinterpret_cast<float*>(smem + OFF_IN2) + ((size_t)row * NSUB + sub) * 8;
-          for (int i = 0; i < 5; ++i) scr[i] = part5[i];
+          const float part5[5] = {p0, p1, p2, p3, p4};
+          // scratch laid out [value][warp of the sample][row]: consecutive lanes hit consecutive banks
+          float* scr = reinterpret_cast<float*>(smem + OFF_IN2);
+          for (int i = 0; i < 5; ++i) scr[(i * NSUB + sub) * TM + row] = part5[i];
           asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
           float tot[5];
           for (int i = 0; i < 5; ++i) {
-            const float* r4 = reinterpret_cast<const float*>(smem + OFF_IN2) + (size_t)row * NSUB * 8 + i;
-            tot[i] = (r4[0] + r4[8]) + (r4[16] + r4[24]);
+            const float* r4 = scr + (size_t)i * NSUB * TM + row;
+            tot[i] = (r4[0] + r4[TM]) + (r4[2 * TM] + r4[3 * TM]);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // the block is re-used by the next reduction
           if (sp.arg == 0) { for (int c = 0; c < 3; ++c) GS.gxw[c] = tot[c]; GS.gom[0] = tot[3]; GS.gom[1] = tot[4]; }
