@@ -211,8 +211,9 @@ __device__ __forceinline__ void ctrl_init(Ctrl* ctl) {
 }
 
 // one arrival per compute warp, after every lane made its writes visible
+template <bool SMEM_WRITES = true>
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
-  fence_proxy_async_smem();     // st.shared operand images -> async proxy (tcgen05.mma)
+  if (SMEM_WRITES) fence_proxy_async_smem();     // st.shared operand images -> async proxy (tcgen05.mma)
   tmem_st_wait();               // tcgen05.st operand images complete
   tc_fence_before_sync();
   __syncwarp();
@@ -392,9 +393,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off + oc0);
   float b[CW];
 #pragma unroll
-  for (int i = 0; i < CW / 4; ++i) {     // issued before the accumulators are awaited: the latency hides in the wait
-    const float4 t = __ldg(bias4 + i);
-    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  for (int i = 0; i < CW / 4; ++i) {
+    // issued BEFORE the accumulators are awaited, so that the latency (an L2 round trip: with 224 KB of shared memory
+    // the L1 holds next to nothing) hides in the wait.  `volatile`: a plain __ldg is sunk below the wait loop by the
+    // compiler, next to its first use, and the first FFMA of every epilogue then stalls on it (ncu: 7.5 % of all
+    // warp samples of the kernel on that one instruction).
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(b[4 * i]), "=f"(b[4 * i + 1]), "=f"(b[4 * i + 2]), "=f"(b[4 * i + 3]) : "l"(bias4 + i));
   }
   mbar_wait(bar, parity);
   tc_fence_after_sync();
@@ -475,15 +480,21 @@ __device__ __forceinline__ void epilogue_dispatch_mask(const TcOp& op, int nc, c
   }
 }
 
-// head (<= 16 outputs): every compute warp of the lane quarter reads all of them
-__device__ __forceinline__ void epilogue_head(const TcOp& op, const float* __restrict__ bias_base, uint32_t tmem_lane,
-                                              float* hv) {
+// head (<= 16 outputs): every compute warp of the lane quarter reads all of them.  The bias (padded to 16) is loaded
+// by head_bias BEFORE the accumulators are awaited (see epilogue_chunk).
+__device__ __forceinline__ void head_bias(const TcOp& op, const float* __restrict__ bias_base, float (&b)[16]) {
+  const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(b[4 * i]), "=f"(b[4 * i + 1]), "=f"(b[4 * i + 2]), "=f"(b[4 * i + 3]) : "l"(bias4 + i));
+}
+__device__ __forceinline__ void epilogue_head(const TcOp& op, const float (&b)[16], uint32_t tmem_lane, float* hv) {
   uint32_t v[16];
   tmem_ld16(tmem_lane + op.d_col[0], v);
   tmem_ld_wait();
-  const float* bias = bias_base + op.bias_off;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) hv[i] = fmaf(__uint_as_float(v[i]), op.inv_scale, __ldg(bias + i));
+  for (int i = 0; i < 16; ++i) hv[i] = fmaf(__uint_as_float(v[i]), op.inv_scale, b[i]);
 }
 
 // sin(x) for the positional encodings (|x| <= 2^max_deg * scene extent, far below the 1e5 limit of the 3-term
@@ -849,16 +860,19 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
             dc ^= 1u << (2 * s + nc);
             if constexpr (GRAD) epilogue_dispatch_mask(op, nc, L.bias, tmem_lane, row, sub, q, &ctl->d_full[s][nc], par, &gst[s].masks[(op.mask_idx + nc) & (MASK_WORDS - 1)]);
             else epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par);
-            warp_arrive(&ctl->part[s][nc], lane);
-            if (op.n_nc == 1) warp_arrive(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
+            // (a plain epilogue only wrote tensor memory: no proxy fence)
+            warp_arrive<false>(&ctl->part[s][nc], lane);
+            if (op.n_nc == 1) warp_arrive<false>(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
           }
         } else if (sp.kind == STEP_HEAD) {
           const TcOp& op = c_ops[sp.op];
+          float hb[16];
+          head_bias(op, L.bias, hb);
           mbar_wait(&ctl->d_full[s][0], (dc >> (2 * s)) & 1u);
           dc ^= 1u << (2 * s);
           tc_fence_after_sync();
           float hv[16];
-          epilogue_head(op, L.bias, tmem_lane, hv);
+          epilogue_head(op, hb, tmem_lane, hv);
           if (op.signal_done) warp_arrive(&ctl->done[s], lane);   // the tile slot's last tensor-memory read
           switch (op.glue) {
             case GLUE_MASK: {            // models.py:967-975
@@ -1190,8 +1204,9 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
     if (op.epi_kind == EPI_HEAD) {
       mbar_wait(&ctl->d_full[0][0], 0);
       tc_fence_after_sync();
-      float hv[16];
-      epilogue_head(op, L.bias, tmem_lane, hv);
+      float hv[16], hb[16];
+      head_bias(op, L.bias, hb);
+      epilogue_head(op, hb, tmem_lane, hv);
       if (sub == 0) for (int i = 0; i < 16 && i < op.N; ++i) out_f32[row * op.N + i] = hv[i];
     } else {
       for (int nc = 0; nc < op.n_nc; ++nc)
