@@ -159,8 +159,9 @@ def run_reference(args):
   line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
           'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-          'config': dict(workload_config(args, 1, 1, rays_per_step=n),
-                         note=f'each timed step is a bounded sample of the frame: {n} of its {args.image * args.image} rays'),
+          'config': dict(workload_config(args, 1, 1), timed_rays_per_step=n, engine='cpu-oracle', precision='f32',
+                         note=f'each timed step is a bounded sample of the workload: {n} of the frame\'s {args.image * args.image} rays '
+                              '(value = sample rays / sample time)'),
           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
           'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
           'gpu_launches': 0}
@@ -497,7 +498,8 @@ def run_train(args):
     print(json.dumps({'impl': 'reference', 'metric': METRIC_TRAIN, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
                       'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                      'config': dict(train_config(args, n), note=f'each timed step is a bounded sample: {n} of the {args.batch} rays'),
+                      'config': dict(train_config(args), timed_rays_per_step=n, engine='cpu-oracle', precision='f32',
+                                     note=f'each timed step is a bounded sample: {n} of the {args.batch} rays'),
                       'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                        'sample': f'{n} rays of the batch per step, PyTorch-CPU fp32 restatement incl. autograd d(sigma)/dx'},
                       'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}), flush=True)
