@@ -366,6 +366,31 @@ def run_ours(args):
   per_ray_out = sum(int(np.prod(ALL_SHAPES[k](Sc + Sf, R.H) or (1,))) for k in RENDER_KEYS) * 4
   d2h = per_ray_out * n_frame * n_frames          # the assembled frame(s), once (rank 0)
 
+  # ---- early-termination scan (ndsr_set_early_termination; OFF in `value` and `e2e` above, which evaluate every
+  # sample like the reference): the same frame with the scan on, and a field with opaque regions (raw densities
+  # x 40) with the scan off / on -- rays/s and the share of the fine level's network evaluations that were skipped
+  term = None
+  if world == 1 and R.engine == 'tc' and args.term_eps > 0 and not args.sweep:
+    from nerfds_b200.params import harden_density
+    ts = max(1, min(args.steps, 2))
+
+    def term_run(eps):
+      R.set_early_termination(eps)
+      step_device()
+      R.termination_stats(reset=True)
+      ms_t, _, _ = timed(step_device, ts)
+      ev, seen = R.termination_stats(reset=True)
+      skipped = (seen - ev) / float(max(seen, 1)) * Sf / float(Sc + Sf) if eps > 0 else 0.0
+      return {'value': rays_step * ts / (ms_t * 1e-3), 'evals_skipped_frac': skipped}
+
+    term = {'transmittance_eps': args.term_eps, 'steps': ts, 'bench_scene': term_run(args.term_eps)}
+    R.load_params(harden_density(params, 40.0))
+    term['opaque_scene'] = {'off': term_run(0.0), 'on': term_run(args.term_eps),
+                            'what': 'same networks, raw density (column 0 of both alpha heads) x 40: hard surfaces'}
+    term['opaque_scene']['speedup'] = term['opaque_scene']['on']['value'] / term['opaque_scene']['off']['value']
+    R.set_early_termination(0.0)
+    R.load_params(params)
+
   # ---- N > 1: the last assembled frame against a single-GPU render of the same rays, shards and keys
   frame_check = None
   if world > 1:
@@ -432,6 +457,8 @@ def run_ours(args):
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu}
     if frame_check is not None:
       line['frame_matches_single_gpu'] = frame_check
+    if term is not None:
+      line['early_termination'] = term
     print(json.dumps(line), flush=True)
   if peer is not None:
     for pf in peer:
@@ -642,6 +669,8 @@ def main():
   ap.add_argument('--batch', type=int, default=4096)
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='weak: N frames per step (per-GPU work fixed); strong: one frame per step over N ranks')
+  ap.add_argument('--term-eps', type=float, default=1e-4,
+                  help='also measure the fine level with the early-termination scan at this transmittance (0: skip)')
   ap.add_argument('--traffic', type=float, default=None, help='DRAM bytes/launch of the dominant kernel from ncu')
   args = ap.parse_args()
   train = args.workload == 'train4096'

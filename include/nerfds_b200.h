@@ -317,6 +317,18 @@ void ndsr_struct_sizes(int32_t* config, int32_t* extra_params, int32_t* outputs)
 /* Upper bound on rays processed per internal pass (scratch = 100 B x rays x samples). */
 int ndsr_set_max_chunk(ndsr_handle* h, int64_t max_rays);
 
+/* Early termination of the fine level (north_star: "early-termination scan"; the reference composites every sample,
+ * model_utils.py:95-159, so this is OFF by default: transmittance_eps = 0).  With eps > 0, ndsr_render_rays* calls
+ * on the tensor-core engine that request only per-ray outputs (render.py's keys) and no render_opts evaluate the
+ * fine network at the coarse depths first and then the newly drawn depths front to back in `rounds` rounds of equal
+ * rank ranges.  Before each round a scan bounds the transmittance T in front of every depth of the round by the
+ * product over the samples evaluated so far (the exact factors (1 - alpha + 1e-10) of model_utils.py:131-136) and
+ * drops the depths with T < eps: together they can hold at most eps of a ray's weight, so every per-ray output moves
+ * by at most 2 eps x (range of the composited quantity).  ndsr_termination_stats returns the new depths evaluated /
+ * seen since the last reset (synchronises `stream`). */
+int ndsr_set_early_termination(ndsr_handle* h, float transmittance_eps, int32_t rounds);
+int ndsr_termination_stats(ndsr_handle* h, void* stream, int64_t* evaluated, int64_t* seen, int reset);
+
 /* Per-stage device timing for bench.py's roofline: when enabled, every kernel
  * the handle launches is bracketed by CUDA events recorded on the call's own
  * stream.  ndsr_profile_read synchronises those events and returns the

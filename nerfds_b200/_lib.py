@@ -145,7 +145,8 @@ EXPORTS = ['ndsr_create', 'ndsr_destroy', 'ndsr_last_error', 'ndsr_load_params',
            'ndsr_struct_sizes', 'ndsr_set_max_chunk', 'ndsr_selftest_tc_dense', 'ndsr_profile_enable',
            'ndsr_profile_read', 'ndsr_camera_rays', 'ndsr_random_uniform', 'ndsr_peer_alloc', 'ndsr_peer_free',
            'ndsr_peer_open', 'ndsr_peer_close', 'ndsr_set_output_mirrors', 'ndsr_render_rays_host_rng',
-           'ndsr_random_uniform_range', 'ndsr_tc_issued_macs']
+           'ndsr_random_uniform_range', 'ndsr_tc_issued_macs', 'ndsr_set_early_termination',
+           'ndsr_termination_stats']
 
 
 def load_library() -> C.CDLL:
@@ -189,6 +190,8 @@ def load_library() -> C.CDLL:
   lib.ndsr_struct_sizes.restype = None
   lib.ndsr_set_max_chunk.argtypes = [vp, i64]
   lib.ndsr_tc_issued_macs.argtypes = [vp, C.POINTER(C.c_double)]
+  lib.ndsr_set_early_termination.argtypes = [vp, C.c_float, i32]
+  lib.ndsr_termination_stats.argtypes = [vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]
   lib.ndsr_profile_enable.argtypes = [vp, C.c_int]
   lib.ndsr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
   lib.ndsr_selftest_tc_dense.argtypes = [C.c_int] * 7 + [vp] * 5

@@ -135,6 +135,28 @@ extern "C" int ndsr_set_max_chunk(ndsr_handle* h, int64_t max_rays) {
   return NDSR_OK;
 }
 
+extern "C" int ndsr_set_early_termination(ndsr_handle* h, float transmittance_eps, int32_t rounds) {
+  if (!h || !(transmittance_eps >= 0.f) || transmittance_eps >= 1.f || rounds < 1 || rounds > 64) return NDSR_ERR_INVALID;
+  h->term_eps = transmittance_eps;
+  h->term_rounds = rounds;
+  return NDSR_OK;
+}
+
+extern "C" int ndsr_termination_stats(ndsr_handle* h, void* stream, int64_t* evaluated, int64_t* seen, int reset) {
+  if (!h) return NDSR_ERR_INVALID;
+  unsigned long long v[2] = {h->term_stats_keep[0], h->term_stats_keep[1]};
+  if (h->term_stats) {
+    NDS_CUDA(h, cudaSetDevice(h->device));
+    NDS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream));
+    NDS_CUDA(h, cudaMemcpy(v, h->term_stats, sizeof v, cudaMemcpyDeviceToHost));
+    if (reset) NDS_CUDA(h, cudaMemset(h->term_stats, 0, sizeof v));
+  }
+  if (reset) h->term_stats_keep[0] = h->term_stats_keep[1] = 0;
+  if (evaluated) *evaluated = (int64_t)v[0];
+  if (seen) *seen = (int64_t)v[1];
+  return NDSR_OK;
+}
+
 extern "C" int ndsr_create(const ndsr_config* cfg, int device, ndsr_handle** out) {
   if (!cfg || !out) { g_create_error = "null argument"; return NDSR_ERR_INVALID; }
   std::string v = validate(*cfg);
@@ -193,6 +215,9 @@ extern "C" int ndsr_create(const ndsr_config* cfg, int device, ndsr_handle** out
 }
 
 static void free_scratch(ndsr_handle* h) {
+  if (h->term_stats)     // the statistics live in the scratch: keep their value while it is regrown
+    cudaMemcpy(h->term_stats_keep, h->term_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  h->term_stats = nullptr; h->term_index = nullptr; h->term_count = nullptr;
   for (void* p : h->scratch_allocs) cudaFree(p);
   h->scratch_allocs.clear();
   h->cap_rays = 0;
@@ -454,6 +479,15 @@ static int ensure_scratch(ndsr_handle* h, int64_t rays, cudaStream_t st) {
     h->src_elem = reinterpret_cast<int32_t*>(pf);
   }
   NDS_CUDA(h, alloc(&h->z_new, rays * (smax > c.num_coarse_samples ? smax - c.num_coarse_samples : 1)));
+  {
+    float* pf = nullptr;
+    NDS_CUDA(h, alloc(&pf, rays * (smax > c.num_coarse_samples ? smax - c.num_coarse_samples : 1) + 8));
+    h->term_index = reinterpret_cast<int32_t*>(pf) + 8;      // 32 bytes in front: the count and the statistics
+    h->term_count = reinterpret_cast<int32_t*>(pf);
+    unsigned long long* stats = reinterpret_cast<unsigned long long*>(pf) + 1;
+    NDS_CUDA(h, cudaMemcpy(stats, h->term_stats_keep, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    h->term_stats = stats;
+  }
   h->cap_rays = rays;
   h->cap_samples = smax;
   return NDSR_OK;
@@ -514,15 +548,38 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
       // split fine pass: the n_carried coarse depths of every ray re-use the coarse pass's warp / hyper / mask
       // results (same points, same shared networks) and only run the template NeRF; the new depths run everything.
       // Dense blocks of the planes: carried samples [0, B n_carried), new samples after them.
-      FieldArgs fb = fa;
-      fb.S = S - n_carried; fb.z = h->z_new; fb.n_samples_total = B * (S - n_carried);
-      fb.planes = h->planes + B * n_carried;
-      int rc = tc_engine_field(h, cp, fb, st);
-      if (rc) return rc;
-      fb.S = n_carried; fb.z = nullptr; fb.n_samples_total = B * n_carried; fb.planes = h->planes;
-      fb.carry = h->carry; fb.carry_stride = B * n_carried;
-      rc = tc_engine_field(h, cp, fb, st);
-      if (rc) return rc;
+      // Early termination (ndsr_set_early_termination; render-mode calls without per-sample outputs or
+      // render_opts): the carried launch goes first, a scan of its sigmas bounds the transmittance in front of
+      // every new depth, and the second launch evaluates only the depths that can still carry weight.
+      const bool term = h->term_eps > 0.f && !wants_per_sample(out) && !(apply_filter && (ep.filter_flags & 3)) &&
+                        B * (int64_t)(S - n_carried) < (int64_t)0x7fffffff;
+      FieldArgs fn = fa, fc = fa;
+      fn.S = S - n_carried; fn.z = h->z_new; fn.n_samples_total = B * (S - n_carried);
+      fn.planes = h->planes + B * n_carried;
+      fc.S = n_carried; fc.z = nullptr; fc.n_samples_total = B * n_carried; fc.planes = h->planes;
+      fc.carry = h->carry; fc.carry_stride = B * n_carried;
+      int rc;
+      if (term) {
+        if ((rc = tc_engine_field(h, cp, fc, st))) return rc;
+        TerminationArgs ta;
+        memset(&ta, 0, sizeof ta);
+        ta.n_rays = B; ta.S = S; ta.n_carried = n_carried; ta.z = z; ta.dirs = dirs; ta.src_elem = src_elem;
+        ta.planes = h->planes; ta.plane_stride = B * S; ta.plane_mask = pm; ta.H = h->H; ta.has_warp = c.use_warp;
+        ta.sample_at_infinity = sample_at_infinity; ta.eps = h->term_eps;
+        ta.index = h->term_index; ta.n_active = h->term_count; ta.stats = h->term_stats;
+        fn.index = h->term_index; fn.n_active = h->term_count;
+        const int n_new = S - n_carried, rounds = h->term_rounds < n_new ? h->term_rounds : n_new;
+        for (int r = 0; r < rounds; ++r) {       // front to back: each round sees the sigmas of the rounds before it
+          ta.rank_lo = (int)((int64_t)n_new * r / rounds); ta.rank_hi = (int)((int64_t)n_new * (r + 1) / rounds);
+          NDS_CUDA(h, launch_termination_scan(ta, h->num_sms, st));
+          h->launches++;
+          fn.n_samples_total = B * (int64_t)(ta.rank_hi - ta.rank_lo);     // (upper bound: sizes the grid)
+          if ((rc = tc_engine_field(h, cp, fn, st))) return rc;
+        }
+      } else {
+        if ((rc = tc_engine_field(h, cp, fn, st))) return rc;
+        if ((rc = tc_engine_field(h, cp, fc, st))) return rc;
+      }
     } else if (h->engine == NDSR_ENGINE_TC && (!need_grad || !ep.use_sigma_gradient)) {
       // (with d(sigma)/dx: one launch of the program that ends every tile with the reverse sweep; only
       //  use_sigma_gradient -- the gradient as the rgb branch's normal input -- stays on the CUDA-core engine)

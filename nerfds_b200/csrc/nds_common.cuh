@@ -100,6 +100,11 @@ struct FieldArgs {
   const float* carry;        // non-null: "carried" launch, reads C_* planes [c * carry_stride + i]
   float* carry_out;          // non-null: also store the C_* planes of every sample
   int64_t carry_stride;
+  // ---- early termination (TerminationArgs, nds_composite.h): the launch evaluates only the *n_active samples
+  // listed in `index` (elements of the dense sample list; both written by termination_scan_kernel earlier on the
+  // stream).  null: all n_samples_total samples in order.
+  const int32_t* index;
+  const int32_t* n_active;
 };
 
 // carried per-sample planes (coarse pass -> fine pass)

@@ -262,6 +262,112 @@ sharpen_weights_kernel(int64_t n_rays, int S, const float* __restrict__ weights_
   }
 }
 
+// ---------------------------------------------------------------------------
+// Early-termination scan (TerminationArgs, nds_composite.h).  One warp per ray: lane l owns the contiguous sorted
+// positions [l c, (l + 1) c), c = ceil(S / 32); ranks and exclusive products over the lanes in front come from
+// shuffle scans.  alpha of an evaluated sample is computed exactly as composite_kernel will compute it (same planes,
+// same distances), so the bound is a bound on the very product the compositing step forms.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(CW * 32)
+termination_scan_kernel(const __grid_constant__ TerminationArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.S, nc = a.n_carried, nn = S - nc;
+  const int chunk = (S + 31) / 32;
+  const int64_t ps = a.plane_stride;
+  const float last = a.sample_at_infinity ? 1e10f : 1e-19f;
+  for (int64_t ray = (int64_t)blockIdx.x * CW + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * CW) {
+    const int64_t base = ray * S;
+    const float dx = a.dirs[ray * 3], dy = a.dirs[ray * 3 + 1], dz = a.dirs[ray * 3 + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const int s0 = min(S, lane * chunk), s1 = min(S, s0 + chunk);
+    // rank (among the new depths, in sorted order) of the first new depth of this lane's chunk
+    int n_new = 0;
+    for (int s = s0; s < s1; ++s) n_new += a.src_elem[base + s] >= nc ? 1 : 0;
+    int rank0 = n_new;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, rank0, o);
+      if (lane >= o) rank0 += up;
+    }
+    rank0 -= n_new;
+    // (1 - alpha + 1e-10) of sample s if its sigma is known: a carried sample, or a new depth of an earlier round
+    // (a skipped one holds sigma_raw = -1e30: alpha 0); 1 otherwise
+    auto factor = [&](int s, int e, int rank) -> float {
+      int64_t pn;
+      if (e < nc) pn = ray * nc + e;
+      else if (rank < a.rank_lo) pn = a.n_rays * nc + ray * nn + (e - nc);
+      else return 1.f;
+      const float sigma = softplus_f(a.planes[P_SIGMA_RAW * ps + pn]);
+      const float dist = ((s == S - 1) ? last : (a.z[base + s + 1] - a.z[base + s])) * dnorm;
+      const float al = 1.f - expf(-sigma * dist);
+      return 1.f - al + 1e-10f;
+    };
+    float prod = 1.f;
+    {
+      int rank = rank0;
+      for (int s = s0; s < s1; ++s) {
+        const int e = a.src_elem[base + s];
+        prod *= factor(s, e, rank);
+        rank += e >= nc ? 1 : 0;
+      }
+    }
+    float incl = prod;                          // inclusive product scan over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= up;
+    }
+    float T0 = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) T0 = 1.f;
+    // decide the new depths of this round
+    int kept = 0;
+    {
+      float T = T0;
+      int rank = rank0;
+      for (int s = s0; s < s1; ++s) {
+        const int e = a.src_elem[base + s];
+        if (e >= nc && rank >= a.rank_lo && rank < a.rank_hi && T >= a.eps) ++kept;
+        T *= factor(s, e, rank);
+        rank += e >= nc ? 1 : 0;
+      }
+    }
+    int off = kept;                             // inclusive sum scan -> exclusive offsets
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, off, o);
+      if (lane >= o) off += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    int dst = 0;
+    if (lane == 0) {
+      dst = atomicAdd(a.n_active, total);
+      atomicAdd(a.stats, (unsigned long long)total);
+      atomicAdd(a.stats + 1, (unsigned long long)(min(a.rank_hi, nn) - min(a.rank_lo, nn)));
+    }
+    dst = __shfl_sync(0xffffffffu, dst, 0) + off - kept;
+    float T = T0;
+    int rank = rank0;
+    for (int s = s0; s < s1; ++s) {
+      const int e = a.src_elem[base + s];
+      const bool mine = e >= nc && rank >= a.rank_lo && rank < a.rank_hi;
+      const float Tb = T;
+      T *= factor(s, e, rank);
+      rank += e >= nc ? 1 : 0;
+      if (!mine) continue;
+      const int64_t li = ray * nn + (e - nc);   // element of the dense new-depth list
+      if (Tb >= a.eps) { a.index[dst++] = (int32_t)li; continue; }
+      const int64_t pn = a.n_rays * nc + li;     // its planes: an empty sample
+      a.planes[P_SIGMA_RAW * ps + pn] = -1e30f;
+      if (a.plane_mask & PG_RGB) for (int i = 0; i < 3; ++i) a.planes[(P_RGB + i) * ps + pn] = 0.f;
+      if (a.plane_mask & PG_NORM) for (int i = 0; i < 3; ++i) a.planes[(P_NORM + i) * ps + pn] = 0.f;
+      if (a.plane_mask & PG_MASK) a.planes[P_MASK * ps + pn] = 0.f;
+      if (a.plane_mask & PG_WARPED) for (int i = 0; i < 3 + a.H; ++i) a.planes[(P_WARPED + i) * ps + pn] = 0.f;
+      if (a.has_warp && (a.plane_mask & PG_ROT)) for (int i = 0; i < 3; ++i) a.planes[(P_ROT + i) * ps + pn] = 0.f;
+      if (a.has_warp && (a.plane_mask & PG_TRANS)) for (int i = 0; i < 3; ++i) a.planes[(P_TRANS + i) * ps + pn] = 0.f;
+    }
+  }
+}
+
 // rgb [n,S,3] + sigma [n,S] -> planes, for the stand-alone volumetric_rendering entry point
 __global__ void pack_rgb_sigma_kernel(int64_t total, const float* __restrict__ rgb, const float* __restrict__ sigma,
                                       float* planes, int64_t ps) {
@@ -455,6 +561,13 @@ cudaError_t launch_composite(const CompositeArgs& a, int num_sms, cudaStream_t s
     if (e != cudaSuccess) return e;
   }
   composite_kernel<<<grid_for(a.n_rays, num_sms), CW * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_termination_scan(const TerminationArgs& a, int num_sms, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(a.n_active, 0, sizeof(int32_t), st);
+  if (e != cudaSuccess || a.n_rays == 0) return e;
+  termination_scan_kernel<<<grid_for(a.n_rays, num_sms), CW * 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -51,6 +51,33 @@ struct SamplePdfArgs {
   int32_t* src_elem_out;  // optional [B, n_coarse + n_fine]: which element of concat(z_coarse, z_samples) sits at sorted position s
 };
 
+// Early-termination scan of the split fine pass (render mode).  After the "carried" launch the fine network's sigma
+// is known at every coarse depth of a ray; the new depths are then evaluated front to back in ROUNDS of equal rank
+// ranges (rank = position among the ray's new depths in sorted order).  Before round r the scan walks the sorted
+// union with every sample whose sigma is known -- carried samples and the new depths of earlier rounds, the others
+// counted as empty -- which gives an upper bound T_ub >= T of the transmittance in front of each depth of the round:
+// every factor (1 - alpha + 1e-10) the compositing product will apply (model_utils.py:131-136) is at most 1 + 1e-10.
+// A depth with T_ub < eps can carry at most eps of weight and is not evaluated: its planes are written as an empty
+// sample (sigma_raw -> softplus 0), the surviving depths of the round are compacted into `index`.
+struct TerminationArgs {
+  int64_t n_rays;
+  int S, n_carried;          // sorted union length, coarse depths per ray
+  const float* z;            // [B,S] sorted union
+  const float* dirs;         // [B,3]
+  const int32_t* src_elem;   // [B,S] (SamplePdfArgs::src_elem_out)
+  float* planes;             // carried block [0, B n_carried), new block after it
+  int64_t plane_stride;
+  uint32_t plane_mask;
+  int H, has_warp;
+  int sample_at_infinity;
+  float eps;
+  int rank_lo, rank_hi;      // this round decides the new depths with rank in [rank_lo, rank_hi)
+  int32_t* index;            // out: surviving new samples (element of the dense new-depth list, ray * n_new + e)
+  int32_t* n_active;         // out: their count (zeroed by the launcher)
+  unsigned long long* stats; // [2] accumulated: new depths evaluated, new depths seen
+};
+cudaError_t launch_termination_scan(const TerminationArgs& a, int num_sms, cudaStream_t st);
+
 cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* out, int num_sms, cudaStream_t st);
 cudaError_t launch_uniform_threefry_range(uint32_t k0, uint32_t k1, int64_t n, int64_t first, int64_t count, float* out,
                                           int num_sms, cudaStream_t st);

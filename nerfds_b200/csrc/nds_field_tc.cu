@@ -50,8 +50,16 @@ constexpr int NSUB = 4;                 // compute warps per TMEM lane quarter
 constexpr int N_CWARPS = 4 * NSUB;
 // The MMA issuer is warp 0: it shares its scheduler with four compute warps, and the oldest warp of a scheduler
 // wins the issue slot.  Warps 2 and 3 only keep the compute warps' TMEM lane quarter = warp % 4.
+#ifndef NDS_ISSUER_LAST
+#define NDS_ISSUER_LAST 0   // experiment: compute warps 0-15, TMA producer 16, MMA issuer = the LAST warp (19)
+#endif
+#if NDS_ISSUER_LAST
+constexpr int WARP_MMA = 19, WARP_TMA = 16, CWARP0 = 0;
+#else
 constexpr int WARP_MMA = 0, WARP_TMA = 1, CWARP0 = 4;
-constexpr int TC_THREADS = (CWARP0 + N_CWARPS) * 32;
+#endif
+constexpr int TC_THREADS = 20 * 32;
+__device__ __forceinline__ bool is_compute_warp(int warp) { return warp >= CWARP0 && warp < CWARP0 + N_CWARPS; }
 constexpr uint32_t KBLK = 16384;        // one 128-row K-block (64 fp16 columns)
 // shared memory map
 constexpr uint32_t OFF_IN = 0;          // IN[tile slot]: hi block at slot * 2 KBLK, lo block right after
@@ -66,6 +74,12 @@ constexpr uint32_t TC_SMEM_PROBE = OFF_CTRL + 1024;          // any size: only t
 constexpr int NPREP = 3;                // the shared feature block of the next pair is written in 3 parts
 #ifndef NDS_EPI_RZ
 #define NDS_EPI_RZ 0    // 1: ReLU folded into cvt.rz.relu (2 instructions fewer per pair, hi truncated -> lo twice as large)
+#endif
+#ifndef NDS_EPI_TRUNC
+#define NDS_EPI_TRUNC 0 // 1: hi = x with the low 13 mantissa bits cleared (LOP3 on the alu pipe instead of HADD2.F32 x2 on
+#endif                  //    the fma pipe), ReLU folded into the two conversions: 4 fma-pipe instructions per pair instead of 6
+#ifndef NDS_SUBTRACE
+#define NDS_SUBTRACE 0  // diagnostics build: clock64 stamps inside the epilogues of the traced warp (NDS_TC_TRACE)
 #endif
 
 enum EpiKind : uint8_t {
@@ -171,7 +185,8 @@ struct TcProgram {       // passed by value as a __grid_constant__ kernel parame
 };
 static_assert(sizeof(TcProgram) < 24576, "kernel parameter budget (32 764 bytes with the other arguments)");
 
-constexpr int TRACE_WORDS = 3 * MAX_BURST + 2 * MAX_STEPS + 8;
+constexpr int TRACE_SUB = 3 * MAX_BURST + 2 * MAX_STEPS + 8;   // sub-step stamps: 8 per step (N-chunk c: 4 c + {waited, loaded, stored, arrived})
+constexpr int TRACE_WORDS = TRACE_SUB + 8 * MAX_STEPS;
 
 struct TcLevel {
   const uint8_t* weights;
@@ -388,7 +403,8 @@ __device__ __forceinline__ void store_in_hi(uint8_t* blk, uint32_t r, uint32_t c
 template <int CW, int MM = MASK_NONE>
 __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const float* __restrict__ bias_base,
                                                uint32_t tmem_lane, uint32_t row, int sub, int q, float* dbg_out,
-                                               int dbg_ld, uint64_t* bar, uint32_t parity, uint32_t* mask_word = nullptr) {
+                                               int dbg_ld, uint64_t* bar, uint32_t parity, uint32_t* mask_word = nullptr,
+                                               unsigned long long* sub_tr = nullptr) {
   const uint32_t oc0 = (uint32_t)nc * op.nc_rows + (uint32_t)sub * CW;   // first output column of this slice
   const float4* bias4 = reinterpret_cast<const float4*>(bias_base + op.bias_off + oc0);
   float b[CW];
@@ -403,16 +419,51 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
   }
   mbar_wait(bar, parity);
   tc_fence_after_sync();
+#if NDS_SUBTRACE
+  if (sub_tr) sub_tr[0] = clock64();
+#endif
   const uint32_t chunk = tmem_lane + op.d_col[nc];
   const uint32_t col = chunk + (uint32_t)sub * CW;
   uint32_t v[CW];
   tmem_ld<CW>(col, v);
   tmem_ld_wait();
+#if NDS_SUBTRACE
+  if (sub_tr) sub_tr[1] = clock64();
+#endif
   const float inv = op.inv_scale;
   const bool relu = op.relu != 0;
   uint32_t hi[CW / 2], lo[CW / 2];
   uint32_t mword = MM == MASK_APPLY ? *mask_word : 0u;
-  if (NDS_EPI_RZ && relu && !dbg_out && MM == MASK_NONE) {
+  if (NDS_EPI_TRUNC && !dbg_out && MM == MASK_NONE) {
+    // hi = x truncated to 11 significant bits by clearing mantissa bits (exactly representable in fp16 for
+    // 2^-14 <= |x| < 65504, so its conversion is exact; below that the conversion rounds by < 2^-25 absolute),
+    // lo = x - hi has the sign of x, so with a ReLU both conversions clamp at 0 and no separate max is needed.
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < CW / 2; ++i) {
+        const float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
+        const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
+        const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+        uint32_t h, l;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(h1), "f"(h0));
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
+        hi[i] = h;
+        lo[i] = l;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < CW / 2; ++i) {
+        const float x0 = fmaf(__uint_as_float(v[2 * i]), inv, b[2 * i]);
+        const float x1 = fmaf(__uint_as_float(v[2 * i + 1]), inv, b[2 * i + 1]);
+        const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+        uint32_t h, l;
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(h1), "f"(h0));
+        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"(x1 - h1), "f"(x0 - h0));
+        hi[i] = h;
+        lo[i] = l;
+      }
+    }
+  } else if (NDS_EPI_RZ && relu && !dbg_out && MM == MASK_NONE) {
     // ReLU folded into the conversions: hi = relu(x) truncated to fp16 (round toward zero, so the residual of a
     // positive x is never negative), lo = relu(x - hi) -- for x < 0 both come out 0.  hi + lo still carries 21+ bits.
 #pragma unroll
@@ -454,14 +505,18 @@ __device__ __forceinline__ void epilogue_chunk(const TcOp& op, int nc, const flo
     tmem_st<CW / 2>(col, hi);
     if (kind == EPI_INPLACE) tmem_st<CW / 2>(col + CW / 2, lo);
   }
+#if NDS_SUBTRACE
+  if (sub_tr) sub_tr[2] = clock64();
+#endif
 }
 
 // waits for the chunk's accumulators (bar / parity) inside, after the bias prefetch
 __device__ __forceinline__ void epilogue_dispatch(const TcOp& op, int nc, const float* bias_base, uint32_t tmem_lane,
                                                   uint32_t row, int sub, int q, float* dbg, int dbg_ld, uint64_t* bar,
-                                                  uint32_t parity, uint32_t* mask_word = nullptr) {
-  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, nullptr);
-  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, nullptr);
+                                                  uint32_t parity, uint32_t* mask_word = nullptr,
+                                                  unsigned long long* sub_tr = nullptr) {
+  if (op.nc_rows == 128) epilogue_chunk<32>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, nullptr, sub_tr);
+  else epilogue_chunk<16>(op, nc, bias_base, tmem_lane, row, sub, q, dbg, dbg_ld, bar, parity, nullptr, sub_tr);
 }
 // reverse-sweep instantiation: the epilogue records (forward) or applies (reverse) a ReLU mask word
 __device__ __forceinline__ void epilogue_dispatch_mask(const TcOp& op, int nc, const float* bias_base, uint32_t tmem_lane,
@@ -667,7 +722,9 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     __trap();
   }
 
-  const int64_t n_tiles = (a.n_samples_total + TM - 1) / TM;
+  // (early termination: the surviving samples were counted on the device by an earlier kernel of the stream)
+  const int64_t n_total = a.n_active ? (int64_t)__ldg(a.n_active) : a.n_samples_total;
+  const int64_t n_tiles = (n_total + TM - 1) / TM;
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const TcLevel& L = K.lvl;
 
@@ -682,7 +739,9 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     // ===================== MMA issuer =====================
     if (elect_one_sync()) {
       uint32_t bits = 0;
-      {   // the very first burst of the kernel: nobody waited for its weights yet
+      if ((int64_t)blockIdx.x < n_pairs) {   // the very first burst of the kernel: nobody waited for its weights yet
+        // (a CTA without a pair -- the early-termination scan left fewer tiles than the grid was sized for -- has no
+        //  producer activity to wait for)
         const uint32_t s0 = P.src[0], u0 = (s0 >> 29) & 3u;
         if (s0 >> 31) { mbar_wait(&ctl->full[u0], 0u); bits ^= 1u << (8 + u0); }
       }
@@ -690,7 +749,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         issue_program(P, ctl, bits, pair + gridDim.x < n_pairs, (K.trace && pair == (int64_t)gridDim.x) ? K.trace : nullptr);
     }
     __syncwarp();
-  } else if (warp >= CWARP0) {
+  } else if (is_compute_warp(warp)) {
     // ===================== compute warps =====================
     const int q = warp & 3, sub = (warp - CWARP0) >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
@@ -703,13 +762,13 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
     auto load_next = [&](int64_t pair_, int s_) {
       NextSample& ns = nxt[s_];
       const int64_t li = (2 * pair_ + s_) * TM + row;      // sample of the launch
-      ns.valid = (pair_ < n_pairs && li < a.n_samples_total) ? 1 : 0;
+      ns.valid = (pair_ < n_pairs && li < n_total) ? 1 : 0;
       ns.x[0] = ns.x[1] = ns.x[2] = 0.f; ns.vd[0] = ns.vd[1] = ns.vd[2] = 0.f; ns.gt = 0.f; ns.wid = 0; ns.n_out = 0;
       ns.xw[0] = ns.xw[1] = ns.xw[2] = 0.f; ns.om[0] = ns.om[1] = 0.f; ns.pmask = 0.f;
       for (int i = 0; i < 9; ++i) ns.R[i] = (i % 4 == 0) ? 1.f : 0.f;
       ns.p[0] = ns.p[1] = ns.p[2] = 0.f;
       if (!ns.valid) return;
-      const int64_t n_ = li, ray = li / a.S;
+      const int64_t n_ = a.index ? (int64_t)__ldg(a.index + li) : li, ray = n_ / a.S;
       ns.n_out = n_;
       ns.vd[0] = a.viewdirs[ray * 3]; ns.vd[1] = a.viewdirs[ray * 3 + 1]; ns.vd[2] = a.viewdirs[ray * 3 + 2];
       if (a.carry) {
@@ -838,7 +897,7 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
         // loads in the VIEW steps do not sit on the critical path of the trunk
         for (int s = 0; s < 2; ++s) {
           const int64_t li = (2 * (pair + gridDim.x) + s) * TM + row;
-          if (li < a.n_samples_total && (sub == s || sub == s + 2))
+          if (li < n_total && (sub == s || sub == s + 2))
             for (int i = (sub >> 1); i < C_COUNT; i += 2)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(a.carry + li + (int64_t)i * a.carry_stride));
         }
@@ -859,10 +918,14 @@ field_tc_kernel(const __grid_constant__ TcProgram P, const __grid_constant__ TcK
             const uint32_t par = (dc >> (2 * s + nc)) & 1u;
             dc ^= 1u << (2 * s + nc);
             if constexpr (GRAD) epilogue_dispatch_mask(op, nc, L.bias, tmem_lane, row, sub, q, &ctl->d_full[s][nc], par, &gst[s].masks[(op.mask_idx + nc) & (MASK_WORDS - 1)]);
-            else epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par);
+            else epilogue_dispatch(op, nc, L.bias, tmem_lane, row, sub, q, nullptr, 0, &ctl->d_full[s][nc], par, nullptr,
+                                   (NDS_SUBTRACE && tr) ? K.trace + TRACE_SUB + 8 * si + 4 * nc : nullptr);
             // (a plain epilogue only wrote tensor memory: no proxy fence)
             warp_arrive<false>(&ctl->part[s][nc], lane);
             if (op.n_nc == 1) warp_arrive<false>(&ctl->part[s][1], lane);   // keeps both barriers on one phase per op
+#if NDS_SUBTRACE
+            if (tr) K.trace[TRACE_SUB + 8 * si + 4 * nc + 3] = clock64();
+#endif
           }
         } else if (sp.kind == STEP_HEAD) {
           const TcOp& op = c_ops[sp.op];
@@ -1172,7 +1235,7 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
       issue_program(P, ctl, bits, false, nullptr);
     }
     __syncwarp();
-  } else if (warp >= CWARP0) {
+  } else if (is_compute_warp(warp)) {
     const int q = warp & 3, sub = (warp - CWARP0) >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
@@ -1219,7 +1282,7 @@ tc_selftest_kernel(const __grid_constant__ TcProgram P, TcLevel L, const float* 
   __syncthreads();
   tc_fence_after_sync();
   // read back the operand image the epilogue left in tensor memory -- what the next layer's MMA would see
-  if (warp >= CWARP0 && op.epi_kind != EPI_HEAD && out_readback) {
+  if (is_compute_warp(warp) && op.epi_kind != EPI_HEAD && out_readback) {
     const int q = warp & 3, sub = (warp - CWARP0) >> 2;
     const uint32_t row = (uint32_t)q * 32u + (uint32_t)lane;
     const uint32_t tmem_lane = tmem_base + (((uint32_t)q * 32u) << 16);
@@ -2254,6 +2317,12 @@ int tc_engine_field(ndsr_handle* h, const CallParams& cp, const FieldArgs& fa, c
         fprintf(f, "step %d kind %d slot %d op %d N %d glue %d arg %d start %lld end %lld\n", i, s.kind, s.tslot, s.op,
                 (s.kind <= STEP_HEAD) ? op.N : 0, (s.kind <= STEP_HEAD) ? op.glue : 0, s.arg,
                 rel(t[3 * MAX_BURST + 2 * i]), rel(t[3 * MAX_BURST + 2 * i + 1]));
+#if NDS_SUBTRACE
+        if (s.kind == STEP_EPI)
+          for (int c = 0; c < op.n_nc; ++c)
+            fprintf(f, "sub %d chunk %d waited %lld loaded %lld stored %lld arrived %lld\n", i, c, rel(t[TRACE_SUB + 8 * i + 4 * c]),
+                    rel(t[TRACE_SUB + 8 * i + 4 * c + 1]), rel(t[TRACE_SUB + 8 * i + 4 * c + 2]), rel(t[TRACE_SUB + 8 * i + 4 * c + 3]));
+#endif
       }
       fclose(f);
     }

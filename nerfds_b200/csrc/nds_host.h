@@ -57,6 +57,13 @@ struct ndsr_handle {
   float* carry = nullptr;      // C_COUNT planes of the coarse samples (tensor-core engine: split fine pass)
   int32_t* src_elem = nullptr; // [rays, S_c + S_f] from sample_pdf: element of concat(coarse, new) at each sorted position
   float* z_new = nullptr;      // [rays, S_f] the new depths in draw order
+  // early termination of the fine level (ndsr_set_early_termination): survivors of the scan, their count, statistics
+  float term_eps = 0.f;
+  int term_rounds = 4;
+  int32_t* term_index = nullptr;
+  int32_t* term_count = nullptr;
+  unsigned long long* term_stats = nullptr;   // device [2]: new depths evaluated / seen since the last reset
+  unsigned long long term_stats_keep[2] = {0, 0};   // their value while the scratch is being regrown
   float *planes = nullptr, *z_coarse = nullptr, *z_fine = nullptr, *w_coarse = nullptr, *w_sg = nullptr,
         *argmax = nullptr;
   void* in_stage = nullptr;       // host-buffer calls: two input staging halves (double-buffered per ray chunk)

@@ -106,6 +106,20 @@ class Renderer:
   def set_max_chunk(self, rays: int):
     self._check(self.lib.ndsr_set_max_chunk(self._h, int(rays)), 'ndsr_set_max_chunk')
 
+  def set_early_termination(self, transmittance_eps: float, rounds: int = 4):
+    """Fine level of `render_rays*` calls that ask for per-ray keys only: evaluate the newly drawn depths front to
+    back in `rounds` rounds and skip those behind which at most `transmittance_eps` of the ray's weight can lie
+    (0 = evaluate everything, like the reference)."""
+    self._check(self.lib.ndsr_set_early_termination(self._h, float(transmittance_eps), int(rounds)),
+                'ndsr_set_early_termination')
+
+  def termination_stats(self, reset: bool = False):
+    """(new fine-level depths evaluated, new fine-level depths seen) since the last reset (synchronises)."""
+    ev, seen = C.c_int64(0), C.c_int64(0)
+    self._check(self.lib.ndsr_termination_stats(self._h, self._stream(), C.byref(ev), C.byref(seen), int(bool(reset))),
+                'ndsr_termination_stats')
+    return int(ev.value), int(seen.value)
+
   STAGES = ('sample', 'field_coarse', 'field_fine', 'composite', 'resample', 'other')
 
   def profile_enable(self, on: bool = True):

@@ -401,6 +401,56 @@ def test_tc_split_fine_pass_is_exact(cuda_device, monkeypatch):
   np.testing.assert_array_equal(a['coarse']['rgb'], b['coarse']['rgb'])
 
 
+def test_early_termination_scan(cuda_device):
+  """ndsr_set_early_termination: on a field with opaque regions the fine level skips the new depths behind which at
+  most eps of transmittance is left; every per-ray output moves by at most 2 eps x (range of the composited
+  quantity), the mostly empty default field skips next to nothing, eps = 0 is the untouched path, and calls that
+  ask for per-sample tensors are never terminated."""
+  from nerfds_b200.params import harden_density
+  cfg, params, rays, t_rand, u = make_case('nerf_ds', image=32, seed=9)          # 1024 rays, 128 + 128 samples
+  solid = harden_density(params, 40.0)
+  keys = ('rgb', 'depth', 'acc', 'ray_norm', 'ray_delta_x', 'ray_hyper_points', 'ray_predicted_mask',
+          'ray_rotation_field', 'ray_translation_field', 'med_depth')
+  eps = 1e-4
+  far = cfg.far
+  scale = {'depth': far, 'ray_delta_x': 2 * far, 'ray_norm': 4.0, 'ray_hyper_points': 2.0, 'med_depth': None}
+  m = _model(cfg, cuda_device, engine='tc')
+  R = m.renderer
+
+  def render(p, e, ks=keys):
+    R.ensure_params(p)
+    R.set_early_termination(e)
+    R.termination_stats(reset=True)
+    o = m.apply({'params': p}, rays, syn.final_extra_params(), t_rand=t_rand, u=u, use_predicted_norm=True, keys=ks,
+                coarse_keys=('rgb',))
+    return _np(o['fine']), R.termination_stats()
+
+  full, st0 = render(solid, 0.0)
+  assert st0 == (0, 0)                                       # the scan did not run
+  term, (ev, seen) = render(solid, eps)
+  B = rays['origins'].shape[0]
+  assert seen == B * cfg.num_fine_samples
+  assert 0 < ev < 0.9 * seen, (ev, seen)                     # a real share of the new depths was skipped
+  for k in keys:
+    if k == 'med_depth':                                     # a selection: the same sample, or one of equal weight rank
+      assert np.mean(full[k] == term[k]) >= 0.99
+      continue
+    bound = 2 * eps * scale.get(k, 1.0) + 1e-6
+    assert linf(full[k], term[k]) <= bound, (k, linf(full[k], term[k]), bound)
+  again, _ = render(solid, 0.0)
+  for k in keys:
+    np.testing.assert_array_equal(full[k], again[k], err_msg=k)
+  # per-sample outputs requested: every sample is evaluated whatever eps says
+  _, st_ps = render(solid, eps, keys + ('weights',))
+  assert st_ps == (0, 0)
+  # the bench scene's field is mostly empty: (almost) nothing to skip, same result within the bound
+  f2, _ = render(params, 0.0)
+  t2, (ev2, seen2) = render(params, eps)
+  assert ev2 > 0.9 * seen2
+  assert linf(f2['rgb'], t2['rgb']) <= 2 * eps + 1e-6
+  R.set_early_termination(0.0)
+
+
 def test_host_buffer_path_matches_device_path(cuda_device):
   """ndsr_render_rays_host (numpy in / numpy out, input copies of chunk k + 1 overlapped with the compute of chunk k
   on a second stream) returns what the device-pointer path returns, for several chunks incl. a ragged last one."""

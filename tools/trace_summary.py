@@ -3,6 +3,8 @@ import sys
 bursts, steps = [], []
 for l in open(sys.argv[1]):
   t = l.split()
+  if t[0] == 'sub':
+    continue
   d = {t[i]: int(t[i + 1]) for i in range(2, len(t) - 1, 2)}
   d['i'] = int(t[1])
   (bursts if t[0] == 'burst' else steps).append(d)
