@@ -1880,6 +1880,12 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, bool grad, u
       const bool t_end = grad ? (s == 0 && i == LB.tb_first + LB.tb_count - 1) : (i == n_fwd - 1);
       prog.ops[op_index(s, i)].signal_done = (t_end || (grad && i == n_ops - 1)) ? 1 : 0;
     }
+  // Slot 1's last per-sample stage of the N phase (SE(3) exponential + trunk input, ~7 k cycles on the compute warps)
+  // runs AFTER slot 0's first trunk epilogue instead of before it, and releases its tensor-memory columns (done[1])
+  // as soon as it has read its head: slot 0's second trunk layer -- which accumulates over those columns -- is then
+  // issued while that stage computes, instead of after it.
+  const bool early_l1 = !carried && !grad && LB.n_narrow > 0 && !getenv("NDS_TC_NO_EARLY_L1");
+  if (early_l1) prog.ops[op_index(1, LB.n_narrow - 1)].signal_done = 1;
   auto step_of = [&](int s, int i) {
     Step st;
     const int ek = LB.ops[s][i].epi_kind;
@@ -1907,7 +1913,7 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, bool grad, u
     bursts.insert(bursts.end(), b0.begin(), b0.end());
     bursts.insert(bursts.end(), b1.begin(), b1.end());
     steps.push_back(step_of(0, i));
-    steps.push_back(step_of(1, i));
+    if (!(early_l1 && i == LB.n_narrow - 1)) steps.push_back(step_of(1, i));
   }
   // ---- T phase: tile slot 0, then tile slot 1
   for (int s = 0; s < 2; ++s) {
@@ -1917,6 +1923,8 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, bool grad, u
       if (carried && i == LB.trunk_first)       // inputs come from the PREP steps; the other slot must have left the T phase
         b[0].flags = (uint16_t)((b[0].flags & ~B_WAIT_GLUE) | B_WAIT_PREP | B_WAIT_DONE_OTHER);
       if (carried && i == LB.trunk_first + 1) b[0].flags &= (uint16_t)~B_PEEK_GLUE_OTHER;
+      // (early_l1: slot 1's last per-sample stage signals done[1] right after its tensor-memory read)
+      if (early_l1 && s == 0 && i == LB.trunk_first + 1) b[0].flags = (uint16_t)((b[0].flags & ~B_PEEK_GLUE_OTHER) | B_WAIT_DONE_OTHER);
       {
         int unit_of[64];
         std::fill(unit_of, unit_of + 64, -1);
@@ -1924,6 +1932,7 @@ static bool assemble(const LevelBuild& LB, bool full, bool carried, bool grad, u
       }
       bursts.insert(bursts.end(), b.begin(), b.end());
       steps.push_back(step_of(s, i));
+      if (early_l1 && s == 0 && i == LB.trunk_first) steps.push_back(step_of(1, LB.n_narrow - 1));
       // next pair's sample fetch + viewdir features: off the critical path, in the slack after the second trunk layer
       // (carried programs fetch 18 carry planes per sample: the two halves go into the slack of different layers)
       if (i == LB.trunk_first + 1 || (carried && i == LB.trunk_first + 2)) {
