@@ -437,6 +437,14 @@ def test_early_termination_scan(cuda_device):
       continue
     bound = 2 * eps * scale.get(k, 1.0) + 1e-6
     assert linf(full[k], term[k]) <= bound, (k, linf(full[k], term[k]), bound)
+  # the host-buffer entry point (chunked, double-buffered uploads) terminates the same way, chunk by chunk
+  R.set_max_chunk(300)
+  extra = R.make_extra(syn.final_extra_params(), use_predicted_norm=True)
+  host = R.render_rays_host(rays['origins'], rays['directions'], warp_id=rays['metadata']['warp'], gt_mask=rays['mask'],
+                            t_rand=t_rand, u=u, extra=extra, fine_keys=keys)
+  R.set_max_chunk(65536)
+  for k in keys:
+    np.testing.assert_array_equal(host[k].reshape(term[k].shape), term[k], err_msg=k)
   again, _ = render(solid, 0.0)
   for k in keys:
     np.testing.assert_array_equal(full[k], again[k], err_msg=k)
