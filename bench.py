@@ -391,6 +391,39 @@ def run_ours(args):
     R.set_early_termination(0.0)
     R.load_params(params)
 
+  # ---- precision='mixed' beside the headline (which stays split3): the rgb branch as ONE fp16 term instead of three
+  # (2.40x instead of 2.54x the algorithmic MACs; strict parity at 16 384 rays: fine rgb max 4.2e-4 instead of 3.2e-4,
+  # profiles/r2_parity_scale_mixed.txt)
+  mixed = None
+  if world == 1 and R.engine == 'tc' and args.precision == 'split3' and not args.sweep and not args.no_mixed:
+    m2 = NerfModel(cfg, device=dev, engine=args.engine, precision='mixed')
+    R2 = m2.renderer
+    R2.load_params(params)
+    R2.set_max_chunk(args.chunk)
+
+    def step_mixed():
+      for fr in frames:
+        t = R2.random_uniform(fr['keys'][0], fr['o'].shape[0], Sc)
+        uu = R2.random_uniform(fr['keys'][1], fr['o'].shape[0], Sf)
+        R2.render_rays(fr['o'], fr['d'], warp_id=fr['w'], t_rand=t, u=uu, extra=extra, coarse_keys=(), fine_keys=RENDER_KEYS)
+      flush.fill_(1)
+
+    step_mixed()
+    ts = max(1, min(args.steps, 2))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(ts):
+      step_mixed()
+    e1.record()
+    barrier()
+    im2 = R2.tc_issued_macs()
+    mixed = {'value': rays_step * ts / (e0.elapsed_time(e1) * 1e-3), 'steps': ts,
+             'issued_over_algorithmic': (Sc * im2[(0, 'sigma')] + Sf * im2[(1, 'full')] + Sc * im2[(1, 'carried')]) /
+                                        float(Sc * MAC_COARSE + (Sc + Sf) * MAC_FINE),
+             'what': "precision='mixed': rgb branch as one fp16 term (not the headline)"}
+    R2.close()
+
   # ---- N > 1: the last assembled frame against a single-GPU render of the same rays, shards and keys
   frame_check = None
   if world > 1:
@@ -459,6 +492,8 @@ def run_ours(args):
       line['frame_matches_single_gpu'] = frame_check
     if term is not None:
       line['early_termination'] = term
+    if mixed is not None:
+      line['mixed_precision'] = mixed
     print(json.dumps(line), flush=True)
   if peer is not None:
     for pf in peer:
@@ -669,6 +704,7 @@ def main():
   ap.add_argument('--batch', type=int, default=4096)
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='weak: N frames per step (per-GPU work fixed); strong: one frame per step over N ranks')
+  ap.add_argument('--no-mixed', action='store_true', help="skip the extra precision='mixed' measurement")
   ap.add_argument('--term-eps', type=float, default=1e-4,
                   help='also measure the fine level with the early-termination scan at this transmittance (0: skip)')
   ap.add_argument('--traffic', type=float, default=None, help='DRAM bytes/launch of the dominant kernel from ncu')
