@@ -392,7 +392,7 @@ def run_ours(args):
     R.load_params(params)
 
   # ---- precision='mixed' beside the headline (which stays split3): the rgb branch as ONE fp16 term instead of three
-  # (2.40x instead of 2.54x the algorithmic MACs; strict parity at 16 384 rays: fine rgb max 4.2e-4 instead of 3.2e-4,
+  # (2.48x instead of 2.54x the algorithmic MACs; strict parity at 16 384 rays: fine rgb max 4.2e-4 instead of 3.2e-4,
   # profiles/r2_parity_scale_mixed.txt)
   mixed = None
   if world == 1 and R.engine == 'tc' and args.precision == 'split3' and not args.sweep and not args.no_mixed:
