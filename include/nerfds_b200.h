@@ -324,8 +324,10 @@ int ndsr_set_max_chunk(ndsr_handle* h, int64_t max_rays);
  * rank ranges.  Before each round a scan bounds the transmittance T in front of every depth of the round by the
  * product over the samples evaluated so far (the exact factors (1 - alpha + 1e-10) of model_utils.py:131-136) and
  * drops the depths with T < eps: together they can hold at most eps of a ray's weight, so every per-ray output moves
- * by at most 2 eps x (range of the composited quantity).  ndsr_termination_stats returns the new depths evaluated /
- * seen since the last reset (synchronises `stream`). */
+ * by at most 2 eps x (range of the composited quantity).  The rounds adapt on the device: a round that finds that fewer
+ * than 1 % of the depths decided so far were dropped takes all remaining depths at once (the later rounds are empty
+ * launches), so a field with nothing to terminate pays for one extra pass, not for `rounds`.
+ * ndsr_termination_stats returns the new depths evaluated / seen since the last reset (synchronises `stream`). */
 int ndsr_set_early_termination(ndsr_handle* h, float transmittance_eps, int32_t rounds);
 int ndsr_termination_stats(ndsr_handle* h, void* stream, int64_t* evaluated, int64_t* seen, int reset);
 

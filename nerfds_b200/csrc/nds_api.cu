@@ -217,7 +217,7 @@ extern "C" int ndsr_create(const ndsr_config* cfg, int device, ndsr_handle** out
 static void free_scratch(ndsr_handle* h) {
   if (h->term_stats)     // the statistics live in the scratch: keep their value while it is regrown
     cudaMemcpy(h->term_stats_keep, h->term_stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-  h->term_stats = nullptr; h->term_index = nullptr; h->term_count = nullptr;
+  h->term_stats = nullptr; h->term_index = nullptr; h->term_count = nullptr; h->term_round_stats = nullptr;
   for (void* p : h->scratch_allocs) cudaFree(p);
   h->scratch_allocs.clear();
   h->cap_rays = 0;
@@ -481,9 +481,13 @@ static int ensure_scratch(ndsr_handle* h, int64_t rays, cudaStream_t st) {
   NDS_CUDA(h, alloc(&h->z_new, rays * (smax > c.num_coarse_samples ? smax - c.num_coarse_samples : 1)));
   {
     float* pf = nullptr;
-    NDS_CUDA(h, alloc(&pf, rays * (smax > c.num_coarse_samples ? smax - c.num_coarse_samples : 1) + 8));
-    h->term_index = reinterpret_cast<int32_t*>(pf) + 8;      // 32 bytes in front: the count and the statistics
+    // header in front of the index list: the count (4 B), the statistics (2 x 8 B at byte 8), the per-round counters
+    // of the adaptive rounds (NDS_TERM_MAX_ROUNDS x 2 x 8 B at byte 32)
+    const int64_t hdr = 8 + 4 * NDS_TERM_MAX_ROUNDS;         // floats
+    NDS_CUDA(h, alloc(&pf, rays * (smax > c.num_coarse_samples ? smax - c.num_coarse_samples : 1) + hdr));
+    h->term_index = reinterpret_cast<int32_t*>(pf) + hdr;
     h->term_count = reinterpret_cast<int32_t*>(pf);
+    h->term_round_stats = reinterpret_cast<unsigned long long*>(pf) + 4;
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(pf) + 1;
     NDS_CUDA(h, cudaMemcpy(stats, h->term_stats_keep, 2 * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     h->term_stats = stats;
@@ -569,7 +573,10 @@ static int run_level(ndsr_handle* h, cudaStream_t st, int level, int64_t B, int 
         ta.index = h->term_index; ta.n_active = h->term_count; ta.stats = h->term_stats;
         fn.index = h->term_index; fn.n_active = h->term_count;
         const int n_new = S - n_carried, rounds = h->term_rounds < n_new ? h->term_rounds : n_new;
+        ta.round_stats = h->term_round_stats; ta.merge_frac = 0.99f;
+        NDS_CUDA(h, cudaMemsetAsync(h->term_round_stats, 0, 2 * sizeof(unsigned long long) * NDS_TERM_MAX_ROUNDS, st));
         for (int r = 0; r < rounds; ++r) {       // front to back: each round sees the sigmas of the rounds before it
+          ta.round = r;
           ta.rank_lo = (int)((int64_t)n_new * r / rounds); ta.rank_hi = (int)((int64_t)n_new * (r + 1) / rounds);
           NDS_CUDA(h, launch_termination_scan(ta, h->num_sms, st));
           h->launches++;

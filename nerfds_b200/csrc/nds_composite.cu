@@ -275,6 +275,18 @@ termination_scan_kernel(const __grid_constant__ TerminationArgs a) {
   const int chunk = (S + 31) / 32;
   const int64_t ps = a.plane_stride;
   const float last = a.sample_at_infinity ? 1e10f : 1e-19f;
+  // adaptive rounds: did an earlier round take everything, or does this one?
+  int rank_lo = a.rank_lo, rank_hi = a.rank_hi;
+  if (a.round_stats && a.round > 0) {
+    unsigned long long ev = 0, seen = 0;
+    int first_merge = -1;
+    for (int r = 1; r <= a.round && first_merge < 0; ++r) {
+      ev += a.round_stats[2 * (r - 1)]; seen += a.round_stats[2 * (r - 1) + 1];
+      if ((double)ev >= (double)a.merge_frac * (double)seen) first_merge = r;
+    }
+    if (first_merge >= 0 && first_merge < a.round) return;      // all ranks were handled by that round
+    if (first_merge == a.round) rank_hi = nn;
+  }
   for (int64_t ray = (int64_t)blockIdx.x * CW + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * CW) {
     const int64_t base = ray * S;
     const float dx = a.dirs[ray * 3], dy = a.dirs[ray * 3 + 1], dz = a.dirs[ray * 3 + 2];
@@ -295,7 +307,7 @@ termination_scan_kernel(const __grid_constant__ TerminationArgs a) {
     auto factor = [&](int s, int e, int rank) -> float {
       int64_t pn;
       if (e < nc) pn = ray * nc + e;
-      else if (rank < a.rank_lo) pn = a.n_rays * nc + ray * nn + (e - nc);
+      else if (rank < rank_lo) pn = a.n_rays * nc + ray * nn + (e - nc);
       else return 1.f;
       const float sigma = softplus_f(a.planes[P_SIGMA_RAW * ps + pn]);
       const float dist = ((s == S - 1) ? last : (a.z[base + s + 1] - a.z[base + s])) * dnorm;
@@ -326,7 +338,7 @@ termination_scan_kernel(const __grid_constant__ TerminationArgs a) {
       int rank = rank0;
       for (int s = s0; s < s1; ++s) {
         const int e = a.src_elem[base + s];
-        if (e >= nc && rank >= a.rank_lo && rank < a.rank_hi && T >= a.eps) ++kept;
+        if (e >= nc && rank >= rank_lo && rank < rank_hi && T >= a.eps) ++kept;
         T *= factor(s, e, rank);
         rank += e >= nc ? 1 : 0;
       }
@@ -342,14 +354,18 @@ termination_scan_kernel(const __grid_constant__ TerminationArgs a) {
     if (lane == 0) {
       dst = atomicAdd(a.n_active, total);
       atomicAdd(a.stats, (unsigned long long)total);
-      atomicAdd(a.stats + 1, (unsigned long long)(min(a.rank_hi, nn) - min(a.rank_lo, nn)));
+      atomicAdd(a.stats + 1, (unsigned long long)(min(rank_hi, nn) - min(rank_lo, nn)));
+      if (a.round_stats) {
+        atomicAdd(a.round_stats + 2 * a.round, (unsigned long long)total);
+        atomicAdd(a.round_stats + 2 * a.round + 1, (unsigned long long)(min(rank_hi, nn) - min(rank_lo, nn)));
+      }
     }
     dst = __shfl_sync(0xffffffffu, dst, 0) + off - kept;
     float T = T0;
     int rank = rank0;
     for (int s = s0; s < s1; ++s) {
       const int e = a.src_elem[base + s];
-      const bool mine = e >= nc && rank >= a.rank_lo && rank < a.rank_hi;
+      const bool mine = e >= nc && rank >= rank_lo && rank < rank_hi;
       const float Tb = T;
       T *= factor(s, e, rank);
       rank += e >= nc ? 1 : 0;

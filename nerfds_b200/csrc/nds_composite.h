@@ -75,7 +75,16 @@ struct TerminationArgs {
   int32_t* index;            // out: surviving new samples (element of the dense new-depth list, ray * n_new + e)
   int32_t* n_active;         // out: their count (zeroed by the launcher)
   unsigned long long* stats; // [2] accumulated: new depths evaluated, new depths seen
+  // Adaptive rounds: round_stats[r] = {evaluated, seen} of round r of THIS fine level (zeroed before round 0).  A round
+  // r >= 1 that finds (almost) nothing was skipped so far -- evaluated >= merge_frac x seen over the rounds before it --
+  // takes all remaining ranks at once, and the rounds after it are empty: on a field with nothing to terminate the
+  // fine level costs one extra launch instead of rounds - 1.  Every kernel recomputes the decision from the counters
+  // of the rounds that have finished, so no flag travels through the host.
+  unsigned long long* round_stats;   // [NDS_TERM_MAX_ROUNDS][2]
+  int round;
+  float merge_frac;
 };
+constexpr int NDS_TERM_MAX_ROUNDS = 64;
 cudaError_t launch_termination_scan(const TerminationArgs& a, int num_sms, cudaStream_t st);
 
 cudaError_t launch_uniform_threefry(uint32_t k0, uint32_t k1, int64_t n, float* out, int num_sms, cudaStream_t st);

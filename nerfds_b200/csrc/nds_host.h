@@ -62,6 +62,7 @@ struct ndsr_handle {
   int term_rounds = 4;
   int32_t* term_index = nullptr;
   int32_t* term_count = nullptr;
+  unsigned long long* term_round_stats = nullptr;   // device [NDS_TERM_MAX_ROUNDS][2], per fine level (adaptive rounds)
   unsigned long long* term_stats = nullptr;   // device [2]: new depths evaluated / seen since the last reset
   unsigned long long term_stats_keep[2] = {0, 0};   // their value while the scratch is being regrown
   float *planes = nullptr, *z_coarse = nullptr, *z_fine = nullptr, *w_coarse = nullptr, *w_sg = nullptr,
